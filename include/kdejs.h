@@ -1,0 +1,145 @@
+/*
+ * kdejs.h -- C ABI of libkdejs.so, the B200 (sm_100a) implementation of PopPUNK-mod's
+ * KDE discrepancy.  Plain pointers and sizes only; no torch / CUDA types cross this line
+ * (a CUDA stream is passed as an opaque void*).
+ *
+ * The reference has no FFI of its own: its hot path is Python calling compiled wheels
+ * (sklearn Cython / scipy C).  Each entry point below replaces the Python-level interface
+ * named beside it (paths relative to the reference repository); INTEGRATION.md shows the
+ * ctypes binding a maintainer would add to KDE_distance.py.
+ *
+ * Conventions
+ *   - point sets are row-major (N,2) float64, column 0 = core distance, 1 = accessory
+ *   - grids are flat (R*R) float64, node k = ix*R + iy at (lin[ix], lin[iy]),
+ *     lin = linspace(gmin, gmax, R): the order of get_grid()'s `xy` (KDE_distance.py:17-23)
+ *   - every function returns KDEJS_OK or an error code; kdejs_last_error() gives the
+ *     message for the calling thread.  There is no CPU fallback: without a usable
+ *     sm_100 device every compute entry point fails with KDEJS_ERR_CUDA.
+ *   - the caller owns all buffers it passes; the library owns its device scratch (grown
+ *     on demand, cached per device, released by kdejs_shutdown).  No pointer is retained
+ *     after a call returns, except by the *_dev entry points until their stream work ends.
+ *   - nothing touches CUDA at load time (fork-safe: ELFI's multiprocessing client and the
+ *     scripts' Pools fork after import); a context is created on first use per process.
+ */
+#ifndef KDEJS_H
+#define KDEJS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDEJS_VERSION 100
+
+/* status codes */
+#define KDEJS_OK 0
+#define KDEJS_ERR_CUDA 1     /* CUDA runtime failure or no device            -> RuntimeError */
+#define KDEJS_ERR_ARG 2      /* bad shape / size / parameter                 -> ValueError   */
+#define KDEJS_ERR_INF 3      /* input contains infinity (sklearn ValueError) -> ValueError   */
+
+/* kernel (sklearn KernelDensity(kernel=...), KDE_distance.py:50-51) */
+#define KDEJS_KERNEL_EPANECHNIKOV 0   /* the reference's kernel                            */
+#define KDEJS_KERNEL_GAUSSIAN 1       /* extra mode; dense algorithm only */
+
+/* algorithm for the density sum (results agree within the documented tolerances) */
+#define KDEJS_ALGO_BINNED 0   /* fp64, points counting-sorted into cells, only in-reach   */
+                              /* (tile, cell) pairs evaluated: the default, exact sum     */
+#define KDEJS_ALGO_DENSE 1    /* fp32 terms / fp64 accumulation brute force over all       */
+                              /* N x G pairs (the north-star kernel; FP32-pipe roofline)   */
+#define KDEJS_ALGO_DENSE64 2  /* fp64 brute force (cross-check; gaussian parity)           */
+
+/* ---- life cycle -------------------------------------------------------------------- */
+int kdejs_version(void);
+int kdejs_device_count(int *count);
+/* Create (idempotent) the context for `device`: streams, scratch.  Called lazily by every
+ * compute entry point; exposed so callers can pay the ~100 ms context cost up front. */
+int kdejs_init(int device);
+void kdejs_shutdown(void);
+const char *kdejs_last_error(void);
+
+/* ---- the hot path ------------------------------------------------------------------ */
+/* KDE_JS_divergence(df1, df2, gamma, eps, log)            KDE_distance.py:104-130
+ * (callers: poppunk_mod.py:373, scripts/pairwise_2D_distance.py:54,
+ *  scripts/distance_to_gridsearch.py:50, KDE_distance.py:143).
+ * a/b: HOST pointers.  resolution/bandwidth/kernel are the reference's hard-coded
+ * 100 / 0.03 / epanechnikov (KDE_distance.py:89, :50-51) made explicit.
+ * Optional outputs (NULL to skip), each (R*R) doubles on the host:
+ *   out_z1/out_z2  the normalised vectors scale_KDE returns    KDE_distance.py:80-95
+ *   out_d1/out_d2  raw densities exp(score_samples)            KDE_distance.py:58-64 */
+int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, int64_t nb,
+                      int resolution, double bandwidth, double gamma, double eps, int log_flag,
+                      int kernel, int algo, double *out_js,
+                      double *out_z1, double *out_z2, double *out_d1, double *out_d2);
+
+/* One target against B simulated sets: B independent KDE_JS_divergence(obs, sims[i], ...)
+ * calls (the per-simulation call at poppunk_mod.py:373 over a BOLFI batch; the
+ * Pool.imap loops at scripts/distance_to_gridsearch.py:109-110).  HOST pointers; sims
+ * in pinned memory (kdejs_host_alloc) are copied asynchronously and overlap compute.
+ * out_js: B doubles.  If some sets contain infinity their out_js is NaN and the call
+ * returns KDEJS_ERR_INF after finishing the others. */
+int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs,
+                            const double *const *sims, const int64_t *n_sims, int B,
+                            int resolution, double bandwidth, double gamma, double eps,
+                            int log_flag, int kernel, int algo, double *out_js);
+
+/* General pairs: out_js[i] = KDE_JS_divergence(sets[ia[i]], sets[ib[i]]) over a pool of
+ * n_sets HOST point sets, each uploaded once (the itertools.combinations loop at
+ * scripts/pairwise_2D_distance.py:112-118). */
+int kdejs_discrepancy_pairs(int device, const double *const *sets, const int64_t *n_pts,
+                            int n_sets, const int32_t *ia, const int32_t *ib, int64_t n_pairs,
+                            int resolution, double bandwidth, double gamma, double eps,
+                            int log_flag, int kernel, int algo, double *out_js);
+
+/* Device-resident variant of kdejs_discrepancy_batch: obs_dev and every sims_dev[i] are
+ * DEVICE pointers (16-byte aligned) on `device`, out_js_dev is B doubles on the device,
+ * status_dev (nullable) B int32.  All work is enqueued on `stream` (a cudaStream_t, NULL =
+ * the library's own stream) and the call returns without synchronising. */
+int kdejs_discrepancy_batch_dev(int device, const double *obs_dev, int64_t n_obs,
+                                const double *const *sims_dev, const int64_t *n_sims, int B,
+                                int resolution, double bandwidth, double gamma, double eps,
+                                int log_flag, int kernel, int algo,
+                                double *out_js_dev, int32_t *status_dev, void *stream);
+
+/* exp(KernelDensity(bandwidth, kernel).fit(pts).score_samples(get_grid(gmin,gmax,R)[2]))
+ * for ALREADY SCALED points -- get_kde + generate_samples, KDE_distance.py:48-64, and the
+ * contour density of plot_scatter, poppunk_mod.py:98-105.  HOST pointers. */
+int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, double gmax,
+                      int resolution, double bandwidth, int kernel, int algo, double *out_dens);
+
+/* ---- one huge evaluation, grid rows sharded over ranks ------
+ * Every rank holds both point sets (HOST pointers) and owns node rows [row_begin,row_end)
+ * of the R x R grid (rows = index of column 0).  Phase 1 fits the joint scaler, evaluates
+ * the rank's rows and returns its partial normalisers sum(z1**gamma+eps), sum(z2**gamma+eps).
+ * The caller all-reduces the two sums (2 doubles) and calls phase 2, which returns the
+ * rank's partial (left,right) relative-entropy sums; JS = sqrt((sum left + sum right)/2). */
+int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b, int64_t nb,
+                       int resolution, double bandwidth, double gamma, double eps, int log_flag,
+                       int kernel, int algo, int row_begin, int row_end, double out_norm[2]);
+int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2]);
+
+/* ---- host memory --------------------------------------------------------------------- */
+void *kdejs_host_alloc(size_t bytes);   /* pinned (page-locked) host memory, NULL on failure */
+void kdejs_host_free(void *p);
+
+/* ---- measurement support (bench.py, tests) ------------------------------------------- */
+/* Per-kernel CUDA-event timing on the launching stream.  which: 0 minmax, 1 scale+count,
+ * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence.  Reading synchronises. */
+#define KDEJS_NUM_KERNELS 6
+int kdejs_profile_enable(int device, int on);
+int kdejs_profile_read(int device, int which, double *ms_total, int64_t *launches);
+int kdejs_profile_reset(int device);
+/* Kernels launched by this library on `device` since init / last reset. */
+int kdejs_launch_count(int device, int64_t *count, int reset);
+/* Work counters of the density launches since the last reset: pair_tests = (point, node)
+ * kernel evaluations executed; in_support is filled only by the CPU-side estimate (0 here). */
+int kdejs_work_counters(int device, double *pair_tests, int reset);
+/* Issue-rate microbenchmarks used as roofline denominators.  which: 0 FFMA fp32,
+ * 1 DFMA fp64, 2 packed FFMA2 (f32x2).  Returns achieved TFLOP/s (2 flop per lane-FMA). */
+int kdejs_peak_flops(int device, int which, double *tflops, double *sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KDEJS_H */
