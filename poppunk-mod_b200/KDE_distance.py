@@ -1,0 +1,264 @@
+"""Drop-in for PopPUNK-mod's ``KDE_distance`` module, computed on a B200 through libkdejs.so.
+
+Same public names, argument meaning and return types as /root/reference/KDE_distance.py:
+
+    get_grid(minimum, maximum, resolution)                       KDE_distance.py:17-23
+    scale_KDE(df1, df2, gamma, eps) -> (z1, z2, grid_params)     KDE_distance.py:80-95
+    KDE_JS_divergence(df1, df2, gamma=1.0, eps=1e-12,
+                      log=False, outplot=None) -> np.float64     KDE_distance.py:104-130
+    KDE_KL_divergence(df1, df2, gamma=1.0, eps=1e-12)            KDE_distance.py:97-102
+    main()  (python KDE_distance.py --infile1 A --infile2 B)     KDE_distance.py:132-144
+
+Callers that keep working unchanged: poppunk_mod.py:373, scripts/pairwise_2D_distance.py:54,
+scripts/distance_to_gridsearch.py:50.  The reference's hard-coded 100x100 grid, bandwidth 0.03
+and Epanechnikov kernel (KDE_distance.py:89, :50-51) are the defaults of extra keyword-only
+arguments.  Added entry points: KDE_JS_divergence_batch / _pairs (many evaluations per call,
+optionally over several GPUs) and kde_density.
+
+All arithmetic of the path runs in hand-written CUDA kernels (poppunk-mod_b200/csrc); there is
+no CPU fallback -- without the library or a B200 the calls raise RuntimeError.
+
+Known, deliberate difference: the reference's sklearn ball tree leaves ~1e-15 residues at grid
+nodes whose density is exactly zero; with gamma < 1 those residues move its result by ~5e-4
+(SURVEY.md section 0.3).  This module returns the exact sum, which equals the reference with
+those residues removed to ~1e-13 (tests/test_parity_gpu.py, tests/golden/golden.json).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+try:
+    from . import _native as nat
+except ImportError:  # used as a top-level drop-in module: `sys.path.insert(0, ".../poppunk-mod_b200")`
+    import importlib.util as _ilu
+
+    _spec = _ilu.spec_from_file_location("_kdejs_native",
+                                         os.path.join(os.path.dirname(os.path.abspath(__file__)), "_native.py"))
+    nat = _ilu.module_from_spec(_spec)
+    _spec.loader.exec_module(nat)
+
+__all__ = ["get_grid", "scale_KDE", "KDE_JS_divergence", "KDE_KL_divergence", "KDE_JS_divergence_batch",
+           "KDE_JS_divergence_pairs", "kde_density", "default_device", "main"]
+
+_DEFAULT_RESOLUTION = 100      # KDE_distance.py:89
+_DEFAULT_BANDWIDTH = 0.03      # KDE_distance.py:50
+
+
+def default_device() -> int:
+    """KDEJS_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    for key in ("KDEJS_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(key)
+        if v not in (None, ""):
+            n = nat.device_count()
+            return int(v) % n if n > 0 else int(v)
+    return 0
+
+
+def get_grid(minimum, maximum, resolution):
+    """(xx, yy, xy) with xy[k] = (lin[k // R], lin[k % R]); KDE_distance.py:17-23."""
+    lin = np.linspace(minimum, maximum, resolution)
+    xx, yy = np.meshgrid(lin, lin)
+    xy = np.column_stack([yy.reshape(-1), xx.reshape(-1)])
+    return xx, yy, xy
+
+
+def _common(resolution, bandwidth, gamma, eps, log, kernel, algo):
+    if kernel not in nat.KERNELS:
+        raise ValueError(f"kernel must be one of {sorted(nat.KERNELS)}; got {kernel!r}")
+    if algo is None:
+        algo = "binned" if kernel == "epanechnikov" else "dense64"
+    if algo not in nat.ALGOS:
+        raise ValueError(f"algo must be one of {sorted(nat.ALGOS)}; got {algo!r}")
+    return (int(resolution), float(bandwidth), float(gamma), float(eps), int(bool(log)),
+            nat.KERNELS[kernel], nat.ALGOS[algo])
+
+
+def _discrepancy(df1, df2, gamma, eps, log, resolution, bandwidth, kernel, algo, device, want_z=False,
+                 want_density=False):
+    a = nat.as_points(df1, "df1")
+    b = nat.as_points(df2, "df2")
+    common = _common(resolution, bandwidth, gamma, eps, log, kernel, algo)
+    G = int(resolution) * int(resolution)
+    out = ctypes.c_double()
+    z1 = z2 = d1 = d2 = None
+    if want_z:
+        z1, z2 = np.empty(G), np.empty(G)
+    if want_density:
+        d1, d2 = np.empty(G), np.empty(G)
+    dev = default_device() if device is None else int(device)
+    nat.check(nat.lib().kdejs_discrepancy(dev, nat.ptr(a), a.shape[0], nat.ptr(b), b.shape[0], *common,
+                                          ctypes.byref(out), nat.ptr(z1), nat.ptr(z2), nat.ptr(d1), nat.ptr(d2)))
+    return np.float64(out.value), z1, z2, d1, d2
+
+
+def scale_KDE(df1, df2, gamma, eps, *, log=False, resolution=_DEFAULT_RESOLUTION,
+              bandwidth=_DEFAULT_BANDWIDTH, kernel="epanechnikov", algo=None, device=None):
+    """Jointly min-max scale both sets, KDE each on the grid, **gamma, +eps, normalise."""
+    _, z1, z2, _, _ = _discrepancy(df1, df2, gamma, eps, log, resolution, bandwidth, kernel, algo, device,
+                                   want_z=True)
+    return z1, z2, get_grid(0, 1, resolution)
+
+
+def KDE_KL_divergence(df1, df2, gamma=1.0, eps=1e-12, **kw):
+    """sum(rel_entr(z1, z2)).  (The reference's version unpacks two of scale_KDE's three return
+    values and raises ValueError, KDE_distance.py:98; this one returns the intended number.)"""
+    z1, z2, _ = scale_KDE(df1, df2, gamma, eps, **kw)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(z1 > 0, z1 * np.log(z1 / z2), np.where(z1 == 0, 0.0, np.inf))
+    return np.float64(t.sum())
+
+
+def KDE_JS_divergence(df1, df2, gamma=1.0, eps=1e-12, log=False, outplot=None, *,
+                      resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BANDWIDTH,
+                      kernel="epanechnikov", algo=None, device=None):
+    """Jensen-Shannon distance between the grid KDEs of two (N,2) point sets."""
+    want_plot = outplot is not None
+    js, z1, z2, _, _ = _discrepancy(df1, df2, gamma, eps, log, resolution, bandwidth, kernel, algo, device,
+                                    want_z=want_plot)
+    if want_plot:
+        _plot_contours(df1, df2, z1, z2, eps, log, resolution, outplot)
+    return js
+
+
+def KDE_JS_divergence_batch(obs, sims, gamma=1.0, eps=1e-12, log=False, *,
+                            resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BANDWIDTH,
+                            kernel="epanechnikov", algo=None, devices=None):
+    """[KDE_JS_divergence(obs, s, gamma, eps, log) for s in sims] as one float64 array.
+
+    devices: None (default device), an int, or a list of device indices; with several devices the
+    sims are dealt round-robin, one host thread per device, and only the B scalars come back."""
+    o = nat.as_points(obs, "obs")
+    arrays = [nat.as_points(s, f"sims[{i}]") for i, s in enumerate(sims)]
+    common = _common(resolution, bandwidth, gamma, eps, log, kernel, algo)
+    B = len(arrays)
+    out = np.empty(B, dtype=np.float64)
+    if B == 0:
+        return out
+    if devices is None:
+        devices = [default_device()]
+    elif isinstance(devices, int):
+        devices = [devices]
+    devices = list(devices)
+
+    def run(dev, idx):
+        sub = [arrays[i] for i in idx]
+        ptrs, counts = nat.pointer_array(sub)
+        res = np.empty(len(sub), dtype=np.float64)
+        rc = nat.lib().kdejs_discrepancy_batch(int(dev), nat.ptr(o), o.shape[0], ptrs, counts, len(sub),
+                                               *common, nat.ptr(res))
+        err = (nat.lib().kdejs_last_error() or b"").decode() if rc else ""
+        return idx, res, rc, err
+
+    if len(devices) == 1:
+        results = [run(devices[0], list(range(B)))]
+    else:
+        results = [None] * len(devices)
+        shards = [list(range(k, B, len(devices))) for k in range(len(devices))]
+
+        def worker(k):
+            results[k] = run(devices[k], shards[k]) if shards[k] else ([], np.empty(0), 0, "")
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(devices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    first_err = None
+    for idx, res, rc, err in results:
+        out[idx] = res
+        if rc and first_err is None:
+            first_err = (rc, err)
+    if first_err:
+        rc, err = first_err
+        if rc in (nat.KDEJS_ERR_ARG, nat.KDEJS_ERR_INF):
+            raise ValueError(err)
+        raise RuntimeError(f"kdejs: {err}")
+    return out
+
+
+def KDE_JS_divergence_pairs(sets, pairs, gamma=1.0, eps=1e-12, log=False, *,
+                            resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BANDWIDTH,
+                            kernel="epanechnikov", algo=None, device=None):
+    """out[k] = KDE_JS_divergence(sets[i_k], sets[j_k]) for (i_k, j_k) in pairs; every set is
+    uploaded once (the all-pairs loop of scripts/pairwise_2D_distance.py:112-118)."""
+    arrays = [nat.as_points(s, f"sets[{i}]") for i, s in enumerate(sets)]
+    pr = np.asarray(list(pairs), dtype=np.int32).reshape(-1, 2)
+    ia = np.ascontiguousarray(pr[:, 0])
+    ib = np.ascontiguousarray(pr[:, 1])
+    common = _common(resolution, bandwidth, gamma, eps, log, kernel, algo)
+    out = np.empty(len(pr), dtype=np.float64)
+    ptrs, counts = nat.pointer_array(arrays)
+    dev = default_device() if device is None else int(device)
+    nat.check(nat.lib().kdejs_discrepancy_pairs(dev, ptrs, counts, len(arrays), nat.ptr(ia), nat.ptr(ib),
+                                                len(pr), *common, nat.ptr(out)))
+    return out
+
+
+def kde_density(df_scaled, resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BANDWIDTH,
+                kernel="epanechnikov", minimum=0.0, maximum=1.0, *, algo=None, device=None):
+    """exp(KernelDensity(bandwidth, kernel).fit(X).score_samples(get_grid(min, max, R)[2])) as an
+    (R, R) array (row = column-0 node): get_kde + generate_samples, KDE_distance.py:48-64, for
+    points that are already scaled; also the density plot_scatter draws (poppunk_mod.py:98-105)."""
+    X = nat.as_points(df_scaled, "df_scaled")
+    if not np.isfinite(X).all():
+        raise ValueError("Input X contains NaN or infinity.")
+    R, h, _, _, _, k, al = _common(resolution, bandwidth, 1.0, 0.0, False, kernel, algo)
+    out = np.empty(R * R, dtype=np.float64)
+    dev = default_device() if device is None else int(device)
+    nat.check(nat.lib().kdejs_kde_density(dev, nat.ptr(X), X.shape[0], float(minimum), float(maximum), R, h, k,
+                                          al, nat.ptr(out)))
+    return out.reshape(R, R)
+
+
+def _plot_contours(df1, df2, z1, z2, eps, log, resolution, outplot):
+    """The two contour PNGs of KDE_distance.py:110-126 (host-side rendering only)."""
+    import matplotlib.pyplot as plt    # optional dependency, exactly as in the reference
+
+    a, b = np.asarray(df1, dtype=np.float64), np.asarray(df2, dtype=np.float64)
+    if log:
+        a, b = np.log(a + eps), np.log(b + eps)
+    both = np.vstack([a, b])
+    lo, hi = np.nanmin(both, axis=0), np.nanmax(both, axis=0)
+    span = np.where(hi - lo < 10 * np.finfo(float).eps, 1.0, hi - lo)
+    xx, yy, _ = get_grid(0, 1, resolution)
+    for pts, z, tag in ((a, z1, "_z1_contours.png"), (b, z2, "_z2_contours.png")):
+        sc = np.nan_to_num((pts - lo) / span, nan=0.0)
+        sq = z.reshape(xx.shape).T
+        plt.figure(figsize=(11, 8), dpi=160, facecolor="w", edgecolor="k")
+        levels = np.linspace(sq.min(), sq.max(), 100)
+        plt.contour(xx, yy, sq, levels=levels[1:], cmap="plasma")
+        plt.scatter(sc[:, 0], sc[:, 1], s=1, alpha=1)
+        plt.savefig(outplot + tag)
+        plt.close()
+
+
+def get_options(argv=None):
+    parser = argparse.ArgumentParser(description="Fit KDE to two 2D distributions and generates a distance.",
+                                     prog="python KDE_distance.py")
+    io = parser.add_argument_group("Input/Output options")
+    io.add_argument("--infile1", required=True, help="Input distance file 1.")
+    io.add_argument("--infile2", required=True, help="Input distance file 2.")
+    io.add_argument("--gamma", default=0.25, type=float,
+                    help="Power to raise KDE distributions to for smoothing (Default = 0.25).")
+    io.add_argument("--plot-outpref", default=None, type=str,
+                    help="Prefix for output plots. If not provided, no plots generated.")
+    io.add_argument("--resolution", default=_DEFAULT_RESOLUTION, type=int, help="Grid nodes per axis (Default = 100).")
+    return parser.parse_args(argv)
+
+
+def main(argv=None):
+    opt = get_options(argv)
+    df1 = np.loadtxt(opt.infile1, delimiter="\t", dtype="float64")
+    df2 = np.loadtxt(opt.infile2, delimiter="\t", dtype="float64")
+    js = KDE_JS_divergence(df1, df2, gamma=opt.gamma, eps=0.0, log=False, outplot=opt.plot_outpref,
+                           resolution=opt.resolution)
+    print(f"js_distance_no_eps: {js}")
+
+
+if __name__ == "__main__":
+    main()

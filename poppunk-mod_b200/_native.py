@@ -1,0 +1,145 @@
+"""ctypes binding of libkdejs.so (include/kdejs.h).  No torch, no numpy fallbacks: if the CUDA
+library is missing or no sm_100 device is usable, every compute call raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkdejs.so")
+
+KDEJS_OK, KDEJS_ERR_CUDA, KDEJS_ERR_ARG, KDEJS_ERR_INF = 0, 1, 2, 3
+KERNELS = {"epanechnikov": 0, "gaussian": 1}
+ALGOS = {"binned": 0, "dense": 1, "dense64": 2}
+KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence")
+
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_dpp = ctypes.POINTER(ctypes.c_void_p)
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_c_i32p = ctypes.POINTER(ctypes.c_int32)
+
+_lib = None
+_lock = threading.Lock()
+
+_COMMON = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+           ctypes.c_int]  # resolution, bandwidth, gamma, eps, log_flag, kernel, algo
+
+_SIGNATURES = {
+    "kdejs_version": (ctypes.c_int, []),
+    "kdejs_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "kdejs_init": (ctypes.c_int, [ctypes.c_int]),
+    "kdejs_shutdown": (None, []),
+    "kdejs_last_error": (ctypes.c_char_p, []),
+    "kdejs_discrepancy": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                         ctypes.c_int64] + _COMMON + [_c_dp] + [ctypes.c_void_p] * 4),
+    "kdejs_discrepancy_batch": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p,
+                                               ctypes.c_int] + _COMMON + [ctypes.c_void_p]),
+    "kdejs_discrepancy_pairs": (ctypes.c_int, [ctypes.c_int, _c_dpp, _c_i64p, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_void_p, ctypes.c_int64] + _COMMON + [ctypes.c_void_p]),
+    "kdejs_discrepancy_batch_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p,
+                                                   ctypes.c_int] + _COMMON + [ctypes.c_void_p, ctypes.c_void_p,
+                                                                              ctypes.c_void_p]),
+    "kdejs_kde_density": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_double,
+                                         ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_void_p]),
+    "kdejs_shard_phase1": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                          ctypes.c_int64] + _COMMON + [ctypes.c_int, ctypes.c_int, _c_dp]),
+    "kdejs_shard_phase2": (ctypes.c_int, [ctypes.c_int, _c_dp, _c_dp]),
+    "kdejs_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "kdejs_host_free": (None, [ctypes.c_void_p]),
+    "kdejs_profile_enable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
+    "kdejs_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_dp, _c_i64p]),
+    "kdejs_profile_reset": (ctypes.c_int, [ctypes.c_int]),
+    "kdejs_launch_count": (ctypes.c_int, [ctypes.c_int, _c_i64p, ctypes.c_int]),
+    "kdejs_work_counters": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int]),
+    "kdejs_peak_flops": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_dp, _c_dp]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load libkdejs.so (dlopen only -- CUDA is not touched until the first compute call, so this
+    is safe to do before a fork)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with poppunk-mod_b200/csrc/build.sh "
+                        "(there is no CPU fallback)")
+                L = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in _SIGNATURES.items():
+                    f = getattr(L, name)
+                    f.restype = res
+                    f.argtypes = args
+                _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc == KDEJS_OK:
+        return
+    msg = (lib().kdejs_last_error() or b"").decode("utf-8", "replace")
+    if rc in (KDEJS_ERR_ARG, KDEJS_ERR_INF):
+        raise ValueError(msg)
+    raise RuntimeError(f"kdejs: {msg}")
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    rc = lib().kdejs_device_count(ctypes.byref(n))
+    return n.value if rc == KDEJS_OK else 0
+
+
+def as_points(x, name="array") -> np.ndarray:
+    """(N,2) C-contiguous float64 copy-or-view; never mutates the caller's array."""
+    a = np.asarray(x)
+    if a.ndim != 2:
+        raise ValueError(f"Expected 2D array, got {a.ndim}D array instead ({name})")
+    if a.shape[1] != 2:
+        raise ValueError(f"{name} must have exactly 2 columns (core, accessory); got shape {a.shape}")
+    if a.shape[0] == 0:
+        raise ValueError(f"Found array with 0 sample(s) (shape={a.shape}) while a minimum of 1 is required.")
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def pointer_array(arrays):
+    arr = (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+    cnt = (ctypes.c_int64 * len(arrays))(*[a.shape[0] for a in arrays])
+    return arr, cnt
+
+
+class PinnedPool:
+    """numpy views over page-locked host memory from kdejs_host_alloc."""
+
+    def __init__(self):
+        self._ptrs = []
+
+    def empty(self, shape, dtype=np.float64) -> np.ndarray:
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = lib().kdejs_host_alloc(max(nbytes, 1))
+        if not p:
+            raise MemoryError("kdejs_host_alloc failed")
+        self._ptrs.append(p)
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        for p in self._ptrs:
+            lib().kdejs_host_free(p)
+        self._ptrs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,824 @@
+// kdejs_api.cu -- C ABI (include/kdejs.h) over the sm_100a kernels in kdejs_kernels.cuh.
+//
+// Host-side structure: one lazily created context per device (two streams, two workspace slots so
+// the H2D copy of wave k+1 overlaps the kernels of wave k).  Evaluations are grouped into waves of
+// up to kMaxWaveItems; a wave's descriptors travel as a __grid_constant__ kernel parameter, so
+// there is no descriptor staging buffer to race with asynchronous callers.
+#include "../../include/kdejs.h"
+#include "kdejs_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace kdejs;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char b_[512];                                                                     \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                     __FILE__, __LINE__);                                                     \
+            return fail(KDEJS_ERR_CUDA, b_);                                                  \
+        }                                                                                     \
+    } while (0)
+#define OKR(call) do { int r_ = (call); if (r_ != KDEJS_OK) return r_; } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KDEJS_OK;
+        if (p) CU(cudaFree(p));      // cudaFree waits for outstanding work on the device
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&p, want));
+        cap = want;
+        return KDEJS_OK;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Slot {
+    DevBuf rawsims, scaled, sorted, cellid, blockhist, cellstart, dens, pz, zout, tilesum;
+    DevBuf rstat, rpart, tickets, jspart, dense_partial;
+    cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
+};
+
+struct Params {
+    int R; double h, gamma, eps; int log_flag, kernel, algo;
+    double gmin = 0.0, gmax = 1.0;
+};
+
+struct Pending { int kind; cudaEvent_t e0, e1; };
+
+struct Ctx {
+    int dev = -1;
+    bool ready = false;
+    int sm_count = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    Slot slot[2];
+    DevBuf pool_raw, js_out, status_out, misc;
+    double *h_js = nullptr; int32_t *h_status = nullptr; size_t h_cap = 0;   // pinned results
+    std::mutex mu;
+    // measurement
+    bool prof_on = false;
+    double prof_ms[KDEJS_NUM_KERNELS] = {0};
+    int64_t prof_n[KDEJS_NUM_KERNELS] = {0};
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> free_events;
+    int64_t launches = 0;
+    unsigned long long *d_work = nullptr;
+    // row-sharded evaluation state (phase 1 -> phase 2)
+    bool shard_valid = false;
+    WaveDesc shard_wd; GridGeom shard_geom; int shard_kb = 0, shard_ke = 0;
+};
+
+constexpr int kMaxDevices = 64;
+Ctx g_ctx[kMaxDevices];
+std::mutex g_init_mu;
+
+int get_ctx(int device, Ctx **out) {
+    if (device < 0 || device >= kMaxDevices) return fail(KDEJS_ERR_ARG, "device index out of range");
+    Ctx &c = g_ctx[device];
+    if (!c.ready) {
+        std::lock_guard<std::mutex> lk(g_init_mu);
+        if (!c.ready) {
+            int n = 0;
+            CU(cudaGetDeviceCount(&n));
+            if (device >= n) return fail(KDEJS_ERR_CUDA, "no such CUDA device (kdejs has no CPU fallback)");
+            CU(cudaSetDevice(device));
+            cudaDeviceProp prop;
+            CU(cudaGetDeviceProperties(&prop, device));
+            if (prop.major < 10)
+                return fail(KDEJS_ERR_CUDA, std::string("kdejs is built for sm_100a only; device is ") + prop.name);
+            c.dev = device;
+            c.sm_count = prop.multiProcessorCount;
+            CU(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&c.s_copy, cudaStreamNonBlocking));
+            for (auto &s : c.slot) {
+                CU(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+                OKR(s.tickets.ensure(sizeof(unsigned) * 2 * kMaxWaveSets));   // self-resetting tickets
+                CU(cudaMemset(s.tickets.p, 0, s.tickets.cap));
+            }
+            CU(cudaMalloc(&c.d_work, sizeof(unsigned long long)));
+            CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
+            CU(cudaFuncSetAttribute(k_scale_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSortWarps * kMaxCells * (int)sizeof(uint32_t)));
+            CU(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSortWarps * kMaxCells * (int)sizeof(uint32_t)));
+            c.ready = true;
+        }
+    }
+    CU(cudaSetDevice(device));
+    *out = &c;
+    return KDEJS_OK;
+}
+
+struct KTimer {       // CUDA-event bracket around one launch on the launching stream
+    Ctx &c; int kind; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KTimer(Ctx &c_, int kind_, cudaStream_t s_) : c(c_), kind(kind_), s(s_) {
+        if (!c.prof_on) return;
+        for (cudaEvent_t *e : {&e0, &e1}) {
+            if (!c.free_events.empty()) { *e = c.free_events.back(); c.free_events.pop_back(); }
+            else cudaEventCreate(e);
+        }
+        cudaEventRecord(e0, s);
+    }
+    ~KTimer() {
+        c.launches++;
+        if (!c.prof_on) return;
+        cudaEventRecord(e1, s);
+        c.pending.push_back({kind, e0, e1});
+    }
+};
+
+int resolve_pending(Ctx &c) {
+    if (c.pending.empty()) return KDEJS_OK;
+    CU(cudaDeviceSynchronize());
+    for (auto &p : c.pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { c.prof_ms[p.kind] += ms; c.prof_n[p.kind]++; }
+        c.free_events.push_back(p.e0);
+        c.free_events.push_back(p.e1);
+    }
+    c.pending.clear();
+    return KDEJS_OK;
+}
+
+int check_params(const Params &p) {
+    if (p.R < 1 || p.R > 16384) return fail(KDEJS_ERR_ARG, "resolution must be in [1, 16384]");
+    if (!(p.h > 0.0) || !std::isfinite(p.h)) return fail(KDEJS_ERR_ARG, "bandwidth must be positive and finite");
+    if (!(p.gmax > p.gmin)) return fail(KDEJS_ERR_ARG, "grid maximum must exceed grid minimum");
+    if (p.kernel != KDEJS_KERNEL_EPANECHNIKOV && p.kernel != KDEJS_KERNEL_GAUSSIAN)
+        return fail(KDEJS_ERR_ARG, "unknown kernel");
+    if (p.algo != KDEJS_ALGO_BINNED && p.algo != KDEJS_ALGO_DENSE && p.algo != KDEJS_ALGO_DENSE64)
+        return fail(KDEJS_ERR_ARG, "unknown algorithm");
+    if (p.kernel == KDEJS_KERNEL_GAUSSIAN && p.algo == KDEJS_ALGO_BINNED)
+        return fail(KDEJS_ERR_ARG, "the gaussian kernel has unbounded support: use a dense algorithm");
+    if (p.algo == KDEJS_ALGO_DENSE)
+        return fail(KDEJS_ERR_ARG, "KDEJS_ALGO_DENSE (fp32) is not available in this build");
+    if (std::isnan(p.gamma) || std::isnan(p.eps)) return fail(KDEJS_ERR_ARG, "gamma/eps must not be NaN");
+    return KDEJS_OK;
+}
+
+GridGeom make_geom(const Params &p) {
+    GridGeom g;
+    const double ext = p.gmax - p.gmin;
+    g.R = p.R;
+    g.NT = (p.R + kTile - 1) / kTile;
+    g.gmin = p.gmin;
+    g.step = (p.R > 1) ? ext / (double)(p.R - 1) : 0.0;   // numpy.linspace step
+    g.h = p.h;
+    g.inv_h = 1.0 / p.h;
+    g.dh = g.step * g.inv_h;
+    g.margin = 1e-9 * ext;
+    // culling cells: side >= h/2, at most kMaxRows cell rows per tile, at most 64 per side
+    double reach = (kTile - 1) * g.step + 2.0 * p.h + 2.0 * g.margin;
+    int C = (int)std::floor(2.0 * ext / p.h);
+    C = std::min(C, (int)std::floor((kMaxRows - 2) * ext / reach));
+    C = std::max(1, std::min(C, kMaxCellsSide));
+    g.C = C;
+    g.cell_x0 = p.gmin;
+    g.cell_invw = (double)C / ext;
+    // sklearn _log_kernel_norm, d = 2 (sklearn:neighbors/_binary_tree.pxi.tp:448-476)
+    const double LOG_PI = 1.1447298858494001741, LOG_2PI = 1.8378770664093454836;
+    double factor = (p.kernel == KDEJS_KERNEL_GAUSSIAN) ? LOG_2PI : (LOG_PI - std::lgamma(2.0)) + std::log(0.5);
+    g.knorm = std::exp(-factor - 2.0 * std::log(p.h));
+    g.gamma = p.gamma;
+    g.eps = p.eps;
+    g.gamma_mode = (p.gamma == 1.0) ? 1 : 0;
+    g.tile_row_begin = 0;
+    g.tile_row_end = g.NT;
+    return g;
+}
+
+// What one wave needs beyond the descriptors.
+struct WaveIO {
+    double *out_js = nullptr;        // device, indexed item_base + item
+    int32_t *out_status = nullptr;   // device
+    int item_base = 0;
+    bool want_z = false;             // fill slot.zout [set][G]
+    bool density_only = false;       // stop after the density kernel (kde_density)
+    bool identity_scaler = false;
+    bool shard = false;              // row-sharded: no k_js, caller runs the phases
+};
+
+int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
+    int nmax = 0;
+    for (int s = 0; s < wd.n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
+    chw = 1024;
+    auto nb_of = [&](int n) { return (int)(((int64_t)n + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)); };
+    if (nb_of(nmax) > sm_count) {
+        int64_t per_warp = ((int64_t)nmax + (int64_t)sm_count * kSortWarps - 1) / ((int64_t)sm_count * kSortWarps);
+        chw = (int)((per_warp + 31) / 32 * 32);
+    }
+    nb_max = std::max(1, nb_of(nmax));
+    return KDEJS_OK;
+}
+
+// Enqueue the six launches of one wave on `st`.  wd.set[].nb is filled here.
+int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom &g, WaveDesc &wd,
+             const WaveIO &io) {
+    const int n_sets = wd.n_sets, n_items = n_sets / 2;
+    const size_t G = (size_t)p.R * p.R;
+    int64_t P = 0;
+    for (int s = 0; s < n_sets; ++s) { wd.set[s].off = P; P += wd.set[s].n; }
+    int chw, nb_max;
+    sort_shape(wd, c.sm_count, chw, nb_max);
+    for (int s = 0; s < n_sets; ++s)
+        wd.set[s].nb = (int)(((int64_t)wd.set[s].n + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps));
+    const int ncells = g.C * g.C;
+    const bool binned = (p.algo == KDEJS_ALGO_BINNED);
+    const int nparts = binned ? g.NT * g.NT : (int)((G + 255) / 256);
+
+    OKR(sl.scaled.ensure((size_t)P * sizeof(double2)));
+    OKR(sl.dens.ensure((size_t)n_sets * G * sizeof(double)));
+    OKR(sl.pz.ensure((size_t)n_sets * G * sizeof(double)));
+    OKR(sl.tilesum.ensure((size_t)n_sets * nparts * sizeof(double)));
+    OKR(sl.rstat.ensure(sizeof(RawStat) * kMaxWaveSets));
+    const int mm_blocks = 64;
+    OKR(sl.rpart.ensure(sizeof(RawStat) * kMaxWaveSets * mm_blocks));
+    const int js_blocks = (int)((G + kJsNodesPerBlock - 1) / kJsNodesPerBlock);
+    OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)std::max(1, n_items) * js_blocks));
+    if (io.want_z) OKR(sl.zout.ensure((size_t)n_sets * G * sizeof(double)));
+    if (binned) {
+        OKR(sl.sorted.ensure((size_t)P * sizeof(double2)));
+        OKR(sl.cellid.ensure((size_t)P * sizeof(uint16_t)));
+        OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * ncells * sizeof(uint32_t)));
+        OKR(sl.cellstart.ensure((size_t)n_sets * (ncells + 1) * sizeof(uint32_t)));
+    }
+
+    unsigned *tk_minmax = sl.tickets.as<unsigned>();
+    unsigned *tk_js = sl.tickets.as<unsigned>() + kMaxWaveSets;
+
+    if (!io.identity_scaler) {
+        KTimer t(c, 0, st);
+        k_minmax<<<dim3(mm_blocks, wd.n_raw), kMinmaxThreads, 0, st>>>(
+            wd, p.log_flag, p.eps, sl.rpart.as<RawStat>(), tk_minmax, sl.rstat.as<RawStat>());
+    }
+    if (binned) {
+        const size_t smem = (size_t)kSortWarps * ncells * sizeof(uint32_t);
+        {
+            KTimer t(c, 1, st);
+            k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
+                wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
+                io.identity_scaler ? 1 : 0, g.C, g.cell_x0, g.cell_invw, chw, nb_max,
+                sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(), sl.blockhist.as<uint32_t>());
+        }
+        {
+            KTimer t(c, 2, st);
+            k_scan<<<n_sets, 1024, 0, st>>>(wd, ncells, nb_max, sl.blockhist.as<uint32_t>(),
+                                            sl.cellstart.as<uint32_t>());
+        }
+        {
+            KTimer t(c, 3, st);
+            k_place<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
+                wd, g.C, chw, nb_max, sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(),
+                sl.blockhist.as<uint32_t>(), sl.sorted.as<double2>());
+        }
+        {
+            KTimer t(c, 4, st);
+            const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
+            k_density_binned<<<dim3(tiles, n_sets), kDensThreads, 0, st>>>(
+                wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.dens.as<double>(),
+                sl.pz.as<double>(), sl.tilesum.as<double>(), c.prof_on ? c.d_work : nullptr);
+        }
+    } else {
+        // dense fp64: scale only (C = 1: every point lands in cell 0, the histogram is unused)
+        {
+            KTimer t(c, 1, st);
+            OKR(sl.cellid.ensure((size_t)P * sizeof(uint16_t)));
+            OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * sizeof(uint32_t)));
+            k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, kSortWarps * sizeof(uint32_t), st>>>(
+                wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
+                io.identity_scaler ? 1 : 0, 1, g.cell_x0, g.cell_invw, chw, nb_max,
+                sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(), sl.blockhist.as<uint32_t>());
+        }
+        const int ntd = (p.R + kDenseTile - 1) / kDenseTile;
+        int nslices = std::max(1, std::min(64, (4 * c.sm_count) / std::max(1, ntd * ntd * n_sets)));
+        OKR(sl.dense_partial.ensure((size_t)nslices * n_sets * G * sizeof(double)));
+        {
+            KTimer t(c, 4, st);
+            dim3 grid(ntd * ntd, n_sets, nslices);
+            if (p.kernel == KDEJS_KERNEL_GAUSSIAN)
+                k_density_dense64<1><<<grid, 256, 0, st>>>(wd, g, sl.scaled.as<double2>(),
+                                                           sl.dense_partial.as<double>(), nslices);
+            else
+                k_density_dense64<0><<<grid, 256, 0, st>>>(wd, g, sl.scaled.as<double2>(),
+                                                           sl.dense_partial.as<double>(), nslices);
+        }
+        {
+            KTimer t(c, 4, st);
+            k_dense_finish<<<dim3(nparts, n_sets), 256, 0, st>>>(
+                wd, g, sl.dense_partial.as<double>(), nslices, sl.dens.as<double>(),
+                sl.pz.as<double>(), sl.tilesum.as<double>(), nparts);
+        }
+    }
+    if (!io.density_only && !io.shard) {
+        KTimer t(c, 5, st);
+        k_js<<<dim3(js_blocks, n_items), kJsThreads, 0, st>>>(
+            wd, (int)G, nparts, 0, (int)G, sl.pz.as<double>(), sl.tilesum.as<double>(),
+            sl.rstat.as<RawStat>(), nullptr, io.want_z ? sl.zout.as<double>() : nullptr,
+            sl.jspart.as<double>(), tk_js, io.out_js, io.out_status, nullptr, nullptr, io.item_base);
+    }
+    CU(cudaGetLastError());
+    return KDEJS_OK;
+}
+
+int ensure_host_results(Ctx &c, size_t n) {
+    if (n <= c.h_cap) return KDEJS_OK;
+    if (c.h_js) { cudaFreeHost(c.h_js); cudaFreeHost(c.h_status); c.h_js = nullptr; c.h_status = nullptr; }
+    size_t want = n + n / 2 + 64;
+    CU(cudaMallocHost(&c.h_js, want * sizeof(double)));
+    CU(cudaMallocHost(&c.h_status, want * sizeof(int32_t)));
+    c.h_cap = want;
+    return KDEJS_OK;
+}
+
+int wave_capacity(const Params &p, int64_t pts_per_item) {
+    // keep a wave's scratch under ~3 GB; at the headline size (200k points, R=256) this is 32
+    const double per_item = (double)pts_per_item * (16 + 16 + 2) + 2.0 * p.R * p.R * 8 * 3 + 2.0 * 150 * 4096 * 4;
+    int cap = (int)std::max(1.0, std::floor(3.0e9 / per_item));
+    return std::min(cap, kMaxWaveItems);
+}
+
+// Pairs over a pool of raw DEVICE sets; items [0, n_items): (ia[i], ib[i]).  Runs on `st`, one slot.
+int run_pairs_dev(Ctx &c, cudaStream_t st, int slot_idx, const Params &p, const std::vector<RawSet> &pool,
+                  const int32_t *ia, const int32_t *ib, int64_t n_items, double *out_js_dev,
+                  int32_t *status_dev, int64_t out_base, bool want_z) {
+    GridGeom g = make_geom(p);
+    int64_t i = 0;
+    while (i < n_items) {
+        WaveDesc wd;
+        memset(&wd, 0, sizeof wd);
+        int local_of_global_n = 0;
+        std::vector<std::pair<int, int>> seen;   // (global raw, local raw)
+        auto local = [&](int gidx) {
+            for (auto &pr : seen) if (pr.first == gidx) return pr.second;
+            wd.raw[local_of_global_n] = pool[gidx];
+            seen.push_back({gidx, local_of_global_n});
+            return local_of_global_n++;
+        };
+        int64_t maxpts = 1;
+        for (int64_t k = i; k < std::min(n_items, i + kMaxWaveItems); ++k)
+            maxpts = std::max<int64_t>(maxpts, pool[ia[k]].n + pool[ib[k]].n);
+        const int cap = wave_capacity(p, maxpts);
+        int items = 0;
+        while (items < cap && i + items < n_items) {
+            const int a = ia[i + items], b = ib[i + items];
+            const int la = local(a), lb = local(b);
+            SetDesc &s0 = wd.set[2 * items], &s1 = wd.set[2 * items + 1];
+            s0.rs_self = la; s0.rs_other = lb; s0.n = (int32_t)pool[a].n; s0.item = items;
+            s1.rs_self = lb; s1.rs_other = la; s1.n = (int32_t)pool[b].n; s1.item = items;
+            ++items;
+        }
+        wd.n_raw = local_of_global_n;
+        wd.n_sets = 2 * items;
+        WaveIO io;
+        io.out_js = out_js_dev; io.out_status = status_dev; io.item_base = (int)(out_base + i); io.want_z = want_z;
+        OKR(run_wave(c, c.slot[slot_idx], st, p, g, wd, io));
+        i += items;
+    }
+    return KDEJS_OK;
+}
+
+int check_set(const double *p, int64_t n, const char *what) {
+    if (!p) return fail(KDEJS_ERR_ARG, std::string(what) + ": null pointer");
+    if (n <= 0) return fail(KDEJS_ERR_ARG, std::string("Found array with 0 sample(s) (") + what + ") while a minimum of 1 is required.");
+    if (n > 0x7fffffffLL / 4) return fail(KDEJS_ERR_ARG, std::string(what) + ": too many points for one set");
+    return KDEJS_OK;
+}
+
+int finish_status(const int32_t *status, int64_t n) {
+    for (int64_t i = 0; i < n; ++i)
+        if (status[i] == KDEJS_ERR_INF)
+            return fail(KDEJS_ERR_INF, "Input X contains infinity or a value too large for dtype('float64').");
+    return KDEJS_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int kdejs_version(void) { return KDEJS_VERSION; }
+
+const char *kdejs_last_error(void) { return g_err.c_str(); }
+
+int kdejs_device_count(int *count) {
+    if (!count) return fail(KDEJS_ERR_ARG, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return fail(KDEJS_ERR_CUDA, cudaGetErrorString(e)); }
+    *count = n;
+    return KDEJS_OK;
+}
+
+int kdejs_init(int device) {
+    Ctx *c;
+    return get_ctx(device, &c);
+}
+
+void kdejs_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    for (auto &c : g_ctx) {
+        if (!c.ready) continue;
+        cudaSetDevice(c.dev);
+        cudaDeviceSynchronize();
+        for (auto &s : c.slot) {
+            for (DevBuf *b : {&s.rawsims, &s.scaled, &s.sorted, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
+                              &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart,
+                              &s.dense_partial}) {
+                if (b->p) cudaFree(b->p);
+                b->p = nullptr; b->cap = 0;
+            }
+            cudaEventDestroy(s.ev_copied);
+            cudaEventDestroy(s.ev_done);
+        }
+        for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.misc}) {
+            if (b->p) cudaFree(b->p);
+            b->p = nullptr; b->cap = 0;
+        }
+        if (c.h_js) { cudaFreeHost(c.h_js); cudaFreeHost(c.h_status); c.h_js = nullptr; c.h_status = nullptr; c.h_cap = 0; }
+        for (auto &pd : c.pending) { cudaEventDestroy(pd.e0); cudaEventDestroy(pd.e1); }
+        c.pending.clear();
+        for (auto e : c.free_events) cudaEventDestroy(e);
+        c.free_events.clear();
+        cudaFree(c.d_work);
+        cudaStreamDestroy(c.s_compute);
+        cudaStreamDestroy(c.s_copy);
+        c.shard_valid = false;
+        c.ready = false;
+    }
+}
+
+void *kdejs_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+void kdejs_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int kdejs_discrepancy_pairs(int device, const double *const *sets, const int64_t *n_pts, int n_sets,
+                            const int32_t *ia, const int32_t *ib, int64_t n_pairs, int resolution,
+                            double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                            double *out_js) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(check_params(p));
+    if (!sets || !n_pts || n_sets < 1) return fail(KDEJS_ERR_ARG, "sets/n_pts missing");
+    if (n_pairs < 0 || (n_pairs > 0 && (!ia || !ib || !out_js))) return fail(KDEJS_ERR_ARG, "pair arrays missing");
+    for (int s = 0; s < n_sets; ++s) OKR(check_set(sets[s], n_pts[s], "point set"));
+    for (int64_t k = 0; k < n_pairs; ++k)
+        if (ia[k] < 0 || ia[k] >= n_sets || ib[k] < 0 || ib[k] >= n_sets) return fail(KDEJS_ERR_ARG, "pair index out of range");
+    if (n_pairs == 0) return KDEJS_OK;
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    // upload the pool once
+    std::vector<RawSet> pool(n_sets);
+    size_t total = 0;
+    std::vector<size_t> offs(n_sets);
+    for (int s = 0; s < n_sets; ++s) { offs[s] = total; total += ((size_t)n_pts[s] * 16 + 255) / 256 * 256; }
+    OKR(c->pool_raw.ensure(total));
+    for (int s = 0; s < n_sets; ++s) {
+        CU(cudaMemcpyAsync((char *)c->pool_raw.p + offs[s], sets[s], (size_t)n_pts[s] * 16, cudaMemcpyHostToDevice, c->s_compute));
+        pool[s] = RawSet{(const double *)((char *)c->pool_raw.p + offs[s]), n_pts[s]};
+    }
+    OKR(c->js_out.ensure(sizeof(double) * (size_t)n_pairs));
+    OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)n_pairs));
+    OKR(ensure_host_results(*c, (size_t)n_pairs));
+    OKR(run_pairs_dev(*c, c->s_compute, 0, p, pool, ia, ib, n_pairs, c->js_out.as<double>(),
+                      c->status_out.as<int32_t>(), 0, false));
+    CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    memcpy(out_js, c->h_js, sizeof(double) * (size_t)n_pairs);
+    return finish_status(c->h_status, n_pairs);
+}
+
+int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, int64_t nb, int resolution,
+                      double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                      double *out_js, double *out_z1, double *out_z2, double *out_d1, double *out_d2) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(check_params(p));
+    OKR(check_set(a, na, "df1"));
+    OKR(check_set(b, nb, "df2"));
+    if (!out_js) return fail(KDEJS_ERR_ARG, "out_js is null");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
+    OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
+    cudaStream_t st = c->s_compute;
+    CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, st));
+    std::vector<RawSet> pool = {RawSet{(const double *)c->pool_raw.p, na},
+                                RawSet{(const double *)((char *)c->pool_raw.p + offb), nb}};
+    OKR(c->js_out.ensure(sizeof(double)));
+    OKR(c->status_out.ensure(sizeof(int32_t)));
+    OKR(ensure_host_results(*c, 1));
+    const int32_t ia = 0, ib = 1;
+    const bool want_z = out_z1 || out_z2;
+    OKR(run_pairs_dev(*c, st, 0, p, pool, &ia, &ib, 1, c->js_out.as<double>(), c->status_out.as<int32_t>(), 0, want_z));
+    CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    const size_t G = (size_t)resolution * resolution;
+    Slot &sl = c->slot[0];
+    if (out_z1) CU(cudaMemcpyAsync(out_z1, sl.zout.as<double>(), G * 8, cudaMemcpyDeviceToHost, st));
+    if (out_z2) CU(cudaMemcpyAsync(out_z2, sl.zout.as<double>() + G, G * 8, cudaMemcpyDeviceToHost, st));
+    if (out_d1) CU(cudaMemcpyAsync(out_d1, sl.dens.as<double>(), G * 8, cudaMemcpyDeviceToHost, st));
+    if (out_d2) CU(cudaMemcpyAsync(out_d2, sl.dens.as<double>() + G, G * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *out_js = c->h_js[0];
+    return finish_status(c->h_status, 1);
+}
+
+int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const double *const *sims,
+                            const int64_t *n_sims, int B, int resolution, double bandwidth, double gamma,
+                            double eps, int log_flag, int kernel, int algo, double *out_js) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(check_params(p));
+    OKR(check_set(obs, n_obs, "obs"));
+    if (B < 0 || (B > 0 && (!sims || !n_sims || !out_js))) return fail(KDEJS_ERR_ARG, "batch arrays missing");
+    for (int i = 0; i < B; ++i) OKR(check_set(sims[i], n_sims[i], "sim"));
+    if (B == 0) return KDEJS_OK;
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    OKR(c->pool_raw.ensure((size_t)n_obs * 16));
+    CU(cudaMemcpyAsync(c->pool_raw.p, obs, (size_t)n_obs * 16, cudaMemcpyHostToDevice, c->s_compute));
+    OKR(c->js_out.ensure(sizeof(double) * (size_t)B));
+    OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)B));
+    OKR(ensure_host_results(*c, (size_t)B));
+    int64_t nmax = 1;
+    for (int i = 0; i < B; ++i) nmax = std::max(nmax, n_sims[i]);
+    const int cap = wave_capacity(p, n_obs + nmax);
+    const size_t sim_stride = ((size_t)nmax * 16 + 255) / 256 * 256;
+    for (auto &s : c->slot) OKR(s.rawsims.ensure(sim_stride * (size_t)cap));
+    int wave = 0;
+    for (int i0 = 0; i0 < B; i0 += cap, ++wave) {
+        const int items = std::min(cap, B - i0);
+        Slot &sl = c->slot[wave & 1];
+        if (wave >= 2) CU(cudaEventSynchronize(sl.ev_done));      // slot's previous wave has finished
+        std::vector<RawSet> pool(items + 1);
+        pool[0] = RawSet{(const double *)c->pool_raw.p, n_obs};
+        std::vector<int32_t> ia(items, 0), ib(items);
+        for (int k = 0; k < items; ++k) {
+            char *dst = (char *)sl.rawsims.p + sim_stride * (size_t)k;
+            CU(cudaMemcpyAsync(dst, sims[i0 + k], (size_t)n_sims[i0 + k] * 16, cudaMemcpyHostToDevice, c->s_copy));
+            pool[k + 1] = RawSet{(const double *)dst, n_sims[i0 + k]};
+            ib[k] = k + 1;
+        }
+        CU(cudaEventRecord(sl.ev_copied, c->s_copy));
+        CU(cudaStreamWaitEvent(c->s_compute, sl.ev_copied, 0));
+        OKR(run_pairs_dev(*c, c->s_compute, wave & 1, p, pool, ia.data(), ib.data(), items,
+                          c->js_out.as<double>(), c->status_out.as<int32_t>(), i0, false));
+        CU(cudaEventRecord(sl.ev_done, c->s_compute));
+    }
+    CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    memcpy(out_js, c->h_js, sizeof(double) * (size_t)B);
+    return finish_status(c->h_status, B);
+}
+
+int kdejs_discrepancy_batch_dev(int device, const double *obs_dev, int64_t n_obs, const double *const *sims_dev,
+                                const int64_t *n_sims, int B, int resolution, double bandwidth, double gamma,
+                                double eps, int log_flag, int kernel, int algo, double *out_js_dev,
+                                int32_t *status_dev, void *stream) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(check_params(p));
+    OKR(check_set(obs_dev, n_obs, "obs"));
+    if (B < 0 || (B > 0 && (!sims_dev || !n_sims || !out_js_dev))) return fail(KDEJS_ERR_ARG, "batch arrays missing");
+    if (((uintptr_t)obs_dev & 15) != 0) return fail(KDEJS_ERR_ARG, "obs_dev must be 16-byte aligned");
+    for (int i = 0; i < B; ++i) {
+        OKR(check_set(sims_dev[i], n_sims[i], "sim"));
+        if (((uintptr_t)sims_dev[i] & 15) != 0) return fail(KDEJS_ERR_ARG, "sims_dev[i] must be 16-byte aligned");
+    }
+    if (B == 0) return KDEJS_OK;
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    std::vector<RawSet> pool(B + 1);
+    pool[0] = RawSet{obs_dev, n_obs};
+    std::vector<int32_t> ia(B, 0), ib(B);
+    for (int i = 0; i < B; ++i) { pool[i + 1] = RawSet{sims_dev[i], n_sims[i]}; ib[i] = i + 1; }
+    return run_pairs_dev(*c, st, 0, p, pool, ia.data(), ib.data(), B, out_js_dev, status_dev, 0, false);
+}
+
+int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, double gmax, int resolution,
+                      double bandwidth, int kernel, int algo, double *out_dens) {
+    Params p{resolution, bandwidth, 1.0, 0.0, 0, kernel, algo};
+    p.gmin = gmin; p.gmax = gmax;
+    OKR(check_params(p));
+    OKR(check_set(pts, n, "points"));
+    if (!out_dens) return fail(KDEJS_ERR_ARG, "out_dens is null");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = c->s_compute;
+    OKR(c->pool_raw.ensure((size_t)n * 16));
+    CU(cudaMemcpyAsync(c->pool_raw.p, pts, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    GridGeom g = make_geom(p);
+    WaveDesc wd;
+    memset(&wd, 0, sizeof wd);
+    wd.raw[0] = RawSet{(const double *)c->pool_raw.p, n};
+    wd.n_raw = 1; wd.n_sets = 1;
+    wd.set[0].rs_self = 0; wd.set[0].rs_other = 0; wd.set[0].n = (int32_t)n; wd.set[0].item = 0;
+    WaveIO io;
+    io.density_only = true; io.identity_scaler = true;
+    OKR(run_wave(*c, c->slot[0], st, p, g, wd, io));
+    CU(cudaMemcpyAsync(out_dens, c->slot[0].dens.p, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return KDEJS_OK;
+}
+
+int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b, int64_t nb, int resolution,
+                       double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                       int row_begin, int row_end, double out_norm[2]) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(check_params(p));
+    OKR(check_set(a, na, "df1"));
+    OKR(check_set(b, nb, "df2"));
+    if (algo != KDEJS_ALGO_BINNED) return fail(KDEJS_ERR_ARG, "row sharding is implemented for the binned algorithm");
+    if (row_begin < 0 || row_end > resolution || row_begin >= row_end) return fail(KDEJS_ERR_ARG, "bad row range");
+    if (row_begin % kTile != 0 || (row_end % kTile != 0 && row_end != resolution))
+        return fail(KDEJS_ERR_ARG, "row range must be aligned to 4 rows (or end at the last row)");
+    if (!out_norm) return fail(KDEJS_ERR_ARG, "out_norm is null");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->shard_valid = false;
+    cudaStream_t st = c->s_compute;
+    const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
+    OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
+    CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, st));
+    GridGeom g = make_geom(p);
+    g.tile_row_begin = row_begin / kTile;
+    g.tile_row_end = (row_end + kTile - 1) / kTile;
+    WaveDesc wd;
+    memset(&wd, 0, sizeof wd);
+    wd.raw[0] = RawSet{(const double *)c->pool_raw.p, na};
+    wd.raw[1] = RawSet{(const double *)((char *)c->pool_raw.p + offb), nb};
+    wd.n_raw = 2; wd.n_sets = 2;
+    wd.set[0].rs_self = 0; wd.set[0].rs_other = 1; wd.set[0].n = (int32_t)na;
+    wd.set[1].rs_self = 1; wd.set[1].rs_other = 0; wd.set[1].n = (int32_t)nb;
+    WaveIO io;
+    io.shard = true;
+    Slot &sl = c->slot[0];
+    OKR(run_wave(*c, sl, st, p, g, wd, io));
+    OKR(c->misc.ensure(64));
+    const int nparts = g.NT * g.NT;
+    const int lo = g.tile_row_begin * g.NT, cnt = (g.tile_row_end - g.tile_row_begin) * g.NT;
+    // local normaliser partials: tiles [lo, lo+cnt) of each set
+    {
+        KTimer t(*c, 5, st);
+        // k_norm_totals expects set 1 at +nparts from set 0: pass pointers offset by lo with stride nparts
+        k_norm_totals<<<1, kJsThreads, 0, st>>>(cnt, nparts, sl.tilesum.as<double>() + lo, c->misc.as<double>());
+    }
+    OKR(ensure_host_results(*c, 4));
+    CU(cudaMemcpyAsync(c->h_js, c->misc.p, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_status, &sl.rstat.as<RawStat>()[0].flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_status + 1, &sl.rstat.as<RawStat>()[1].flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if ((c->h_status[0] | c->h_status[1]) & 1)
+        return fail(KDEJS_ERR_INF, "Input X contains infinity or a value too large for dtype('float64').");
+    out_norm[0] = c->h_js[0];
+    out_norm[1] = c->h_js[1];
+    c->shard_wd = wd; c->shard_geom = g;
+    c->shard_kb = row_begin * resolution;
+    c->shard_ke = row_end * resolution;
+    c->shard_valid = true;
+    return KDEJS_OK;
+}
+
+int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2]) {
+    if (!total_norm || !out_lr) return fail(KDEJS_ERR_ARG, "null argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->shard_valid) return fail(KDEJS_ERR_ARG, "kdejs_shard_phase2 called without a successful phase 1");
+    cudaStream_t st = c->s_compute;
+    Slot &sl = c->slot[0];
+    const GridGeom &g = c->shard_geom;
+    const int G = g.R * g.R;
+    double *d = c->misc.as<double>();      // [0,1] totals in, [2,3] (left,right) out
+    CU(cudaMemcpyAsync(d, total_norm, 16, cudaMemcpyHostToDevice, st));
+    const int n = c->shard_ke - c->shard_kb;
+    const int js_blocks = (n + kJsNodesPerBlock - 1) / kJsNodesPerBlock;
+    OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)js_blocks));
+    {
+        KTimer t(*c, 5, st);
+        k_js<<<dim3(js_blocks, 1), kJsThreads, 0, st>>>(
+            c->shard_wd, G, g.NT * g.NT, c->shard_kb, c->shard_ke, sl.pz.as<double>(), sl.tilesum.as<double>(),
+            sl.rstat.as<RawStat>(), d, nullptr, sl.jspart.as<double>(),
+            sl.tickets.as<unsigned>() + kMaxWaveSets, nullptr, nullptr, d + 2, nullptr, 0);
+    }
+    CU(cudaGetLastError());
+    OKR(ensure_host_results(*c, 4));
+    CU(cudaMemcpyAsync(c->h_js, d + 2, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    out_lr[0] = c->h_js[0];
+    out_lr[1] = c->h_js[1];
+    return KDEJS_OK;
+}
+
+int kdejs_profile_enable(int device, int on) {
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    OKR(resolve_pending(*c));
+    c->prof_on = on != 0;
+    return KDEJS_OK;
+}
+
+int kdejs_profile_read(int device, int which, double *ms_total, int64_t *launches) {
+    if (which < 0 || which >= KDEJS_NUM_KERNELS) return fail(KDEJS_ERR_ARG, "bad kernel index");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    OKR(resolve_pending(*c));
+    if (ms_total) *ms_total = c->prof_ms[which];
+    if (launches) *launches = c->prof_n[which];
+    return KDEJS_OK;
+}
+
+int kdejs_profile_reset(int device) {
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    OKR(resolve_pending(*c));
+    for (int i = 0; i < KDEJS_NUM_KERNELS; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    return KDEJS_OK;
+}
+
+int kdejs_launch_count(int device, int64_t *count, int reset) {
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (count) *count = c->launches;
+    if (reset) c->launches = 0;
+    return KDEJS_OK;
+}
+
+int kdejs_work_counters(int device, double *pair_tests, int reset) {
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, c->d_work, sizeof v, cudaMemcpyDeviceToHost));
+    if (pair_tests) *pair_tests = (double)v;
+    if (reset) CU(cudaMemset(c->d_work, 0, sizeof v));
+    return KDEJS_OK;
+}
+
+int kdejs_peak_flops(int device, int which, double *tflops, double *sm_clock_mhz) {
+    if (which < 0 || which > 2 || !tflops) return fail(KDEJS_ERR_ARG, "bad argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    OKR(c->misc.ensure(64));
+    const int blocks = c->sm_count * 8, iters = 1 << 15;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, c->s_compute));
+        if (which == 0) k_peak<0><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
+        else if (which == 1) k_peak<1><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
+        else k_peak<2><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
+        CU(cudaEventRecord(e1, c->s_compute));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double fmas = (double)blocks * 256.0 * iters * 8.0 * (which == 2 ? 2.0 : 1.0);
+    *tflops = 2.0 * fmas / (best * 1e-3) / 1e12;
+    if (sm_clock_mhz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+        *sm_clock_mhz = khz / 1000.0;
+    }
+    return KDEJS_OK;
+}
+
+}  // extern "C"

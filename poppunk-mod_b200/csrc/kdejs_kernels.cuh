@@ -1,0 +1,664 @@
+// kdejs_kernels.cuh -- hand-written sm_100a kernels for PopPUNK-mod's KDE discrepancy.
+//
+// One evaluation = KDE_JS_divergence(df1, df2, gamma, eps, log)  (/root/reference/KDE_distance.py:104-130).
+// A "wave" is up to kMaxWaveItems independent evaluations processed by the same six launches:
+//
+//   k_minmax       joint NaN-ignoring min/max per raw point set (MinMaxScaler.fit, KDE_distance.py:81-82)
+//   k_scale_count  X*scale_+min_, NaN->0 (KDE_distance.py:85-86, :53) + per-block cell histogram
+//   k_scan         exclusive scan of the (cell, block) counts -> cell starts and block bases
+//   k_place        stable counting-sort placement of the scaled points by cell
+//   k_density_*    Epanechnikov sums on the R x R grid (get_kde + generate_samples, :48-64),
+//                  **gamma + eps and per-tile normaliser partials (:71-76)
+//   k_js           normalise, Jensen-Shannon distance (scipy jensenshannon, :129)
+//
+// Everything is fp64 unless a kernel says otherwise; every reduction has a fixed shape, so results
+// are bit-reproducible run to run and independent of batch composition.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace kdejs {
+
+constexpr int kMaxWaveItems = 32;
+constexpr int kMaxWaveSets = 2 * kMaxWaveItems;
+constexpr int kMaxCellsSide = 64;                 // cells per side of the culling grid
+constexpr int kMaxCells = kMaxCellsSide * kMaxCellsSide;
+constexpr int kSortWarps = 4;
+constexpr int kSortThreads = kSortWarps * 32;
+constexpr int kTile = 4;                          // nodes per tile side (16 accumulators per thread)
+constexpr int kDensThreads = 128;
+constexpr int kMaxRows = 32;                      // cell rows a tile may have to visit
+constexpr int kJsThreads = 256;
+constexpr int kJsNodesPerBlock = 1024;
+constexpr int kMinmaxThreads = 256;
+
+struct RawSet {            // a point set as the caller gave it: (n,2) interleaved fp64, device memory
+    const double *p;
+    int64_t n;
+};
+struct SetDesc {           // one KDE to build: `rs_self` scaled jointly with `rs_other`
+    int32_t rs_self, rs_other, n, nb;   // nb = blocks that own a chunk of it in the sort
+    int64_t off;                        // first point in the wave's scaled/sorted arrays
+    int32_t item, pad;
+};
+struct WaveDesc {          // passed by value as a __grid_constant__ kernel parameter (< 4 KB)
+    RawSet raw[kMaxWaveSets];
+    SetDesc set[kMaxWaveSets];
+    int32_t n_raw, n_sets;
+};
+struct RawStat {           // NaN-ignoring column extrema of one raw set (after the optional log)
+    double mn[2], mx[2];
+    int32_t flags, pad;    // bit 0: a non-NaN infinity is present
+};
+struct GridGeom {
+    int32_t R, NT, C, gamma_mode;        // NT tiles per side, C cells per side; gamma_mode 1: gamma==1
+    double gmin, step, h, inv_h, dh;     // dh = step/h
+    double margin, cell_x0, cell_invw;   // cell(x) = clamp(floor((x-cell_x0)*cell_invw), 0, C-1)
+    double knorm, gamma, eps;
+    int32_t tile_row_begin, tile_row_end;   // tile rows (index of column 0) this launch covers
+};
+
+__device__ __forceinline__ double pre_transform(double v, int log_flag, double eps) {
+    return log_flag ? log(v + eps) : v;    // KDE_distance.py:105-106
+}
+__device__ __forceinline__ int cell_of(double x, double x0, double invw, int C) {
+    double f = floor((x - x0) * invw);     // monotone in x: the tile side below relies on it
+    f = fmin(fmax(f, 0.0), (double)(C - 1));
+    return (int)f;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Fixed-shape block sum (blockDim.x multiple of 32, <= 1024); result valid in every thread.
+__device__ __forceinline__ double block_sum(double v, double *s_warp /*[32]*/) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_warp[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += s_warp[i];
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_minmax: grid (nblk, n_raw).  Last block per raw set (ticket) folds the block partials.
+// min/max are exact in any order, so the result does not depend on the launch shape.
+__global__ void __launch_bounds__(kMinmaxThreads)
+k_minmax(const __grid_constant__ WaveDesc wd, int log_flag, double eps,
+         RawStat *__restrict__ part, unsigned *__restrict__ ticket, RawStat *__restrict__ out) {
+    const int r = blockIdx.y;
+    const double2 *__restrict__ p = reinterpret_cast<const double2 *>(wd.raw[r].p);
+    const int64_t n = wd.raw[r].n;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double mn0 = INF, mx0 = -INF, mn1 = INF, mx1 = -INF;
+    int flags = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double2 v = p[i];
+        double x = pre_transform(v.x, log_flag, eps), y = pre_transform(v.y, log_flag, eps);
+        if (x == x) { mn0 = fmin(mn0, x); mx0 = fmax(mx0, x); flags |= isinf(x) ? 1 : 0; }
+        if (y == y) { mn1 = fmin(mn1, y); mx1 = fmax(mx1, y); flags |= isinf(y) ? 1 : 0; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn0 = fmin(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
+        mx0 = fmax(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+        mn1 = fmin(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+        mx1 = fmax(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+        flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+    }
+    __shared__ RawStat s_part[kMinmaxThreads / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_part[w].mn[0] = mn0; s_part[w].mx[0] = mx0; s_part[w].mn[1] = mn1;
+                     s_part[w].mx[1] = mx1; s_part[w].flags = flags; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        RawStat a = s_part[0];
+        for (int i = 1; i < kMinmaxThreads / 32; ++i) {
+            a.mn[0] = fmin(a.mn[0], s_part[i].mn[0]); a.mx[0] = fmax(a.mx[0], s_part[i].mx[0]);
+            a.mn[1] = fmin(a.mn[1], s_part[i].mn[1]); a.mx[1] = fmax(a.mx[1], s_part[i].mx[1]);
+            a.flags |= s_part[i].flags;
+        }
+        a.pad = 0;
+        part[(size_t)r * gridDim.x + blockIdx.x] = a;
+        __threadfence();
+        unsigned t = atomicAdd(&ticket[r], 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const volatile RawStat *vp = part + (size_t)r * gridDim.x;
+        RawStat a;
+        a.mn[0] = vp[0].mn[0]; a.mx[0] = vp[0].mx[0]; a.mn[1] = vp[0].mn[1]; a.mx[1] = vp[0].mx[1];
+        a.flags = vp[0].flags; a.pad = 0;
+        for (unsigned i = 1; i < gridDim.x; ++i) {
+            a.mn[0] = fmin(a.mn[0], vp[i].mn[0]); a.mx[0] = fmax(a.mx[0], vp[i].mx[0]);
+            a.mn[1] = fmin(a.mn[1], vp[i].mn[1]); a.mx[1] = fmax(a.mx[1], vp[i].mx[1]);
+            a.flags |= vp[i].flags;
+        }
+        out[r] = a;
+        ticket[r] = 0;     // self-resetting: the next wave needs no memset
+    }
+}
+
+// sklearn MinMaxScaler parameters from the joint extrema of two raw sets
+// (sklearn:preprocessing/_data.py:476-545; _handle_zeros_in_scale :101-133).
+__device__ __forceinline__ void joint_scaler(const RawStat &a, const RawStat &b, int col,
+                                             double &scale, double &min_) {
+    double mn = fmin(a.mn[col], b.mn[col]), mx = fmax(a.mx[col], b.mx[col]);
+    double range = mx - mn;
+    if (range < 10.0 * 2.220446049250313e-16) range = 1.0;
+    scale = 1.0 / range;
+    min_ = 0.0 - __dmul_rn(mn, scale);
+}
+
+// ------------------------------------------------------------------------------------------
+// k_scale_count: grid (nb_max, n_sets), kSortThreads threads, dyn smem kSortWarps*ncells u32.
+// Block b owns points [b*chw*kSortWarps, ...), warp w the w-th sub-chunk: index order == (block,
+// warp, lane) order, which is what makes the later placement stable.
+__global__ void __launch_bounds__(kSortThreads)
+k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat,
+              int log_flag, double eps, int identity_scaler, int C, double cell_x0,
+              double cell_invw, int chw, int nb_max, double2 *__restrict__ scaled,
+              uint16_t *__restrict__ cellid, uint32_t *__restrict__ blockhist) {
+    extern __shared__ uint32_t s_hist[];
+    const SetDesc sd = wd.set[blockIdx.y];
+    if ((int)blockIdx.x >= sd.nb) return;
+    const int ncells = C * C;
+    for (int i = threadIdx.x; i < kSortWarps * ncells; i += kSortThreads) s_hist[i] = 0u;
+    __shared__ double s_sc[4];
+    if (threadIdx.x == 0) {
+        if (identity_scaler) { s_sc[0] = 1.0; s_sc[1] = 0.0; s_sc[2] = 1.0; s_sc[3] = 0.0; }
+        else {
+            joint_scaler(rstat[sd.rs_self], rstat[sd.rs_other], 0, s_sc[0], s_sc[1]);
+            joint_scaler(rstat[sd.rs_self], rstat[sd.rs_other], 1, s_sc[2], s_sc[3]);
+        }
+    }
+    __syncthreads();
+    const double sx = s_sc[0], mx = s_sc[1], sy = s_sc[2], my = s_sc[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double2 *__restrict__ raw = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p);
+    const int64_t beg = ((int64_t)blockIdx.x * kSortWarps + warp) * chw;
+    const int64_t end = min(beg + (int64_t)chw, (int64_t)sd.n);
+    uint32_t *hw = s_hist + warp * ncells;
+    for (int64_t j0 = beg; j0 < end; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool valid = j < end;
+        int cell = 0;
+        if (valid) {
+            double2 v = raw[j];
+            // X *= scale_; X += min_  -- two separately rounded operations, never an FMA
+            double X = __dadd_rn(__dmul_rn(pre_transform(v.x, log_flag, eps), sx), mx);
+            double Y = __dadd_rn(__dmul_rn(pre_transform(v.y, log_flag, eps), sy), my);
+            if (!identity_scaler) {           // KDE_distance.py:53
+                if (X != X) X = 0.0;
+                if (Y != Y) Y = 0.0;
+            }
+            scaled[sd.off + j] = make_double2(X, Y);
+            cell = cell_of(Y, cell_x0, cell_invw, C) * C + cell_of(X, cell_x0, cell_invw, C);
+            cellid[sd.off + j] = (uint16_t)cell;
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned m = __match_any_sync(act, cell);
+            if (lane == __ffs(m) - 1) hw[cell] += __popc(m);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    uint32_t *bh = blockhist + ((size_t)blockIdx.y * nb_max + blockIdx.x) * ncells;
+    for (int c = threadIdx.x; c < ncells; c += kSortThreads) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) t += s_hist[w * ncells + c];
+        bh[c] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_scan: grid (n_sets), 1024 threads, 4 cells per thread.  Turns blockhist[set][b][c] into the
+// first sorted position of block b's points of cell c, and writes cellstart[set][0..ncells].
+__global__ void __launch_bounds__(1024)
+k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
+       uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart) {
+    const int set = blockIdx.x;
+    const int nb = wd.set[set].nb;
+    uint32_t *bh = blockhist + (size_t)set * nb_max * ncells;
+    const int c0 = threadIdx.x * 4;
+    uint32_t tot[4] = {0u, 0u, 0u, 0u};
+    for (int b = 0; b < nb; ++b)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c0 + k < ncells) tot[k] += bh[(size_t)b * ncells + c0 + k];
+    uint32_t tsum = tot[0] + tot[1] + tot[2] + tot[3];
+    // exclusive scan of tsum over the block
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __shared__ uint32_t s_w[32];
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t v = s_w[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_w[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = s_w[w] + inc - tsum;
+    uint32_t *cs = cellstart + (size_t)set * (ncells + 1);
+    uint32_t base[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        base[k] = run;
+        if (c0 + k < ncells) cs[c0 + k] = run;
+        run += tot[k];
+    }
+    if (threadIdx.x == 0) cs[ncells] = (uint32_t)wd.set[set].n;
+    for (int b = 0; b < nb; ++b)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c0 + k < ncells) {
+                uint32_t t = bh[(size_t)b * ncells + c0 + k];
+                bh[(size_t)b * ncells + c0 + k] = base[k];
+                base[k] += t;
+            }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_place: same launch shape as k_scale_count.  Stable: a point's rank inside its cell is
+// (#same-cell points in earlier blocks) + (earlier warps of this block) + (earlier in this warp).
+__global__ void __launch_bounds__(kSortThreads)
+k_place(const __grid_constant__ WaveDesc wd, int C, int chw, int nb_max,
+        const double2 *__restrict__ scaled, const uint16_t *__restrict__ cellid,
+        const uint32_t *__restrict__ blockbase, double2 *__restrict__ sorted) {
+    extern __shared__ uint32_t s_run[];
+    const SetDesc sd = wd.set[blockIdx.y];
+    if ((int)blockIdx.x >= sd.nb) return;
+    const int ncells = C * C;
+    for (int i = threadIdx.x; i < kSortWarps * ncells; i += kSortThreads) s_run[i] = 0u;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t beg = ((int64_t)blockIdx.x * kSortWarps + warp) * chw;
+    const int64_t end = min(beg + (int64_t)chw, (int64_t)sd.n);
+    uint32_t *rw = s_run + warp * ncells;
+    for (int64_t j0 = beg; j0 < end; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool valid = j < end;
+        const int cell = valid ? (int)cellid[sd.off + j] : 0;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned m = __match_any_sync(act, cell);
+            if (lane == __ffs(m) - 1) rw[cell] += __popc(m);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    const uint32_t *bb = blockbase + ((size_t)blockIdx.y * nb_max + blockIdx.x) * ncells;
+    for (int c = threadIdx.x; c < ncells; c += kSortThreads) {
+        uint32_t acc = bb[c];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            uint32_t t = s_run[w * ncells + c];
+            s_run[w * ncells + c] = acc;
+            acc += t;
+        }
+    }
+    __syncthreads();
+    for (int64_t j0 = beg; j0 < end; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool valid = j < end;
+        const int cell = valid ? (int)cellid[sd.off + j] : 0;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        uint32_t base = 0u;
+        int leader = lane;
+        unsigned m = 0u;
+        if (valid) {
+            m = __match_any_sync(act, cell);
+            leader = __ffs(m) - 1;
+            if (lane == leader) { base = rw[cell]; rw[cell] = base + __popc(m); }
+        }
+        __syncwarp();
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) {
+            const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+            sorted[sd.off + base + rank] = scaled[sd.off + j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-node epilogue shared by the density kernels: density -> **gamma + eps.
+__device__ __forceinline__ double gamma_eps(double dens, const GridGeom &g) {
+    double z = (g.gamma_mode == 1) ? dens : pow(dens, g.gamma);   // KDE_distance.py:71
+    return z + g.eps;                                              // :75
+}
+
+// k_density_binned: grid (tiles in [tile_row_begin, tile_row_end) x NT, n_sets), 128 threads.
+// A block owns one 4x4-node tile; its candidates are the sorted points of the cells that can reach
+// the tile (a few contiguous runs, one per cell row).  Lanes take candidates round-robin, every
+// lane keeps the tile's 16 fp64 sums in registers:  t = 1 - ux^2 - uy^2 in units of h, added when
+// positive (strict dist < h, sklearn:_binary_tree.pxi.tp:389-394).  Fixed-shape reduction across
+// the 128 lanes, then the 16 node values, their **gamma+eps and the tile's share of the normaliser.
+__global__ void __launch_bounds__(kDensThreads)
+k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
+                 const double2 *__restrict__ sorted, const uint32_t *__restrict__ cellstart,
+                 double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
+                 unsigned long long *__restrict__ work_counter) {
+    __shared__ uint32_t s_rs[kMaxRows];
+    __shared__ uint32_t s_cum[kMaxRows + 1];
+    __shared__ double s_red[kDensThreads / 32][kTile * kTile];
+    const int set = blockIdx.y;
+    const SetDesc sd = wd.set[set];
+    const int tx = g.tile_row_begin + blockIdx.x / g.NT, ty = blockIdx.x % g.NT;
+    const int ix0 = tx * kTile, iy0 = ty * kTile;
+    const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncells = g.C * g.C;
+    const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
+
+    if (warp == 0) {
+        const double xhi = (double)min(ix0 + kTile - 1, g.R - 1) * g.step + g.gmin;
+        const double yhi = (double)min(iy0 + kTile - 1, g.R - 1) * g.step + g.gmin;
+        const int cx_lo = cell_of(gx0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
+        const int cx_hi = cell_of(xhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
+        const int cy_lo = cell_of(gy0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
+        const int cy_hi = cell_of(yhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
+        const int rows = cy_hi - cy_lo + 1;          // <= kMaxRows by the host's choice of C
+        uint32_t s = 0u, len = 0u;
+        if (lane < rows) {
+            s = cs[(cy_lo + lane) * g.C + cx_lo];
+            len = cs[(cy_lo + lane) * g.C + cx_hi + 1] - s;
+        }
+        uint32_t inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        s_rs[lane] = s;
+        s_cum[lane + 1] = inc;
+        if (lane == 0) s_cum[0] = 0u;
+    }
+    __syncthreads();
+    const uint32_t total = s_cum[kMaxRows];
+
+    double acc[kTile][kTile];
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
+
+    const double2 *__restrict__ pts = sorted + sd.off;
+    int r = 0;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += kDensThreads) {
+        while (idx >= s_cum[r + 1]) ++r;
+        const double2 p = pts[s_rs[r] + (idx - s_cum[r])];
+        const double ux0 = (p.x - gx0) * g.inv_h;      // node i sits at i*dh - ux0 (units of h)
+        const double uy0 = (p.y - gy0) * g.inv_h;
+        double a[kTile], v[kTile];
+#pragma unroll
+        for (int i = 0; i < kTile; ++i) {
+            const double ux = (double)i * g.dh - ux0;
+            a[i] = fma(-ux, ux, 1.0);
+            v[i] = (double)i * g.dh - uy0;
+        }
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) {
+                const double t = fma(-v[j], v[j], a[i]);
+                if (__double2hiint(t) >= 0) acc[i][j] += t;   // t > 0 (adding +0 is harmless)
+            }
+    }
+
+    // fixed-shape reduction: xor butterfly inside each warp, then warps in index order
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) {
+            const double s = warp_sum(acc[i][j]);
+            if (lane == 0) s_red[warp][i * kTile + j] = s;
+        }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double P = 0.0;
+        if (threadIdx.x < kTile * kTile) {
+            double S = 0.0;
+#pragma unroll
+            for (int w = 0; w < kDensThreads / 32; ++w) S += s_red[w][threadIdx.x];
+            const int ix = ix0 + threadIdx.x / kTile, iy = iy0 + threadIdx.x % kTile;
+            if (ix < g.R && iy < g.R) {
+                const double d = S * (g.knorm / (double)sd.n);   // exp(logsum + log_knorm - log N)
+                P = gamma_eps(d, g);
+                const size_t k = (size_t)set * g.R * g.R + (size_t)ix * g.R + iy;
+                dens[k] = d;
+                pz[k] = P;
+            }
+        }
+        // 16 lanes, shuffle-down tree: fixed order
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) P += __shfl_down_sync(0xffffffffu, P, o);
+        if (threadIdx.x == 0) {
+            tilesum[(size_t)set * g.NT * g.NT + (size_t)tx * g.NT + ty] = P;
+            if (work_counter) atomicAdd(work_counter, (unsigned long long)total * (kTile * kTile));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_density_dense64: brute force in fp64, every node against every point (cross-check path and the
+// gaussian kernel).  grid (tiles of 32x32 nodes, n_sets, point slices); 256 threads, 2x2 nodes per
+// thread; points staged through shared memory.  Slice partials go to `partial[slice][set][G]`.
+constexpr int kDenseTile = 32;
+constexpr int kDenseChunk = 512;
+template <int KERNEL>
+__global__ void __launch_bounds__(256)
+k_density_dense64(const __grid_constant__ WaveDesc wd, const GridGeom g,
+                  const double2 *__restrict__ pts_all, double *__restrict__ partial, int nslices) {
+    __shared__ double2 s_p[kDenseChunk];
+    const int set = blockIdx.y;
+    const SetDesc sd = wd.set[set];
+    const int ntd = (g.R + kDenseTile - 1) / kDenseTile;
+    const int tx = blockIdx.x / ntd, ty = blockIdx.x % ntd;
+    const int ix = tx * kDenseTile + (threadIdx.x / 16) * 2, iy = ty * kDenseTile + (threadIdx.x % 16) * 2;
+    const double gx[2] = {(double)ix * g.step + g.gmin, (double)(ix + 1) * g.step + g.gmin};
+    const double gy[2] = {(double)iy * g.step + g.gmin, (double)(iy + 1) * g.step + g.gmin};
+    const double2 *__restrict__ pts = pts_all + sd.off;
+    const int per = (sd.n + nslices - 1) / nslices;
+    const int beg = blockIdx.z * per, end = min(beg + per, sd.n);
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int c0 = beg; c0 < end; c0 += kDenseChunk) {
+        const int m = min(kDenseChunk, end - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += 256) s_p[i] = pts[c0 + i];
+        __syncthreads();
+        for (int i = 0; i < m; ++i) {
+            const double2 p = s_p[i];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const double ux = (gx[a] - p.x) * g.inv_h, uy = (gy[b] - p.y) * g.inv_h;
+                    if (KERNEL == 0) {
+                        const double t = 1.0 - (ux * ux + uy * uy);
+                        if (t > 0.0) acc[a][b] += t;
+                    } else {
+                        acc[a][b] += exp(-0.5 * (ux * ux + uy * uy));
+                    }
+                }
+        }
+    }
+    const size_t G = (size_t)g.R * g.R;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+            if (ix + a < g.R && iy + b < g.R)
+                partial[((size_t)blockIdx.z * wd.n_sets + set) * G + (size_t)(ix + a) * g.R + iy + b] = acc[a][b];
+}
+
+// Fold the dense slice partials in slice order and apply the per-node epilogue; also produces the
+// per-"tile" normaliser partials in the layout k_js expects (here one entry per 256 nodes).
+__global__ void __launch_bounds__(256)
+k_dense_finish(const __grid_constant__ WaveDesc wd, const GridGeom g, const double *__restrict__ partial,
+               int nslices, double *__restrict__ dens, double *__restrict__ pz,
+               double *__restrict__ tilesum, int nparts) {
+    __shared__ double s_w[32];
+    const int set = blockIdx.y;
+    const size_t G = (size_t)g.R * g.R;
+    const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
+    double P = 0.0;
+    if (k < G) {
+        double S = 0.0;
+        for (int s = 0; s < nslices; ++s) S += partial[((size_t)s * wd.n_sets + set) * G + k];
+        const double d = S * (g.knorm / (double)wd.set[set].n);
+        P = gamma_eps(d, g);
+        dens[(size_t)set * G + k] = d;
+        pz[(size_t)set * G + k] = P;
+    }
+    const double tot = block_sum(P, s_w);
+    if (threadIdx.x == 0) tilesum[(size_t)set * nparts + blockIdx.x] = tot;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_js: grid (node blocks, n_items), 256 threads.  Each block re-derives both normalisers from the
+// per-tile partials in a fixed order (identical in every block), then accumulates its nodes'
+// rel_entr(p,m) and rel_entr(q,m); the last block per item (ticket) folds the block partials:
+// js = sqrt((left + right) / 2)          scipy:spatial/distance.py:1278-1290.
+// totals_override (nullable, 2 doubles): normalisers supplied by the caller (row-sharded mode).
+__global__ void __launch_bounds__(kJsThreads)
+k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_end,
+     const double *__restrict__ pz, const double *__restrict__ tilesum,
+     const RawStat *__restrict__ rstat, const double *__restrict__ totals_override,
+     double *__restrict__ z_out, double *__restrict__ jspart, unsigned *__restrict__ ticket,
+     double *__restrict__ out_js, int32_t *__restrict__ out_status, double *__restrict__ out_lr,
+     double *__restrict__ out_norm, int item_base) {
+    __shared__ double s_w[32];
+    __shared__ bool s_last;
+    const int item = blockIdx.y;
+    const int s0 = 2 * item, s1 = 2 * item + 1;
+    double tp = 0.0, tq = 0.0;
+    if (totals_override) { tp = totals_override[0]; tq = totals_override[1]; }
+    else {
+        double a = 0.0, b = 0.0;
+        for (int k = threadIdx.x; k < nparts; k += kJsThreads) {
+            a += tilesum[(size_t)s0 * nparts + k];
+            b += tilesum[(size_t)s1 * nparts + k];
+        }
+        tp = block_sum(a, s_w);
+        tq = block_sum(b, s_w);
+    }
+    double left = 0.0, right = 0.0;
+    const int kb = k_begin + blockIdx.x * kJsNodesPerBlock;
+    const int ke = min(kb + kJsNodesPerBlock, k_end);
+    for (int k = kb + threadIdx.x; k < ke; k += kJsThreads) {
+        const double p = pz[(size_t)s0 * G + k] / tp;      // z /= z.sum()  KDE_distance.py:76
+        const double q = pz[(size_t)s1 * G + k] / tq;
+        const double m = (p + q) / 2.0;
+        if (p > 0.0) left += p * log(p / m);               // rel_entr(0, m) = 0
+        if (q > 0.0) right += q * log(q / m);
+        if (p != p) left = p;                              // NaN normaliser (empty KDE) propagates
+        if (q != q) right = q;
+        if (z_out) { z_out[(size_t)s0 * G + k] = p; z_out[(size_t)s1 * G + k] = q; }
+    }
+    left = block_sum(left, s_w);
+    right = block_sum(right, s_w);
+    if (threadIdx.x == 0) {
+        jspart[((size_t)item * gridDim.x + blockIdx.x) * 2 + 0] = left;
+        jspart[((size_t)item * gridDim.x + blockIdx.x) * 2 + 1] = right;
+        __threadfence();
+        unsigned t = atomicAdd(&ticket[item], 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const volatile double *vp = jspart + (size_t)item * gridDim.x * 2;
+        double L = 0.0, Rr = 0.0;
+        for (unsigned i = 0; i < gridDim.x; ++i) { L += vp[2 * i]; Rr += vp[2 * i + 1]; }
+        const int bad = (rstat[wd.set[s0].rs_self].flags | rstat[wd.set[s0].rs_other].flags) & 1;
+        if (out_lr) { out_lr[0] = L; out_lr[1] = Rr; }
+        if (out_norm) { out_norm[0] = tp; out_norm[1] = tq; }
+        if (out_js) out_js[item_base + item] = bad ? __longlong_as_double(0x7ff8000000000000LL)
+                                                   : sqrt((L + Rr) / 2.0);
+        if (out_status) out_status[item_base + item] = bad ? 3 : 0;
+        ticket[item] = 0;
+    }
+}
+
+// Sum of `count` per-tile normaliser partials of both sets of one item (row-sharded phase 1):
+// 1 block; set 1's partials start `stride` doubles after set 0's.
+__global__ void __launch_bounds__(kJsThreads)
+k_norm_totals(int count, int stride, const double *__restrict__ tilesum, double *__restrict__ out_norm) {
+    __shared__ double s_w[32];
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < count; k += kJsThreads) { a += tilesum[k]; b += tilesum[stride + k]; }
+    a = block_sum(a, s_w);
+    b = block_sum(b, s_w);
+    if (threadIdx.x == 0) { out_norm[0] = a; out_norm[1] = b; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Issue-rate microbenchmarks (roofline denominators measured on the box, not quoted).
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_peak(int iters, float *sink_f, double *sink_d) {
+    if (WHICH == 0) {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 1.0f + threadIdx.x * 1e-6f + i;
+        const float b = 0.999999f, c = 1e-7f;
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], b, c);
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += a[i];
+        if (s == 12345.678f) sink_f[0] = s;
+    } else if (WHICH == 1) {
+        double a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = 1.0 + threadIdx.x * 1e-6 + i;
+        const double b = 0.999999, c = 1e-7;
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], b, c);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += a[i];
+        if (s == 12345.678) sink_d[0] = s;
+    } else {
+        unsigned long long a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float2 f = make_float2(1.0f + threadIdx.x * 1e-6f + i, 2.0f + i);
+            a[i] = *reinterpret_cast<unsigned long long *>(&f);
+        }
+        float2 bf = make_float2(0.999999f, 0.999998f), cf = make_float2(1e-7f, 2e-7f);
+        const unsigned long long b = *reinterpret_cast<unsigned long long *>(&bf);
+        const unsigned long long c = *reinterpret_cast<unsigned long long *>(&cf);
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(b), "l"(c));
+        unsigned long long s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s ^= a[i];
+        if (s == 0x12345678ULL) sink_d[0] = (double)s;
+    }
+}
+
+}  // namespace kdejs

@@ -1,0 +1,135 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _no_gpu():
+    import poppunk_mod_b200 as pk
+
+    return pk._native.device_count() == 0
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import poppunk_mod_b200 as pk
+
+    L = pk._native.lib()
+    header = open(os.path.join(ROOT, "include", "kdejs.h")).read()
+    declared = set(re.findall(r"\b(kdejs_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in include/kdejs.h"
+    for name in declared:
+        assert hasattr(L, name), f"libkdejs.so does not export {name}"
+    assert declared == set(pk._native.EXPORTED_SYMBOLS)
+    assert L.kdejs_version() == 100
+
+
+def test_alias_and_drop_in_import_paths():
+    import importlib
+    import sys
+
+    import poppunk_mod_b200 as pk
+
+    assert callable(pk.KDE_JS_divergence) and callable(pk.KDE_KL_divergence) and callable(pk.get_grid)
+    sys.path.insert(0, os.path.join(ROOT, "poppunk-mod_b200"))
+    try:
+        sys.modules.pop("KDE_distance", None)
+        K = importlib.import_module("KDE_distance")      # `from KDE_distance import ...` as poppunk_mod.py:20 does
+        for name in ("KDE_JS_divergence", "KDE_KL_divergence", "get_grid", "scale_KDE", "main"):
+            assert hasattr(K, name)
+    finally:
+        sys.path.pop(0)
+        sys.modules.pop("KDE_distance", None)
+
+
+def test_signature_matches_reference():
+    import inspect
+
+    import poppunk_mod_b200 as pk
+
+    sig = inspect.signature(pk.KDE_JS_divergence)
+    names = list(sig.parameters)
+    assert names[:6] == ["df1", "df2", "gamma", "eps", "log", "outplot"]        # KDE_distance.py:104
+    p = sig.parameters
+    assert (p["gamma"].default, p["eps"].default, p["log"].default, p["outplot"].default) == (1.0, 1e-12, False, None)
+    assert p["resolution"].default == 100 and p["bandwidth"].default == 0.03    # KDE_distance.py:89, :50
+    assert all(p[n].kind is inspect.Parameter.KEYWORD_ONLY for n in names[6:])
+
+
+def test_get_grid_order():
+    import poppunk_mod_b200 as pk
+
+    xx, yy, xy = pk.get_grid(0, 1, 100)
+    lin = np.linspace(0, 1, 100)
+    assert xx.shape == yy.shape == (100, 100) and xy.shape == (10000, 2)
+    k = np.arange(10000)
+    np.testing.assert_array_equal(xy[:, 0], lin[k // 100])     # column 0 varies slowest
+    np.testing.assert_array_equal(xy[:, 1], lin[k % 100])
+    np.testing.assert_array_equal(xx[0], lin)
+
+
+def test_argument_validation_happens_before_cuda():
+    import poppunk_mod_b200 as pk
+
+    good = np.random.default_rng(0).random((5, 2))
+    with pytest.raises(ValueError):
+        pk.KDE_JS_divergence(np.zeros((5, 3)), good)
+    with pytest.raises(ValueError):
+        pk.KDE_JS_divergence(np.zeros(5), good)
+    with pytest.raises(ValueError, match="0 sample"):
+        pk.KDE_JS_divergence(np.zeros((0, 2)), good)
+    with pytest.raises(ValueError):
+        pk.KDE_JS_divergence(good, good, kernel="tophat")
+    with pytest.raises(ValueError):
+        pk.KDE_JS_divergence(good, good, resolution=0)
+    with pytest.raises(ValueError):
+        pk.KDE_JS_divergence(good, good, bandwidth=-1.0)
+    with pytest.raises(ValueError):
+        pk.KDE_JS_divergence(good, good, kernel="gaussian", algo="binned")
+
+
+def test_inputs_are_not_mutated_and_views_are_accepted():
+    import poppunk_mod_b200 as pk
+
+    big = np.asfortranarray(np.random.default_rng(1).random((50, 4)))
+    view = big[:, 2:]                       # non-contiguous last-two-columns slice (pairwise_2D_distance.py:45)
+    pts = pk._native.as_points(view)
+    assert pts.flags["C_CONTIGUOUS"] and pts.dtype == np.float64
+    np.testing.assert_array_equal(pts, view)
+    assert pk._native.as_points([[1, 2], [3, 4]]).dtype == np.float64
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback_without_a_gpu():
+    import poppunk_mod_b200 as pk
+
+    a = np.random.default_rng(0).random((20, 2))
+    with pytest.raises(RuntimeError, match="kdejs"):
+        pk.KDE_JS_divergence(a, a)
+    with pytest.raises(RuntimeError, match="kdejs"):
+        pk.KDE_JS_divergence_batch(a, [a, a])
+    with pytest.raises(RuntimeError, match="kdejs"):
+        pk.kde_density(a)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "poppunk-mod_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_default_device_env(monkeypatch):
+    import poppunk_mod_b200 as pk
+
+    monkeypatch.delenv("KDEJS_DEVICE", raising=False)
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    assert pk.default_device() == 0
+    monkeypatch.setenv("KDEJS_DEVICE", "3")
+    assert pk.default_device() in (3, 3 % max(1, pk._native.device_count()))

@@ -1,0 +1,131 @@
+"""CPU: the oracle against the golden vectors generated from the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import case_kwargs, golden_inputs
+from oracle import kde_oracle as ko
+from oracle import ref_shim
+
+SMALL = ["G1_default", "G1_g025", "G1_gridsearch", "G1_nan", "G1_R37", "G2_disjoint", "G2_disjoint_default",
+         "G3_identical", "G5_ragged", "G5_ragged_default", "G6_const_col", "G7_tiny"]
+FULL = ["G4_R100_g025", "G4_R100_g1", "G4_R256_g025", "G4_gridsearch", "C3_member0", "C3_member2"]
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("name", SMALL + FULL)
+def test_oracle_matches_masked_reference(golden, name):
+    case = golden["cases"][name]
+    a, b = golden_inputs(name)
+    js = ko.discrepancy(a, b, resolution=case["R"], **case_kwargs(case))
+    assert js == pytest.approx(case["oracle"], rel=1e-13, abs=1e-15)      # regenerated == stored
+    # reference with its ball-tree residue removed: the bar is 1e-5, observed <= 2e-12
+    assert rel(js, case["ref_masked"]) < 1e-9 or abs(js - case["ref_masked"]) < 1e-12
+    # the raw reference differs only by that residue: exact for gamma=1-ish, ~5e-4 at gamma=0.25
+    if case["gamma"] == 1.0:
+        assert rel(js, case["ref_raw"]) < 1e-9
+
+
+def test_raw_reference_gap_is_the_residue(golden):
+    """Documents SURVEY.md 0.3: at gamma=0.25 raw != masked by ~5e-4, and the port reproduces raw."""
+    c = golden["cases"]["G4_R100_g025"]
+    assert 1e-4 < rel(c["ref_raw"], c["ref_masked"]) < 1e-3
+    assert c["port"] == c["ref_raw"]
+    c = golden["cases"]["G1_gridsearch"]           # gamma=1e-12: the raw value is residue-dominated
+    assert rel(c["ref_raw"], c["ref_masked"]) > 0.05
+
+
+@pytest.mark.parametrize("name", ["G1_g025", "G5_ragged", "G4_R100_g025"])
+def test_oracle_per_node_density(golden, golden_grids, name):
+    case = golden["cases"][name]
+    a, b = golden_inputs(name)
+    _, z1, z2, d1, d2 = ko.discrepancy(a, b, resolution=case["R"], return_grids=True, **case_kwargs(case))
+    for d, key in ((d1, "dens1"), (d2, "dens2")):
+        ref = golden_grids[f"{name}_{key}"]
+        # masked nodes (ref == 0) are < 1e-9*max in truth; elsewhere the reference's log-space noise is
+        # ~1e-12*max absolute, i.e. the north-star bound "1e-6 relative per grid density" with that floor
+        assert np.all(np.abs(d - ref)[ref == 0] <= 1e-9 * ref.max())
+        nz = ref > 0
+        assert np.all(np.abs(d[nz] - ref[nz]) <= 1e-6 * ref[nz] + 1e-11 * ref.max())
+        big = ref > 1e-4 * ref.max()
+        assert np.max(np.abs(d[big] - ref[big]) / ref[big]) < 1e-7
+    assert z1.sum() == pytest.approx(1.0, abs=1e-12) and z2.sum() == pytest.approx(1.0, abs=1e-12)
+
+
+def test_dense_and_window_sums_agree():
+    rng = np.random.default_rng(5)
+    X = rng.random((3000, 2))
+    d0 = ko.kde_density(X, 64, 0.03, dense=True)
+    d1 = ko.kde_density(X, 64, 0.03, dense=False)
+    np.testing.assert_allclose(d1, d0, rtol=1e-14, atol=0)
+    assert d0.sum() / 63**2 == pytest.approx(1.0, rel=0.05)      # integrates to ~1 (edge loss aside)
+
+
+def test_scaler_follows_sklearn():
+    from sklearn.preprocessing import MinMaxScaler
+
+    rng = np.random.default_rng(2)
+    a = rng.normal(0.002, 0.001, (500, 2))
+    b = rng.normal(0.3, 0.1, (700, 2))
+    a[3, 0] = np.nan
+    b[:, 1] = 0.25                                   # constant column in one set only
+    sc = MinMaxScaler().fit(np.vstack([a, b]))
+    scale, min_, has_inf = ko.fit_scaler(a, b)
+    assert not has_inf
+    np.testing.assert_array_equal(scale, sc.scale_)
+    np.testing.assert_array_equal(min_, sc.min_)
+    exp = sc.transform(a)
+    exp[np.isnan(exp)] = 0.0
+    np.testing.assert_array_equal(ko.transform(a, scale, min_), exp)
+    both_const = np.full((10, 2), 0.5)
+    scale, min_, _ = ko.fit_scaler(both_const, both_const)
+    np.testing.assert_array_equal(scale, [1.0, 1.0])  # zero range -> scale 1
+
+
+def test_infinity_is_an_error():
+    a = np.random.default_rng(0).random((10, 2))
+    b = a.copy()
+    b[2, 0] = np.inf
+    with pytest.raises(ValueError, match="infinity"):
+        ko.discrepancy(a, b)
+    with pytest.raises(ValueError, match="infinity"):
+        ko.discrepancy(np.zeros((4, 2)), a, log=True, eps=0.0)      # log(0) = -inf
+
+
+def test_js_bounds_and_symmetry():
+    from oracle import workloads as wl
+
+    a, b = wl.ragged_inputs()
+    j1 = ko.discrepancy(a, b, 0.25, 0.0)
+    j2 = ko.discrepancy(b, a, 0.25, 0.0)
+    assert j1 == pytest.approx(j2, rel=1e-14)
+    assert 0.0 <= j1 <= ko.SQRT_LN2
+
+
+def test_gaussian_kernel_against_sklearn():
+    from sklearn.neighbors import KernelDensity
+
+    rng = np.random.default_rng(4)
+    X = rng.random((400, 2))
+    R = 21
+    lin = np.linspace(0, 1, R)
+    xy = np.stack(np.meshgrid(lin, lin, indexing="ij"), -1).reshape(-1, 2)
+    ref = np.exp(KernelDensity(bandwidth=0.05, kernel="gaussian").fit(X).score_samples(xy))
+    got = ko.kde_density(X, R, 0.05, kernel="gaussian")
+    np.testing.assert_allclose(got, ref, rtol=1e-10)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present (GPU box)")
+def test_live_reference_agrees_with_golden_and_port(golden):
+    from oracle import ref_port
+
+    for name in ["G1_default", "G1_g025", "G5_ragged", "G1_gridsearch"]:
+        case = golden["cases"][name]
+        a, b = golden_inputs(name)
+        raw = float(ref_shim.js(a.copy(), b.copy(), R=case["R"], **case_kwargs(case)))
+        assert raw == case["ref_raw"]
+        assert float(ref_port.js_port(a, b, resolution=case["R"], **case_kwargs(case))) == raw
+        masked, _, _ = ref_shim.js_masked(a, b, R=case["R"], **case_kwargs(case))
+        assert rel(ko.discrepancy(a, b, resolution=case["R"], **case_kwargs(case)), float(masked)) < 1e-11

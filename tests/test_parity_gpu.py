@@ -1,0 +1,290 @@
+"""GPU: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+from conftest import case_kwargs, golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+ALL_CASES = ["G1_default", "G1_g025", "G1_gridsearch", "G1_nan", "G1_R256", "G1_R37", "G2_disjoint",
+             "G2_disjoint_default", "G3_identical", "G5_ragged", "G5_ragged_default", "G6_const_col", "G7_tiny",
+             "G4_R100_g025", "G4_R100_g1", "G4_R256_g025", "G4_gridsearch", "C3_member0", "C3_member1",
+             "C3_member2", "C3_member3"]
+JS_RTOL = 1e-5          # the north-star bar (BASELINE.json); observed ~1e-13
+JS_RTOL_EXPECT = 1e-10  # what the fp64 path actually has to deliver
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import poppunk_mod_b200 as pkg
+
+    assert pkg._native.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def ko():
+    from oracle import kde_oracle
+
+    return kde_oracle
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_golden_cases(pk, ko, golden, name):
+    case = golden["cases"][name]
+    a, b = golden_inputs(name)
+    a0, b0 = a.copy(), b.copy()
+    js = pk.KDE_JS_divergence(a, b, resolution=case["R"], **case_kwargs(case))
+    assert isinstance(js, np.float64)
+    np.testing.assert_array_equal(a, a0)
+    np.testing.assert_array_equal(b, b0)
+    for key in ("oracle", "ref_masked"):
+        want = case[key]
+        assert abs(js - want) <= JS_RTOL_EXPECT * abs(want) + 1e-12, (name, key, js, want)
+        assert abs(js - want) <= JS_RTOL * abs(want) + 1e-12
+    if case["gamma"] == 1.0:      # raw reference is residue-free here
+        assert abs(js - case["ref_raw"]) <= 1e-9 * abs(case["ref_raw"]) + 1e-12
+
+
+@pytest.mark.parametrize("name", ["G1_g025", "G5_ragged", "G4_R100_g025"])
+def test_per_node_density_and_probabilities(pk, ko, golden, golden_grids, name):
+    case = golden["cases"][name]
+    a, b = golden_inputs(name)
+    kw = case_kwargs(case)
+    js, z1, z2, d1, d2 = pk.KDE_distance._discrepancy(a, b, kw["gamma"], kw["eps"], kw["log"], case["R"], 0.03,
+                                                      "epanechnikov", None, None, want_z=True, want_density=True)
+    _, oz1, oz2, od1, od2 = ko.discrepancy(a, b, resolution=case["R"], return_grids=True, **kw)
+    for got, want in ((d1, od1), (d2, od2)):
+        # SURVEY.md 8c(i), fp64 kernel: |dz| <= 1e-6 z + 1e-12 z_max   (observed ~1e-15 z_max)
+        assert np.all(np.abs(got - want) <= 1e-6 * want + 1e-12 * want.max())
+        assert np.array_equal(got == 0, want == 0)            # exact zeros stay exact zeros
+    for got, want in ((z1, oz1), (z2, oz2)):
+        assert np.all(np.abs(got - want) <= 1e-6 * want + 1e-12 * want.max())
+        assert got.sum() == pytest.approx(1.0, abs=1e-12)
+    for got, key in ((d1, "dens1"), (d2, "dens2")):           # 8c(ii): masked reference
+        ref = golden_grids[f"{name}_{key}"]
+        nz = ref > 0
+        assert np.all(np.abs(got[nz] - ref[nz]) <= 1e-6 * ref[nz] + 1e-11 * ref.max())
+    z1b, z2b, grid = pk.scale_KDE(a, b, kw["gamma"], kw["eps"], log=kw["log"], resolution=case["R"])
+    np.testing.assert_array_equal(z1b, z1)
+    assert grid[2].shape == (case["R"] ** 2, 2)
+
+
+def test_batch_equals_singles_bitwise(pk, ko):
+    from oracle import workloads as wl
+
+    obs = wl.synthetic_target(20000)
+    sims = [wl.sim_batch_member(s, n=5000 + 997 * s) for s in range(37)]       # ragged sizes, > one wave
+    got = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0)
+    assert got.shape == (37,) and got.dtype == np.float64
+    for i in (0, 5, 31, 32, 36):
+        single = pk.KDE_JS_divergence(obs, sims[i], gamma=0.25, eps=0.0)
+        assert got[i] == single                                                # same kernels, same order
+        want = ko.discrepancy(obs, sims[i], 0.25, 0.0)
+        assert rel(got[i], want) < JS_RTOL_EXPECT
+    again = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0)
+    np.testing.assert_array_equal(again, got)                                  # run-to-run reproducible
+
+
+def test_pairs_entry(pk, ko):
+    from oracle import workloads as wl
+
+    sets = [wl.sim_batch_member(s, n=3000 + 500 * s) for s in range(5)]
+    pairs = [(i, j) for i in range(5) for j in range(i + 1, 5)]
+    got = pk.KDE_JS_divergence_pairs(sets, pairs, gamma=0.25, eps=0.0)
+    for k, (i, j) in enumerate(pairs):
+        assert rel(got[k], ko.discrepancy(sets[i], sets[j], 0.25, 0.0)) < JS_RTOL_EXPECT
+    sym = pk.KDE_JS_divergence_pairs(sets, [(j, i) for i, j in pairs], gamma=0.25, eps=0.0)
+    np.testing.assert_allclose(sym, got, rtol=1e-13)
+
+
+def test_full_size_properties(pk, ko):
+    """BASELINE config 2 size (100k vs 100k, R=256): oracle check plus size-independent properties."""
+    from oracle import workloads as wl
+
+    T = wl.synthetic_target(100_000)
+    S = wl.sim_S(254, 2500, 0.38)
+    js = pk.KDE_JS_divergence(T, S, gamma=0.25, eps=0.0, resolution=256)
+    assert rel(js, ko.discrepancy(T, S, 0.25, 0.0, resolution=256)) < JS_RTOL_EXPECT
+    assert 0.0 < js < ko.SQRT_LN2
+    assert pk.KDE_JS_divergence(T, T.copy(), gamma=0.25, eps=0.0, resolution=256) == 0.0     # identity
+    assert pk.KDE_JS_divergence(S, T, gamma=0.25, eps=0.0, resolution=256) == pytest.approx(js, rel=1e-13)
+    perm = np.random.default_rng(0).permutation(len(S))
+    assert pk.KDE_JS_divergence(T, S[perm], gamma=0.25, eps=0.0, resolution=256) == pytest.approx(js, rel=1e-12)
+    far = S + [10.0, 10.0]                                                     # disjoint after joint scaling
+    assert pk.KDE_JS_divergence(T, far, gamma=0.25, eps=0.0, resolution=256) == pytest.approx(ko.SQRT_LN2, rel=1e-14)
+    z1, z2, _ = pk.scale_KDE(T, S, 0.25, 0.0, resolution=256)
+    assert z1.sum() == pytest.approx(1.0, abs=1e-12) and z1.min() >= 0.0
+    # affine invariance of the joint min-max scaling
+    js_aff = pk.KDE_JS_divergence(T * [2.0, 0.5] + [1.0, -3.0], S * [2.0, 0.5] + [1.0, -3.0], gamma=0.25, eps=0.0,
+                                  resolution=256)
+    assert js_aff == pytest.approx(js, rel=1e-9)
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 5, 17, 100, 129, 256, 511])
+def test_resolutions(pk, ko, R):
+    from oracle import workloads as wl
+
+    a, b = wl.ragged_inputs()
+    got = pk.KDE_JS_divergence(a, b, gamma=0.5, eps=1e-12, resolution=R)
+    want = ko.discrepancy(a, b, 0.5, 1e-12, resolution=R)
+    assert (np.isnan(got) and np.isnan(want)) or rel(got, want) < JS_RTOL_EXPECT
+
+
+@pytest.mark.parametrize("h", [0.005, 0.03, 0.2, 0.7])
+def test_bandwidths(pk, ko, h):
+    from oracle import workloads as wl
+
+    a, b = wl.g1_inputs()
+    got = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, bandwidth=h)
+    assert rel(got, ko.discrepancy(a, b, 0.25, 0.0, bandwidth=h)) < JS_RTOL_EXPECT
+
+
+def test_dense64_matches_binned(pk, ko):
+    from oracle import workloads as wl
+
+    a, b = wl.ragged_inputs()
+    j0 = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, algo="binned")
+    j1 = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, algo="dense64")
+    assert rel(j1, j0) < 1e-11
+
+
+def test_gaussian_kernel(pk, ko):
+    from oracle import workloads as wl
+
+    a, b = wl.g1_inputs()
+    got = pk.KDE_JS_divergence(a[:800], b[:900], gamma=1.0, eps=1e-12, kernel="gaussian", resolution=64)
+    want = ko.discrepancy(a[:800], b[:900], 1.0, 1e-12, kernel="gaussian", resolution=64)
+    assert rel(got, want) < 1e-9
+
+
+def test_kde_density(pk, ko):
+    rng = np.random.default_rng(8)
+    X = rng.random((5000, 2))
+    got = pk.kde_density(X, resolution=100)
+    want = ko.kde_density(X, 100, 0.03).reshape(100, 100)
+    assert np.all(np.abs(got - want) <= 1e-6 * want + 1e-12 * want.max())
+    # off-unit grid and points outside it (plot_scatter scales by the maximum only)
+    Y = rng.normal(0.5, 0.4, (3000, 2))
+    got = pk.kde_density(Y, resolution=80, bandwidth=0.05, minimum=-0.2, maximum=1.3)
+    want = ko.kde_density(Y, 80, 0.05, gmin=-0.2, gmax=1.3).reshape(80, 80)
+    assert np.all(np.abs(got - want) <= 1e-6 * want + 1e-12 * want.max())
+    with pytest.raises(ValueError):
+        pk.kde_density(np.array([[np.nan, 0.1]]))
+
+
+def test_nan_and_infinity_handling(pk, ko):
+    a, b = golden_inputs("G1_default")
+    a = a.copy()
+    a[::7, 0] = np.nan
+    a[3] = np.nan
+    got = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0)
+    assert rel(got, ko.discrepancy(a, b, 0.25, 0.0)) < JS_RTOL_EXPECT
+    b2 = b.copy()
+    b2[10, 1] = np.inf
+    with pytest.raises(ValueError, match="infinity"):
+        pk.KDE_JS_divergence(a, b2)
+    with pytest.raises(ValueError, match="infinity"):
+        pk.KDE_JS_divergence(np.zeros((4, 2)), b, log=True, eps=0.0)
+    out = None
+    try:
+        pk.KDE_JS_divergence_batch(a, [b, b2, b], gamma=0.25, eps=0.0)
+    except ValueError as e:
+        out = str(e)
+    assert out and "infinity" in out
+    # all-NaN column: every scaled value becomes 0 (sklearn: NaN scale, then KDE_distance.py:53)
+    c = b.copy()
+    c[:, 0] = np.nan
+    a3 = a.copy()
+    a3[:, 0] = np.nan
+    got = pk.KDE_JS_divergence(a3, c, gamma=1.0, eps=1e-12)
+    assert rel(got, ko.discrepancy(a3, c, 1.0, 1e-12)) < JS_RTOL_EXPECT
+
+
+def test_log_mode_and_kl(pk, ko):
+    a, b = golden_inputs("G1_default")
+    got = pk.KDE_JS_divergence(a, b, 1e-12, 1e-12, True)            # positional, as distance_to_gridsearch.py:50
+    assert rel(got, ko.discrepancy(a, b, 1e-12, 1e-12, True)) < JS_RTOL_EXPECT
+    kl = pk.KDE_KL_divergence(a, b)
+    _, z1, z2, _, _ = ko.discrepancy(a, b, 1.0, 1e-12, return_grids=True)
+    assert kl == pytest.approx(float(np.sum(z1 * np.log(z1 / z2))), rel=1e-9)
+
+
+def test_row_sharded_phases_reproduce_the_full_result(pk, ko):
+    import ctypes
+
+    from oracle import workloads as wl
+
+    nat = pk._native
+    a, b = wl.synthetic_target(30000), wl.sim_S(3, 1500, 0.33, n=25000)
+    R = 130
+    full = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=R)
+    bounds = [0, 32, 64, 100, R]
+    norms, lrs = [], []
+    common = (R, 0.03, 0.25, 0.0, 0, 0, 0)
+    for lo, hi in zip(bounds[:-1], bounds[1:]):     # one "rank" at a time on the single test GPU
+        n = (ctypes.c_double * 2)()
+        nat.check(nat.lib().kdejs_shard_phase1(0, nat.ptr(a), len(a), nat.ptr(b), len(b), *common, lo, hi, n))
+        norms.append((n[0], n[1]))
+    tot = (ctypes.c_double * 2)(sum(x for x, _ in norms), sum(y for _, y in norms))
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        n = (ctypes.c_double * 2)()
+        lr = (ctypes.c_double * 2)()
+        nat.check(nat.lib().kdejs_shard_phase1(0, nat.ptr(a), len(a), nat.ptr(b), len(b), *common, lo, hi, n))
+        nat.check(nat.lib().kdejs_shard_phase2(0, tot, lr))
+        lrs.append((lr[0], lr[1]))
+    js = np.sqrt((sum(x for x, _ in lrs) + sum(y for _, y in lrs)) / 2.0)
+    assert js == pytest.approx(full, rel=1e-12)
+    assert rel(js, ko.discrepancy(a, b, 0.25, 0.0, resolution=R)) < JS_RTOL_EXPECT
+
+
+def test_device_resident_entry_matches_host_entry(pk):
+    import ctypes
+
+    import torch
+
+    from oracle import workloads as wl
+
+    nat = pk._native
+    obs = wl.synthetic_target(20000)
+    sims = [wl.sim_batch_member(s, n=15000) for s in range(5)]
+    want = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0, resolution=128)
+    dobs = torch.from_numpy(obs).cuda()
+    dsims = [torch.from_numpy(s).cuda() for s in sims]
+    out = torch.empty(5, dtype=torch.float64, device="cuda")
+    status = torch.empty(5, dtype=torch.int32, device="cuda")
+    ptrs = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in dsims])
+    cnt = (ctypes.c_int64 * 5)(*[t.shape[0] for t in dsims])
+    st = torch.cuda.current_stream().cuda_stream
+    nat.check(nat.lib().kdejs_discrepancy_batch_dev(0, dobs.data_ptr(), len(obs), ptrs, cnt, 5, 128, 0.03, 0.25,
+                                                    0.0, 0, 0, 0, out.data_ptr(), status.data_ptr(), st))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    assert status.cpu().numpy().tolist() == [0] * 5
+
+
+def test_profile_counters(pk):
+    import ctypes
+
+    nat = pk._native
+    a, b = golden_inputs("G1_default")
+    L = nat.lib()
+    nat.check(L.kdejs_profile_reset(0))
+    nat.check(L.kdejs_profile_enable(0, 1))
+    n0 = ctypes.c_int64()
+    nat.check(L.kdejs_launch_count(0, ctypes.byref(n0), 1))
+    pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0)
+    ms, n = ctypes.c_double(), ctypes.c_int64()
+    nat.check(L.kdejs_profile_read(0, 4, ctypes.byref(ms), ctypes.byref(n)))
+    assert n.value == 1 and ms.value > 0.0
+    cnt = ctypes.c_int64()
+    nat.check(L.kdejs_launch_count(0, ctypes.byref(cnt), 0))
+    assert cnt.value == 6
+    w = ctypes.c_double()
+    nat.check(L.kdejs_work_counters(0, ctypes.byref(w), 1))
+    assert w.value > 0
+    nat.check(L.kdejs_profile_enable(0, 0))
