@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- KDE discrepancy evaluations/s on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config C2 of SURVEY.md 8d, batched as C3): every step each GPU evaluates BATCH=64
+independent discrepancies KDE_JS_divergence(target, sim_i, gamma=0.25, eps=0) with a 100 000-pair
+target, 100 000-pair simulated sets, a 256x256 grid, bandwidth 0.03, Epanechnikov kernel.
+Sims are distinct per step and per rank (a resident pool larger than L2 is rotated).
+
+value  : evaluations/s, device-resident inputs, CUDA-event timed on the launching stream, max over ranks
+e2e    : evaluations/s through the public Python API (KDE_JS_divergence_batch) from pinned HOST
+         buffers, H2D of every input and D2H of the results inside the timed region
+roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PAIRS = 100_000
+RES = 256
+BANDWIDTH = 0.03
+GAMMA = 0.25
+EPS = 0.0
+BATCH = 64
+POOL = 192          # resident sims per GPU: 192 x 1.6 MB = 307 MB > 126 MB L2
+METRIC = "kde_discrepancy_evals_per_sec"
+UNIT = "evals/s"
+WORKLOAD = ("C2 single discrepancy 100k sim pairs vs 100k target pairs, 256x256 grid, gamma=0.25, eps=0, "
+            f"epanechnikov h=0.03; one step = {BATCH} such evaluations per GPU (distinct sims, one target)")
+
+
+def rank_env():
+    return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+            int(os.environ.get("WORLD_SIZE", 1)))
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def in_support_pairs(a, b, R, h):
+    """Exact count of (point, node) pairs with non-zero Epanechnikov weight for one evaluation:
+    the minimum any exact algorithm must touch.  Vectorised over points, one node column at a time."""
+    both = np.vstack([a, b])
+    lo, hi = both.min(0), both.max(0)
+    step = 1.0 / (R - 1)
+    total = 0
+    H = int(np.ceil(h / step)) + 1
+    for pts in (a, b):
+        X = (pts - lo) / (hi - lo)
+        ic = np.rint(X[:, 0] / step).astype(np.int64)
+        for off in range(-H, H + 1):
+            ix = ic + off
+            dx = ix * step - X[:, 0]
+            ok = (ix >= 0) & (ix < R) & (np.abs(dx) < h)
+            w = np.sqrt(np.maximum(h * h - dx * dx, 0.0))
+            j0 = np.maximum(np.ceil((X[:, 1] - w) / step - 1e-12), 0)
+            j1 = np.minimum(np.floor((X[:, 1] + w) / step + 1e-12), R - 1)
+            total += int(np.sum(np.where(ok, np.maximum(j1 - j0 + 1, 0), 0)))
+    return total
+
+
+def make_inputs(rank, n_sims):
+    from oracle import workloads as wl      # seeded numpy generators only (no oracle code runs here)
+
+    target = wl.synthetic_target(N_PAIRS)
+    sims = [wl.sim_batch_member(100_000 * rank + s, n=N_PAIRS) for s in range(n_sims)]
+    return target, sims
+
+
+def cpu_reference_rate(target, sims, processes):
+    """The reference's CPU arithmetic (sklearn ball-tree KDE + scipy JS) on the host cores."""
+    from oracle import ref_port
+
+    pairs = [(target, s) for s in sims]
+    kw = dict(gamma=GAMMA, eps=EPS, log=False, resolution=RES, bandwidth=BANDWIDTH)
+    t0 = time.perf_counter()
+    vals = ref_port.js_port_many(pairs, processes=processes, **kw)
+    dt = time.perf_counter() - t0
+    return len(pairs) / dt, dt, vals
+
+
+def run_reference(args):
+    rank, _, world = rank_env()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    target, sims = make_inputs(0, procs)
+    times = []
+    for it in range(args.warmup + args.steps):
+        rate, dt, _ = cpu_reference_rate(target, sims, procs)
+        if it >= args.warmup:
+            times.append(dt)
+    t = float(np.sum(times))
+    value = procs * args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
+                   "evals_per_step": procs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{procs} evaluations per step, one per process (fork pool), the reference's "
+                                   "call sequence on sklearn/scipy (oracle/ref_port.py)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="kdejs", choices=["kdejs", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--algo", default="binned", choices=["binned", "dense", "dense64"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "kdejs" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import poppunk_mod_b200 as pk
+
+    nat = pk._native
+    L = nat.lib()
+    rank, local_rank, world = rank_env()
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if torch.cuda.device_count() > local_rank else 0
+    torch.cuda.set_device(dev)
+    os.environ["KDEJS_DEVICE"] = str(dev)
+    nat.check(L.kdejs_init(dev))
+
+    target, sims = make_inputs(rank, POOL)
+    algo = nat.ALGOS[args.algo]
+    common = (RES, BANDWIDTH, GAMMA, EPS, 0, 0, algo)
+
+    # ---- device-resident inputs --------------------------------------------------------------
+    d_target = torch.from_numpy(target).cuda()
+    d_sims = [torch.from_numpy(s).cuda() for s in sims]
+    d_out = torch.zeros(BATCH, dtype=torch.float64, device="cuda")
+    d_status = torch.zeros(BATCH, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+    cnt = (ctypes.c_int64 * BATCH)(*([N_PAIRS] * BATCH))
+
+    def step_dev(s):
+        first = (s * BATCH) % POOL
+        idx = [(first + k) % POOL for k in range(BATCH)]
+        ptrs = (ctypes.c_void_p * BATCH)(*[d_sims[i].data_ptr() for i in idx])
+        nat.check(L.kdejs_discrepancy_batch_dev(dev, d_target.data_ptr(), N_PAIRS, ptrs, cnt, BATCH, *common,
+                                                d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for s in range(args.warmup):
+        step_dev(s)
+    barrier()
+    nat.check(L.kdejs_profile_reset(dev))
+    nat.check(L.kdejs_profile_enable(dev, 1))
+    w = ctypes.c_double()
+    nat.check(L.kdejs_work_counters(dev, ctypes.byref(w), 1))
+    n_launch = ctypes.c_int64()
+    nat.check(L.kdejs_launch_count(dev, ctypes.byref(n_launch), 1))
+    sampler = ClockSampler(dev)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for s in range(args.steps):
+        step_dev(args.warmup + s)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    nat.check(L.kdejs_launch_count(dev, ctypes.byref(n_launch), 0))
+    nat.check(L.kdejs_work_counters(dev, ctypes.byref(w), 1))
+    prof = {}
+    for k, nm in enumerate(nat.KERNEL_NAMES):
+        pm, pn = ctypes.c_double(), ctypes.c_int64()
+        nat.check(L.kdejs_profile_read(dev, k, ctypes.byref(pm), ctypes.byref(pn)))
+        prof[nm] = (pm.value, pn.value)
+    nat.check(L.kdejs_profile_enable(dev, 0))
+    js_last = d_out.cpu().numpy().copy()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * BATCH / (ms_max * 1e-3)
+
+    # ---- end to end through the public API, pinned host inputs ----------------------------------
+    pool = nat.PinnedPool()
+    h_target = pool.empty((N_PAIRS, 2)); h_target[:] = target
+    h_sims = []
+    for s in sims[:2 * BATCH]:
+        buf = pool.empty((N_PAIRS, 2)); buf[:] = s
+        h_sims.append(buf)
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def step_e2e(s):
+        first = (s % 2) * BATCH
+        return pk.KDE_JS_divergence_batch(h_target, h_sims[first:first + BATCH], gamma=GAMMA, eps=EPS,
+                                          resolution=RES, algo=args.algo, devices=dev)
+
+    for s in range(2):
+        step_e2e(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        res = step_e2e(s)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * BATCH / float(t.item())
+    assert np.all(np.isfinite(res)) and np.all(res > 0) and np.all(res < 0.8326)
+
+    # ---- single-call latency (BOLFI acquisition phase: batch of one) ------------------------------
+    lat = []
+    for s in range(8):
+        t0 = time.perf_counter()
+        pk.KDE_JS_divergence(h_target, h_sims[s], gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, device=dev)
+        lat.append(time.perf_counter() - t0)
+    single_ms = 1e3 * float(np.median(lat[2:]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (density) ------------------------------------------------
+    tf64, mhz = ctypes.c_double(), ctypes.c_double()
+    nat.check(L.kdejs_peak_flops(dev, 1, ctypes.byref(tf64), ctypes.byref(mhz)))
+    tf32 = ctypes.c_double()
+    nat.check(L.kdejs_peak_flops(dev, 0, ctypes.byref(tf32), ctypes.byref(mhz)))
+    dens_ms, dens_n = prof["density"]
+    evals_timed = args.steps * BATCH
+    sample = [in_support_pairs(target, sims[i], RES, BANDWIDTH) for i in (0, 7, 19)]
+    pairs_per_eval = float(np.mean(sample))
+    flop_per_pair = 8.0            # 2 sub, 2 mul+add, max, add
+    evals_per_launch = evals_timed / max(dens_n, 1)
+    alg_flops_per_launch = pairs_per_eval * flop_per_pair * evals_per_launch
+    avg_launch_s = dens_ms * 1e-3 / max(dens_n, 1)
+    achieved = alg_flops_per_launch / avg_launch_s / 1e12 if dens_n else 0.0
+    total_kernel_ms = sum(v[0] for v in prof.values())
+    roofline = {
+        "bound": "fp64-pipe", "achieved": achieved, "peak": tf64.value, "unit": "TFLOP/s",
+        "frac": achieved / tf64.value if tf64.value else None, "traffic": None,
+        "kernel": "k_density_binned", "peak_source": "DFMA issue-rate microbenchmark run in this process "
+        "(kdejs_peak_flops); MEASURED_PEAKS.json holds only HBM and bf16 tensor peaks",
+        "algorithmic_flops_per_launch": alg_flops_per_launch,
+        "in_support_pairs_per_eval": pairs_per_eval,
+        "executed_pair_tests_per_eval": w.value / evals_timed if evals_timed else None,
+        "dense_equivalent_pairs_per_eval": 2.0 * N_PAIRS * RES * RES,
+        "avg_launch_ms": 1e3 * avg_launch_s, "launches": dens_n,
+        "kernel_share_of_step": dens_ms / total_kernel_ms if total_kernel_ms else None,
+        "fp32_ffma_peak_tflops": tf32.value,
+        "per_kernel_ms": {k: v[0] for k, v in prof.items()},
+    }
+    hbm_bytes = (2 * N_PAIRS * 16) * evals_timed     # every input point read once per evaluation
+    roofline["hbm_algorithmic_gbs"] = hbm_bytes / (ms_max * 1e-3) / 1e9
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        n_cpu = 4
+        rate, cdt, vals = cpu_reference_rate(target, sims[:n_cpu], 1)
+        gpu_vals = pk.KDE_JS_divergence_batch(target, sims[:n_cpu], gamma=GAMMA, eps=EPS, resolution=RES, devices=dev)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"{n_cpu} of the step's evaluations, sequential, one process ({cdt:.1f} s): the "
+                                  "reference's call sequence on sklearn/scipy (oracle/ref_port.py)",
+                        "max_rel_gap_to_gpu": float(np.max(np.abs(vals - gpu_vals) / gpu_vals)),
+                        "gap_note": "the gap is the reference's ball-tree residue amplified by gamma=0.25 "
+                                    "(SURVEY.md 0.3); against the exact oracle the GPU agrees to ~1e-13"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
+                   "evals_per_step_per_gpu": BATCH, "algo": args.algo,
+                   "l2": f"resident pool of {POOL} sims ({POOL * N_PAIRS * 16 / 1e6:.0f} MB) rotated: inputs "
+                         "larger than the 126 MB L2 between reuse"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": (BATCH + 1) * N_PAIRS * 16, "d2h_bytes_per_step": BATCH * 12,
+                "steps": e2e_steps, "api": "KDE_JS_divergence_batch (ctypes -> kdejs_discrepancy_batch), "
+                                           "pinned host arrays"},
+        "gpu_launches": int(n_launch.value),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "single_call_latency_ms": single_ms,
+        "js_sample": [float(x) for x in js_last[:3]],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
