@@ -207,7 +207,9 @@ def main():
     d_sims = [torch.from_numpy(s).cuda() for s in sims]
     d_out = torch.zeros(BATCH, dtype=torch.float64, device="cuda")
     d_status = torch.zeros(BATCH, dtype=torch.int32, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the C ABI treats a NULL stream as "the library's own", and
+    # torch's default stream handle is NULL -- events must be recorded on the stream the kernels use
+    stream = torch.cuda.Stream()
     cnt = (ctypes.c_int64 * BATCH)(*([N_PAIRS] * BATCH))
 
     def step_dev(s):

@@ -125,8 +125,9 @@ void kdejs_host_free(void *p);
 
 /* ---- measurement support (bench.py, tests) ------------------------------------------- */
 /* Per-kernel CUDA-event timing on the launching stream.  which: 0 minmax, 1 scale+count,
- * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence.  Reading synchronises. */
-#define KDEJS_NUM_KERNELS 6
+ * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence, 6 tile classification.
+ * Reading synchronises. */
+#define KDEJS_NUM_KERNELS 7
 int kdejs_profile_enable(int device, int on);
 int kdejs_profile_read(int device, int which, double *ms_total, int64_t *launches);
 int kdejs_profile_reset(int device);

@@ -51,7 +51,7 @@ struct DevBuf {
 
 struct Slot {
     DevBuf rawsims, scaled, sorted, cellid, blockhist, cellstart, dens, pz, zout, tilesum;
-    DevBuf rstat, rpart, tickets, jspart, dense_partial;
+    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, counters;
     cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
 };
 
@@ -66,6 +66,7 @@ struct Ctx {
     int dev = -1;
     bool ready = false;
     int sm_count = 0;
+    int dens_blocks_per_sm = 1;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     Slot slot[2];
     DevBuf pool_raw, js_out, status_out, misc;
@@ -118,6 +119,8 @@ int get_ctx(int device, Ctx **out) {
                                     kSortWarps * kMaxCells * (int)sizeof(uint32_t)));
             CU(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSortWarps * kMaxCells * (int)sizeof(uint32_t)));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned, kDensThreads, 0));
+            c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
             c.ready = true;
         }
     }
@@ -198,7 +201,7 @@ GridGeom make_geom(const Params &p) {
     g.knorm = std::exp(-factor - 2.0 * std::log(p.h));
     g.gamma = p.gamma;
     g.eps = p.eps;
-    g.gamma_mode = (p.gamma == 1.0) ? 1 : 0;
+    g.gamma_mode = (p.gamma == 1.0) ? 1 : (p.gamma == 0.5) ? 2 : (p.gamma == 0.25) ? 3 : 0;
     g.tile_row_begin = 0;
     g.tile_row_end = g.NT;
     return g;
@@ -258,6 +261,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         OKR(sl.cellid.ensure((size_t)P * sizeof(uint16_t)));
         OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * ncells * sizeof(uint32_t)));
         OKR(sl.cellstart.ensure((size_t)n_sets * (ncells + 1) * sizeof(uint32_t)));
+        OKR(sl.worklist.ensure((size_t)kNumClasses * n_sets * g.NT * g.NT * sizeof(uint32_t)));
+        OKR(sl.counters.ensure(8 * sizeof(unsigned)));
     }
 
     unsigned *tk_minmax = sl.tickets.as<unsigned>();
@@ -280,7 +285,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         {
             KTimer t(c, 2, st);
             k_scan<<<n_sets, 1024, 0, st>>>(wd, ncells, nb_max, sl.blockhist.as<uint32_t>(),
-                                            sl.cellstart.as<uint32_t>());
+                                            sl.cellstart.as<uint32_t>(), sl.counters.as<unsigned>());
         }
         {
             KTimer t(c, 3, st);
@@ -288,12 +293,22 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 wd, g.C, chw, nb_max, sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(),
                 sl.blockhist.as<uint32_t>(), sl.sorted.as<double2>());
         }
+        const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
+        const unsigned capacity = (unsigned)tiles * (unsigned)n_sets;
+        {
+            KTimer t(c, 6, st);
+            k_tile_classify<<<dim3((tiles + 255) / 256, n_sets), 256, 0, st>>>(
+                wd, g, sl.cellstart.as<uint32_t>(), sl.dens.as<double>(), sl.pz.as<double>(),
+                sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity,
+                c.prof_on ? c.d_work : nullptr);
+        }
         {
             KTimer t(c, 4, st);
-            const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
-            k_density_binned<<<dim3(tiles, n_sets), kDensThreads, 0, st>>>(
+            const int blocks = (int)std::min<int64_t>((int64_t)capacity, (int64_t)c.sm_count * c.dens_blocks_per_sm);
+            k_density_binned<<<blocks, kDensThreads, 0, st>>>(
                 wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.dens.as<double>(),
-                sl.pz.as<double>(), sl.tilesum.as<double>(), c.prof_on ? c.d_work : nullptr);
+                sl.pz.as<double>(), sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(),
+                sl.counters.as<unsigned>(), capacity);
         }
     } else {
         // dense fp64: scale only (C = 1: every point lands in cell 0, the histogram is unused)
@@ -440,7 +455,7 @@ void kdejs_shutdown(void) {
         for (auto &s : c.slot) {
             for (DevBuf *b : {&s.rawsims, &s.scaled, &s.sorted, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
                               &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart,
-                              &s.dense_partial}) {
+                              &s.dense_partial, &s.worklist, &s.counters}) {
                 if (b->p) cudaFree(b->p);
                 b->p = nullptr; b->cap = 0;
             }

@@ -226,8 +226,10 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
 // first sorted position of block b's points of cell c, and writes cellstart[set][0..ncells].
 __global__ void __launch_bounds__(1024)
 k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
-       uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart) {
+       uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart,
+       unsigned *__restrict__ counters) {
     const int set = blockIdx.x;
+    if (set == 0 && threadIdx.x < 8) counters[threadIdx.x] = 0u;   // work-list counters of this wave
     const int nb = wd.set[set].nb;
     uint32_t *bh = blockhist + (size_t)set * nb_max * ncells;
     const int c0 = threadIdx.x * 4;
@@ -342,120 +344,302 @@ k_place(const __grid_constant__ WaveDesc wd, int C, int chw, int nb_max,
 
 // ------------------------------------------------------------------------------------------
 // Per-node epilogue shared by the density kernels: density -> **gamma + eps.
+// gamma_mode: 1 gamma==1, 2 gamma==0.5 (sqrt), 3 gamma==0.25 (sqrt of sqrt), 0 general pow().
 __device__ __forceinline__ double gamma_eps(double dens, const GridGeom &g) {
-    double z = (g.gamma_mode == 1) ? dens : pow(dens, g.gamma);   // KDE_distance.py:71
+    double z;
+    if (g.gamma_mode == 1) z = dens;
+    else if (g.gamma_mode == 2) z = sqrt(dens);
+    else if (g.gamma_mode == 3) z = sqrt(sqrt(dens));
+    else z = pow(dens, g.gamma);                                   // KDE_distance.py:71
     return z + g.eps;                                              // :75
 }
 
-// k_density_binned: grid (tiles in [tile_row_begin, tile_row_end) x NT, n_sets), 128 threads.
-// A block owns one 4x4-node tile; its candidates are the sorted points of the cells that can reach
-// the tile (a few contiguous runs, one per cell row).  Lanes take candidates round-robin, every
-// lane keeps the tile's 16 fp64 sums in registers:  t = 1 - ux^2 - uy^2 in units of h, added when
-// positive (strict dist < h, sklearn:_binary_tree.pxi.tp:389-394).  Fixed-shape reduction across
-// the 128 lanes, then the 16 node values, their **gamma+eps and the tile's share of the normaliser.
-__global__ void __launch_bounds__(kDensThreads)
+// Cells a 4x4-node tile has to visit: every point within h of one of its nodes lies in
+// [cx_lo, cx_hi] x [cy_lo, cy_hi] (cell_of is monotone; `margin` covers the rounding of the bounds).
+struct TileCells { int cx_lo, cx_hi, cy_lo, cy_hi; };
+__device__ __forceinline__ TileCells tile_cells(const GridGeom &g, int ix0, int iy0) {
+    const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
+    const double xhi = (double)min(ix0 + kTile - 1, g.R - 1) * g.step + g.gmin;
+    const double yhi = (double)min(iy0 + kTile - 1, g.R - 1) * g.step + g.gmin;
+    TileCells t;
+    t.cx_lo = cell_of(gx0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
+    t.cx_hi = cell_of(xhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
+    t.cy_lo = cell_of(gy0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
+    t.cy_hi = cell_of(yhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
+    return t;
+}
+
+// Work-list layout.  counters: [0..3] entries per class, [4] next ticket (zeroed by k_scan each wave).
+constexpr int kNumClasses = 4;
+__device__ __forceinline__ int tile_class(uint32_t total) {
+    return total >= 16384u ? 0 : total >= 2048u ? 1 : total >= 256u ? 2 : 3;   // heavy tiles first
+}
+
+// k_tile_classify: one thread per (tile, set).  Counts the tile's candidate points; a tile with none
+// gets its 16 node values written here (density 0), the others are appended to the work list of
+// their weight class.  The order inside a class is arbitrary and does not affect any result.
+__global__ void __launch_bounds__(256)
+k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
+                const uint32_t *__restrict__ cellstart, double *__restrict__ dens,
+                double *__restrict__ pz, double *__restrict__ tilesum, uint32_t *__restrict__ worklist,
+                unsigned *__restrict__ counters, unsigned capacity,
+                unsigned long long *__restrict__ work_counter) {
+    const int ntl = (g.tile_row_end - g.tile_row_begin) * g.NT;
+    const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int set = blockIdx.y;
+    uint32_t total = 0u;
+    if (tl < ntl) {
+        const int tx = g.tile_row_begin + tl / g.NT, ty = tl % g.NT;
+        const int ix0 = tx * kTile, iy0 = ty * kTile;
+        const TileCells tc = tile_cells(g, ix0, iy0);
+        const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
+        for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy)
+            total += cs[cy * g.C + tc.cx_hi + 1] - cs[cy * g.C + tc.cx_lo];
+        const int tile = tx * g.NT + ty;
+        if (total == 0u) {
+            const double P0 = gamma_eps(0.0, g);
+            double s = 0.0;
+            for (int i = 0; i < kTile; ++i)
+                for (int j = 0; j < kTile; ++j) {
+                    const int ix = ix0 + i, iy = iy0 + j;
+                    if (ix < g.R && iy < g.R) {
+                        const size_t k = (size_t)set * g.R * g.R + (size_t)ix * g.R + iy;
+                        dens[k] = 0.0;
+                        pz[k] = P0;
+                        s += P0;
+                    }
+                }
+            tilesum[(size_t)set * g.NT * g.NT + tile] = s;
+        } else {
+            const int cls = tile_class(total);
+            const unsigned slot = atomicAdd(&counters[cls], 1u);
+            worklist[(size_t)cls * capacity + slot] = ((uint32_t)set << 24) | (uint32_t)tile;
+        }
+    }
+    if (work_counter) {
+        unsigned long long t = total;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0 && t)
+            atomicAdd(work_counter, t * (kTile * kTile));
+    }
+}
+
+// Clamp-and-accumulate for the Epanechnikov term t = 1 - d^2/h^2:  acc += (t >= +0) ? t * 2^-7 : 0.
+// The clamp is an exact multiply folded into the accumulating DFMA.  The multiplier's high word is made
+// on the FP32 (FMA) pipe from the high word of t read as a float: sat(f * 2^126) is 1.0f (0x3F800000)
+// for every positive normal f and 0 for negative/zero f, and 0x3F800000:00000000 read as a double is
+// exactly 2^-7.  A pair therefore costs two fp64-pipe instructions plus ONE full-rate FMUL.SAT -- no
+// compare/select chain on the half-rate ALU pipe -- and the kernel stays fp64-pipe bound.  The power-
+// of-two scale commutes with rounding, so 128 * acc is bit-identical to the plain fp64 sum.
+constexpr double kAccUnscale = 128.0;
+__device__ __forceinline__ double clamp_mask(double t) {
+    const float m = __saturatef(__int_as_float(__double2hiint(t)) * 8.507059173023462e37f);   // 2^126
+    return __hiloint2double(__float_as_int(m), 0);
+}
+
+constexpr int kRedStride = kDensThreads + 8;   // padded row of the block-level transposed reduction buffer
+constexpr int kWarpRedStride = 33;             // padded row of the warp-level one
+constexpr int kRedDoubles = kTile * kTile * kRedStride;   // >= 4 warps * 16 * 33
+
+// One candidate point against the tile's 16 nodes (46 fp64-pipe + 16 FP32-pipe instructions).
+__device__ __forceinline__ void accumulate_point(const double2 p, const double gx0, const double gy0,
+                                                 const double inv_h, const double c1, const double c2,
+                                                 const double c3, double (&acc)[kTile][kTile]) {
+    const double ux0 = (p.x - gx0) * inv_h;      // node i sits at i*dh - ux0 (units of h)
+    const double uy0 = (p.y - gy0) * inv_h;
+    const double u1 = c1 - ux0, u2 = c2 - ux0, u3 = c3 - ux0;
+    const double v1 = c1 - uy0, v2 = c2 - uy0, v3 = c3 - uy0;
+    const double a[kTile] = {fma(-ux0, ux0, 1.0), fma(-u1, u1, 1.0), fma(-u2, u2, 1.0), fma(-u3, u3, 1.0)};
+    const double w[kTile] = {-uy0, -v1, -v2, -v3};
+    const double q[kTile] = {uy0, v1, v2, v3};
+#pragma unroll
+    for (int i = 0; i < kTile; ++i) {
+        double t[kTile], m[kTile];
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) t[j] = fma(w[j], q[j], a[i]);
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) m[j] = clamp_mask(t[j]);
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) acc[i][j] = fma(t[j], m[j], acc[i][j]);
+    }
+}
+
+__device__ __forceinline__ uint32_t worklist_entry(const uint32_t *__restrict__ worklist, unsigned capacity,
+                                                   unsigned item, unsigned n1, unsigned n2) {
+    // item indexes the concatenation of classes 1, 2, 3
+    if (item < n1) return worklist[(size_t)capacity + item];
+    if (item < n1 + n2) return worklist[(size_t)2 * capacity + (item - n1)];
+    return worklist[(size_t)3 * capacity + (item - n1 - n2)];
+}
+
+// k_density_binned: persistent, (#SM x resident) blocks of 128 threads pulling 4x4-node tiles from
+// the work list.  A tile's candidates are the sorted points of the cells that can reach it (one
+// contiguous run per cell row).  Lanes take candidates round-robin and keep the tile's 16 fp64 sums in
+// registers:  t = 1 - ux^2 - uy^2 in units of h, added when non-negative (strict dist < h,
+// sklearn:_binary_tree.pxi.tp:389-394; a zero term changes nothing).
+//   phase A  the few very heavy tiles (class 0, >= 16384 candidates): one tile per BLOCK
+//   phase B  everything else: one tile per WARP, no block-level synchronisation at all
+// Each phase ends a tile with a fixed-shape reduction through shared memory, the 16 node values,
+// their **gamma+eps and the tile's share of the normaliser.  Which warp or block processes a tile is
+// decided at run time (atomic tickets) but never changes a result.
+__global__ void __launch_bounds__(kDensThreads, 6)
 k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
                  const double2 *__restrict__ sorted, const uint32_t *__restrict__ cellstart,
                  double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
-                 unsigned long long *__restrict__ work_counter) {
+                 const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
+                 unsigned capacity) {
     __shared__ uint32_t s_rs[kMaxRows];
     __shared__ uint32_t s_cum[kMaxRows + 1];
-    __shared__ double s_red[kDensThreads / 32][kTile * kTile];
-    const int set = blockIdx.y;
-    const SetDesc sd = wd.set[set];
-    const int tx = g.tile_row_begin + blockIdx.x / g.NT, ty = blockIdx.x % g.NT;
-    const int ix0 = tx * kTile, iy0 = ty * kTile;
-    const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
+    __shared__ double s_red[kRedDoubles];
+    __shared__ unsigned s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncells = g.C * g.C;
-    const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
+    const unsigned n0 = counters[0], n1 = counters[1], n2 = counters[2], n3 = counters[3];
+    const double c1 = g.dh, c2 = 2.0 * g.dh, c3 = 3.0 * g.dh;
+    const size_t G = (size_t)g.R * g.R;
 
-    if (warp == 0) {
-        const double xhi = (double)min(ix0 + kTile - 1, g.R - 1) * g.step + g.gmin;
-        const double yhi = (double)min(iy0 + kTile - 1, g.R - 1) * g.step + g.gmin;
-        const int cx_lo = cell_of(gx0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
-        const int cx_hi = cell_of(xhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
-        const int cy_lo = cell_of(gy0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
-        const int cy_hi = cell_of(yhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
-        const int rows = cy_hi - cy_lo + 1;          // <= kMaxRows by the host's choice of C
-        uint32_t s = 0u, len = 0u;
-        if (lane < rows) {
-            s = cs[(cy_lo + lane) * g.C + cx_lo];
-            len = cs[(cy_lo + lane) * g.C + cx_hi + 1] - s;
+    // ---------------- phase A: block per tile ----------------
+    for (;;) {
+        if (n0 == 0u) break;
+        if (threadIdx.x == 0) s_item = atomicAdd(&counters[4], 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= n0) break;
+        const uint32_t entry = worklist[item];
+        const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
+        const SetDesc sd = wd.set[set];
+        const int tx = tile / g.NT, ty = tile % g.NT;
+        const int ix0 = tx * kTile, iy0 = ty * kTile;
+        const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
+        if (warp == 0) {
+            const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
+            const TileCells tc = tile_cells(g, ix0, iy0);
+            const int rows = tc.cy_hi - tc.cy_lo + 1;       // <= kMaxRows by the host's choice of C
+            uint32_t s = 0u, len = 0u;
+            if (lane < rows) {
+                s = cs[(tc.cy_lo + lane) * g.C + tc.cx_lo];
+                len = cs[(tc.cy_lo + lane) * g.C + tc.cx_hi + 1] - s;
+            }
+            uint32_t inc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            s_rs[lane] = s;
+            s_cum[lane + 1] = inc;
+            if (lane == 0) s_cum[0] = 0u;
         }
-        uint32_t inc = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        s_rs[lane] = s;
-        s_cum[lane + 1] = inc;
-        if (lane == 0) s_cum[0] = 0u;
-    }
-    __syncthreads();
-    const uint32_t total = s_cum[kMaxRows];
-
-    double acc[kTile][kTile];
-#pragma unroll
-    for (int i = 0; i < kTile; ++i)
-#pragma unroll
-        for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
-
-    const double2 *__restrict__ pts = sorted + sd.off;
-    int r = 0;
-    for (uint32_t idx = threadIdx.x; idx < total; idx += kDensThreads) {
-        while (idx >= s_cum[r + 1]) ++r;
-        const double2 p = pts[s_rs[r] + (idx - s_cum[r])];
-        const double ux0 = (p.x - gx0) * g.inv_h;      // node i sits at i*dh - ux0 (units of h)
-        const double uy0 = (p.y - gy0) * g.inv_h;
-        double a[kTile], v[kTile];
-#pragma unroll
-        for (int i = 0; i < kTile; ++i) {
-            const double ux = (double)i * g.dh - ux0;
-            a[i] = fma(-ux, ux, 1.0);
-            v[i] = (double)i * g.dh - uy0;
-        }
+        __syncthreads();
+        const uint32_t total = s_cum[kMaxRows];
+        double acc[kTile][kTile];
 #pragma unroll
         for (int i = 0; i < kTile; ++i)
 #pragma unroll
-            for (int j = 0; j < kTile; ++j) {
-                const double t = fma(-v[j], v[j], a[i]);
-                if (__double2hiint(t) >= 0) acc[i][j] += t;   // t > 0 (adding +0 is harmless)
-            }
+            for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
+        const double2 *__restrict__ pts = sorted + sd.off;
+        int r = 0;
+        for (uint32_t idx = threadIdx.x; idx < total; idx += kDensThreads) {
+            while (idx >= s_cum[r + 1]) ++r;
+            accumulate_point(pts[s_rs[r] + (idx - s_cum[r])], gx0, gy0, g.inv_h, c1, c2, c3, acc);
+        }
+        // transpose through shared memory: 8 partial sums of 16 lanes per node, then a 3-step butterfly
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) s_red[(i * kTile + j) * kRedStride + threadIdx.x] = acc[i][j];
+        __syncthreads();
+        const int node = threadIdx.x >> 3, part = threadIdx.x & 7;
+        double S = 0.0;
+#pragma unroll
+        for (int k = 0; k < kDensThreads / 8; ++k) S += s_red[node * kRedStride + part + 8 * k];
+        S += __shfl_xor_sync(0xffffffffu, S, 1);
+        S += __shfl_xor_sync(0xffffffffu, S, 2);
+        S += __shfl_xor_sync(0xffffffffu, S, 4);
+        const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
+        double P = 0.0;
+        if (part == 0 && ix < g.R && iy < g.R) {
+            const double d = (S * kAccUnscale) * (g.knorm / (double)sd.n);   // exp(logsum + log_knorm - log N)
+            P = gamma_eps(d, g);
+            dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
+            pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
+        }
+        P += __shfl_xor_sync(0xffffffffu, P, 8);       // nodes 4w..4w+3 live in lanes 0,8,16,24 of warp w
+        P += __shfl_xor_sync(0xffffffffu, P, 16);
+        __syncthreads();                               // everyone is done reading s_red
+        if (lane == 0) s_red[warp] = P;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            tilesum[(size_t)set * g.NT * g.NT + tile] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+        __syncthreads();                               // s_item, s_rs, s_cum, s_red free for the next tile
     }
 
-    // fixed-shape reduction: xor butterfly inside each warp, then warps in index order
-#pragma unroll
-    for (int i = 0; i < kTile; ++i)
-#pragma unroll
-        for (int j = 0; j < kTile; ++j) {
-            const double s = warp_sum(acc[i][j]);
-            if (lane == 0) s_red[warp][i * kTile + j] = s;
+    // ---------------- phase B: warp per tile ----------------
+    const unsigned nB = n1 + n2 + n3;
+    double *__restrict__ wred = s_red + warp * (kTile * kTile * kWarpRedStride);
+    __syncthreads();                                   // phase A's last readers of s_red are done
+    for (;;) {
+        unsigned item = 0u;
+        if (lane == 0) item = atomicAdd(&counters[5], 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nB) break;
+        const uint32_t entry = worklist_entry(worklist, capacity, item, n1, n2);
+        const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
+        const int n_set = wd.set[set].n;
+        const double2 *__restrict__ pts = sorted + wd.set[set].off;
+        const int tx = tile / g.NT, ty = tile % g.NT;
+        const int ix0 = tx * kTile, iy0 = ty * kTile;
+        const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
+        const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
+        const TileCells tc = tile_cells(g, ix0, iy0);
+        const int rows = tc.cy_hi - tc.cy_lo + 1;
+        uint32_t row_s = 0u, row_len = 0u;
+        if (lane < rows) {
+            row_s = cs[(tc.cy_lo + lane) * g.C + tc.cx_lo];
+            row_len = cs[(tc.cy_lo + lane) * g.C + tc.cx_hi + 1] - row_s;
         }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double P = 0.0;
-        if (threadIdx.x < kTile * kTile) {
-            double S = 0.0;
+        double acc[kTile][kTile];
 #pragma unroll
-            for (int w = 0; w < kDensThreads / 32; ++w) S += s_red[w][threadIdx.x];
-            const int ix = ix0 + threadIdx.x / kTile, iy = iy0 + threadIdx.x % kTile;
-            if (ix < g.R && iy < g.R) {
-                const double d = S * (g.knorm / (double)sd.n);   // exp(logsum + log_knorm - log N)
-                P = gamma_eps(d, g);
-                const size_t k = (size_t)set * g.R * g.R + (size_t)ix * g.R + iy;
-                dens[k] = d;
-                pz[k] = P;
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
+        for (int r = 0; r < rows; ++r) {
+            const uint32_t len = __shfl_sync(0xffffffffu, row_len, r);
+            const double2 *__restrict__ rp = pts + __shfl_sync(0xffffffffu, row_s, r);
+            uint32_t j = lane;
+            double2 pn = make_double2(0.0, 0.0);
+            if (j < len) pn = rp[j];
+            while (j < len) {
+                const double2 p = pn;
+                j += 32;
+                if (j < len) pn = rp[j];               // the lane's next candidate is in flight
+                accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
             }
         }
-        // 16 lanes, shuffle-down tree: fixed order
+        // warp-level transpose: lane l sums 16 lanes' partials of node l/2, then one butterfly step
+        __syncwarp();
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) P += __shfl_down_sync(0xffffffffu, P, o);
-        if (threadIdx.x == 0) {
-            tilesum[(size_t)set * g.NT * g.NT + (size_t)tx * g.NT + ty] = P;
-            if (work_counter) atomicAdd(work_counter, (unsigned long long)total * (kTile * kTile));
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) wred[(i * kTile + j) * kWarpRedStride + lane] = acc[i][j];
+        __syncwarp();
+        const int node = lane >> 1, half = lane & 1;
+        double S = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) S += wred[node * kWarpRedStride + half + 2 * k];
+        S += __shfl_xor_sync(0xffffffffu, S, 1);
+        const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
+        double P = 0.0;
+        if (half == 0 && ix < g.R && iy < g.R) {
+            const double d = (S * kAccUnscale) * (g.knorm / (double)n_set);
+            P = gamma_eps(d, g);
+            dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
+            pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
         }
+#pragma unroll
+        for (int o = 2; o < 32; o <<= 1) P += __shfl_xor_sync(0xffffffffu, P, o);   // 16 node values, fixed tree
+        if (lane == 0) tilesum[(size_t)set * g.NT * g.NT + tile] = P;
     }
 }
 

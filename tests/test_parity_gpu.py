@@ -283,7 +283,7 @@ def test_profile_counters(pk):
     assert n.value == 1 and ms.value > 0.0
     cnt = ctypes.c_int64()
     nat.check(L.kdejs_launch_count(0, ctypes.byref(cnt), 0))
-    assert cnt.value == 6
+    assert cnt.value == 7
     w = ctypes.c_double()
     nat.check(L.kdejs_work_counters(0, ctypes.byref(w), 1))
     assert w.value > 0

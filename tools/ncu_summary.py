@@ -1,0 +1,75 @@
+"""Summarise ncu outputs brought back in gpurun_out/ into small tracked files under profiles/.
+
+    python tools/ncu_summary.py launches gpurun_out/launches_X.csv profiles/X_launches.txt
+    python tools/ncu_summary.py full gpurun_out/prof_X.ncu-rep profiles/X_density_full.txt
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "l1tex__t_bytes.sum", "sm__cycles_active.avg", "sm__cycles_elapsed.max",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+    "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_not_selected_per_warp_active.pct",
+    "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
+    "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_membar_per_warp_active.pct",
+]
+
+
+def launches(src, dst):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        name = r[ki].split("(")[0]
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    ours = {k: v for k, v in agg.items() if k.startswith("kdejs::k_") and "k_peak" not in k}
+    tot = sum(v[1] for v in ours.values())
+    with open(dst, "w") as f:
+        f.write(f"# source: {src} (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised)\n")
+        f.write(f"# pipeline kernels only (k_peak microbenchmarks and torch fills listed below the line)\n")
+        f.write(f"{'kernel':28s} {'launches':>8s} {'total_us':>12s} {'avg_us':>10s} {'share':>7s}\n")
+        for k, (n, t) in ours.items():
+            f.write(f"{k:28s} {n:8d} {t:12.1f} {t / n:10.1f} {t / tot:7.3f}\n")
+        f.write("-" * 70 + "\n")
+        for k, (n, t) in agg.items():
+            if k not in ours:
+                f.write(f"{k[:60]:60s} {n:5d} {t:12.1f}\n")
+    print(open(dst).read())
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write(f"# source: {src} (ncu --set full --clock-control none --import-source on)\n")
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            f.write(f"\n## launch {d.get('ID')}: {d.get('Kernel Name', '')[:80]}\n")
+            for k in KEYS:
+                if k in d:
+                    f.write(f"{k:80s} {d[k]:>16s} {units[hdr.index(k)]}\n")
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
