@@ -246,7 +246,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     const bool binned = (p.algo == KDEJS_ALGO_BINNED);
     const int nparts = binned ? g.NT * g.NT : (int)((G + 255) / 256);
 
-    OKR(sl.scaled.ensure((size_t)P * sizeof(double2)));
+    if (!binned) OKR(sl.scaled.ensure((size_t)P * sizeof(double2)));
     OKR(sl.dens.ensure((size_t)n_sets * G * sizeof(double)));
     OKR(sl.pz.ensure((size_t)n_sets * G * sizeof(double)));
     OKR(sl.tilesum.ensure((size_t)n_sets * nparts * sizeof(double)));
@@ -262,7 +262,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * ncells * sizeof(uint32_t)));
         OKR(sl.cellstart.ensure((size_t)n_sets * (ncells + 1) * sizeof(uint32_t)));
         OKR(sl.worklist.ensure((size_t)kNumClasses * n_sets * g.NT * g.NT * sizeof(uint32_t)));
-        OKR(sl.counters.ensure(8 * sizeof(unsigned)));
+        OKR(sl.counters.ensure(16 * sizeof(unsigned)));
     }
 
     unsigned *tk_minmax = sl.tickets.as<unsigned>();
@@ -280,7 +280,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
                 io.identity_scaler ? 1 : 0, g.C, g.cell_x0, g.cell_invw, chw, nb_max,
-                sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(), sl.blockhist.as<uint32_t>());
+                nullptr, sl.cellid.as<uint16_t>(), sl.blockhist.as<uint32_t>());
         }
         {
             KTimer t(c, 2, st);
@@ -290,7 +290,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         {
             KTimer t(c, 3, st);
             k_place<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
-                wd, g.C, chw, nb_max, sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(),
+                wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
+                io.identity_scaler ? 1 : 0, g.C, chw, nb_max, sl.cellid.as<uint16_t>(),
                 sl.blockhist.as<uint32_t>(), sl.sorted.as<double2>());
         }
         const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
@@ -579,7 +580,9 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     OKR(ensure_host_results(*c, (size_t)B));
     int64_t nmax = 1;
     for (int i = 0; i < B; ++i) nmax = std::max(nmax, n_sims[i]);
-    const int cap = wave_capacity(p, n_obs + nmax);
+    // wave size: small enough that the copy of wave k+1 hides behind the kernels of wave k even for a
+    // modest batch (8 waves per call), never above the scratch budget
+    const int cap = std::min(wave_capacity(p, n_obs + nmax), std::max(4, (B + 7) / 8));
     const size_t sim_stride = ((size_t)nmax * 16 + 255) / 256 * 256;
     for (auto &s : c->slot) OKR(s.rawsims.ensure(sim_stride * (size_t)cap));
     int wave = 0;

@@ -159,9 +159,35 @@ __device__ __forceinline__ void joint_scaler(const RawStat &a, const RawStat &b,
 }
 
 // ------------------------------------------------------------------------------------------
+// The scaler of one set (joint with its partner set) and the transform of one raw point:
+// X *= scale_; X += min_  as two separately rounded operations (never an FMA), then NaN -> 0.
+struct Scaler { double sx, mx, sy, my; };
+__device__ __forceinline__ Scaler make_scaler(const RawStat *__restrict__ rstat, const SetDesc &sd, int identity) {
+    Scaler sc;
+    if (identity) { sc.sx = 1.0; sc.mx = 0.0; sc.sy = 1.0; sc.my = 0.0; }
+    else {
+        joint_scaler(rstat[sd.rs_self], rstat[sd.rs_other], 0, sc.sx, sc.mx);
+        joint_scaler(rstat[sd.rs_self], rstat[sd.rs_other], 1, sc.sy, sc.my);
+    }
+    return sc;
+}
+__device__ __forceinline__ double2 scale_point(double2 v, const Scaler &sc, int log_flag, double eps, int identity) {
+    double X = __dadd_rn(__dmul_rn(pre_transform(v.x, log_flag, eps), sc.sx), sc.mx);
+    double Y = __dadd_rn(__dmul_rn(pre_transform(v.y, log_flag, eps), sc.sy), sc.my);
+    if (!identity) {                  // KDE_distance.py:53
+        if (X != X) X = 0.0;
+        if (Y != Y) Y = 0.0;
+    }
+    return make_double2(X, Y);
+}
+
+constexpr int kSortUnroll = 4;        // independent 32-point groups a warp keeps in flight
+
 // k_scale_count: grid (nb_max, n_sets), kSortThreads threads, dyn smem kSortWarps*ncells u32.
 // Block b owns points [b*chw*kSortWarps, ...), warp w the w-th sub-chunk: index order == (block,
-// warp, lane) order, which is what makes the later placement stable.
+// warp, lane) order, which is what makes the later placement stable.  Writes the cell id of every
+// point and the per-block cell histogram; the scaled coordinates themselves are written only when
+// `scaled` is non-null (dense path) -- the binned path recomputes them in k_place.
 __global__ void __launch_bounds__(kSortThreads)
 k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat,
               int log_flag, double eps, int identity_scaler, int C, double cell_x0,
@@ -172,44 +198,38 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
     if ((int)blockIdx.x >= sd.nb) return;
     const int ncells = C * C;
     for (int i = threadIdx.x; i < kSortWarps * ncells; i += kSortThreads) s_hist[i] = 0u;
-    __shared__ double s_sc[4];
-    if (threadIdx.x == 0) {
-        if (identity_scaler) { s_sc[0] = 1.0; s_sc[1] = 0.0; s_sc[2] = 1.0; s_sc[3] = 0.0; }
-        else {
-            joint_scaler(rstat[sd.rs_self], rstat[sd.rs_other], 0, s_sc[0], s_sc[1]);
-            joint_scaler(rstat[sd.rs_self], rstat[sd.rs_other], 1, s_sc[2], s_sc[3]);
-        }
-    }
     __syncthreads();
-    const double sx = s_sc[0], mx = s_sc[1], sy = s_sc[2], my = s_sc[3];
+    const Scaler sc = make_scaler(rstat, sd, identity_scaler);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double2 *__restrict__ raw = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p);
     const int64_t beg = ((int64_t)blockIdx.x * kSortWarps + warp) * chw;
     const int64_t end = min(beg + (int64_t)chw, (int64_t)sd.n);
     uint32_t *hw = s_hist + warp * ncells;
-    for (int64_t j0 = beg; j0 < end; j0 += 32) {
-        const int64_t j = j0 + lane;
-        const bool valid = j < end;
-        int cell = 0;
-        if (valid) {
-            double2 v = raw[j];
-            // X *= scale_; X += min_  -- two separately rounded operations, never an FMA
-            double X = __dadd_rn(__dmul_rn(pre_transform(v.x, log_flag, eps), sx), mx);
-            double Y = __dadd_rn(__dmul_rn(pre_transform(v.y, log_flag, eps), sy), my);
-            if (!identity_scaler) {           // KDE_distance.py:53
-                if (X != X) X = 0.0;
-                if (Y != Y) Y = 0.0;
+    for (int64_t j0 = beg; j0 < end; j0 += 32 * kSortUnroll) {
+        double2 v[kSortUnroll];
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            const int64_t j = j0 + u * 32 + lane;
+            v[u] = (j < end) ? raw[j] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            const int64_t j = j0 + u * 32 + lane;
+            const bool valid = j < end;
+            int cell = 0;
+            if (valid) {
+                const double2 X = scale_point(v[u], sc, log_flag, eps, identity_scaler);
+                if (scaled) scaled[sd.off + j] = X;
+                cell = cell_of(X.y, cell_x0, cell_invw, C) * C + cell_of(X.x, cell_x0, cell_invw, C);
+                cellid[sd.off + j] = (uint16_t)cell;
             }
-            scaled[sd.off + j] = make_double2(X, Y);
-            cell = cell_of(Y, cell_x0, cell_invw, C) * C + cell_of(X, cell_x0, cell_invw, C);
-            cellid[sd.off + j] = (uint16_t)cell;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned m = __match_any_sync(act, cell);
+                if (lane == __ffs(m) - 1) hw[cell] += __popc(m);
+            }
+            __syncwarp();
         }
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned m = __match_any_sync(act, cell);
-            if (lane == __ffs(m) - 1) hw[cell] += __popc(m);
-        }
-        __syncwarp();
     }
     __syncthreads();
     uint32_t *bh = blockhist + ((size_t)blockIdx.y * nb_max + blockIdx.x) * ncells;
@@ -229,7 +249,7 @@ k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
        uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart,
        unsigned *__restrict__ counters) {
     const int set = blockIdx.x;
-    if (set == 0 && threadIdx.x < 8) counters[threadIdx.x] = 0u;   // work-list counters of this wave
+    if (set == 0 && threadIdx.x < 16) counters[threadIdx.x] = 0u;  // work-list counters of this wave
     const int nb = wd.set[set].nb;
     uint32_t *bh = blockhist + (size_t)set * nb_max * ncells;
     const int c0 = threadIdx.x * 4;
@@ -283,9 +303,11 @@ k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
 // ------------------------------------------------------------------------------------------
 // k_place: same launch shape as k_scale_count.  Stable: a point's rank inside its cell is
 // (#same-cell points in earlier blocks) + (earlier warps of this block) + (earlier in this warp).
+// Re-derives the scaled coordinates from the raw point (same arithmetic as k_scale_count) and writes
+// them straight to their sorted position.
 __global__ void __launch_bounds__(kSortThreads)
-k_place(const __grid_constant__ WaveDesc wd, int C, int chw, int nb_max,
-        const double2 *__restrict__ scaled, const uint16_t *__restrict__ cellid,
+k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, int log_flag, double eps,
+        int identity_scaler, int C, int chw, int nb_max, const uint16_t *__restrict__ cellid,
         const uint32_t *__restrict__ blockbase, double2 *__restrict__ sorted) {
     extern __shared__ uint32_t s_run[];
     const SetDesc sd = wd.set[blockIdx.y];
@@ -293,20 +315,30 @@ k_place(const __grid_constant__ WaveDesc wd, int C, int chw, int nb_max,
     const int ncells = C * C;
     for (int i = threadIdx.x; i < kSortWarps * ncells; i += kSortThreads) s_run[i] = 0u;
     __syncthreads();
+    const Scaler sc = make_scaler(rstat, sd, identity_scaler);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double2 *__restrict__ raw = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p);
+    const uint16_t *__restrict__ cid = cellid + sd.off;
     const int64_t beg = ((int64_t)blockIdx.x * kSortWarps + warp) * chw;
     const int64_t end = min(beg + (int64_t)chw, (int64_t)sd.n);
     uint32_t *rw = s_run + warp * ncells;
-    for (int64_t j0 = beg; j0 < end; j0 += 32) {
-        const int64_t j = j0 + lane;
-        const bool valid = j < end;
-        const int cell = valid ? (int)cellid[sd.off + j] : 0;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const unsigned m = __match_any_sync(act, cell);
-            if (lane == __ffs(m) - 1) rw[cell] += __popc(m);
+    for (int64_t j0 = beg; j0 < end; j0 += 32 * kSortUnroll) {
+        int cell[kSortUnroll];
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            const int64_t j = j0 + u * 32 + lane;
+            cell[u] = (j < end) ? (int)cid[j] : -1;
         }
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            const bool valid = cell[u] >= 0;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned m = __match_any_sync(act, cell[u]);
+                if (lane == __ffs(m) - 1) rw[cell[u]] += __popc(m);
+            }
+            __syncwarp();
+        }
     }
     __syncthreads();
     const uint32_t *bb = blockbase + ((size_t)blockIdx.y * nb_max + blockIdx.x) * ncells;
@@ -320,24 +352,35 @@ k_place(const __grid_constant__ WaveDesc wd, int C, int chw, int nb_max,
         }
     }
     __syncthreads();
-    for (int64_t j0 = beg; j0 < end; j0 += 32) {
-        const int64_t j = j0 + lane;
-        const bool valid = j < end;
-        const int cell = valid ? (int)cellid[sd.off + j] : 0;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        uint32_t base = 0u;
-        int leader = lane;
-        unsigned m = 0u;
-        if (valid) {
-            m = __match_any_sync(act, cell);
-            leader = __ffs(m) - 1;
-            if (lane == leader) { base = rw[cell]; rw[cell] = base + __popc(m); }
+    double2 *__restrict__ out = sorted + sd.off;
+    for (int64_t j0 = beg; j0 < end; j0 += 32 * kSortUnroll) {
+        int cell[kSortUnroll];
+        double2 v[kSortUnroll];
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            const int64_t j = j0 + u * 32 + lane;
+            const bool valid = j < end;
+            cell[u] = valid ? (int)cid[j] : -1;
+            v[u] = valid ? raw[j] : make_double2(0.0, 0.0);
         }
-        __syncwarp();
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid) {
-            const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-            sorted[sd.off + base + rank] = scaled[sd.off + j];
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            const bool valid = cell[u] >= 0;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            uint32_t base = 0u;
+            int leader = lane;
+            unsigned m = 0u;
+            if (valid) {
+                m = __match_any_sync(act, cell[u]);
+                leader = __ffs(m) - 1;
+                if (lane == leader) { base = rw[cell[u]]; rw[cell[u]] = base + __popc(m); }
+            }
+            __syncwarp();
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) {
+                const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+                out[base + rank] = scale_point(v[u], sc, log_flag, eps, identity_scaler);
+            }
         }
     }
 }
@@ -369,10 +412,16 @@ __device__ __forceinline__ TileCells tile_cells(const GridGeom &g, int ix0, int 
     return t;
 }
 
-// Work-list layout.  counters: [0..3] entries per class, [4] next ticket (zeroed by k_scan each wave).
-constexpr int kNumClasses = 4;
+// Work-list layout.  Tiles are bucketed by candidate count so that the persistent density kernel can
+// hand them out heaviest first (longest-processing-time order keeps the tail short):
+//   class 0: >= 8192 candidates (one tile per block), class c in 1..9: [2^(13-c), 2^(14-c)) (per warp),
+//   class 9 also takes everything below 16.
+// counters: [0..9] entries per class, [10] block ticket, [11] warp ticket (zeroed by k_scan each wave).
+constexpr int kNumClasses = 10;
+constexpr int kTicketA = kNumClasses, kTicketB = kNumClasses + 1;
 __device__ __forceinline__ int tile_class(uint32_t total) {
-    return total >= 16384u ? 0 : total >= 2048u ? 1 : total >= 256u ? 2 : 3;   // heavy tiles first
+    const int lg = 31 - __clz((int)total);          // floor(log2(total)), total >= 1
+    return lg >= 13 ? 0 : min(13 - lg, kNumClasses - 1);
 }
 
 // k_tile_classify: one thread per (tile, set).  Counts the tile's candidate points; a tile with none
@@ -466,11 +515,11 @@ __device__ __forceinline__ void accumulate_point(const double2 p, const double g
 }
 
 __device__ __forceinline__ uint32_t worklist_entry(const uint32_t *__restrict__ worklist, unsigned capacity,
-                                                   unsigned item, unsigned n1, unsigned n2) {
-    // item indexes the concatenation of classes 1, 2, 3
-    if (item < n1) return worklist[(size_t)capacity + item];
-    if (item < n1 + n2) return worklist[(size_t)2 * capacity + (item - n1)];
-    return worklist[(size_t)3 * capacity + (item - n1 - n2)];
+                                                   unsigned item, const unsigned *s_cnt) {
+    // item indexes the concatenation of classes 1..kNumClasses-1
+    int c = 1;
+    while (item >= s_cnt[c]) { item -= s_cnt[c]; ++c; }
+    return worklist[(size_t)c * capacity + item];
 }
 
 // k_density_binned: persistent, (#SM x resident) blocks of 128 threads pulling 4x4-node tiles from
@@ -478,7 +527,7 @@ __device__ __forceinline__ uint32_t worklist_entry(const uint32_t *__restrict__ 
 // contiguous run per cell row).  Lanes take candidates round-robin and keep the tile's 16 fp64 sums in
 // registers:  t = 1 - ux^2 - uy^2 in units of h, added when non-negative (strict dist < h,
 // sklearn:_binary_tree.pxi.tp:389-394; a zero term changes nothing).
-//   phase A  the few very heavy tiles (class 0, >= 16384 candidates): one tile per BLOCK
+//   phase A  the few very heavy tiles (class 0, >= 8192 candidates): one tile per BLOCK
 //   phase B  everything else: one tile per WARP, no block-level synchronisation at all
 // Each phase ends a tile with a fixed-shape reduction through shared memory, the 16 node values,
 // their **gamma+eps and the tile's share of the normaliser.  Which warp or block processes a tile is
@@ -495,14 +544,20 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
     __shared__ unsigned s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncells = g.C * g.C;
-    const unsigned n0 = counters[0], n1 = counters[1], n2 = counters[2], n3 = counters[3];
+    __shared__ unsigned s_cnt[kNumClasses];
+    if (threadIdx.x < kNumClasses) s_cnt[threadIdx.x] = counters[threadIdx.x];
+    __syncthreads();
+    const unsigned n0 = s_cnt[0];
+    unsigned nB = 0u;
+#pragma unroll
+    for (int c = 1; c < kNumClasses; ++c) nB += s_cnt[c];
     const double c1 = g.dh, c2 = 2.0 * g.dh, c3 = 3.0 * g.dh;
     const size_t G = (size_t)g.R * g.R;
 
     // ---------------- phase A: block per tile ----------------
     for (;;) {
         if (n0 == 0u) break;
-        if (threadIdx.x == 0) s_item = atomicAdd(&counters[4], 1u);
+        if (threadIdx.x == 0) s_item = atomicAdd(&counters[kTicketA], 1u);
         __syncthreads();
         const unsigned item = s_item;
         if (item >= n0) break;
@@ -576,15 +631,14 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
     }
 
     // ---------------- phase B: warp per tile ----------------
-    const unsigned nB = n1 + n2 + n3;
     double *__restrict__ wred = s_red + warp * (kTile * kTile * kWarpRedStride);
     __syncthreads();                                   // phase A's last readers of s_red are done
     for (;;) {
         unsigned item = 0u;
-        if (lane == 0) item = atomicAdd(&counters[5], 1u);
+        if (lane == 0) item = atomicAdd(&counters[kTicketB], 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nB) break;
-        const uint32_t entry = worklist_entry(worklist, capacity, item, n1, n2);
+        const uint32_t entry = worklist_entry(worklist, capacity, item, s_cnt);
         const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
         const int n_set = wd.set[set].n;
         const double2 *__restrict__ pts = sorted + wd.set[set].off;
