@@ -360,10 +360,56 @@ def main():
         "avg_launch_ms": 1e3 * avg_launch_s, "launches": dens_n,
         "kernel_share_of_step": dens_ms / total_kernel_ms if total_kernel_ms else None,
         "fp32_ffma_peak_tflops": tf32.value,
+        "fp64_pipe_lane_ops_per_pair_test": 46.0 / 16.0,
+        "fp64_pipe_utilisation": ((w.value / max(dens_n, 1)) * (46.0 / 16.0) / avg_launch_s) / (tf64.value * 1e12 / 2.0)
+        if dens_n else None,
         "per_kernel_ms": {k: v[0] for k, v in prof.items()},
     }
     hbm_bytes = (2 * N_PAIRS * 16) * evals_timed     # every input point read once per evaluation
     roofline["hbm_algorithmic_gbs"] = hbm_bytes / (ms_max * 1e-3) / 1e9
+
+    # ---- the dense fp32 brute-force kernel (north-star kernel), a short side measurement ----------
+    dense = None
+    if args.algo == "binned":
+        nd = 8
+        dptrs = (ctypes.c_void_p * nd)(*[d_sims[i].data_ptr() for i in range(nd)])
+        dcnt = (ctypes.c_int64 * nd)(*([N_PAIRS] * nd))
+        dcommon = (RES, BANDWIDTH, GAMMA, EPS, 0, 0, nat.ALGOS["dense"])
+
+        def step_dense():
+            nat.check(L.kdejs_discrepancy_batch_dev(dev, d_target.data_ptr(), N_PAIRS, dptrs, dcnt, nd, *dcommon,
+                                                    d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream))
+        step_dense()
+        torch.cuda.synchronize()
+        nat.check(L.kdejs_profile_reset(dev))
+        nat.check(L.kdejs_profile_enable(dev, 1))
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        for _ in range(3):
+            step_dense()
+        d1.record(stream)
+        torch.cuda.synchronize()
+        pm, pn = ctypes.c_double(), ctypes.c_int64()
+        nat.check(L.kdejs_profile_read(dev, 4, ctypes.byref(pm), ctypes.byref(pn)))
+        nat.check(L.kdejs_profile_enable(dev, 0))
+        dense_js = d_out.cpu().numpy()[:nd].copy()
+        step_dev(0)
+        torch.cuda.synchronize()
+        exact_js = d_out.cpu().numpy()[:nd].copy()
+        dms = d0.elapsed_time(d1)
+        dpairs = 2.0 * N_PAIRS * RES * RES * nd * 3          # pair evaluations in the 3 timed steps
+        dens_s = pm.value * 1e-3                             # density (+finish) launches only
+        dense = {
+            "kernel": "k_density_dense32", "bound": "fp32-pipe", "evals_per_s": 3 * nd / (dms * 1e-3),
+            "pairs_per_s": dpairs / dens_s, "achieved": dpairs * 8.0 / dens_s / 1e12, "peak": tf32.value,
+            "unit": "TFLOP/s", "frac": dpairs * 8.0 / dens_s / 1e12 / tf32.value, "flop_per_pair": 8.0,
+            "fma_pipe_lane_ops_per_pair": 152.0 / 64.0,
+            "fma_pipe_utilisation": (dpairs * 152.0 / 64.0 / dens_s) / (tf32.value * 1e12 / 2.0),
+            "max_rel_gap_to_fp64_path": float(np.max(np.abs(dense_js - exact_js) / exact_js)),
+            "note": "frac uses SURVEY.md 8d's canonical 8 flop/pair; the kernel issues 2.375 FMA-pipe lane-ops per "
+                    "pair (FFMA.SAT fuses multiply, add and clamp; coordinate work is amortised over 8x8 patches), so "
+                    "fma_pipe_utilisation is the pipe-occupancy figure",
+        }
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
@@ -394,6 +440,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "single_call_latency_ms": single_ms,
+        "dense_fp32": dense,
         "js_sample": [float(x) for x in js_last[:3]],
     }
     _emit(real_stdout, line)

@@ -170,8 +170,6 @@ int check_params(const Params &p) {
         return fail(KDEJS_ERR_ARG, "unknown algorithm");
     if (p.kernel == KDEJS_KERNEL_GAUSSIAN && p.algo == KDEJS_ALGO_BINNED)
         return fail(KDEJS_ERR_ARG, "the gaussian kernel has unbounded support: use a dense algorithm");
-    if (p.algo == KDEJS_ALGO_DENSE)
-        return fail(KDEJS_ERR_ARG, "KDEJS_ALGO_DENSE (fp32) is not available in this build");
     if (std::isnan(p.gamma) || std::isnan(p.eps)) return fail(KDEJS_ERR_ARG, "gamma/eps must not be NaN");
     return KDEJS_OK;
 }
@@ -322,10 +320,25 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 io.identity_scaler ? 1 : 0, 1, g.cell_x0, g.cell_invw, chw, nb_max,
                 sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(), sl.blockhist.as<uint32_t>());
         }
-        const int ntd = (p.R + kDenseTile - 1) / kDenseTile;
-        int nslices = std::max(1, std::min(64, (4 * c.sm_count) / std::max(1, ntd * ntd * n_sets)));
-        OKR(sl.dense_partial.ensure((size_t)nslices * n_sets * G * sizeof(double)));
-        {
+        int nslices;
+        if (p.algo == KDEJS_ALGO_DENSE) {
+            int nmax = 0;
+            for (int s = 0; s < n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
+            nslices = (nmax + kD32Slice - 1) / kD32Slice;
+            OKR(sl.dense_partial.ensure((size_t)nslices * n_sets * G * sizeof(double)));
+            KTimer t(c, 4, st);
+            const int nbx = (p.R + kD32NodesX - 1) / kD32NodesX, nby = (p.R + kD32NodesY - 1) / kD32NodesY;
+            dim3 grid(nbx * nby, n_sets, nslices);
+            if (p.kernel == KDEJS_KERNEL_GAUSSIAN)
+                k_density_dense32<1><<<grid, kD32Threads, 0, st>>>(wd, g, sl.scaled.as<double2>(),
+                                                                  sl.dense_partial.as<double>());
+            else
+                k_density_dense32<0><<<grid, kD32Threads, 0, st>>>(wd, g, sl.scaled.as<double2>(),
+                                                                  sl.dense_partial.as<double>());
+        } else {
+            const int ntd = (p.R + kDenseTile - 1) / kDenseTile;
+            nslices = std::max(1, std::min(64, (4 * c.sm_count) / std::max(1, ntd * ntd * n_sets)));
+            OKR(sl.dense_partial.ensure((size_t)nslices * n_sets * G * sizeof(double)));
             KTimer t(c, 4, st);
             dim3 grid(ntd * ntd, n_sets, nslices);
             if (p.kernel == KDEJS_KERNEL_GAUSSIAN)
@@ -365,7 +378,9 @@ int ensure_host_results(Ctx &c, size_t n) {
 
 int wave_capacity(const Params &p, int64_t pts_per_item) {
     // keep a wave's scratch under ~3 GB; at the headline size (200k points, R=256) this is 32
-    const double per_item = (double)pts_per_item * (16 + 16 + 2) + 2.0 * p.R * p.R * 8 * 3 + 2.0 * 150 * 4096 * 4;
+    double per_item = (double)pts_per_item * (16 + 16 + 2) + 2.0 * p.R * p.R * 8 * 3 + 2.0 * 150 * 4096 * 4;
+    if (p.algo == KDEJS_ALGO_DENSE)     // fp64 slice partials: one grid per 1024 points per set
+        per_item += 2.0 * ((double)pts_per_item / 2 / kD32Slice + 1) * p.R * p.R * 8;
     int cap = (int)std::max(1.0, std::floor(3.0e9 / per_item));
     return std::min(cap, kMaxWaveItems);
 }

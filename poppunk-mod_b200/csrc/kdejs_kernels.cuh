@@ -749,6 +749,78 @@ k_density_dense64(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 partial[((size_t)blockIdx.z * wd.n_sets + set) * G + (size_t)(ix + a) * g.R + iy + b] = acc[a][b];
 }
 
+// ------------------------------------------------------------------------------------------
+// k_density_dense32: the brute-force N x G kernel of the north star -- every node against every point,
+// fp32 terms on the FP32 (FMA) pipe.  grid (node blocks of 128x64, n_sets, point slices); 128 threads;
+// each thread keeps an 8x8 patch of nodes in 64 fp32 registers.  A slice (<= kD32Slice points) is staged
+// once in shared memory as fp64 and broadcast to all threads; every thread re-centres a point on ITS OWN
+// first node in fp64 (2 DADD + 2 DMUL on the otherwise idle fp64 pipe) before rounding to fp32, so the
+// fp32 coordinates are small (|u| < ~2 for any pair that can be in support) and the per-term error stays
+// ~1e-7.  Per pair: FFMA.SAT (t = sat(a_i - v_j^2): an exact ReLU because t <= 1) + FADD, i.e. 2
+// FMA-pipe lane-ops; 24 more per point per thread -> 152 per 64 pairs.  fp32 partial sums never run
+// longer than one slice; slices are folded in fp64 by k_dense_finish.
+// KERNEL 1 (gaussian): t = ex2(-(0.5 log2 e) d^2): FFMA + MUFU.EX2 + FADD per pair (SFU bound).
+constexpr int kD32Threads = 128;
+constexpr int kD32Patch = 8;
+constexpr int kD32TilesX = 16, kD32TilesY = 8;                 // threads per block along x / y
+constexpr int kD32NodesX = kD32TilesX * kD32Patch;             // 128
+constexpr int kD32NodesY = kD32TilesY * kD32Patch;             // 64
+constexpr int kD32Slice = 1024;
+template <int KERNEL>
+__global__ void __launch_bounds__(kD32Threads)
+k_density_dense32(const __grid_constant__ WaveDesc wd, const GridGeom g,
+                  const double2 *__restrict__ pts_all, double *__restrict__ partial) {
+    __shared__ double2 s_p[kD32Slice];
+    const int set = blockIdx.y;
+    const SetDesc sd = wd.set[set];
+    const int beg = blockIdx.z * kD32Slice;
+    const size_t G = (size_t)g.R * g.R;
+    const int nby = (g.R + kD32NodesY - 1) / kD32NodesY;
+    const int bx = blockIdx.x / nby, by = blockIdx.x % nby;
+    const int ix0 = bx * kD32NodesX + (threadIdx.x / kD32TilesY) * kD32Patch;
+    const int iy0 = by * kD32NodesY + (threadIdx.x % kD32TilesY) * kD32Patch;
+    float acc[kD32Patch][kD32Patch];
+#pragma unroll
+    for (int i = 0; i < kD32Patch; ++i)
+#pragma unroll
+        for (int j = 0; j < kD32Patch; ++j) acc[i][j] = 0.f;
+    if (beg < sd.n) {
+        const int m = min(kD32Slice, sd.n - beg);
+        const double2 *__restrict__ pts = pts_all + sd.off + beg;
+        for (int i = threadIdx.x; i < m; i += kD32Threads) s_p[i] = pts[i];
+        __syncthreads();
+        const double x0 = (double)ix0 * g.step + g.gmin, y0 = (double)iy0 * g.step + g.gmin;
+        const float dh = (float)g.dh;
+        const float kexp = 0.72134752044448170368f;            // 0.5 * log2(e)
+#pragma unroll 2
+        for (int k = 0; k < m; ++k) {
+            const double2 p = s_p[k];
+            const float u0 = (float)((p.x - x0) * g.inv_h);    // node i sits at i*dh - u0 (units of h)
+            const float w0 = (float)((p.y - y0) * g.inv_h);
+            float a[kD32Patch], v[kD32Patch];
+#pragma unroll
+            for (int i = 0; i < kD32Patch; ++i) {
+                const float ux = (float)i * dh - u0;
+                a[i] = (KERNEL == 0) ? fmaf(-ux, ux, 1.0f) : -kexp * ux * ux;
+                v[i] = (float)i * dh - w0;
+            }
+#pragma unroll
+            for (int i = 0; i < kD32Patch; ++i)
+#pragma unroll
+                for (int j = 0; j < kD32Patch; ++j) {
+                    if (KERNEL == 0) acc[i][j] += __saturatef(fmaf(-v[j], v[j], a[i]));
+                    else acc[i][j] += exp2f(fmaf(-kexp * v[j], v[j], a[i]));
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kD32Patch; ++i)
+#pragma unroll
+        for (int j = 0; j < kD32Patch; ++j)
+            if (ix0 + i < g.R && iy0 + j < g.R)
+                partial[((size_t)blockIdx.z * wd.n_sets + set) * G + (size_t)(ix0 + i) * g.R + iy0 + j] = (double)acc[i][j];
+}
+
 // Fold the dense slice partials in slice order and apply the per-node epilogue; also produces the
 // per-"tile" normaliser partials in the layout k_js expects (here one entry per 256 nodes).
 __global__ void __launch_bounds__(256)

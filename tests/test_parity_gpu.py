@@ -288,3 +288,31 @@ def test_profile_counters(pk):
     nat.check(L.kdejs_work_counters(0, ctypes.byref(w), 1))
     assert w.value > 0
     nat.check(L.kdejs_profile_enable(0, 0))
+
+
+# ---- the dense fp32 kernel (north-star brute force): fp32 tolerance of SURVEY.md 8c(i) -------------
+@pytest.mark.parametrize("name", ["G1_g025", "G5_ragged", "G1_R256", "G2_disjoint", "G3_identical", "G4_R100_g025"])
+def test_dense_fp32_kernel(pk, ko, golden, name):
+    case = golden["cases"][name]
+    a, b = golden_inputs(name)
+    kw = case_kwargs(case)
+    js, z1, z2, d1, d2 = pk.KDE_distance._discrepancy(a, b, kw["gamma"], kw["eps"], kw["log"], case["R"], 0.03,
+                                                      "epanechnikov", "dense", None, want_z=True, want_density=True)
+    _, oz1, oz2, od1, od2 = ko.discrepancy(a, b, resolution=case["R"], return_grids=True, **kw)
+    assert abs(js - case["oracle"]) <= 1e-5 * case["oracle"] + 1e-7          # the north-star bar for the JS value
+    for got, want in ((d1, od1), (d2, od2)):
+        assert np.all(np.abs(got - want) <= 1e-6 * want + 1e-7 * want.max())  # fp32 kernel: absolute floor 1e-7 z_max
+
+
+def test_dense_fp32_gaussian_and_batch(pk, ko):
+    from oracle import workloads as wl
+
+    a, b = wl.g1_inputs()
+    got = pk.KDE_JS_divergence(a[:800], b[:900], gamma=1.0, eps=1e-12, kernel="gaussian", resolution=64, algo="dense")
+    want = ko.discrepancy(a[:800], b[:900], 1.0, 1e-12, kernel="gaussian", resolution=64)
+    assert rel(got, want) < 1e-5
+    obs = wl.synthetic_target(20000)
+    sims = [wl.sim_batch_member(s, n=3000 + 700 * s) for s in range(5)]
+    dense = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0, algo="dense")
+    exact = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0)
+    np.testing.assert_allclose(dense, exact, rtol=1e-5)
