@@ -123,6 +123,20 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
 void *kdejs_host_alloc(size_t bytes);   /* pinned (page-locked) host memory, NULL on failure */
 void kdejs_host_free(void *p);
 
+/* ---- input tables -------------------------------------------------------------------- */
+/* Multi-threaded ingest of a tab-separated distance table into (rows,2) float64: the LAST TWO
+ * columns of every data row (2-column Pansim output, 4-column PopPUNK tables).  Replaces
+ * np.loadtxt(file, delimiter='\t') (poppunk_mod.py:360, :264; KDE_distance.py:138-139;
+ * scripts/distance_to_gridsearch.py:49) and pandas read_csv + last two columns
+ * (scripts/pairwise_2D_distance.py:38-45, poppunk_mod.py:266-267) for this path's inputs.
+ * skip_rows: data rows to drop from the top, -1 = drop one row only if it is not numeric.
+ * pinned != 0: memory comes from kdejs_host_alloc (async H2D).  Free with kdejs_tsv_free.
+ * Errors are reported through kdejs_io_last_error(). */
+int kdejs_tsv_load(const char *path, int skip_rows, int pinned, int threads, double **out_pts,
+                   int64_t *out_rows);
+void kdejs_tsv_free(double *pts, int pinned);
+const char *kdejs_io_last_error(void);
+
 /* ---- measurement support (bench.py, tests) ------------------------------------------- */
 /* Per-kernel CUDA-event timing on the launching stream.  which: 0 minmax, 1 scale+count,
  * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence, 6 tile classification.

@@ -50,6 +50,10 @@ _SIGNATURES = {
     "kdejs_shard_phase2": (ctypes.c_int, [ctypes.c_int, _c_dp, _c_dp]),
     "kdejs_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "kdejs_host_free": (None, [ctypes.c_void_p]),
+    "kdejs_tsv_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_void_p), _c_i64p]),
+    "kdejs_tsv_free": (None, [ctypes.c_void_p, ctypes.c_int]),
+    "kdejs_io_last_error": (ctypes.c_char_p, []),
     "kdejs_profile_enable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "kdejs_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_dp, _c_i64p]),
     "kdejs_profile_reset": (ctypes.c_int, [ctypes.c_int]),
@@ -143,3 +147,39 @@ class PinnedPool:
             self.close()
         except Exception:
             pass
+
+
+class _TsvMemory:
+    """Owns one kdejs_tsv_load allocation; numpy arrays built from it keep it alive (array.base)."""
+
+    def __init__(self, ptr, rows, pinned):
+        self._ptr, self._rows, self._pinned = ptr, rows, pinned
+        self.__array_interface__ = {"shape": (rows, 2), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                lib().kdejs_tsv_free(self._ptr, int(self._pinned))
+                self._ptr = None
+        except Exception:
+            pass
+
+
+class TsvTable:
+    """(rows,2) float64 table read by kdejs_tsv_load (pinned memory when a GPU is present).  `.array`
+    stays valid for as long as any reference to it exists, independently of this object."""
+
+    def __init__(self, path, skip_rows=-1, pinned=None, threads=0):
+        if pinned is None:
+            pinned = device_count() > 0
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        rc = lib().kdejs_tsv_load(os.fsencode(path), int(skip_rows), int(bool(pinned)), int(threads),
+                                  ctypes.byref(p), ctypes.byref(n))
+        if rc != KDEJS_OK:
+            msg = (lib().kdejs_io_last_error() or b"").decode("utf-8", "replace")
+            raise (ValueError if rc == KDEJS_ERR_ARG else RuntimeError)(msg)
+        self.rows, self.pinned = n.value, bool(pinned)
+        self.array = np.asarray(_TsvMemory(p.value, n.value, bool(pinned)))
+
+    def close(self):
+        self.array = None       # the memory is released when the last array referencing it goes away

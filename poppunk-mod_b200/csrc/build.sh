@@ -6,5 +6,5 @@ OUT="$HERE/../libkdejs.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
     -Xcompiler -fPIC -Xcompiler -O2 -shared ${KDEJS_PTXAS_V:+-Xptxas -v} \
-    -o "$OUT" "$HERE/kdejs_api.cu" -lcudart
+    -o "$OUT" "$HERE/kdejs_api.cu" "$HERE/kdejs_io.cpp" -lcudart
 echo "built $OUT"

@@ -1,0 +1,174 @@
+"""Batch drivers: the two sweep scripts of the reference on top of the batched GPU entry points.
+
+    pairwise_distances   scripts/pairwise_2D_distance.py:47-79, :100-118  (all pairs of species files,
+                         optional euclidean combination with gene-class fractions)
+    gridsearch_best      scripts/distance_to_gridsearch.py:48-55, :75-125 (one reference against every
+                         simulation of a grid search; running arg-min under optional bounds)
+    read_file / read_distfile   the scripts' and poppunk_mod.py's table readers (:38-45, :255-269)
+
+Files are parsed by the library's multi-threaded reader straight into pinned memory while the GPU works
+on the previous chunk; the discrepancies come from KDE_JS_divergence_pairs / _batch.  Command line:
+
+    python -m poppunk_mod_b200.sweeps pairwise --infile table.txt --outpref out
+    python -m poppunk_mod_b200.sweeps gridsearch --indir runs/ --ref obs.txt
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import math
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+from . import _native as nat
+from . import KDE_distance as kd
+
+
+def read_file(path, pinned=None):
+    """Last two columns of a headerless tab-separated table (pairwise_2D_distance.py:38-45)."""
+    return nat.TsvTable(path, skip_rows=0, pinned=pinned)
+
+
+def read_distfile(path, pinned=None):
+    """poppunk_mod.read_distfile (:255-269): a 2-column file is read whole; otherwise pandas' inferred
+    header consumes the first line and the first two (id) columns are dropped."""
+    with open(path, "r") as f:
+        two_column = len(f.readline().rstrip().split("\t")) == 2
+    return nat.TsvTable(path, skip_rows=0 if two_column else 1, pinned=pinned)
+
+
+def _bounds(a):
+    return (np.min(a[:, 0]), np.max(a[:, 0]), np.min(a[:, 1]), np.max(a[:, 1]))
+
+
+def _load_many(paths, reader, workers):
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:      # ctypes releases the GIL while parsing
+        return list(ex.map(reader, paths))
+
+
+def pairwise_distances(files, gamma=0.25, eps=0.0, log=False, *, io_threads=8, device=None, resolution=100):
+    """files: list of paths, or of (path, core_frac, intermediate_frac, rare_frac) tuples.
+    Returns [(file1, file2, distance, (min_core, max_core, min_acc, max_acc) of file2), ...] in
+    itertools.combinations order.  With fractions the distance is the euclidean combination the
+    reference builds (pairwise_2D_distance.py:60-77): dist((0,c1,i1,r1), (JS,c2,i2,r2))."""
+    entries = [(f,) if isinstance(f, (str, Path)) else tuple(f) for f in files]
+    tables = _load_many([str(e[0]) for e in entries], read_file, io_threads)
+    sets = [t.array for t in tables]
+    pairs = list(itertools.combinations(range(len(entries)), 2))
+    js = kd.KDE_JS_divergence_pairs(sets, pairs, gamma, eps, log, device=device, resolution=resolution)
+    bounds = [_bounds(s) for s in sets]
+    out = []
+    for (i, j), d in zip(pairs, js):
+        e1, e2 = entries[i], entries[j]
+        dist = d if len(e1) == 1 else math.dist((0, e1[1], e1[2], e1[3]), (d, e2[1], e2[2], e2[3]))
+        out.append((str(e1[0]), str(e2[0]), dist, bounds[j]))
+    for t in tables:
+        t.close()
+    return out
+
+
+def _in(value, bounds):
+    return bounds[0] <= value <= bounds[1]
+
+
+def gridsearch_best(ref, files, gamma=1e-12, eps=1e-12, log=True, *, core_min_bounds=None, core_max_bounds=None,
+                    acc_min_bounds=None, acc_max_bounds=None, chunk=64, io_threads=8, devices=None,
+                    resolution=100):
+    """One reference against many simulations.  Defaults are the reference's call
+    KDE_JS_divergence(df1, df2, 1e-12, log=True) (distance_to_gridsearch.py:50).  Bounds are absolute
+    [lo, hi] pairs (the script multiplies its fractions by the reference's column maxima, :89-99).
+    Returns (best, distances) with best = (file, distance, bounds) or (None, 1.0), distances in file order."""
+    ref_arr = ref if isinstance(ref, np.ndarray) else read_file(ref).array
+    files = [str(f) for f in files]
+    best = (None, 1.0)
+    distances = np.empty(len(files))
+    chunks = [files[i:i + chunk] for i in range(0, len(files), chunk)]
+    with ThreadPoolExecutor(max_workers=1) as prefetch:
+        load = lambda names: _load_many(names, lambda p: nat.TsvTable(p, skip_rows=0), io_threads)   # np.loadtxt, :49
+        pending = prefetch.submit(load, chunks[0]) if chunks else None
+        pos = 0
+        for ci, names in enumerate(chunks):
+            tables = pending.result()
+            pending = prefetch.submit(load, chunks[ci + 1]) if ci + 1 < len(chunks) else None
+            js = kd.KDE_JS_divergence_batch(ref_arr, [t.array for t in tables], gamma, eps, log, devices=devices,
+                                            resolution=resolution)
+            for name, t, d in zip(names, tables, js):
+                distances[pos] = d
+                pos += 1
+                if d < best[1]:                                     # :112-125
+                    b = _bounds(t.array)
+                    ok = True
+                    if core_min_bounds is not None and core_max_bounds is not None:
+                        ok &= _in(b[0], core_min_bounds) and _in(b[1], core_max_bounds)
+                    if acc_min_bounds is not None and acc_max_bounds is not None:
+                        ok &= _in(b[2], acc_min_bounds) and _in(b[3], acc_max_bounds)
+                    if ok:
+                        best = (name, d, b)
+            for t in tables:
+                t.close()
+    return best, distances
+
+
+def _pairwise_main(o):
+    if o.indir is None and o.infile is None:
+        print("Please specify one of --indir or --infile")
+        return 1
+    if o.indir is not None:
+        files = [str(p) for p in Path(o.indir).glob("*.txt")]
+    else:
+        files = []
+        with open(o.infile) as f:
+            f.readline()
+            for line in f:
+                s = line.rstrip().split("\t")
+                pan = int(s[1])
+                files.append((s[6], int(s[2]) / pan, int(s[3]) / pan, int(s[4]) / pan))
+    rows = pairwise_distances(files, io_threads=o.threads)
+    with open(o.outpref + ".tsv", "w") as out:
+        out.write("File1\tFile2\tDistance\n")
+        for f1, f2, d, _ in rows:
+            out.write(f"{f1}\t{f2}\t{d}\n")
+    return 0
+
+
+def _gridsearch_main(o):
+    files = [str(p) for p in Path(o.indir).glob("**/*.tsv")]
+    ref = read_file(o.ref).array
+    mc, ma = np.max(ref[:, 0]), np.max(ref[:, 1])
+    print(f"max_core_ref: {mc}, max_acc_ref: {ma}")
+    frac = lambda s, m: None if s is None else [float(x) * m for x in s.split(",")]
+    kw = dict(core_min_bounds=frac(o.core_min_bounds, mc), core_max_bounds=frac(o.core_max_bounds, mc),
+              acc_min_bounds=frac(o.acc_min_bounds, ma), acc_max_bounds=frac(o.acc_max_bounds, ma))
+    best, _ = gridsearch_best(ref, files, io_threads=o.threads, **kw)
+    if len(best) == 2:
+        print("No best fitting distribution found.")
+    else:
+        b = best[2]
+        print(f"File: {best[0]}, Min distance: {best[1]}, Min core: {b[0]}, Max core: {b[1]}, Min acc: {b[2]}, Max acc: {b[3]}")
+    return 0
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="python -m poppunk_mod_b200.sweeps")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    p = sub.add_parser("pairwise", help="scripts/pairwise_2D_distance.py on the GPU")
+    p.add_argument("--indir", default=None)
+    p.add_argument("--infile", default=None)
+    p.add_argument("--outpref", default="output")
+    p.add_argument("--threads", type=int, default=8)
+    g = sub.add_parser("gridsearch", help="scripts/distance_to_gridsearch.py on the GPU")
+    g.add_argument("--indir", required=True)
+    g.add_argument("--ref", required=True)
+    g.add_argument("--outpref", default="output")
+    for name in ("core-min-bounds", "core-max-bounds", "acc-min-bounds", "acc-max-bounds"):
+        g.add_argument("--" + name, type=str, default=None)
+    g.add_argument("--threads", type=int, default=8)
+    o = ap.parse_args(argv)
+    return _pairwise_main(o) if o.cmd == "pairwise" else _gridsearch_main(o)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

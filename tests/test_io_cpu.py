@@ -1,0 +1,72 @@
+"""CPU: the C++ table reader against numpy / pandas, and the sweep drivers' host-side logic."""
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import poppunk_mod_b200 as pk
+
+    return pk._native
+
+
+def _write(path, rows, header=None):
+    with open(path, "w") as f:
+        if header:
+            f.write(header + "\n")
+        for r in rows:
+            f.write("\t".join(r) + "\n")
+
+
+def test_two_column_matches_loadtxt(nat, tmp_path):
+    rng = np.random.default_rng(0)
+    a = np.column_stack([rng.integers(0, 2000, 20000) / 1e6, rng.random(20000)])
+    a[17] = [0.0, 1.0]
+    a[18, 1] = np.nan
+    p = tmp_path / "two.tsv"
+    _write(p, [[repr(float(x)), repr(float(y))] for x, y in a])
+    t = nat.TsvTable(str(p), pinned=False)
+    ref = np.loadtxt(p, delimiter="\t", dtype="float64")
+    np.testing.assert_array_equal(t.array, ref)            # bit-identical parsing, NaN included
+    assert t.array.shape == (20000, 2)
+    t.close()
+
+
+def test_four_column_last_two_and_header_rules(nat, tmp_path):
+    import pandas as pd
+    from poppunk_mod_b200 import sweeps
+
+    rows = [[f"S{i}", f"T{i}", f"{i * 1.25e-5:.8g}", f"{0.1 + i * 1e-3:.7g}"] for i in range(5000)]
+    p = tmp_path / "four.txt"
+    _write(p, rows)
+    df = pd.read_csv(p, header=None, sep="\t", index_col=False)
+    want = df[df.columns[[-2, -1]]].to_numpy()
+    np.testing.assert_array_equal(sweeps.read_file(str(p), pinned=False).array, want)     # pairwise_2D_distance.py:38-45
+    # poppunk_mod.read_distfile: pandas' inferred header eats the first row of a 4-column table
+    want2 = pd.read_csv(p, sep="\t").to_numpy()[:, 2:].astype(float)
+    np.testing.assert_array_equal(sweeps.read_distfile(str(p), pinned=False).array, want2)
+    h = tmp_path / "hdr.tsv"
+    _write(h, [["1e-3", "0.5"], ["2e-3", "+0.25"]], header="core\taccessory")
+    np.testing.assert_array_equal(nat.TsvTable(str(h), pinned=False).array, [[1e-3, 0.5], [2e-3, 0.25]])
+
+
+def test_reader_errors(nat, tmp_path):
+    with pytest.raises(ValueError, match="cannot open"):
+        nat.TsvTable(str(tmp_path / "missing.tsv"), pinned=False)
+    bad = tmp_path / "bad.tsv"
+    _write(bad, [["1.0", "2.0"], ["x", "y"]])
+    with pytest.raises(ValueError, match="row 2"):
+        nat.TsvTable(str(bad), pinned=False)
+    empty = tmp_path / "empty.tsv"
+    empty.write_text("\n\n")
+    with pytest.raises(ValueError, match="no data rows"):
+        nat.TsvTable(str(empty), pinned=False)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/distances/2_column/Escherichia_coli.txt"),
+                    reason="reference fixtures not present")
+def test_reference_fixture_files(nat):
+    f = "/root/reference/distances/2_column/Escherichia_coli.txt"
+    np.testing.assert_array_equal(nat.TsvTable(f, pinned=False).array, np.loadtxt(f, delimiter="\t"))
