@@ -595,14 +595,15 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     OKR(ensure_host_results(*c, (size_t)B));
     int64_t nmax = 1;
     for (int i = 0; i < B; ++i) nmax = std::max(nmax, n_sims[i]);
-    // wave size: small enough that the copy of wave k+1 hides behind the kernels of wave k even for a
-    // modest batch (8 waves per call), never above the scratch budget
-    const int cap = std::min(wave_capacity(p, n_obs + nmax), std::max(4, (B + 7) / 8));
+    // Waves ramp up 4, 8, 16, ... to the scratch-budget cap: the first H2D copy (the only one that cannot
+    // hide behind kernels) stays short, later waves are large enough to run the kernels efficiently.
+    const int cap = wave_capacity(p, n_obs + nmax);
     const size_t sim_stride = ((size_t)nmax * 16 + 255) / 256 * 256;
     for (auto &s : c->slot) OKR(s.rawsims.ensure(sim_stride * (size_t)cap));
-    int wave = 0;
-    for (int i0 = 0; i0 < B; i0 += cap, ++wave) {
-        const int items = std::min(cap, B - i0);
+    int wave = 0, next_size = std::min(cap, 4);
+    for (int i0 = 0; i0 < B; ++wave) {
+        const int items = std::min(next_size, B - i0);
+        next_size = std::min(cap, next_size * 2);
         Slot &sl = c->slot[wave & 1];
         if (wave >= 2) CU(cudaEventSynchronize(sl.ev_done));      // slot's previous wave has finished
         std::vector<RawSet> pool(items + 1);
@@ -619,6 +620,7 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
         OKR(run_pairs_dev(*c, c->s_compute, wave & 1, p, pool, ia.data(), ib.data(), items,
                           c->js_out.as<double>(), c->status_out.as<int32_t>(), i0, false));
         CU(cudaEventRecord(sl.ev_done, c->s_compute));
+        i0 += items;
     }
     CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute));
     CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute));

@@ -491,6 +491,7 @@ constexpr int kRedStride = kDensThreads + 8;   // padded row of the block-level 
 constexpr int kWarpRedStride = 33;             // padded row of the warp-level one
 constexpr int kRedDoubles = kTile * kTile * kRedStride;   // >= 4 warps * 16 * 33
 
+constexpr int kStageRows = 1;
 // One candidate point against the tile's 16 nodes (46 fp64-pipe + 16 FP32-pipe instructions).
 __device__ __forceinline__ void accumulate_point(const double2 p, const double gx0, const double gy0,
                                                  const double inv_h, const double c1, const double c2,
@@ -503,14 +504,22 @@ __device__ __forceinline__ void accumulate_point(const double2 p, const double g
     const double w[kTile] = {-uy0, -v1, -v2, -v3};
     const double q[kTile] = {uy0, v1, v2, v3};
 #pragma unroll
-    for (int i = 0; i < kTile; ++i) {
-        double t[kTile], m[kTile];
+    for (int i = 0; i < kTile; i += kStageRows) {
+        // kStageRows*4 independent terms per stage: each dependent stage starts only after that many
+        // issues, which covers the fp64 pipe's latency without leaning on other warps
+        double t[kStageRows][kTile], m[kStageRows][kTile];
 #pragma unroll
-        for (int j = 0; j < kTile; ++j) t[j] = fma(w[j], q[j], a[i]);
+        for (int ii = 0; ii < kStageRows; ++ii)
 #pragma unroll
-        for (int j = 0; j < kTile; ++j) m[j] = clamp_mask(t[j]);
+            for (int j = 0; j < kTile; ++j) t[ii][j] = fma(w[j], q[j], a[i + ii]);
 #pragma unroll
-        for (int j = 0; j < kTile; ++j) acc[i][j] = fma(t[j], m[j], acc[i][j]);
+        for (int ii = 0; ii < kStageRows; ++ii)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) m[ii][j] = clamp_mask(t[ii][j]);
+#pragma unroll
+        for (int ii = 0; ii < kStageRows; ++ii)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) acc[i + ii][j] = fma(t[ii][j], m[ii][j], acc[i + ii][j]);
     }
 }
 
@@ -595,9 +604,22 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
             for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
         const double2 *__restrict__ pts = sorted + sd.off;
         int r = 0;
-        for (uint32_t idx = threadIdx.x; idx < total; idx += kDensThreads) {
+        uint32_t idx = threadIdx.x;
+        bool more = idx < total;
+        double2 pn = make_double2(0.0, 0.0);
+        if (more) {
             while (idx >= s_cum[r + 1]) ++r;
-            accumulate_point(pts[s_rs[r] + (idx - s_cum[r])], gx0, gy0, g.inv_h, c1, c2, c3, acc);
+            pn = pts[s_rs[r] + (idx - s_cum[r])];
+        }
+        while (more) {
+            const double2 p = pn;
+            idx += kDensThreads;                            // the lane's next candidate is in flight
+            more = idx < total;
+            if (more) {
+                while (idx >= s_cum[r + 1]) ++r;
+                pn = pts[s_rs[r] + (idx - s_cum[r])];
+            }
+            accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
         }
         // transpose through shared memory: 8 partial sums of 16 lanes per node, then a 3-step butterfly
 #pragma unroll
