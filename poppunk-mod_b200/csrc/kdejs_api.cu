@@ -51,7 +51,7 @@ struct DevBuf {
 
 struct Slot {
     DevBuf rawsims, scaled, sorted, cellid, blockhist, cellstart, dens, pz, zout, tilesum;
-    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, counters;
+    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, counters, totals, rank16, warpprefix;
     cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
 };
 
@@ -116,8 +116,6 @@ int get_ctx(int device, Ctx **out) {
             CU(cudaMalloc(&c.d_work, sizeof(unsigned long long)));
             CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
             CU(cudaFuncSetAttribute(k_scale_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSortWarps * kMaxCells * (int)sizeof(uint32_t)));
-            CU(cudaFuncSetAttribute(k_place, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSortWarps * kMaxCells * (int)sizeof(uint32_t)));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned, kDensThreads, 0));
             c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
@@ -193,6 +191,7 @@ GridGeom make_geom(const Params &p) {
     g.C = C;
     g.cell_x0 = p.gmin;
     g.cell_invw = (double)C / ext;
+    g.cell_w = ext / (double)C;
     // sklearn _log_kernel_norm, d = 2 (sklearn:neighbors/_binary_tree.pxi.tp:448-476)
     const double LOG_PI = 1.1447298858494001741, LOG_2PI = 1.8378770664093454836;
     double factor = (p.kernel == KDEJS_KERNEL_GAUSSIAN) ? LOG_2PI : (LOG_PI - std::lgamma(2.0)) + std::log(0.5);
@@ -217,15 +216,14 @@ struct WaveIO {
 };
 
 int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
+    // Points per warp sub-chunk.  Every sort block pays a fixed cost for its C*C counters (zeroing, prefix,
+    // histogram write-out), so chunks grow with the wave until the launch still has ~4 blocks per SM.
     int nmax = 0;
-    for (int s = 0; s < wd.n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
-    chw = 1024;
-    auto nb_of = [&](int n) { return (int)(((int64_t)n + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)); };
-    if (nb_of(nmax) > sm_count) {
-        int64_t per_warp = ((int64_t)nmax + (int64_t)sm_count * kSortWarps - 1) / ((int64_t)sm_count * kSortWarps);
-        chw = (int)((per_warp + 31) / 32 * 32);
-    }
-    nb_max = std::max(1, nb_of(nmax));
+    int64_t total = 0;
+    for (int s = 0; s < wd.n_sets; ++s) { nmax = std::max(nmax, wd.set[s].n); total += wd.set[s].n; }
+    int64_t per_warp = total / ((int64_t)4 * sm_count * kSortWarps);
+    chw = (int)std::min<int64_t>(std::max<int64_t>((per_warp + 31) / 32 * 32, 512), kMaxChw);
+    nb_max = std::max(1, (int)(((int64_t)nmax + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)));
     return KDEJS_OK;
 }
 
@@ -257,6 +255,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     if (binned) {
         OKR(sl.sorted.ensure((size_t)P * sizeof(double2)));
         OKR(sl.cellid.ensure((size_t)P * sizeof(uint16_t)));
+        OKR(sl.rank16.ensure((size_t)P * sizeof(uint16_t)));
+        OKR(sl.warpprefix.ensure((size_t)n_sets * nb_max * kSortWarps * ncells * sizeof(uint16_t)));
         OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * ncells * sizeof(uint32_t)));
         OKR(sl.cellstart.ensure((size_t)n_sets * (ncells + 1) * sizeof(uint32_t)));
         OKR(sl.worklist.ensure((size_t)kNumClasses * n_sets * g.NT * g.NT * sizeof(uint32_t)));
@@ -272,13 +272,14 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             wd, p.log_flag, p.eps, sl.rpart.as<RawStat>(), tk_minmax, sl.rstat.as<RawStat>());
     }
     if (binned) {
-        const size_t smem = (size_t)kSortWarps * ncells * sizeof(uint32_t);
+        const size_t smem = (size_t)kSortWarps * ncells * sizeof(uint16_t);
         {
             KTimer t(c, 1, st);
             k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
                 io.identity_scaler ? 1 : 0, g.C, g.cell_x0, g.cell_invw, chw, nb_max,
-                nullptr, sl.cellid.as<uint16_t>(), sl.blockhist.as<uint32_t>());
+                nullptr, sl.cellid.as<uint16_t>(), sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(),
+                sl.blockhist.as<uint32_t>());
         }
         {
             KTimer t(c, 2, st);
@@ -287,10 +288,13 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         }
         {
             KTimer t(c, 3, st);
-            k_place<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
+            int nmax = 0;
+            for (int s = 0; s < n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
+            k_place<<<dim3((nmax + 255) / 256, n_sets), 256, 0, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
-                io.identity_scaler ? 1 : 0, g.C, chw, nb_max, sl.cellid.as<uint16_t>(),
-                sl.blockhist.as<uint32_t>(), sl.sorted.as<double2>());
+                io.identity_scaler ? 1 : 0, ncells, chw, nb_max, sl.cellid.as<uint16_t>(),
+                sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
+                sl.sorted.as<double2>());
         }
         const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
         const unsigned capacity = (unsigned)tiles * (unsigned)n_sets;
@@ -315,10 +319,10 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             KTimer t(c, 1, st);
             OKR(sl.cellid.ensure((size_t)P * sizeof(uint16_t)));
             OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * sizeof(uint32_t)));
-            k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, kSortWarps * sizeof(uint32_t), st>>>(
+            k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, kSortWarps * sizeof(uint16_t), st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
                 io.identity_scaler ? 1 : 0, 1, g.cell_x0, g.cell_invw, chw, nb_max,
-                sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(), sl.blockhist.as<uint32_t>());
+                sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(), nullptr, nullptr, sl.blockhist.as<uint32_t>());
         }
         int nslices;
         if (p.algo == KDEJS_ALGO_DENSE) {
@@ -356,10 +360,15 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         }
     }
     if (!io.density_only && !io.shard) {
+        OKR(sl.totals.ensure(sizeof(double) * kMaxWaveSets));
+        {
+            KTimer t(c, 5, st);
+            k_set_totals<<<n_sets, kJsThreads, 0, st>>>(nparts, sl.tilesum.as<double>(), sl.totals.as<double>());
+        }
         KTimer t(c, 5, st);
         k_js<<<dim3(js_blocks, n_items), kJsThreads, 0, st>>>(
-            wd, (int)G, nparts, 0, (int)G, sl.pz.as<double>(), sl.tilesum.as<double>(),
-            sl.rstat.as<RawStat>(), nullptr, io.want_z ? sl.zout.as<double>() : nullptr,
+            wd, (int)G, nparts, 0, (int)G, sl.pz.as<double>(), sl.totals.as<double>(),
+            sl.rstat.as<RawStat>(), io.want_z ? sl.zout.as<double>() : nullptr,
             sl.jspart.as<double>(), tk_js, io.out_js, io.out_status, nullptr, nullptr, io.item_base);
     }
     CU(cudaGetLastError());
@@ -471,7 +480,7 @@ void kdejs_shutdown(void) {
         for (auto &s : c.slot) {
             for (DevBuf *b : {&s.rawsims, &s.scaled, &s.sorted, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
                               &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart,
-                              &s.dense_partial, &s.worklist, &s.counters}) {
+                              &s.dense_partial, &s.worklist, &s.counters, &s.totals, &s.rank16, &s.warpprefix}) {
                 if (b->p) cudaFree(b->p);
                 b->p = nullptr; b->cap = 0;
             }
@@ -759,8 +768,8 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
     {
         KTimer t(*c, 5, st);
         k_js<<<dim3(js_blocks, 1), kJsThreads, 0, st>>>(
-            c->shard_wd, G, g.NT * g.NT, c->shard_kb, c->shard_ke, sl.pz.as<double>(), sl.tilesum.as<double>(),
-            sl.rstat.as<RawStat>(), d, nullptr, sl.jspart.as<double>(),
+            c->shard_wd, G, g.NT * g.NT, c->shard_kb, c->shard_ke, sl.pz.as<double>(), d,
+            sl.rstat.as<RawStat>(), nullptr, sl.jspart.as<double>(),
             sl.tickets.as<unsigned>() + kMaxWaveSets, nullptr, nullptr, d + 2, nullptr, 0);
     }
     CU(cudaGetLastError());

@@ -55,6 +55,7 @@ struct GridGeom {
     int32_t R, NT, C, gamma_mode;        // NT tiles per side, C cells per side; gamma_mode 1: gamma==1
     double gmin, step, h, inv_h, dh;     // dh = step/h
     double margin, cell_x0, cell_invw;   // cell(x) = clamp(floor((x-cell_x0)*cell_invw), 0, C-1)
+    double cell_w;                       // nominal cell side = extent / C
     double knorm, gamma, eps;
     int32_t tile_row_begin, tile_row_end;   // tile rows (index of column 0) this launch covers
 };
@@ -96,12 +97,21 @@ k_minmax(const __grid_constant__ WaveDesc wd, int log_flag, double eps,
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     double mn0 = INF, mx0 = -INF, mn1 = INF, mx1 = -INF;
     int flags = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        double2 v = p[i];
-        double x = pre_transform(v.x, log_flag, eps), y = pre_transform(v.y, log_flag, eps);
-        if (x == x) { mn0 = fmin(mn0, x); mx0 = fmax(mx0, x); flags |= isinf(x) ? 1 : 0; }
-        if (y == y) { mn1 = fmin(mn1, y); mx1 = fmax(mx1, y); flags |= isinf(y) ? 1 : 0; }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                  // four independent loads in flight per thread
+            const int64_t i = i0 + u * stride;
+            v[u] = (i < n) ? p[i] : make_double2(__longlong_as_double(0x7ff8000000000000LL),
+                                                 __longlong_as_double(0x7ff8000000000000LL));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double x = pre_transform(v[u].x, log_flag, eps), y = pre_transform(v[u].y, log_flag, eps);
+            if (x == x) { mn0 = fmin(mn0, x); mx0 = fmax(mx0, x); flags |= isinf(x) ? 1 : 0; }
+            if (y == y) { mn1 = fmin(mn1, y); mx1 = fmax(mx1, y); flags |= isinf(y) ? 1 : 0; }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -181,30 +191,57 @@ __device__ __forceinline__ double2 scale_point(double2 v, const Scaler &sc, int 
     return make_double2(X, Y);
 }
 
-constexpr int kSortUnroll = 4;        // independent 32-point groups a warp keeps in flight
+// Lanes of `act` that hold the same cell id as the caller (ids < 2^12): twelve independent ballots
+// combined with AND -- the same mask __match_any_sync returns, but built from full-rate ALU
+// instructions instead of one long-latency MATCH.
+__device__ __forceinline__ unsigned match_cell(unsigned act, int cell) {
+    unsigned m = act;
+#pragma unroll
+    for (int b = 0; b < 12; ++b) {
+        const unsigned bal = __ballot_sync(act, (cell >> b) & 1);
+        m &= ((cell >> b) & 1) ? bal : ~bal;
+    }
+    return m;
+}
 
-// k_scale_count: grid (nb_max, n_sets), kSortThreads threads, dyn smem kSortWarps*ncells u32.
+// Zero n u16 counters in dynamic shared memory (16-byte aligned) with 128-bit stores.
+__device__ __forceinline__ void zero_u16(uint16_t *p, int n) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    const int n16 = n / 8;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) q[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = n16 * 8 + threadIdx.x; i < n; i += blockDim.x) p[i] = 0;
+}
+
+constexpr int kSortUnroll = 4;        // independent 32-point groups a warp keeps in flight
+constexpr int kMaxChw = 16352;        // points per warp sub-chunk: 4 warps * kMaxChw < 65536 (u16 counters)
+
+// k_scale_count: grid (nb_max, n_sets), kSortThreads threads, dyn smem kSortWarps*ncells u16 (a warp's
+// sub-chunk holds at most kMaxChw points, so 16-bit counters cannot overflow).
 // Block b owns points [b*chw*kSortWarps, ...), warp w the w-th sub-chunk: index order == (block,
-// warp, lane) order, which is what makes the later placement stable.  Writes the cell id of every
-// point and the per-block cell histogram; the scaled coordinates themselves are written only when
-// `scaled` is non-null (dense path) -- the binned path recomputes them in k_place.
+// warp, lane) order.  For every point it writes the cell id and the point's RANK among the same-cell
+// points of its warp sub-chunk (earlier iterations + lower lanes); per block it writes the cell
+// histogram and, per warp, the number of same-cell points in earlier warps of the block.  With the
+// block bases from k_scan these three numbers are the point's stable sorted position, so k_place needs
+// no ranking of its own.  The scaled coordinates are written only when `scaled` is non-null (dense
+// path) -- the binned path recomputes them in k_place.
 __global__ void __launch_bounds__(kSortThreads)
 k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat,
               int log_flag, double eps, int identity_scaler, int C, double cell_x0,
               double cell_invw, int chw, int nb_max, double2 *__restrict__ scaled,
-              uint16_t *__restrict__ cellid, uint32_t *__restrict__ blockhist) {
-    extern __shared__ uint32_t s_hist[];
+              uint16_t *__restrict__ cellid, uint16_t *__restrict__ rank16,
+              uint16_t *__restrict__ warpprefix, uint32_t *__restrict__ blockhist) {
+    extern __shared__ uint16_t s_hist[];
     const SetDesc sd = wd.set[blockIdx.y];
     if ((int)blockIdx.x >= sd.nb) return;
     const int ncells = C * C;
-    for (int i = threadIdx.x; i < kSortWarps * ncells; i += kSortThreads) s_hist[i] = 0u;
+    zero_u16(s_hist, kSortWarps * ncells);
     __syncthreads();
     const Scaler sc = make_scaler(rstat, sd, identity_scaler);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double2 *__restrict__ raw = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p);
     const int64_t beg = ((int64_t)blockIdx.x * kSortWarps + warp) * chw;
     const int64_t end = min(beg + (int64_t)chw, (int64_t)sd.n);
-    uint32_t *hw = s_hist + warp * ncells;
+    uint16_t *hw = s_hist + warp * ncells;
     for (int64_t j0 = beg; j0 < end; j0 += 32 * kSortUnroll) {
         double2 v[kSortUnroll];
 #pragma unroll
@@ -224,19 +261,30 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
                 cellid[sd.off + j] = (uint16_t)cell;
             }
             const unsigned act = __ballot_sync(0xffffffffu, valid);
+            uint32_t before = 0u;
+            int leader = lane;
+            unsigned m = 0u;
             if (valid) {
-                const unsigned m = __match_any_sync(act, cell);
-                if (lane == __ffs(m) - 1) hw[cell] += __popc(m);
+                m = match_cell(act, cell);
+                leader = __ffs(m) - 1;
+                if (lane == leader) { before = hw[cell]; hw[cell] = (uint16_t)(before + __popc(m)); }
             }
             __syncwarp();
+            before = __shfl_sync(0xffffffffu, before, leader);
+            if (valid && rank16) rank16[sd.off + j] = (uint16_t)(before + __popc(m & ((1u << lane) - 1u)));
         }
     }
     __syncthreads();
-    uint32_t *bh = blockhist + ((size_t)blockIdx.y * nb_max + blockIdx.x) * ncells;
+    const size_t row = (size_t)blockIdx.y * nb_max + blockIdx.x;
+    uint32_t *bh = blockhist + row * ncells;
+    uint16_t *wp = warpprefix ? warpprefix + row * kSortWarps * ncells : nullptr;
     for (int c = threadIdx.x; c < ncells; c += kSortThreads) {
         uint32_t t = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) t += s_hist[w * ncells + c];
+        for (int w = 0; w < kSortWarps; ++w) {
+            if (wp) wp[w * ncells + c] = (uint16_t)t;      // same-cell points in earlier warps of this block
+            t += s_hist[w * ncells + c];
+        }
         bh[c] = t;
     }
 }
@@ -301,88 +349,27 @@ k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
 }
 
 // ------------------------------------------------------------------------------------------
-// k_place: same launch shape as k_scale_count.  Stable: a point's rank inside its cell is
-// (#same-cell points in earlier blocks) + (earlier warps of this block) + (earlier in this warp).
-// Re-derives the scaled coordinates from the raw point (same arithmetic as k_scale_count) and writes
-// them straight to their sorted position.
-__global__ void __launch_bounds__(kSortThreads)
+// k_place: grid (ceil(n_max/256), n_sets), 256 threads, one point per thread.  The point's stable sorted
+// position is  block base (k_scan) + earlier warps of its block (k_scale_count) + its rank inside its
+// warp sub-chunk (k_scale_count); the scaled coordinates are re-derived from the raw point with the same
+// arithmetic as k_scale_count and written straight to that slot.  No shared memory, no ranking.
+__global__ void __launch_bounds__(256)
 k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, int log_flag, double eps,
-        int identity_scaler, int C, int chw, int nb_max, const uint16_t *__restrict__ cellid,
+        int identity_scaler, int ncells, int chw, int nb_max, const uint16_t *__restrict__ cellid,
+        const uint16_t *__restrict__ rank16, const uint16_t *__restrict__ warpprefix,
         const uint32_t *__restrict__ blockbase, double2 *__restrict__ sorted) {
-    extern __shared__ uint32_t s_run[];
     const SetDesc sd = wd.set[blockIdx.y];
-    if ((int)blockIdx.x >= sd.nb) return;
-    const int ncells = C * C;
-    for (int i = threadIdx.x; i < kSortWarps * ncells; i += kSortThreads) s_run[i] = 0u;
-    __syncthreads();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= sd.n) return;
+    const double2 v = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p)[j];
+    const int cell = cellid[sd.off + j];
+    const uint32_t rank = rank16[sd.off + j];
+    const int64_t wchunk = j / chw;                       // global warp sub-chunk index of the point
+    const size_t row = (size_t)blockIdx.y * nb_max + (size_t)(wchunk / kSortWarps);
+    const uint32_t pos = blockbase[row * ncells + cell] +
+                         warpprefix[(row * kSortWarps + (size_t)(wchunk % kSortWarps)) * ncells + cell] + rank;
     const Scaler sc = make_scaler(rstat, sd, identity_scaler);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double2 *__restrict__ raw = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p);
-    const uint16_t *__restrict__ cid = cellid + sd.off;
-    const int64_t beg = ((int64_t)blockIdx.x * kSortWarps + warp) * chw;
-    const int64_t end = min(beg + (int64_t)chw, (int64_t)sd.n);
-    uint32_t *rw = s_run + warp * ncells;
-    for (int64_t j0 = beg; j0 < end; j0 += 32 * kSortUnroll) {
-        int cell[kSortUnroll];
-#pragma unroll
-        for (int u = 0; u < kSortUnroll; ++u) {
-            const int64_t j = j0 + u * 32 + lane;
-            cell[u] = (j < end) ? (int)cid[j] : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < kSortUnroll; ++u) {
-            const bool valid = cell[u] >= 0;
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const unsigned m = __match_any_sync(act, cell[u]);
-                if (lane == __ffs(m) - 1) rw[cell[u]] += __popc(m);
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    const uint32_t *bb = blockbase + ((size_t)blockIdx.y * nb_max + blockIdx.x) * ncells;
-    for (int c = threadIdx.x; c < ncells; c += kSortThreads) {
-        uint32_t acc = bb[c];
-#pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) {
-            uint32_t t = s_run[w * ncells + c];
-            s_run[w * ncells + c] = acc;
-            acc += t;
-        }
-    }
-    __syncthreads();
-    double2 *__restrict__ out = sorted + sd.off;
-    for (int64_t j0 = beg; j0 < end; j0 += 32 * kSortUnroll) {
-        int cell[kSortUnroll];
-        double2 v[kSortUnroll];
-#pragma unroll
-        for (int u = 0; u < kSortUnroll; ++u) {
-            const int64_t j = j0 + u * 32 + lane;
-            const bool valid = j < end;
-            cell[u] = valid ? (int)cid[j] : -1;
-            v[u] = valid ? raw[j] : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int u = 0; u < kSortUnroll; ++u) {
-            const bool valid = cell[u] >= 0;
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            uint32_t base = 0u;
-            int leader = lane;
-            unsigned m = 0u;
-            if (valid) {
-                m = __match_any_sync(act, cell[u]);
-                leader = __ffs(m) - 1;
-                if (lane == leader) { base = rw[cell[u]]; rw[cell[u]] = base + __popc(m); }
-            }
-            __syncwarp();
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (valid) {
-                const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-                out[base + rank] = scale_point(v[u], sc, log_flag, eps, identity_scaler);
-            }
-        }
-    }
+    sorted[sd.off + pos] = scale_point(v, sc, log_flag, eps, identity_scaler);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -397,19 +384,38 @@ __device__ __forceinline__ double gamma_eps(double dens, const GridGeom &g) {
     return z + g.eps;                                              // :75
 }
 
-// Cells a 4x4-node tile has to visit: every point within h of one of its nodes lies in
-// [cx_lo, cx_hi] x [cy_lo, cy_hi] (cell_of is monotone; `margin` covers the rounding of the bounds).
-struct TileCells { int cx_lo, cx_hi, cy_lo, cy_hi; };
+// Cells a 4x4-node tile has to visit: every point within h of one of its nodes lies in cell rows
+// [cy_lo, cy_hi] (cell_of is monotone; `margin` covers the rounding of the bounds), and inside cell row
+// cy only in the columns tile_row_run() returns: a row whose y-interval is dy away from the tile's
+// y-extent can only hold in-support points within sqrt(h^2 - dy^2) of its x-extent (a disc, not a box).
+struct TileCells { int cy_lo, cy_hi; double gx0, xhi, gy0, yhi; };
 __device__ __forceinline__ TileCells tile_cells(const GridGeom &g, int ix0, int iy0) {
-    const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
-    const double xhi = (double)min(ix0 + kTile - 1, g.R - 1) * g.step + g.gmin;
-    const double yhi = (double)min(iy0 + kTile - 1, g.R - 1) * g.step + g.gmin;
     TileCells t;
-    t.cx_lo = cell_of(gx0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
-    t.cx_hi = cell_of(xhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
-    t.cy_lo = cell_of(gy0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
-    t.cy_hi = cell_of(yhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
+    t.gx0 = (double)ix0 * g.step + g.gmin;
+    t.gy0 = (double)iy0 * g.step + g.gmin;
+    t.xhi = (double)min(ix0 + kTile - 1, g.R - 1) * g.step + g.gmin;
+    t.yhi = (double)min(iy0 + kTile - 1, g.R - 1) * g.step + g.gmin;
+    t.cy_lo = cell_of(t.gy0 - g.h - g.margin, g.cell_x0, g.cell_invw, g.C);
+    t.cy_hi = cell_of(t.yhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
     return t;
+}
+// First sorted index and length of the candidate run of cell row cy (tc.cy_lo <= cy <= tc.cy_hi).
+__device__ __forceinline__ void tile_row_run(const GridGeom &g, const TileCells &tc,
+                                             const uint32_t *__restrict__ cs, int cy,
+                                             uint32_t &start, uint32_t &len) {
+    // nominal y-interval of the row; the border rows also hold everything beyond the grid's extent, which
+    // only lies farther from the tile than the nominal edge used here
+    const double row_lo = g.cell_x0 + (double)cy * g.cell_w, row_hi = row_lo + g.cell_w;
+    const double dy = fmax(fmax(row_lo - tc.yhi, tc.gy0 - row_hi) - g.margin, 0.0);
+    const double rx2 = g.h * g.h - dy * dy;
+    start = 0u; len = 0u;
+    if (rx2 > 0.0) {
+        const double rx = sqrt(rx2) + g.margin;
+        const int cx_lo = cell_of(tc.gx0 - rx, g.cell_x0, g.cell_invw, g.C);
+        const int cx_hi = cell_of(tc.xhi + rx, g.cell_x0, g.cell_invw, g.C);
+        start = cs[cy * g.C + cx_lo];
+        len = cs[cy * g.C + cx_hi + 1] - start;
+    }
 }
 
 // Work-list layout.  Tiles are bucketed by candidate count so that the persistent density kernel can
@@ -442,8 +448,12 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int ix0 = tx * kTile, iy0 = ty * kTile;
         const TileCells tc = tile_cells(g, ix0, iy0);
         const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
-        for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy)
-            total += cs[cy * g.C + tc.cx_hi + 1] - cs[cy * g.C + tc.cx_lo];
+#pragma unroll 4
+        for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy) {     // independent loads: keep several rows in flight
+            uint32_t s0, l0;
+            tile_row_run(g, tc, cs, cy, s0, l0);
+            total += l0;
+        }
         const int tile = tx * g.NT + ty;
         if (total == 0u) {
             const double P0 = gamma_eps(0.0, g);
@@ -581,10 +591,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
             const TileCells tc = tile_cells(g, ix0, iy0);
             const int rows = tc.cy_hi - tc.cy_lo + 1;       // <= kMaxRows by the host's choice of C
             uint32_t s = 0u, len = 0u;
-            if (lane < rows) {
-                s = cs[(tc.cy_lo + lane) * g.C + tc.cx_lo];
-                len = cs[(tc.cy_lo + lane) * g.C + tc.cx_hi + 1] - s;
-            }
+            if (lane < rows) tile_row_run(g, tc, cs, tc.cy_lo + lane, s, len);
             uint32_t inc = len;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -671,10 +678,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const TileCells tc = tile_cells(g, ix0, iy0);
         const int rows = tc.cy_hi - tc.cy_lo + 1;
         uint32_t row_s = 0u, row_len = 0u;
-        if (lane < rows) {
-            row_s = cs[(tc.cy_lo + lane) * g.C + tc.cx_lo];
-            row_len = cs[(tc.cy_lo + lane) * g.C + tc.cx_hi + 1] - row_s;
-        }
+        if (lane < rows) tile_row_run(g, tc, cs, tc.cy_lo + lane, row_s, row_len);
         double acc[kTile][kTile];
 #pragma unroll
         for (int i = 0; i < kTile; ++i)
@@ -867,15 +871,26 @@ k_dense_finish(const __grid_constant__ WaveDesc wd, const GridGeom g, const doub
 }
 
 // ------------------------------------------------------------------------------------------
-// k_js: grid (node blocks, n_items), 256 threads.  Each block re-derives both normalisers from the
-// per-tile partials in a fixed order (identical in every block), then accumulates its nodes'
-// rel_entr(p,m) and rel_entr(q,m); the last block per item (ticket) folds the block partials:
+// k_set_totals: grid (n_sets), 256 threads: a set's normaliser = its per-tile partials summed in a
+// fixed order (KDE_distance.py:76, z.sum()).
+__global__ void __launch_bounds__(kJsThreads)
+k_set_totals(int nparts, const double *__restrict__ tilesum, double *__restrict__ totals) {
+    __shared__ double s_w[32];
+    const double *__restrict__ ts = tilesum + (size_t)blockIdx.x * nparts;
+    double a = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += kJsThreads) a += ts[k];
+    a = block_sum(a, s_w);
+    if (threadIdx.x == 0) totals[blockIdx.x] = a;
+}
+
+// k_js: grid (node blocks, n_items), 256 threads.  Normalises with totals[set] (k_set_totals, or the
+// all-reduced normalisers in row-sharded mode), accumulates its nodes' rel_entr(p,m) and rel_entr(q,m);
+// the last block per item (ticket) folds the block partials in block order:
 // js = sqrt((left + right) / 2)          scipy:spatial/distance.py:1278-1290.
-// totals_override (nullable, 2 doubles): normalisers supplied by the caller (row-sharded mode).
 __global__ void __launch_bounds__(kJsThreads)
 k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_end,
-     const double *__restrict__ pz, const double *__restrict__ tilesum,
-     const RawStat *__restrict__ rstat, const double *__restrict__ totals_override,
+     const double *__restrict__ pz, const double *__restrict__ totals,
+     const RawStat *__restrict__ rstat,
      double *__restrict__ z_out, double *__restrict__ jspart, unsigned *__restrict__ ticket,
      double *__restrict__ out_js, int32_t *__restrict__ out_status, double *__restrict__ out_lr,
      double *__restrict__ out_norm, int item_base) {
@@ -883,17 +898,7 @@ k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_
     __shared__ bool s_last;
     const int item = blockIdx.y;
     const int s0 = 2 * item, s1 = 2 * item + 1;
-    double tp = 0.0, tq = 0.0;
-    if (totals_override) { tp = totals_override[0]; tq = totals_override[1]; }
-    else {
-        double a = 0.0, b = 0.0;
-        for (int k = threadIdx.x; k < nparts; k += kJsThreads) {
-            a += tilesum[(size_t)s0 * nparts + k];
-            b += tilesum[(size_t)s1 * nparts + k];
-        }
-        tp = block_sum(a, s_w);
-        tq = block_sum(b, s_w);
-    }
+    const double tp = totals[s0], tq = totals[s1];
     double left = 0.0, right = 0.0;
     const int kb = k_begin + blockIdx.x * kJsNodesPerBlock;
     const int ke = min(kb + kJsNodesPerBlock, k_end);

@@ -283,7 +283,7 @@ def test_profile_counters(pk):
     assert n.value == 1 and ms.value > 0.0
     cnt = ctypes.c_int64()
     nat.check(L.kdejs_launch_count(0, ctypes.byref(cnt), 0))
-    assert cnt.value == 7
+    assert cnt.value == 8
     w = ctypes.c_double()
     nat.check(L.kdejs_work_counters(0, ctypes.byref(w), 1))
     assert w.value > 0
@@ -316,3 +316,35 @@ def test_dense_fp32_gaussian_and_batch(pk, ko):
     dense = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0, algo="dense")
     exact = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0)
     np.testing.assert_allclose(dense, exact, rtol=1e-5)
+
+
+def test_randomised_configurations(pk, ko):
+    """40 seeded random configurations (sizes, resolution, bandwidth, gamma, eps, log, NaNs, duplicates,
+    clustered vs spread clouds) against the exact oracle."""
+    rng = np.random.default_rng(20261019)
+    worst = 0.0
+    for trial in range(40):
+        n1, n2 = int(rng.integers(1, 6000)), int(rng.integers(1, 6000))
+        R = int(rng.choice([7, 20, 64, 100, 101, 130, 200]))
+        h = float(rng.choice([0.01, 0.03, 0.03, 0.08, 0.3]))
+        gamma = float(rng.choice([0.25, 0.25, 0.5, 1.0, 0.1, 2.0]))
+        eps = float(rng.choice([0.0, 0.0, 1e-12, 1e-6]))
+        log = bool(rng.integers(0, 4) == 0)
+        spread = rng.choice([1e-4, 1e-2, 0.3])
+        a = np.abs(rng.normal([0.002, 0.3], [spread * 0.01, spread], (n1, 2))) + 1e-9
+        b = np.abs(rng.normal([0.0025, 0.28], [spread * 0.02, spread * 1.5], (n2, 2))) + 1e-9
+        if rng.integers(0, 3) == 0:
+            a[rng.integers(0, n1, max(1, n1 // 20))] = a[0]            # duplicates
+        if rng.integers(0, 3) == 0:
+            b[rng.integers(0, n2, max(1, n2 // 10)), rng.integers(0, 2)] = np.nan
+        if rng.integers(0, 5) == 0:
+            b[:, 0] = np.round(b[:, 0], 4)
+        got = pk.KDE_JS_divergence(a, b, gamma, eps, log, resolution=R, bandwidth=h)
+        want = ko.discrepancy(a, b, gamma, eps, log, resolution=R, bandwidth=h)
+        if np.isnan(want):
+            assert np.isnan(got), (trial, got, want)
+            continue
+        err = abs(got - want) / max(abs(want), 1e-12)
+        worst = max(worst, err)
+        assert err < 1e-9, (trial, n1, n2, R, h, gamma, eps, log, got, want)
+    print("worst relative error over random configurations:", worst)
