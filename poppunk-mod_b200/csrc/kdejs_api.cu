@@ -69,7 +69,8 @@ struct Ctx {
     int dens_blocks_per_sm = 1;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     Slot slot[2];
-    DevBuf pool_raw, js_out, status_out, misc;
+    DevBuf pool_raw, js_out, status_out, misc, sim_ring;
+    std::vector<cudaEvent_t> free_plain_events;
     double *h_js = nullptr; int32_t *h_status = nullptr; size_t h_cap = 0;   // pinned results
     std::mutex mu;
     // measurement
@@ -487,7 +488,9 @@ void kdejs_shutdown(void) {
             cudaEventDestroy(s.ev_copied);
             cudaEventDestroy(s.ev_done);
         }
-        for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.misc}) {
+        for (auto e : c.free_plain_events) cudaEventDestroy(e);
+        c.free_plain_events.clear();
+        for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.misc, &c.sim_ring}) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr; b->cap = 0;
         }
@@ -604,36 +607,66 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     OKR(ensure_host_results(*c, (size_t)B));
     int64_t nmax = 1;
     for (int i = 0; i < B; ++i) nmax = std::max(nmax, n_sims[i]);
-    // Waves ramp up 4, 8, 16, ... to the scratch-budget cap: the first H2D copy (the only one that cannot
-    // hide behind kernels) stays short, later waves are large enough to run the kernels efficiently.
+    // H2D and kernels run on two streams.  The raw sims land in a ring of device buffers (up to 2 GB) that
+    // the copy stream fills as far ahead as it can; the kernels of a wave wait only for that wave's copies.
+    // The first wave is short (its copy is the only one that cannot hide behind kernels), later ones are
+    // large enough to run the kernels efficiently.  All waves share one scratch slot: they are ordered on
+    // the compute stream anyway.
     const int cap = wave_capacity(p, n_obs + nmax);
     const size_t sim_stride = ((size_t)nmax * 16 + 255) / 256 * 256;
-    for (auto &s : c->slot) OKR(s.rawsims.ensure(sim_stride * (size_t)cap));
-    int wave = 0, next_size = std::min(cap, 4);
-    for (int i0 = 0; i0 < B; ++wave) {
-        const int items = std::min(next_size, B - i0);
-        next_size = std::min(cap, next_size * 2);
-        Slot &sl = c->slot[wave & 1];
-        if (wave >= 2) CU(cudaEventSynchronize(sl.ev_done));      // slot's previous wave has finished
+    const int ring_items = (int)std::min<int64_t>(B, std::max<int64_t>(cap, (int64_t)(2.0e9 / (double)sim_stride)));
+    OKR(c->sim_ring.ensure(sim_stride * (size_t)ring_items));
+    const int wave_size = std::min(cap, 16);
+    std::vector<int> wave_of_item(B);
+    std::vector<cudaEvent_t> ev_copied, ev_done;
+    auto new_event = [&](cudaEvent_t &e) -> int {
+        if (!c->free_plain_events.empty()) { e = c->free_plain_events.back(); c->free_plain_events.pop_back(); return KDEJS_OK; }
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return KDEJS_OK;
+    };
+    int rc = KDEJS_OK;
+    int wave = 0;
+    for (int i0 = 0; i0 < B && rc == KDEJS_OK; ++wave) {
+        const int items = std::min(wave == 0 ? std::min(cap, 4) : wave_size, B - i0);
+        cudaEvent_t ec, ed;
+        if ((rc = new_event(ec)) != KDEJS_OK || (rc = new_event(ed)) != KDEJS_OK) break;
+        ev_copied.push_back(ec);
+        ev_done.push_back(ed);
         std::vector<RawSet> pool(items + 1);
         pool[0] = RawSet{(const double *)c->pool_raw.p, n_obs};
         std::vector<int32_t> ia(items, 0), ib(items);
         for (int k = 0; k < items; ++k) {
-            char *dst = (char *)sl.rawsims.p + sim_stride * (size_t)k;
-            CU(cudaMemcpyAsync(dst, sims[i0 + k], (size_t)n_sims[i0 + k] * 16, cudaMemcpyHostToDevice, c->s_copy));
-            pool[k + 1] = RawSet{(const double *)dst, n_sims[i0 + k]};
+            const int i = i0 + k;
+            wave_of_item[i] = wave;
+            if (i >= ring_items)        // ring slot reuse: the evaluation that read it must have finished
+                if (cudaEventSynchronize(ev_done[wave_of_item[i - ring_items]]) != cudaSuccess) { rc = fail(KDEJS_ERR_CUDA, "event wait failed"); break; }
+            char *dst = (char *)c->sim_ring.p + sim_stride * (size_t)(i % ring_items);
+            if (cudaMemcpyAsync(dst, sims[i], (size_t)n_sims[i] * 16, cudaMemcpyHostToDevice, c->s_copy) != cudaSuccess) {
+                rc = fail(KDEJS_ERR_CUDA, "H2D copy of a simulated set failed");
+                break;
+            }
+            pool[k + 1] = RawSet{(const double *)dst, n_sims[i]};
             ib[k] = k + 1;
         }
-        CU(cudaEventRecord(sl.ev_copied, c->s_copy));
-        CU(cudaStreamWaitEvent(c->s_compute, sl.ev_copied, 0));
-        OKR(run_pairs_dev(*c, c->s_compute, wave & 1, p, pool, ia.data(), ib.data(), items,
-                          c->js_out.as<double>(), c->status_out.as<int32_t>(), i0, false));
-        CU(cudaEventRecord(sl.ev_done, c->s_compute));
+        if (rc != KDEJS_OK) break;
+        cudaEventRecord(ec, c->s_copy);
+        cudaStreamWaitEvent(c->s_compute, ec, 0);
+        rc = run_pairs_dev(*c, c->s_compute, 0, p, pool, ia.data(), ib.data(), items,
+                           c->js_out.as<double>(), c->status_out.as<int32_t>(), i0, false);
+        cudaEventRecord(ed, c->s_compute);
         i0 += items;
     }
-    CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute));
-    CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute));
-    CU(cudaStreamSynchronize(c->s_compute));
+    if (rc == KDEJS_OK) {
+        if (cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
+            cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess)
+            rc = fail(KDEJS_ERR_CUDA, "D2H copy of the results failed");
+    }
+    cudaError_t se = cudaStreamSynchronize(c->s_compute);
+    cudaStreamSynchronize(c->s_copy);
+    for (auto e : ev_copied) c->free_plain_events.push_back(e);
+    for (auto e : ev_done) c->free_plain_events.push_back(e);
+    if (rc != KDEJS_OK) return rc;
+    if (se != cudaSuccess) return fail(KDEJS_ERR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(se));
     memcpy(out_js, c->h_js, sizeof(double) * (size_t)B);
     return finish_status(c->h_status, B);
 }
