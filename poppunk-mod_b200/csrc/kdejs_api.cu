@@ -228,7 +228,7 @@ int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
     return KDEJS_OK;
 }
 
-// Enqueue the six launches of one wave on `st`.  wd.set[].nb is filled here.
+// Enqueue the launches of one wave on `st`.  wd.set[].nb is filled here.
 int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom &g, WaveDesc &wd,
              const WaveIO &io) {
     const int n_sets = wd.n_sets, n_items = n_sets / 2;

@@ -1,15 +1,18 @@
 // kdejs_kernels.cuh -- hand-written sm_100a kernels for PopPUNK-mod's KDE discrepancy.
 //
 // One evaluation = KDE_JS_divergence(df1, df2, gamma, eps, log)  (/root/reference/KDE_distance.py:104-130).
-// A "wave" is up to kMaxWaveItems independent evaluations processed by the same six launches:
+// A "wave" is up to kMaxWaveItems independent evaluations processed by the same eight launches:
 //
-//   k_minmax       joint NaN-ignoring min/max per raw point set (MinMaxScaler.fit, KDE_distance.py:81-82)
-//   k_scale_count  X*scale_+min_, NaN->0 (KDE_distance.py:85-86, :53) + per-block cell histogram
-//   k_scan         exclusive scan of the (cell, block) counts -> cell starts and block bases
-//   k_place        stable counting-sort placement of the scaled points by cell
-//   k_density_*    Epanechnikov sums on the R x R grid (get_kde + generate_samples, :48-64),
-//                  **gamma + eps and per-tile normaliser partials (:71-76)
-//   k_js           normalise, Jensen-Shannon distance (scipy jensenshannon, :129)
+//   k_minmax         joint NaN-ignoring min/max per raw point set (MinMaxScaler.fit, KDE_distance.py:81-82)
+//   k_scale_count    X*scale_+min_, NaN->0 (KDE_distance.py:85-86, :53): cell id and in-warp rank per point,
+//                    per-warp / per-block cell histograms
+//   k_scan           exclusive scan of the (cell, block) counts -> cell starts and block bases
+//   k_place          stable counting-sort placement of the scaled points by cell (pure scatter)
+//   k_tile_classify  candidates per 4x4-node tile -> work list in ten weight classes; empty tiles finished here
+//   k_density_*      Epanechnikov sums on the R x R grid (get_kde + generate_samples, :48-64),
+//                    **gamma + eps and per-tile normaliser partials (:71-76)
+//   k_set_totals     per-set normaliser (z.sum(), :76)
+//   k_js             normalise, Jensen-Shannon distance (scipy jensenshannon, :129)
 //
 // Everything is fp64 unless a kernel says otherwise; every reduction has a fixed shape, so results
 // are bit-reproducible run to run and independent of batch composition.
