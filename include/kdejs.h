@@ -117,6 +117,20 @@ int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, dou
 int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b, int64_t nb,
                        int resolution, double bandwidth, double gamma, double eps, int log_flag,
                        int kernel, int algo, int row_begin, int row_end, double out_norm[2]);
+/* Same as phase 1 with both point sets already in DEVICE memory (e.g. assembled by an NCCL all-gather of
+ * per-rank slices).  Work from other streams that produced them must have completed. */
+int kdejs_shard_phase1_dev(int device, const double *a_dev, int64_t na, const double *b_dev, int64_t nb,
+                           int resolution, double bandwidth, double gamma, double eps, int log_flag,
+                           int kernel, int algo, int row_begin, int row_end, double out_norm[2]);
+/* Phase 1 with the row bands chosen by the library: after sorting, the estimated density work of every
+ * tile row is summed and the rows are cut into `world` equally heavy bands (real distance clouds are
+ * concentrated, equal row counts are not equal work); every rank derives the same cuts from the same
+ * data and evaluates band `rank`.  on_device != 0: a/b are DEVICE pointers.  out_rows: the node rows
+ * [begin, end) this rank evaluated (may be empty). */
+int kdejs_shard_phase1_balanced(int device, const double *a, int64_t na, const double *b, int64_t nb,
+                                int on_device, int resolution, double bandwidth, double gamma, double eps,
+                                int log_flag, int kernel, int algo, int rank, int world,
+                                double out_norm[2], int out_rows[2]);
 int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2]);
 
 /* ---- host memory --------------------------------------------------------------------- */

@@ -47,6 +47,11 @@ _SIGNATURES = {
                                          ctypes.c_int, ctypes.c_void_p]),
     "kdejs_shard_phase1": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                           ctypes.c_int64] + _COMMON + [ctypes.c_int, ctypes.c_int, _c_dp]),
+    "kdejs_shard_phase1_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                              ctypes.c_int64] + _COMMON + [ctypes.c_int, ctypes.c_int, _c_dp]),
+    "kdejs_shard_phase1_balanced": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                   ctypes.c_int64, ctypes.c_int] + _COMMON +
+                                    [ctypes.c_int, ctypes.c_int, _c_dp, ctypes.POINTER(ctypes.c_int)]),
     "kdejs_shard_phase2": (ctypes.c_int, [ctypes.c_int, _c_dp, _c_dp]),
     "kdejs_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "kdejs_host_free": (None, [ctypes.c_void_p]),

@@ -214,6 +214,8 @@ struct WaveIO {
     bool density_only = false;       // stop after the density kernel (kde_density)
     bool identity_scaler = false;
     bool shard = false;              // row-sharded: no k_js, caller runs the phases
+    int balance_rank = -1, balance_world = 0;   // row-sharded with work-balanced bands chosen here
+    int *out_tile_rows = nullptr;               // [2]: the tile rows this rank ended up with
 };
 
 int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
@@ -229,8 +231,9 @@ int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
 }
 
 // Enqueue the launches of one wave on `st`.  wd.set[].nb is filled here.
-int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom &g, WaveDesc &wd,
+int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom &g_in, WaveDesc &wd,
              const WaveIO &io) {
+    GridGeom g = g_in;
     const int n_sets = wd.n_sets, n_items = n_sets / 2;
     const size_t G = (size_t)p.R * p.R;
     int64_t P = 0;
@@ -297,16 +300,41 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
                 sl.sorted.as<double2>());
         }
+        if (io.balance_world > 0) {
+            // cut the tile rows into bands of equal estimated work; all ranks derive the same cuts
+            OKR(c.misc.ensure(64 + sizeof(double) * (size_t)g.NT));
+            double *d_rw = c.misc.as<double>() + 8;
+            {
+                KTimer t(c, 6, st);
+                k_tile_rowwork<<<g.NT, 128, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_rw);
+            }
+            std::vector<double> rw(g.NT);
+            CU(cudaMemcpyAsync(rw.data(), d_rw, sizeof(double) * (size_t)g.NT, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            double total = 0.0;
+            for (double v : rw) total += v;
+            std::vector<int> cut(io.balance_world + 1, g.NT);
+            cut[0] = 0;
+            double run = 0.0;
+            int r = 1;
+            for (int t = 0; t < g.NT && r < io.balance_world; ++t) {
+                run += rw[t];
+                while (r < io.balance_world && run >= total * r / io.balance_world) cut[r++] = t + 1;
+            }
+            g.tile_row_begin = cut[io.balance_rank];
+            g.tile_row_end = cut[io.balance_rank + 1];
+        }
+        if (io.out_tile_rows) { io.out_tile_rows[0] = g.tile_row_begin; io.out_tile_rows[1] = g.tile_row_end; }
         const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
         const unsigned capacity = (unsigned)tiles * (unsigned)n_sets;
-        {
+        if (tiles > 0) {
             KTimer t(c, 6, st);
             k_tile_classify<<<dim3((tiles + 255) / 256, n_sets), 256, 0, st>>>(
                 wd, g, sl.cellstart.as<uint32_t>(), sl.dens.as<double>(), sl.pz.as<double>(),
                 sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity,
                 c.prof_on ? c.d_work : nullptr);
         }
-        {
+        if (tiles > 0) {
             KTimer t(c, 4, st);
             const int blocks = (int)std::min<int64_t>((int64_t)capacity, (int64_t)c.sm_count * c.dens_blocks_per_sm);
             k_density_binned<<<blocks, kDensThreads, 0, st>>>(
@@ -723,48 +751,38 @@ int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, dou
     return KDEJS_OK;
 }
 
-int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b, int64_t nb, int resolution,
-                       double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
-                       int row_begin, int row_end, double out_norm[2]) {
-    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
-    OKR(check_params(p));
-    OKR(check_set(a, na, "df1"));
-    OKR(check_set(b, nb, "df2"));
-    if (algo != KDEJS_ALGO_BINNED) return fail(KDEJS_ERR_ARG, "row sharding is implemented for the binned algorithm");
-    if (row_begin < 0 || row_end > resolution || row_begin >= row_end) return fail(KDEJS_ERR_ARG, "bad row range");
-    if (row_begin % kTile != 0 || (row_end % kTile != 0 && row_end != resolution))
-        return fail(KDEJS_ERR_ARG, "row range must be aligned to 4 rows (or end at the last row)");
-    if (!out_norm) return fail(KDEJS_ERR_ARG, "out_norm is null");
-    Ctx *c;
-    OKR(get_ctx(device, &c));
-    std::lock_guard<std::mutex> lk(c->mu);
+static int shard_phase1_core(Ctx *c, const Params &p, RawSet ra, RawSet rb, int row_begin, int row_end,
+                             double out_norm[2], int balance_rank = -1, int balance_world = 0,
+                             int *out_rows = nullptr) {
     c->shard_valid = false;
     cudaStream_t st = c->s_compute;
-    const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
-    OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
-    CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, st));
     GridGeom g = make_geom(p);
     g.tile_row_begin = row_begin / kTile;
     g.tile_row_end = (row_end + kTile - 1) / kTile;
     WaveDesc wd;
     memset(&wd, 0, sizeof wd);
-    wd.raw[0] = RawSet{(const double *)c->pool_raw.p, na};
-    wd.raw[1] = RawSet{(const double *)((char *)c->pool_raw.p + offb), nb};
+    wd.raw[0] = ra;
+    wd.raw[1] = rb;
     wd.n_raw = 2; wd.n_sets = 2;
-    wd.set[0].rs_self = 0; wd.set[0].rs_other = 1; wd.set[0].n = (int32_t)na;
-    wd.set[1].rs_self = 1; wd.set[1].rs_other = 0; wd.set[1].n = (int32_t)nb;
+    wd.set[0].rs_self = 0; wd.set[0].rs_other = 1; wd.set[0].n = (int32_t)ra.n;
+    wd.set[1].rs_self = 1; wd.set[1].rs_other = 0; wd.set[1].n = (int32_t)rb.n;
     WaveIO io;
     io.shard = true;
+    int tile_rows[2] = {g.tile_row_begin, g.tile_row_end};
+    io.out_tile_rows = tile_rows;
+    if (balance_world > 0) { io.balance_rank = balance_rank; io.balance_world = balance_world; }
     Slot &sl = c->slot[0];
     OKR(run_wave(*c, sl, st, p, g, wd, io));
+    g.tile_row_begin = tile_rows[0];
+    g.tile_row_end = tile_rows[1];
+    row_begin = std::min(p.R, g.tile_row_begin * kTile);
+    row_end = std::min(p.R, g.tile_row_end * kTile);
+    if (out_rows) { out_rows[0] = row_begin; out_rows[1] = row_end; }
     OKR(c->misc.ensure(64));
     const int nparts = g.NT * g.NT;
     const int lo = g.tile_row_begin * g.NT, cnt = (g.tile_row_end - g.tile_row_begin) * g.NT;
-    // local normaliser partials: tiles [lo, lo+cnt) of each set
-    {
+    {   // local normaliser partials: tiles [lo, lo+cnt) of each set (set 1 sits nparts after set 0)
         KTimer t(*c, 5, st);
-        // k_norm_totals expects set 1 at +nparts from set 0: pass pointers offset by lo with stride nparts
         k_norm_totals<<<1, kJsThreads, 0, st>>>(cnt, nparts, sl.tilesum.as<double>() + lo, c->misc.as<double>());
     }
     OKR(ensure_host_results(*c, 4));
@@ -777,10 +795,75 @@ int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b,
     out_norm[0] = c->h_js[0];
     out_norm[1] = c->h_js[1];
     c->shard_wd = wd; c->shard_geom = g;
-    c->shard_kb = row_begin * resolution;
-    c->shard_ke = row_end * resolution;
+    c->shard_kb = row_begin * p.R;
+    c->shard_ke = row_end * p.R;
     c->shard_valid = true;
     return KDEJS_OK;
+}
+
+static int shard_check(const Params &p, const double *a, int64_t na, const double *b, int64_t nb, int row_begin,
+                       int row_end, const double *out_norm) {
+    OKR(check_params(p));
+    OKR(check_set(a, na, "df1"));
+    OKR(check_set(b, nb, "df2"));
+    if (p.algo != KDEJS_ALGO_BINNED) return fail(KDEJS_ERR_ARG, "row sharding is implemented for the binned algorithm");
+    if (row_begin < 0 || row_end > p.R || row_begin >= row_end) return fail(KDEJS_ERR_ARG, "bad row range");
+    if (row_begin % kTile != 0 || (row_end % kTile != 0 && row_end != p.R))
+        return fail(KDEJS_ERR_ARG, "row range must be aligned to 4 rows (or end at the last row)");
+    if (!out_norm) return fail(KDEJS_ERR_ARG, "out_norm is null");
+    return KDEJS_OK;
+}
+
+int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b, int64_t nb, int resolution,
+                       double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                       int row_begin, int row_end, double out_norm[2]) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(shard_check(p, a, na, b, nb, row_begin, row_end, out_norm));
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
+    OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
+    CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, c->s_compute));
+    CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, c->s_compute));
+    return shard_phase1_core(c, p, RawSet{(const double *)c->pool_raw.p, na},
+                             RawSet{(const double *)((char *)c->pool_raw.p + offb), nb}, row_begin, row_end, out_norm);
+}
+
+int kdejs_shard_phase1_dev(int device, const double *a_dev, int64_t na, const double *b_dev, int64_t nb,
+                           int resolution, double bandwidth, double gamma, double eps, int log_flag, int kernel,
+                           int algo, int row_begin, int row_end, double out_norm[2]) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(shard_check(p, a_dev, na, b_dev, nb, row_begin, row_end, out_norm));
+    if ((((uintptr_t)a_dev) | ((uintptr_t)b_dev)) & 15) return fail(KDEJS_ERR_ARG, "device point sets must be 16-byte aligned");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    return shard_phase1_core(c, p, RawSet{a_dev, na}, RawSet{b_dev, nb}, row_begin, row_end, out_norm);
+}
+
+int kdejs_shard_phase1_balanced(int device, const double *a, int64_t na, const double *b, int64_t nb,
+                                int on_device, int resolution, double bandwidth, double gamma, double eps,
+                                int log_flag, int kernel, int algo, int rank, int world, double out_norm[2],
+                                int out_rows[2]) {
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(shard_check(p, a, na, b, nb, 0, resolution, out_norm));
+    if (world < 1 || rank < 0 || rank >= world || !out_rows) return fail(KDEJS_ERR_ARG, "bad rank/world");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    RawSet ra{a, na}, rb{b, nb};
+    if (!on_device) {
+        const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
+        OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
+        CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, c->s_compute));
+        CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, c->s_compute));
+        ra.p = (const double *)c->pool_raw.p;
+        rb.p = (const double *)((char *)c->pool_raw.p + offb);
+    } else if ((((uintptr_t)a) | ((uintptr_t)b)) & 15) {
+        return fail(KDEJS_ERR_ARG, "device point sets must be 16-byte aligned");
+    }
+    return shard_phase1_core(c, p, ra, rb, 0, resolution, out_norm, rank, world, out_rows);
 }
 
 int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2]) {
@@ -796,6 +879,7 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
     double *d = c->misc.as<double>();      // [0,1] totals in, [2,3] (left,right) out
     CU(cudaMemcpyAsync(d, total_norm, 16, cudaMemcpyHostToDevice, st));
     const int n = c->shard_ke - c->shard_kb;
+    if (n <= 0) { out_lr[0] = 0.0; out_lr[1] = 0.0; return KDEJS_OK; }     // this rank owns no rows
     const int js_blocks = (n + kJsNodesPerBlock - 1) / kJsNodesPerBlock;
     OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)js_blocks));
     {

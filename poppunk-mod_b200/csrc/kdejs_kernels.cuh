@@ -487,6 +487,31 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
     }
 }
 
+// k_tile_rowwork: grid (NT tile rows), 128 threads.  Estimated density work of one tile row over all sets
+// of the wave: candidates plus a fixed per-tile cost.  Used to cut the node rows of one huge evaluation
+// into equally heavy bands, one per rank (every rank computes the same numbers from the same sorted data).
+__global__ void __launch_bounds__(128)
+k_tile_rowwork(const __grid_constant__ WaveDesc wd, const GridGeom g,
+               const uint32_t *__restrict__ cellstart, double *__restrict__ rowwork) {
+    __shared__ double s_w[32];
+    const int tx = blockIdx.x;
+    double work = 0.0;
+    for (int idx = threadIdx.x; idx < wd.n_sets * g.NT; idx += blockDim.x) {
+        const int set = idx / g.NT, ty = idx % g.NT;
+        const TileCells tc = tile_cells(g, tx * kTile, ty * kTile);
+        const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
+        uint32_t total = 0u;
+        for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy) {
+            uint32_t s0, l0;
+            tile_row_run(g, tc, cs, cy, s0, l0);
+            total += l0;
+        }
+        work += (double)total + (total ? 64.0 : 2.0);
+    }
+    work = block_sum(work, s_w);
+    if (threadIdx.x == 0) rowwork[tx] = work;
+}
+
 // Clamp-and-accumulate for the Epanechnikov term t = 1 - d^2/h^2:  acc += (t >= +0) ? t * 2^-7 : 0.
 // The clamp is an exact multiply folded into the accumulating DFMA.  The multiplier's high word is made
 // on the FP32 (FMA) pipe from the high word of t read as a float: sat(f * 2^126) is 1.0f (0x3F800000)

@@ -92,20 +92,66 @@ def _phase2_gpu(totals, device):
     return np.array([lr[0], lr[1]])
 
 
+def _gather_slices(local, group, device):
+    """All ranks contribute a (n_r, 2) slice; every rank gets the rank-ordered concatenation.  NCCL:
+    the slice goes H2D once (1/world of the table per rank), the exchange runs GPU-to-GPU over
+    NVLink/NVSwitch, and the result is returned as a device tensor.  gloo: numpy (CPU tests)."""
+    import torch
+
+    dist = _dist()
+    world = dist.get_world_size(group)
+    loc = nat.as_points(local, "slice")
+    sizes = _all_gather_f64(np.array([loc.shape[0]], dtype=np.float64), group, device)[:, 0].astype(np.int64)
+    nmax = int(sizes.max())
+    if dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", device)
+        pad = torch.zeros((nmax, 2), dtype=torch.float64, device=dev)
+        pad[:loc.shape[0]].copy_(torch.from_numpy(loc), non_blocking=True)
+        out = torch.empty((world, nmax, 2), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, pad, group=group)
+        full = out.reshape(-1, 2) if bool((sizes == nmax).all()) else \
+            torch.cat([out[r, :int(sizes[r])] for r in range(world)], dim=0)
+        torch.cuda.synchronize(dev)
+        return full.contiguous()
+    pad = torch.zeros((nmax, 2), dtype=torch.float64)
+    pad[:loc.shape[0]] = torch.from_numpy(loc)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return np.concatenate([out[r][:int(sizes[r])].numpy() for r in range(world)], axis=0)
+
+
 def row_sharded_discrepancy(df1, df2, gamma=1.0, eps=1e-12, log=False, *, resolution=100, bandwidth=0.03,
-                            group=None, device=None, phase1=None, phase2=None):
+                            group=None, device=None, sliced=False, phase1=None, phase2=None):
     """KDE_JS_divergence of ONE pair of (large) point sets with the grid's node rows split over
-    the ranks of `group`.  Every rank must hold both sets.  Returns the same np.float64 on all ranks."""
+    the ranks of `group`.  Returns the same np.float64 on all ranks.
+
+    sliced=False: every rank passes both complete sets (each rank uploads everything).
+    sliced=True : every rank passes only ITS contiguous slice of each set (rank order = row order of the
+                  table); slices are exchanged GPU-to-GPU with one all-gather per set."""
     dist = _dist()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    lo, hi = row_ranges(resolution, world)[rank]
     dev = kd.default_device() if device is None else int(device)
     common = kd._common(resolution, bandwidth, gamma, eps, log, "epanechnikov", "binned")
-    if lo < hi:
-        norms = phase1(df1, df2, lo, hi) if phase1 else _phase1_gpu(df1, df2, common, lo, hi, dev)
+    if sliced and dist.is_initialized():
+        df1, df2 = _gather_slices(df1, group, dev), _gather_slices(df2, group, dev)
+    if phase1 is not None:                       # injected compute (CPU tests): equal row counts
+        lo, hi = row_ranges(resolution, world)[rank]
+        norms = phase1(df1, df2, lo, hi) if lo < hi else np.zeros(2)
     else:
-        norms = np.zeros(2)
+        # the library cuts the rows into bands of equal estimated work (same cuts on every rank)
+        n = (ctypes.c_double * 2)()
+        rows = (ctypes.c_int * 2)()
+        if isinstance(df1, np.ndarray) or not hasattr(df1, "data_ptr"):
+            a, b = nat.as_points(df1, "df1"), nat.as_points(df2, "df2")
+            pa, pb, on_dev = nat.ptr(a), nat.ptr(b), 0
+            na, nb = a.shape[0], b.shape[0]
+        else:                                    # device tensors from the all-gather
+            pa, pb, on_dev = df1.data_ptr(), df2.data_ptr(), 1
+            na, nb = df1.shape[0], df2.shape[0]
+        nat.check(nat.lib().kdejs_shard_phase1_balanced(dev, pa, na, pb, nb, on_dev, *common, rank, world, n, rows))
+        norms = np.array([n[0], n[1]])
+        lo, hi = rows[0], rows[1]
     totals = _all_gather_f64(norms, group, dev).sum(axis=0)          # rank order: deterministic
     if lo < hi:
         lr = phase2(totals) if phase2 else _phase2_gpu(totals, dev)

@@ -60,6 +60,17 @@ def _worker(rank, world, port, q):
         return np.array([l, r])
 
     js = D.row_sharded_discrepancy(a, b, 0.25, 0.0, resolution=R, phase1=phase1, phase2=phase2)
+    # sliced inputs: each rank holds a ragged contiguous slice; the all-gather must rebuild the table
+    cut_a, cut_b = (0, 1700, len(a)), (0, 901, len(b))
+    seen = {}
+
+    def phase1_sliced(df1, df2, lo, hi):
+        seen["ok"] = bool(np.array_equal(df1, a) and np.array_equal(df2, b))
+        return phase1(df1, df2, lo, hi)
+
+    js_sliced = D.row_sharded_discrepancy(a[cut_a[rank]:cut_a[rank + 1]], b[cut_b[rank]:cut_b[rank + 1]], 0.25, 0.0,
+                                          resolution=R, sliced=True, phase1=phase1_sliced, phase2=phase2)
+    assert seen["ok"] and js_sliced == js
     q.put((rank, batch, float(js), float(ko.discrepancy(a, b, 0.25, 0.0, resolution=R)),
            [float(ko.discrepancy(obs, s, 0.25, 0.0)) for s in sims]))
     dist.barrier()

@@ -348,3 +348,40 @@ def test_randomised_configurations(pk, ko):
         worst = max(worst, err)
         assert err < 1e-9, (trial, n1, n2, R, h, gamma, eps, log, got, want)
     print("worst relative error over random configurations:", worst)
+
+
+def test_work_balanced_row_bands(pk, ko):
+    """kdejs_shard_phase1_balanced: bands are contiguous, cover all rows, and reproduce the full result."""
+    import ctypes
+
+    from oracle import workloads as wl
+
+    nat = pk._native
+    a, b = wl.synthetic_target(40000), wl.sim_S(9, 2200, 0.3, n=30000)
+    R, world = 200, 3
+    common = (R, 0.03, 0.25, 0.0, 0, 0, 0)
+    full = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=R)
+
+    def phase1(rank):
+        n, rows = (ctypes.c_double * 2)(), (ctypes.c_int * 2)()
+        nat.check(nat.lib().kdejs_shard_phase1_balanced(0, nat.ptr(a), len(a), nat.ptr(b), len(b), 0, *common,
+                                                        rank, world, n, rows))
+        return (n[0], n[1]), (rows[0], rows[1])
+
+    norms, bands = zip(*[phase1(r) for r in range(world)])
+    assert bands[0][0] == 0 and bands[-1][1] == R
+    for (lo, hi), (lo2, _) in zip(bands[:-1], bands[1:]):
+        assert hi == lo2 and lo <= hi
+    sizes = [hi - lo for lo, hi in bands]
+    assert max(sizes) > min(sizes)                 # concentrated data: equal work is not equal row counts
+    tot = (ctypes.c_double * 2)(sum(x for x, _ in norms), sum(y for _, y in norms))
+    L = Rr = 0.0
+    for r in range(world):
+        phase1(r)
+        lr = (ctypes.c_double * 2)()
+        nat.check(nat.lib().kdejs_shard_phase2(0, tot, lr))
+        L += lr[0]
+        Rr += lr[1]
+    js = np.sqrt((L + Rr) / 2.0)
+    assert js == pytest.approx(full, rel=1e-12)
+    assert rel(js, ko.discrepancy(a, b, 0.25, 0.0, resolution=R)) < JS_RTOL_EXPECT

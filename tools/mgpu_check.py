@@ -30,7 +30,16 @@ for n, R in ((1_000_000, 512), (int(os.environ.get("C5_N", 10_000_000)), 1024)):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
     js = D.row_sharded_discrepancy(a, b, 0.25, 0.0, resolution=R)
     torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+    # the same evaluation with the TABLE sharded too: each rank uploads 1/world of the rows, NCCL all-gather
+    ca = [len(a) * r // world for r in range(world + 1)]; cb = [len(b) * r // world for r in range(world + 1)]
+    sa, sb = a[ca[rank]:ca[rank + 1]], b[cb[rank]:cb[rank + 1]]
+    D.row_sharded_discrepancy(sa, sb, 0.25, 0.0, resolution=R, sliced=True)
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    js2 = D.row_sharded_discrepancy(sa, sb, 0.25, 0.0, resolution=R, sliced=True)
+    torch.cuda.synchronize(); dist.barrier(); dt2 = time.perf_counter() - t0
+    assert js2 == js, (js2, js)
     if rank == 0:
+        print(f"   sliced inputs + NCCL all-gather: {dt2*1e3:.1f} ms", flush=True)
         pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R)
         t0 = time.perf_counter(); full = pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R); d1 = time.perf_counter() - t0
         print(f"C5-like n={n} R={R}: sharded over {world} = {js!r} in {dt*1e3:.1f} ms ; single GPU = {full!r} in {d1*1e3:.1f} ms ; rel {abs(js-full)/full:.2e}", flush=True)
