@@ -367,6 +367,13 @@ def main():
     }
     hbm_bytes = (2 * N_PAIRS * 16) * evals_timed     # every input point read once per evaluation
     roofline["hbm_algorithmic_gbs"] = hbm_bytes / (ms_max * 1e-3) / 1e9
+    try:                                             # driver-written HBM / bf16 peaks: context only, the path
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:     # is bound by neither
+            mp = json.load(f)
+        roofline["hbm_peak_gbs_measured"] = mp.get("hbm_gbs")
+        roofline["hbm_frac_of_measured"] = roofline["hbm_algorithmic_gbs"] / mp["hbm_gbs"] if mp.get("hbm_gbs") else None
+    except (OSError, ValueError, KeyError):
+        roofline["hbm_peak_gbs_measured"] = None
 
     # ---- the dense fp32 brute-force kernel (north-star kernel), a short side measurement ----------
     dense = None

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -202,6 +203,9 @@ GridGeom make_geom(const Params &p) {
     g.gamma_mode = (p.gamma == 1.0) ? 1 : (p.gamma == 0.5) ? 2 : (p.gamma == 0.25) ? 3 : 0;
     g.tile_row_begin = 0;
     g.tile_row_end = g.NT;
+    g.heavy_log2 = 13;
+    if (const char *e = getenv("KDEJS_HEAVY_LOG2")) g.heavy_log2 = std::max(6, std::min(30, atoi(e)));
+    g.pad2 = 0;
     return g;
 }
 

@@ -61,6 +61,7 @@ struct GridGeom {
     double cell_w;                       // nominal cell side = extent / C
     double knorm, gamma, eps;
     int32_t tile_row_begin, tile_row_end;   // tile rows (index of column 0) this launch covers
+    int32_t heavy_log2, pad2;               // tiles with >= 2^heavy_log2 candidates are processed per block
 };
 
 __device__ __forceinline__ double pre_transform(double v, int log_flag, double eps) {
@@ -428,9 +429,9 @@ __device__ __forceinline__ void tile_row_run(const GridGeom &g, const TileCells 
 // counters: [0..9] entries per class, [10] block ticket, [11] warp ticket (zeroed by k_scan each wave).
 constexpr int kNumClasses = 10;
 constexpr int kTicketA = kNumClasses, kTicketB = kNumClasses + 1;
-__device__ __forceinline__ int tile_class(uint32_t total) {
+__device__ __forceinline__ int tile_class(uint32_t total, int heavy_log2) {
     const int lg = 31 - __clz((int)total);          // floor(log2(total)), total >= 1
-    return lg >= 13 ? 0 : min(13 - lg, kNumClasses - 1);
+    return lg >= heavy_log2 ? 0 : min(heavy_log2 - lg, kNumClasses - 1);
 }
 
 // k_tile_classify: one thread per (tile, set).  Counts the tile's candidate points; a tile with none
@@ -473,7 +474,7 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 }
             tilesum[(size_t)set * g.NT * g.NT + tile] = s;
         } else {
-            const int cls = tile_class(total);
+            const int cls = tile_class(total, g.heavy_log2);
             const unsigned slot = atomicAdd(&counters[cls], 1u);
             worklist[(size_t)cls * capacity + slot] = ((uint32_t)set << 24) | (uint32_t)tile;
         }
@@ -529,7 +530,7 @@ constexpr int kRedStride = kDensThreads + 8;   // padded row of the block-level 
 constexpr int kWarpRedStride = 33;             // padded row of the warp-level one
 constexpr int kRedDoubles = kTile * kTile * kRedStride;   // >= 4 warps * 16 * 33
 
-constexpr int kStageRows = 1;
+constexpr int kStageRows = 1;   // rows of 4 independent terms per dependent stage (2 and 4 measured slower: registers)
 // One candidate point against the tile's 16 nodes (46 fp64-pipe + 16 FP32-pipe instructions).
 __device__ __forceinline__ void accumulate_point(const double2 p, const double gx0, const double gy0,
                                                  const double inv_h, const double c1, const double c2,
