@@ -513,24 +513,23 @@ k_tile_rowwork(const __grid_constant__ WaveDesc wd, const GridGeom g,
     if (threadIdx.x == 0) rowwork[tx] = work;
 }
 
-// Clamp-and-accumulate for the Epanechnikov term t = 1 - d^2/h^2:  acc += (t >= +0) ? t * 2^-7 : 0.
-// The clamp is an exact multiply folded into the accumulating DFMA.  The multiplier's high word is made
-// on the FP32 (FMA) pipe from the high word of t read as a float: sat(f * 2^126) is 1.0f (0x3F800000)
-// for every positive normal f and 0 for negative/zero f, and 0x3F800000:00000000 read as a double is
-// exactly 2^-7.  A pair therefore costs two fp64-pipe instructions plus ONE full-rate FMUL.SAT -- no
-// compare/select chain on the half-rate ALU pipe -- and the kernel stays fp64-pipe bound.  The power-
-// of-two scale commutes with rounding, so 128 * acc is bit-identical to the plain fp64 sum.
-constexpr double kAccUnscale = 128.0;
-__device__ __forceinline__ double clamp_mask(double t) {
-    const float m = __saturatef(__int_as_float(__double2hiint(t)) * 8.507059173023462e37f);   // 2^126
-    return __hiloint2double(__float_as_int(m), 0);
+// Clamp-and-accumulate for the Epanechnikov term t = 1 - d^2/h^2:  acc += max(t, 0).
+// The clamp is ONE integer max on the high word (ALU pipe, otherwise idle here): hi' = max(hi32(t), 0).
+// For t >= 0 nothing changes; for t < 0 the value collapses to {0, lo32(t)}, a subnormal below 2^-1042.
+// Genuine terms are 0 or >= 2^-53 (t = 1 - u^2 with u^2 < 1), so that residue can never reach the last bit
+// of a non-zero sum, and a sum made only of residues (< N * 2^-1042) is recognised in the epilogue and
+// written as the exact 0 it stands for (kResidueFloor).  A pair costs two fp64-pipe instructions (DFMA for
+// t, DADD into the accumulator) plus that one ALU op -- no compare/select chain, no mask registers.
+constexpr double kResidueFloor = 1e-280;
+__device__ __forceinline__ double clamp_nonneg(double t) {
+    return __hiloint2double(max(__double2hiint(t), 0), __double2loint(t));
 }
+__device__ __forceinline__ double unresidue(double S) { return S < kResidueFloor ? 0.0 : S; }
 
 constexpr int kRedStride = kDensThreads + 8;   // padded row of the block-level transposed reduction buffer
 constexpr int kWarpRedStride = 33;             // padded row of the warp-level one
 constexpr int kRedDoubles = kTile * kTile * kRedStride;   // >= 4 warps * 16 * 33
 
-constexpr int kStageRows = 1;   // rows of 4 independent terms per dependent stage (2 and 4 measured slower: registers)
 // One candidate point against the tile's 16 nodes (46 fp64-pipe + 16 FP32-pipe instructions).
 __device__ __forceinline__ void accumulate_point(const double2 p, const double gx0, const double gy0,
                                                  const double inv_h, const double c1, const double c2,
@@ -543,22 +542,12 @@ __device__ __forceinline__ void accumulate_point(const double2 p, const double g
     const double w[kTile] = {-uy0, -v1, -v2, -v3};
     const double q[kTile] = {uy0, v1, v2, v3};
 #pragma unroll
-    for (int i = 0; i < kTile; i += kStageRows) {
-        // kStageRows*4 independent terms per stage: each dependent stage starts only after that many
-        // issues, which covers the fp64 pipe's latency without leaning on other warps
-        double t[kStageRows][kTile], m[kStageRows][kTile];
+    for (int i = 0; i < kTile; ++i) {
+        double t[kTile];
 #pragma unroll
-        for (int ii = 0; ii < kStageRows; ++ii)
+        for (int j = 0; j < kTile; ++j) t[j] = fma(w[j], q[j], a[i]);
 #pragma unroll
-            for (int j = 0; j < kTile; ++j) t[ii][j] = fma(w[j], q[j], a[i + ii]);
-#pragma unroll
-        for (int ii = 0; ii < kStageRows; ++ii)
-#pragma unroll
-            for (int j = 0; j < kTile; ++j) m[ii][j] = clamp_mask(t[ii][j]);
-#pragma unroll
-        for (int ii = 0; ii < kStageRows; ++ii)
-#pragma unroll
-            for (int j = 0; j < kTile; ++j) acc[i + ii][j] = fma(t[ii][j], m[ii][j], acc[i + ii][j]);
+        for (int j = 0; j < kTile; ++j) acc[i][j] += clamp_nonneg(t[j]);
     }
 }
 
@@ -673,7 +662,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         double P = 0.0;
         if (part == 0 && ix < g.R && iy < g.R) {
-            const double d = (S * kAccUnscale) * (g.knorm / (double)sd.n);   // exp(logsum + log_knorm - log N)
+            const double d = unresidue(S) * (g.knorm / (double)sd.n);   // exp(logsum + log_knorm - log N)
             P = gamma_eps(d, g);
             dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
             pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
@@ -741,7 +730,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         double P = 0.0;
         if (half == 0 && ix < g.R && iy < g.R) {
-            const double d = (S * kAccUnscale) * (g.knorm / (double)n_set);
+            const double d = unresidue(S) * (g.knorm / (double)n_set);
             P = gamma_eps(d, g);
             dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
             pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
