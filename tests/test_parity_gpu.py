@@ -385,3 +385,46 @@ def test_work_balanced_row_bands(pk, ko):
     js = np.sqrt((L + Rr) / 2.0)
     assert js == pytest.approx(full, rel=1e-12)
     assert rel(js, ko.discrepancy(a, b, 0.25, 0.0, resolution=R)) < JS_RTOL_EXPECT
+
+
+def _fork_child(q):
+    import numpy as _np
+
+    import poppunk_mod_b200 as _pk
+    from oracle import workloads as _wl
+
+    a, b = _wl.g1_inputs()
+    q.put(float(_pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0)))
+
+
+def test_fork_after_import_before_first_use(golden):
+    """ELFI's multiprocessing client and the scripts' Pools fork AFTER importing KDE_distance
+    (poppunk_mod.py:427-429, pairwise_2D_distance.py:116): loading the library must not touch CUDA, so a
+    forked worker can create its own context.  Runs in a fresh interpreter so that no CUDA context exists
+    in the forking process."""
+    import subprocess
+    import sys
+    import textwrap
+
+    from conftest import ROOT
+
+    code = textwrap.dedent(f"""
+        import sys, multiprocessing as mp
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {ROOT + '/tests'!r})
+        import poppunk_mod_b200 as pk            # dlopen only
+        pk._native.lib()
+        from test_parity_gpu import _fork_child
+        ctx = mp.get_context("fork")
+        q = ctx.Queue()
+        ps = [ctx.Process(target=_fork_child, args=(q,)) for _ in range(2)]
+        [p.start() for p in ps]
+        vals = [q.get(timeout=120) for _ in ps]
+        [p.join(60) for p in ps]
+        assert all(p.exitcode == 0 for p in ps), [p.exitcode for p in ps]
+        print(vals[0], vals[1])
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    v0, v1 = (float(x) for x in out.stdout.split()[-2:])
+    want = golden["cases"]["G1_g025"]["oracle"]
+    assert v0 == v1 and abs(v0 - want) <= 1e-10 * want
