@@ -320,6 +320,19 @@ def main():
     e2e_value = world * e2e_steps * BATCH / float(t.item())
     assert np.all(np.isfinite(res)) and np.all(res > 0) and np.all(res < 0.8326)
 
+    # ---- one long sweep call (config C4 shape: many parameter sets per call, pipeline fill amortised) ---
+    sweep_n = 512
+    sweep_list = [h_sims[k % len(h_sims)] for k in range(sweep_n)]
+    pk.KDE_JS_divergence_batch(h_target, sweep_list[:64], gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
+    barrier()
+    t0 = time.perf_counter()
+    pk.KDE_JS_divergence_batch(h_target, sweep_list, gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_sweep = world * sweep_n / float(t.item())
+
     # ---- single-call latency (BOLFI acquisition phase: batch of one) ------------------------------
     lat = []
     for s in range(8):
@@ -446,6 +459,8 @@ def main():
         "gpu_launches": int(n_launch.value),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "e2e_sweep_call": {"value": e2e_sweep, "unit": UNIT, "evals_per_call": sweep_n,
+                           "note": "one KDE_JS_divergence_batch call over 512 pinned host sims (H2D inside)"},
         "single_call_latency_ms": single_ms,
         "dense_fp32": dense,
         "js_sample": [float(x) for x in js_last[:3]],

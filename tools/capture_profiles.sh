@@ -1,0 +1,15 @@
+#!/bin/bash
+# Run ON the GPU box (through gpurun): bench lines + ncu launch list + ncu full captures -> gpurun_out/.
+# usage: tools/capture_profiles.sh <tag>
+set -u
+TAG="${1:-rX}"
+OUT=gpurun_out
+python bench.py > $OUT/bench_${TAG}_n1.json 2> $OUT/bench_${TAG}_n1.err || exit 1
+python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err
+CMD="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
+$CMD > $OUT/plain_${TAG}.log 2>&1 || exit 2
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_l.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_density_binned -s 10 -c 2 -o $OUT/prof_binned_${TAG} $CMD > $OUT/ncu_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_density_dense32 -c 1 -o $OUT/prof_dense32_${TAG} $CMD > $OUT/ncu_d.log 2>&1
+ncu --set full --clock-control none -k regex:"k_minmax|k_scale_count|k_scan|k_place|k_tile_classify|k_set_totals|k_js" -s 21 -c 7 -o $OUT/prof_small_${TAG} $CMD > $OUT/ncu_s.log 2>&1
+tail -1 $OUT/ncu_b.log $OUT/ncu_d.log $OUT/ncu_s.log
