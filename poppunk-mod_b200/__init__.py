@@ -8,5 +8,6 @@ from . import KDE_distance  # noqa: F401
 from .KDE_distance import (KDE_JS_divergence, KDE_JS_divergence_batch, KDE_JS_divergence_pairs,  # noqa: F401
                            KDE_KL_divergence, default_device, get_grid, kde_density, scale_KDE)
 from . import _native  # noqa: F401
+from . import distributed, simulator, sweeps  # noqa: F401
 
 __version__ = "0.1.0"

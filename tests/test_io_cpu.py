@@ -70,3 +70,17 @@ def test_reader_errors(nat, tmp_path):
 def test_reference_fixture_files(nat):
     f = "/root/reference/distances/2_column/Escherichia_coli.txt"
     np.testing.assert_array_equal(nat.TsvTable(f, pinned=False).array, np.loadtxt(f, delimiter="\t"))
+
+
+def test_gene_frequency_classes_and_log_discrepancy():
+    from poppunk_mod_b200 import simulator as sim
+
+    X = np.array([0.0, 0.0, 0.01, 0.04, 0.5, 0.95, 0.99, 1.0])
+    fc, fi, fr = sim.calculate_gene_freqs(X, core_threshold=0.95, rare_threshold=0.05)
+    assert (fc, fi, fr) == (3 / 6, 1 / 6, 2 / 6)                # poppunk_mod.py:285-291 on the 6 present genes
+    s = np.array([[0.3, 0.5, 0.2, 0.3], [0.0, 0.4, 0.3, 0.3]])
+    o = np.array([0.0, 0.4, 0.3, 0.3])
+    with np.errstate(divide="ignore"):
+        d = sim.log_euclidean_discrepancy(s, o)
+    assert d[0] == pytest.approx(np.log(np.sqrt(0.09 + 0.01 + 0.01)))
+    assert d[1] == -np.inf

@@ -428,3 +428,48 @@ def test_fork_after_import_before_first_use(golden):
     v0, v1 = (float(x) for x in out.stdout.split()[-2:])
     want = golden["cases"]["G1_g025"]["oracle"]
     assert v0 == v1 and abs(v0 - want) <= 1e-10 * want
+
+
+def test_sweep_drivers_and_simulator_summary(pk, ko, tmp_path):
+    """scripts/pairwise_2D_distance.py, scripts/distance_to_gridsearch.py and process_result on files."""
+    import math
+
+    from oracle import workloads as wl
+    from poppunk_mod_b200 import simulator, sweeps
+
+    sets = [wl.sim_batch_member(s, n=2000 + 300 * s) for s in range(4)]
+    paths = []
+    for i, a in enumerate(sets):
+        p = tmp_path / f"species{i}.txt"
+        if i % 2:      # 4-column PopPUNK table: two id columns first
+            p.write_text("".join(f"A{k}\tB{k}\t{x!r}\t{y!r}\n" for k, (x, y) in enumerate(a)))
+        else:
+            np.savetxt(p, a, delimiter="\t", fmt="%.17g")
+        paths.append(str(p))
+    rows = sweeps.pairwise_distances(paths)
+    assert [(r[0], r[1]) for r in rows] == [(paths[i], paths[j]) for i in range(4) for j in range(i + 1, 4)]
+    k = 0
+    for i in range(4):
+        for j in range(i + 1, 4):
+            assert rel(rows[k][2], ko.discrepancy(sets[i], sets[j], 0.25, 0.0)) < JS_RTOL_EXPECT
+            assert rows[k][3] == (sets[j][:, 0].min(), sets[j][:, 0].max(), sets[j][:, 1].min(), sets[j][:, 1].max())
+            k += 1
+    with_fracs = [(paths[0], 0.3, 0.2, 0.5), (paths[1], 0.25, 0.25, 0.5)]
+    d = sweeps.pairwise_distances(with_fracs)[0][2]
+    js = ko.discrepancy(sets[0], sets[1], 0.25, 0.0)
+    assert d == pytest.approx(math.dist((0, 0.3, 0.2, 0.5), (js, 0.25, 0.25, 0.5)), rel=1e-12)
+
+    # grid search: reference = set 0, candidates = the others; the reference's call is (1e-12, log=True)
+    best, dists = sweeps.gridsearch_best(paths[0], paths[1:], chunk=2)
+    want = [ko.discrepancy(sets[0], s, 1e-12, 1e-12, True) for s in sets[1:]]
+    np.testing.assert_allclose(dists, want, rtol=1e-9)
+    assert best[0] == paths[1 + int(np.argmin(want))]
+    none, _ = sweeps.gridsearch_best(paths[0], paths[1:], core_min_bounds=[9, 10], core_max_bounds=[9, 10])
+    assert none == (None, 1.0)
+
+    freqs = np.array([0.0, 0.02, 0.5, 0.97, 1.0])
+    vec = simulator.process_result(paths[2], freqs, paths[0], 0.25, 0.95, 0.05)
+    assert rel(vec[0], ko.discrepancy(sets[0][1:] if False else sets[0], sets[2], 0.25, 0.0)) < JS_RTOL_EXPECT
+    assert tuple(vec[1:]) == (2 / 4, 1 / 4, 1 / 4)
+    batch = simulator.process_results_batch([paths[2], sets[3]], [freqs, freqs], sets[0], 0.25, 0.95, 0.05)
+    assert batch.shape == (2, 4) and batch[0, 0] == vec[0]
