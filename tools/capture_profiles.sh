@@ -12,4 +12,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:k_density_binned -s 10 -c 2 -o $OUT/prof_binned_${TAG} $CMD > $OUT/ncu_b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_density_dense32 -c 1 -o $OUT/prof_dense32_${TAG} $CMD > $OUT/ncu_d.log 2>&1
 ncu --set full --clock-control none -k regex:"k_minmax|k_scale_count|k_scan|k_place|k_tile_classify|k_set_totals|k_js" -s 21 -c 7 -o $OUT/prof_small_${TAG} $CMD > $OUT/ncu_s.log 2>&1
-tail -1 $OUT/ncu_b.log $OUT/ncu_d.log $OUT/ncu_s.log
+for f in ncu_b ncu_d ncu_s; do tail -n 1 $OUT/$f.log; done
