@@ -224,11 +224,12 @@ struct WaveIO {
 
 int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
     // Points per warp sub-chunk.  Every sort block pays a fixed cost for its C*C counters (zeroing, prefix,
-    // histogram write-out), so chunks grow with the wave until the launch still has ~4 blocks per SM.
+    // histogram write-out), so chunks grow with the wave until the launch still has ~8 blocks per SM (more than one
+    // full wave of resident blocks: the tail of a single partial wave cost 20 %).
     int nmax = 0;
     int64_t total = 0;
     for (int s = 0; s < wd.n_sets; ++s) { nmax = std::max(nmax, wd.set[s].n); total += wd.set[s].n; }
-    int64_t per_warp = total / ((int64_t)4 * sm_count * kSortWarps);
+    int64_t per_warp = total / ((int64_t)8 * sm_count * kSortWarps);
     chw = (int)std::min<int64_t>(std::max<int64_t>((per_warp + 31) / 32 * 32, 512), kMaxChw);
     nb_max = std::max(1, (int)(((int64_t)nmax + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)));
     return KDEJS_OK;
@@ -333,7 +334,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         const unsigned capacity = (unsigned)tiles * (unsigned)n_sets;
         if (tiles > 0) {
             KTimer t(c, 6, st);
-            k_tile_classify<<<dim3((tiles + 255) / 256, n_sets), 256, 0, st>>>(
+            k_tile_classify<<<dim3((tiles + 31) / 32, n_sets), 256, 0, st>>>(
                 wd, g, sl.cellstart.as<uint32_t>(), sl.dens.as<double>(), sl.pz.as<double>(),
                 sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity,
                 c.prof_on ? c.d_work : nullptr);

@@ -145,19 +145,30 @@ k_minmax(const __grid_constant__ WaveDesc wd, int log_flag, double eps,
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last && threadIdx.x < 32) {          // warp 0 of the last block folds the block partials
         __threadfence();
         const volatile RawStat *vp = part + (size_t)r * gridDim.x;
-        RawStat a;
-        a.mn[0] = vp[0].mn[0]; a.mx[0] = vp[0].mx[0]; a.mn[1] = vp[0].mn[1]; a.mx[1] = vp[0].mx[1];
-        a.flags = vp[0].flags; a.pad = 0;
-        for (unsigned i = 1; i < gridDim.x; ++i) {
-            a.mn[0] = fmin(a.mn[0], vp[i].mn[0]); a.mx[0] = fmax(a.mx[0], vp[i].mx[0]);
-            a.mn[1] = fmin(a.mn[1], vp[i].mn[1]); a.mx[1] = fmax(a.mx[1], vp[i].mx[1]);
-            a.flags |= vp[i].flags;
+        double a0 = INF, b0 = -INF, a1 = INF, b1 = -INF;
+        int fl = 0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) {
+            a0 = fmin(a0, vp[i].mn[0]); b0 = fmax(b0, vp[i].mx[0]);
+            a1 = fmin(a1, vp[i].mn[1]); b1 = fmax(b1, vp[i].mx[1]);
+            fl |= vp[i].flags;
         }
-        out[r] = a;
-        ticket[r] = 0;     // self-resetting: the next wave needs no memset
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 = fmin(a0, __shfl_xor_sync(0xffffffffu, a0, o));
+            b0 = fmax(b0, __shfl_xor_sync(0xffffffffu, b0, o));
+            a1 = fmin(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+            b1 = fmax(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+            fl |= __shfl_xor_sync(0xffffffffu, fl, o);
+        }
+        if (threadIdx.x == 0) {
+            RawStat a;
+            a.mn[0] = a0; a.mx[0] = b0; a.mn[1] = a1; a.mx[1] = b1; a.flags = fl; a.pad = 0;
+            out[r] = a;
+            ticket[r] = 0;     // self-resetting: the next wave needs no memset
+        }
     }
 }
 
@@ -193,19 +204,6 @@ __device__ __forceinline__ double2 scale_point(double2 v, const Scaler &sc, int 
         if (Y != Y) Y = 0.0;
     }
     return make_double2(X, Y);
-}
-
-// Lanes of `act` that hold the same cell id as the caller (ids < 2^12): twelve independent ballots
-// combined with AND -- the same mask __match_any_sync returns, but built from full-rate ALU
-// instructions instead of one long-latency MATCH.
-__device__ __forceinline__ unsigned match_cell(unsigned act, int cell) {
-    unsigned m = act;
-#pragma unroll
-    for (int b = 0; b < 12; ++b) {
-        const unsigned bal = __ballot_sync(act, (cell >> b) & 1);
-        m &= ((cell >> b) & 1) ? bal : ~bal;
-    }
-    return m;
 }
 
 // Zero n u16 counters in dynamic shared memory (16-byte aligned) with 128-bit stores.
@@ -269,7 +267,7 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
             int leader = lane;
             unsigned m = 0u;
             if (valid) {
-                m = match_cell(act, cell);
+                m = __match_any_sync(act, cell);      // one MATCH beats twelve ballots here: the kernel is ALU-bound
                 leader = __ffs(m) - 1;
                 if (lane == leader) { before = hw[cell]; hw[cell] = (uint16_t)(before + __popc(m)); }
             }
@@ -434,9 +432,12 @@ __device__ __forceinline__ int tile_class(uint32_t total, int heavy_log2) {
     return lg >= heavy_log2 ? 0 : min(heavy_log2 - lg, kNumClasses - 1);
 }
 
-// k_tile_classify: one thread per (tile, set).  Counts the tile's candidate points; a tile with none
-// gets its 16 node values written here (density 0), the others are appended to the work list of
-// their weight class.  The order inside a class is arbitrary and does not affect any result.
+// k_tile_classify: grid (ceil(tiles/32), n_sets), 256 threads = 32 tiles x 8 lanes.  The 8 lanes of a tile
+// fetch its cell-row runs in parallel (one L2 round trip instead of a dependent chain) and add up the
+// candidate count.  A tile with none gets its 16 node values written here (density 0), the others are
+// appended to the work list of their weight class; the order inside a class is arbitrary and does not
+// affect any result.
+constexpr int kClassifyLanes = 8;
 __global__ void __launch_bounds__(256)
 k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 const uint32_t *__restrict__ cellstart, double *__restrict__ dens,
@@ -444,43 +445,50 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 unsigned *__restrict__ counters, unsigned capacity,
                 unsigned long long *__restrict__ work_counter) {
     const int ntl = (g.tile_row_end - g.tile_row_begin) * g.NT;
-    const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tl = blockIdx.x * (blockDim.x / kClassifyLanes) + threadIdx.x / kClassifyLanes;
+    const int sub = threadIdx.x % kClassifyLanes;
     const int set = blockIdx.y;
+    const bool live = tl < ntl;
+    const int tx = g.tile_row_begin + (live ? tl / g.NT : 0), ty = live ? tl % g.NT : 0;
+    const int ix0 = tx * kTile, iy0 = ty * kTile;
     uint32_t total = 0u;
-    if (tl < ntl) {
-        const int tx = g.tile_row_begin + tl / g.NT, ty = tl % g.NT;
-        const int ix0 = tx * kTile, iy0 = ty * kTile;
+    if (live) {
         const TileCells tc = tile_cells(g, ix0, iy0);
         const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
-#pragma unroll 4
-        for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy) {     // independent loads: keep several rows in flight
+        for (int cy = tc.cy_lo + sub; cy <= tc.cy_hi; cy += kClassifyLanes) {
             uint32_t s0, l0;
             tile_row_run(g, tc, cs, cy, s0, l0);
             total += l0;
         }
+    }
+    total += __shfl_xor_sync(0xffffffffu, total, 1);
+    total += __shfl_xor_sync(0xffffffffu, total, 2);
+    total += __shfl_xor_sync(0xffffffffu, total, 4);
+    if (live) {
         const int tile = tx * g.NT + ty;
         if (total == 0u) {
             const double P0 = gamma_eps(0.0, g);
-            double s = 0.0;
-            for (int i = 0; i < kTile; ++i)
-                for (int j = 0; j < kTile; ++j) {
-                    const int ix = ix0 + i, iy = iy0 + j;
-                    if (ix < g.R && iy < g.R) {
-                        const size_t k = (size_t)set * g.R * g.R + (size_t)ix * g.R + iy;
-                        dens[k] = 0.0;
-                        pz[k] = P0;
-                        s += P0;
-                    }
+#pragma unroll
+            for (int k = sub; k < kTile * kTile; k += kClassifyLanes) {      // two nodes per lane
+                const int ix = ix0 + k / kTile, iy = iy0 + k % kTile;
+                if (ix < g.R && iy < g.R) {
+                    const size_t n = (size_t)set * g.R * g.R + (size_t)ix * g.R + iy;
+                    dens[n] = 0.0;
+                    pz[n] = P0;
                 }
-            tilesum[(size_t)set * g.NT * g.NT + tile] = s;
-        } else {
+            }
+            if (sub == 0) {
+                const int nv = min(kTile, g.R - ix0) * min(kTile, g.R - iy0);
+                tilesum[(size_t)set * g.NT * g.NT + tile] = P0 * (double)nv;
+            }
+        } else if (sub == 0) {
             const int cls = tile_class(total, g.heavy_log2);
             const unsigned slot = atomicAdd(&counters[cls], 1u);
             worklist[(size_t)cls * capacity + slot] = ((uint32_t)set << 24) | (uint32_t)tile;
         }
     }
     if (work_counter) {
-        unsigned long long t = total;
+        unsigned long long t = (live && sub == 0) ? total : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if ((threadIdx.x & 31) == 0 && t)
@@ -940,18 +948,22 @@ k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
+    if (s_last && threadIdx.x < 32) {          // warp 0 of the last block folds the block partials, fixed shape
         __threadfence();
         const volatile double *vp = jspart + (size_t)item * gridDim.x * 2;
         double L = 0.0, Rr = 0.0;
-        for (unsigned i = 0; i < gridDim.x; ++i) { L += vp[2 * i]; Rr += vp[2 * i + 1]; }
-        const int bad = (rstat[wd.set[s0].rs_self].flags | rstat[wd.set[s0].rs_other].flags) & 1;
-        if (out_lr) { out_lr[0] = L; out_lr[1] = Rr; }
-        if (out_norm) { out_norm[0] = tp; out_norm[1] = tq; }
-        if (out_js) out_js[item_base + item] = bad ? __longlong_as_double(0x7ff8000000000000LL)
-                                                   : sqrt((L + Rr) / 2.0);
-        if (out_status) out_status[item_base + item] = bad ? 3 : 0;
-        ticket[item] = 0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) { L += vp[2 * i]; Rr += vp[2 * i + 1]; }
+        L = warp_sum(L);
+        Rr = warp_sum(Rr);
+        if (threadIdx.x == 0) {
+            const int bad = (rstat[wd.set[s0].rs_self].flags | rstat[wd.set[s0].rs_other].flags) & 1;
+            if (out_lr) { out_lr[0] = L; out_lr[1] = Rr; }
+            if (out_norm) { out_norm[0] = tp; out_norm[1] = tq; }
+            if (out_js) out_js[item_base + item] = bad ? __longlong_as_double(0x7ff8000000000000LL)
+                                                       : sqrt((L + Rr) / 2.0);
+            if (out_status) out_status[item_base + item] = bad ? 3 : 0;
+            ticket[item] = 0;
+        }
     }
 }
 

@@ -442,7 +442,7 @@ def test_sweep_drivers_and_simulator_summary(pk, ko, tmp_path):
     for i, a in enumerate(sets):
         p = tmp_path / f"species{i}.txt"
         if i % 2:      # 4-column PopPUNK table: two id columns first
-            p.write_text("".join(f"A{k}\tB{k}\t{x!r}\t{y!r}\n" for k, (x, y) in enumerate(a)))
+            p.write_text("".join(f"A{k}\tB{k}\t{float(x)!r}\t{float(y)!r}\n" for k, (x, y) in enumerate(a)))
         else:
             np.savetxt(p, a, delimiter="\t", fmt="%.17g")
         paths.append(str(p))
