@@ -224,12 +224,12 @@ struct WaveIO {
 
 int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
     // Points per warp sub-chunk.  Every sort block pays a fixed cost for its C*C counters (zeroing, prefix,
-    // histogram write-out), so chunks grow with the wave until the launch still has ~8 blocks per SM (more than one
-    // full wave of resident blocks: the tail of a single partial wave cost 20 %).
+    // histogram write-out), so chunks grow with the wave until the launch still has ~4 blocks per SM
+    // (8 per SM was measured: k_scale_count -4 %, k_scan +75 %).
     int nmax = 0;
     int64_t total = 0;
     for (int s = 0; s < wd.n_sets; ++s) { nmax = std::max(nmax, wd.set[s].n); total += wd.set[s].n; }
-    int64_t per_warp = total / ((int64_t)8 * sm_count * kSortWarps);
+    int64_t per_warp = total / ((int64_t)4 * sm_count * kSortWarps);
     chw = (int)std::min<int64_t>(std::max<int64_t>((per_warp + 31) / 32 * 32, 512), kMaxChw);
     nb_max = std::max(1, (int)(((int64_t)nmax + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)));
     return KDEJS_OK;
