@@ -39,7 +39,8 @@ BATCH = 64
 POOL = 192          # resident sims per GPU: 192 x 1.6 MB = 307 MB > 126 MB L2
 METRIC = "kde_discrepancy_evals_per_sec"
 UNIT = "evals/s"
-WORKLOAD = ("C2 single discrepancy 100k sim pairs vs 100k target pairs, 256x256 grid, gamma=0.25, eps=0, "
+def workload():
+    return (f"C2 single discrepancy 100k sim pairs vs 100k target pairs, {RES}x{RES} grid, gamma=0.25, eps=0, "
             f"epanechnikov h=0.03; one step = {BATCH} such evaluations per GPU (distinct sims, one target)")
 
 
@@ -177,7 +178,7 @@ def run_reference(args, real_stdout):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
+        "config": {"workload": workload(), "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
                    "evals_per_step": procs},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -209,8 +210,11 @@ def main():
     ap.add_argument("--impl", default="kdejs", choices=["kdejs", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--algo", default="binned", choices=["binned", "dense", "dense64"])
+    ap.add_argument("--resolution", type=int, default=RES,
+                    help="grid nodes per axis (headline: 256; the reference's hard-coded default is 100)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kdejs" else args.warmup
+    globals()["RES"] = args.resolution
     real_stdout = _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args, real_stdout)
@@ -447,7 +451,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
+        "config": {"workload": workload(), "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
                    "evals_per_step_per_gpu": BATCH, "algo": args.algo,
                    "l2": f"resident pool of {POOL} sims ({POOL * N_PAIRS * 16 / 1e6:.0f} MB) rotated: inputs "
                          "larger than the 126 MB L2 between reuse"},
