@@ -156,7 +156,7 @@ const char *kdejs_io_last_error(void);
  * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence, 6 tile classification.
  * Reading synchronises. */
 #define KDEJS_NUM_KERNELS 7
-int kdejs_profile_enable(int device, int on);
+int kdejs_profile_enable(int device, int on);   /* 0 off, 1 every kernel, 2 the density kernel only */
 int kdejs_profile_read(int device, int which, double *ms_total, int64_t *launches);
 int kdejs_profile_reset(int device);
 /* Kernels launched by this library on `device` since init / last reset. */

@@ -76,6 +76,7 @@ struct Ctx {
     std::mutex mu;
     // measurement
     bool prof_on = false;
+    int prof_mode = 0;                 // 1: every kernel, 2: the density kernel only
     double prof_ms[KDEJS_NUM_KERNELS] = {0};
     int64_t prof_n[KDEJS_NUM_KERNELS] = {0};
     std::vector<Pending> pending;
@@ -131,8 +132,10 @@ int get_ctx(int device, Ctx **out) {
 
 struct KTimer {       // CUDA-event bracket around one launch on the launching stream
     Ctx &c; int kind; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool active = false;
     KTimer(Ctx &c_, int kind_, cudaStream_t s_) : c(c_), kind(kind_), s(s_) {
-        if (!c.prof_on) return;
+        active = c.prof_on && (c.prof_mode == 1 || kind == 4);
+        if (!active) return;
         for (cudaEvent_t *e : {&e0, &e1}) {
             if (!c.free_events.empty()) { *e = c.free_events.back(); c.free_events.pop_back(); }
             else cudaEventCreate(e);
@@ -141,7 +144,7 @@ struct KTimer {       // CUDA-event bracket around one launch on the launching s
     }
     ~KTimer() {
         c.launches++;
-        if (!c.prof_on) return;
+        if (!active) return;
         cudaEventRecord(e1, s);
         c.pending.push_back({kind, e0, e1});
     }
@@ -649,7 +652,8 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     const size_t sim_stride = ((size_t)nmax * 16 + 255) / 256 * 256;
     const int ring_items = (int)std::min<int64_t>(B, std::max<int64_t>(cap, (int64_t)(2.0e9 / (double)sim_stride)));
     OKR(c->sim_ring.ensure(sim_stride * (size_t)ring_items));
-    const int wave_size = std::min(cap, 16);
+    int wave_size = std::min(cap, 16);
+    if (const char *e = getenv("KDEJS_HOST_WAVE")) wave_size = std::max(1, std::min(cap, atoi(e)));
     std::vector<int> wave_of_item(B);
     std::vector<cudaEvent_t> ev_copied, ev_done;
     auto new_event = [&](cudaEvent_t &e) -> int {
@@ -909,6 +913,7 @@ int kdejs_profile_enable(int device, int on) {
     std::lock_guard<std::mutex> lk(c->mu);
     OKR(resolve_pending(*c));
     c->prof_on = on != 0;
+    c->prof_mode = on;
     return KDEJS_OK;
 }
 
