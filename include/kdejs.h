@@ -165,7 +165,9 @@ int kdejs_launch_count(int device, int64_t *count, int reset);
  * kernel evaluations executed; in_support is filled only by the CPU-side estimate (0 here). */
 int kdejs_work_counters(int device, double *pair_tests, int reset);
 /* Issue-rate microbenchmarks used as roofline denominators.  which: 0 FFMA fp32,
- * 1 DFMA fp64, 2 packed FFMA2 (f32x2).  Returns achieved TFLOP/s (2 flop per lane-FMA). */
+ * 1 DFMA fp64, 2 packed FFMA2 (f32x2), 3 / 4 DFMA interleaved with one / two independent ALU-pipe
+ * instructions per DFMA (reports the DFMA rate only: does a co-issued instruction slow the fp64 pipe?).
+ * Returns achieved TFLOP/s (2 flop per lane-FMA). */
 int kdejs_peak_flops(int device, int which, double *tflops, double *sm_clock_mhz);
 
 #ifdef __cplusplus

@@ -959,7 +959,7 @@ int kdejs_work_counters(int device, double *pair_tests, int reset) {
 }
 
 int kdejs_peak_flops(int device, int which, double *tflops, double *sm_clock_mhz) {
-    if (which < 0 || which > 2 || !tflops) return fail(KDEJS_ERR_ARG, "bad argument");
+    if (which < 0 || which > 4 || !tflops) return fail(KDEJS_ERR_ARG, "bad argument");
     Ctx *c;
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
@@ -973,7 +973,9 @@ int kdejs_peak_flops(int device, int which, double *tflops, double *sm_clock_mhz
         CU(cudaEventRecord(e0, c->s_compute));
         if (which == 0) k_peak<0><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
         else if (which == 1) k_peak<1><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
-        else k_peak<2><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
+        else if (which == 2) k_peak<2><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
+        else if (which == 3) k_peak<3><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
+        else k_peak<4><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
         CU(cudaEventRecord(e1, c->s_compute));
         CU(cudaEventSynchronize(e1));
         float ms = 0.f;

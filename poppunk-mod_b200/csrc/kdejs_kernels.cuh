@@ -1007,6 +1007,28 @@ __global__ void __launch_bounds__(256) k_peak(int iters, float *sink_f, double *
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += a[i];
         if (s == 12345.678) sink_d[0] = s;
+    } else if (WHICH == 3 || WHICH == 4) {
+        // DFMA stream with WHICH==3: one, WHICH==4: two independent FFMA (full-rate FP32 pipe) per DFMA.
+        // Measured on B200: 36.5 TFLOP/s alone, 34.7 with one FFMA per DFMA, 22.4 with two -- i.e. the SMSP
+        // issues one instruction per cycle and a second instruction fits beside each 2-cycle fp64 issue for
+        // free; an fp64-bound loop therefore tolerates about one non-fp64 instruction per fp64 instruction.
+        double a[8];
+        float f[8], h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] = 1.0 + threadIdx.x * 1e-6 + i; f[i] = 1.0f + i; h[i] = 2.0f + i; }
+        const double b = 0.999999, c = 1e-7;
+        const float bf = 0.999999f, cf = 1e-7f;
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = fma(a[i], b, c);
+                f[i] = fmaf(f[i], bf, cf);
+                if (WHICH == 4) h[i] = fmaf(h[i], bf, cf);
+            }
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += a[i] + f[i] + h[i];
+        if (s == 12345.678) sink_d[0] = s;
     } else {
         unsigned long long a[8];
 #pragma unroll
