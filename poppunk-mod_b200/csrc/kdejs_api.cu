@@ -245,7 +245,11 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     const int n_sets = wd.n_sets, n_items = n_sets / 2;
     const size_t G = (size_t)p.R * p.R;
     int64_t P = 0;
-    for (int s = 0; s < n_sets; ++s) { wd.set[s].off = P; P += wd.set[s].n; }
+    for (int s = 0; s < n_sets; ++s) {
+        wd.set[s].off = P;
+        P += wd.set[s].n;
+        wd.set[s].knorm_over_n = g.knorm / (double)wd.set[s].n;
+    }
     int chw, nb_max;
     sort_shape(wd, c.sm_count, chw, nb_max);
     for (int s = 0; s < n_sets; ++s)
@@ -457,8 +461,8 @@ int run_pairs_dev(Ctx &c, cudaStream_t st, int slot_idx, const Params &p, const 
             const int a = ia[i + items], b = ib[i + items];
             const int la = local(a), lb = local(b);
             SetDesc &s0 = wd.set[2 * items], &s1 = wd.set[2 * items + 1];
-            s0.rs_self = la; s0.rs_other = lb; s0.n = (int32_t)pool[a].n; s0.item = items;
-            s1.rs_self = lb; s1.rs_other = la; s1.n = (int32_t)pool[b].n; s1.item = items;
+            s0.rs_self = la; s0.rs_other = lb; s0.n = (int32_t)pool[a].n;
+            s1.rs_self = lb; s1.rs_other = la; s1.n = (int32_t)pool[b].n;
             ++items;
         }
         wd.n_raw = local_of_global_n;
@@ -751,7 +755,7 @@ int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, dou
     memset(&wd, 0, sizeof wd);
     wd.raw[0] = RawSet{(const double *)c->pool_raw.p, n};
     wd.n_raw = 1; wd.n_sets = 1;
-    wd.set[0].rs_self = 0; wd.set[0].rs_other = 0; wd.set[0].n = (int32_t)n; wd.set[0].item = 0;
+    wd.set[0].rs_self = 0; wd.set[0].rs_other = 0; wd.set[0].n = (int32_t)n;
     WaveIO io;
     io.density_only = true; io.identity_scaler = true;
     OKR(run_wave(*c, c->slot[0], st, p, g, wd, io));

@@ -43,7 +43,7 @@ struct RawSet {            // a point set as the caller gave it: (n,2) interleav
 struct SetDesc {           // one KDE to build: `rs_self` scaled jointly with `rs_other`
     int32_t rs_self, rs_other, n, nb;   // nb = blocks that own a chunk of it in the sort
     int64_t off;                        // first point in the wave's scaled/sorted arrays
-    int32_t item, pad;
+    double knorm_over_n;                // kernel normaliser / n: density = sum * knorm_over_n
 };
 struct WaveDesc {          // passed by value as a __grid_constant__ kernel parameter (< 4 KB)
     RawSet raw[kMaxWaveSets];
@@ -670,7 +670,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         double P = 0.0;
         if (part == 0 && ix < g.R && iy < g.R) {
-            const double d = unresidue(S) * (g.knorm / (double)sd.n);   // exp(logsum + log_knorm - log N)
+            const double d = unresidue(S) * sd.knorm_over_n;   // exp(logsum + log_knorm - log N)
             P = gamma_eps(d, g);
             dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
             pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
@@ -695,7 +695,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         if (item >= nB) break;
         const uint32_t entry = worklist_entry(worklist, capacity, item, s_cnt);
         const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
-        const int n_set = wd.set[set].n;
+        const double knorm_over_n = wd.set[set].knorm_over_n;
         const double2 *__restrict__ pts = sorted + wd.set[set].off;
         const int tx = tile / g.NT, ty = tile % g.NT;
         const int ix0 = tx * kTile, iy0 = ty * kTile;
@@ -738,7 +738,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         double P = 0.0;
         if (half == 0 && ix < g.R && iy < g.R) {
-            const double d = unresidue(S) * (g.knorm / (double)n_set);
+            const double d = unresidue(S) * knorm_over_n;
             P = gamma_eps(d, g);
             dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
             pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
@@ -887,7 +887,7 @@ k_dense_finish(const __grid_constant__ WaveDesc wd, const GridGeom g, const doub
     if (k < G) {
         double S = 0.0;
         for (int s = 0; s < nslices; ++s) S += partial[((size_t)s * wd.n_sets + set) * G + k];
-        const double d = S * (g.knorm / (double)wd.set[set].n);
+        const double d = S * wd.set[set].knorm_over_n;
         P = gamma_eps(d, g);
         dens[(size_t)set * G + k] = d;
         pz[(size_t)set * G + k] = P;
