@@ -473,3 +473,19 @@ def test_sweep_drivers_and_simulator_summary(pk, ko, tmp_path):
     assert tuple(vec[1:]) == (2 / 4, 1 / 4, 1 / 4)
     batch = simulator.process_results_batch([paths[2], sets[3]], [freqs, freqs], sets[0], 0.25, 0.95, 0.05)
     assert batch.shape == (2, 4) and batch[0, 0] == vec[0]
+
+
+def test_large_evaluation_against_oracle(pk, ko):
+    """1 M + 0.7 M pairs on a 512^2 grid (one wave of one, large sort chunks, many heavy tiles) and the
+    chunk-size switch of the sort (kMaxChw) at 3 M points."""
+    from oracle import workloads as wl
+
+    a = wl.synthetic_target(1_000_000, seed=21)
+    b = wl.sim_S(17, 1500, 0.33, n=700_000)
+    got = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=512)
+    want = ko.discrepancy(a, b, 0.25, 0.0, resolution=512)
+    assert rel(got, want) < JS_RTOL_EXPECT
+    big = wl.sim_S(3, 900, 0.4, n=3_000_000)
+    got = pk.KDE_JS_divergence(big, b, gamma=1.0, eps=1e-12, resolution=100)
+    want = ko.discrepancy(big, b, 1.0, 1e-12, resolution=100)
+    assert rel(got, want) < JS_RTOL_EXPECT
