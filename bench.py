@@ -394,6 +394,15 @@ def main():
         "per_kernel_us_per_eval": {k: 1e3 * v[0] / (prof_steps * BATCH) for k, v in prof.items()},
         "per_kernel_note": f"separate pass of {prof_steps} steps with CUDA events around every launch",
     }
+    try:      # DRAM traffic of the dominant kernel from the committed ncu --set full capture (cannot be measured live)
+        with open(os.path.join(ROOT, "profiles", "traffic_r1v.json")) as f:
+            tr = json.load(f)["k_density_binned"]
+        scale = evals_per_launch / tr["evals_per_launch"]
+        roofline["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * scale
+        roofline["traffic_source"] = tr["source"]
+        roofline["traffic_algorithmic_bytes"] = evals_per_launch * (2 * N_PAIRS * 16 + 2 * RES * RES * 16)
+    except (OSError, ValueError, KeyError):
+        pass
     hbm_bytes = (2 * N_PAIRS * 16) * evals_timed     # every input point read once per evaluation
     roofline["hbm_algorithmic_gbs"] = hbm_bytes / (ms_max * 1e-3) / 1e9
     try:                                             # driver-written HBM / bf16 peaks: context only, the path
