@@ -253,8 +253,10 @@ def get_options(argv=None):
 
 def main(argv=None):
     opt = get_options(argv)
-    df1 = np.loadtxt(opt.infile1, delimiter="\t", dtype="float64")
-    df2 = np.loadtxt(opt.infile2, delimiter="\t", dtype="float64")
+    # same values np.loadtxt(..., delimiter='\t') gives (KDE_distance.py:138-139), parsed by the library's
+    # multi-threaded reader straight into pinned memory
+    df1 = nat.TsvTable(opt.infile1, skip_rows=0).array
+    df2 = nat.TsvTable(opt.infile2, skip_rows=0).array
     js = KDE_JS_divergence(df1, df2, gamma=opt.gamma, eps=0.0, log=False, outplot=opt.plot_outpref,
                            resolution=opt.resolution)
     print(f"js_distance_no_eps: {js}")

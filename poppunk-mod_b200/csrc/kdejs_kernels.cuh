@@ -68,9 +68,9 @@ __device__ __forceinline__ double pre_transform(double v, int log_flag, double e
     return log_flag ? log(v + eps) : v;    // KDE_distance.py:105-106
 }
 __device__ __forceinline__ int cell_of(double x, double x0, double invw, int C) {
-    double f = floor((x - x0) * invw);     // monotone in x: the tile side below relies on it
-    f = fmin(fmax(f, 0.0), (double)(C - 1));
-    return (int)f;
+    // floor, then clamp: monotone in x (the tile side below relies on it).  __double2int_rd saturates for
+    // out-of-range values and maps NaN to 0, so the integer clamp covers every input.
+    return min(max(__double2int_rd((x - x0) * invw), 0), C - 1);
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -489,3 +489,18 @@ def test_large_evaluation_against_oracle(pk, ko):
     got = pk.KDE_JS_divergence(big, b, gamma=1.0, eps=1e-12, resolution=100)
     want = ko.discrepancy(big, b, 1.0, 1e-12, resolution=100)
     assert rel(got, want) < JS_RTOL_EXPECT
+
+
+def test_command_line_entry_point(pk, ko, tmp_path, capsys):
+    """python KDE_distance.py --infile1 A --infile2 B prints `js_distance_no_eps: <value>` (KDE_distance.py:132-144)."""
+    from oracle import workloads as wl
+
+    a, b = wl.ragged_inputs()
+    a = np.nan_to_num(a, nan=0.001)
+    b = np.nan_to_num(b, nan=0.2)
+    np.savetxt(tmp_path / "a.tsv", a, delimiter="\t", fmt="%.17g")
+    np.savetxt(tmp_path / "b.tsv", b, delimiter="\t", fmt="%.17g")
+    pk.KDE_distance.main(["--infile1", str(tmp_path / "a.tsv"), "--infile2", str(tmp_path / "b.tsv")])
+    out = capsys.readouterr().out.strip()
+    assert out.startswith("js_distance_no_eps: ")
+    assert rel(float(out.split(": ")[1]), ko.discrepancy(a, b, 0.25, 0.0)) < JS_RTOL_EXPECT
