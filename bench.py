@@ -395,7 +395,7 @@ def main():
         "per_kernel_note": f"separate pass of {prof_steps} steps with CUDA events around every launch",
     }
     try:      # DRAM traffic of the dominant kernel from the committed ncu --set full capture (cannot be measured live)
-        with open(os.path.join(ROOT, "profiles", "traffic_r1v.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tr = json.load(f)["k_density_binned"]
         scale = evals_per_launch / tr["evals_per_launch"]
         roofline["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * scale
