@@ -113,7 +113,8 @@ int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, dou
  * of the R x R grid (rows = index of column 0).  Phase 1 fits the joint scaler, evaluates
  * the rank's rows and returns its partial normalisers sum(z1**gamma+eps), sum(z2**gamma+eps).
  * The caller all-reduces the two sums (2 doubles) and calls phase 2, which returns the
- * rank's partial (left,right) relative-entropy sums; JS = sqrt((sum left + sum right)/2). */
+ * rank's partial relative-entropy sums; JS = sqrt(max(0, (sum of all out_lr[0] + out_lr[1]) / 2)).  (The library
+ * accumulates rel_entr(p,m)+rel_entr(q,m) per node -- non-negative, well conditioned -- into out_lr[0]; [1] is 0.) */
 int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b, int64_t nb,
                        int resolution, double bandwidth, double gamma, double eps, int log_flag,
                        int kernel, int algo, int row_begin, int row_end, double out_norm[2]);

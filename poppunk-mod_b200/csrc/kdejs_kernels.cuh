@@ -897,6 +897,14 @@ k_dense_finish(const __grid_constant__ WaveDesc wd, const GridGeom g, const doub
 }
 
 // ------------------------------------------------------------------------------------------
+// log(x/m).  Where x and m almost coincide it is taken as log1p((x-m)/m), which keeps the d^2/m term that
+// log(x/m) loses to rounding (x - m is exact there); elsewhere it is the plain log of the quotient (log1p
+// would lose x entirely once x/m < 1e-16, which gamma > 1 produces routinely).
+__device__ __forceinline__ double log_ratio(double x, double m) {
+    const double d = x - m;
+    return (fabs(d) < 0.25 * m) ? log1p(d / m) : log(x / m);
+}
+
 // k_set_totals: grid (n_sets), 256 threads: a set's normaliser = its per-tile partials summed in a
 // fixed order (KDE_distance.py:76, z.sum()).
 __global__ void __launch_bounds__(kJsThreads)
@@ -932,10 +940,16 @@ k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_
         const double p = pz[(size_t)s0 * G + k] / tp;      // z /= z.sum()  KDE_distance.py:76
         const double q = pz[(size_t)s1 * G + k] / tq;
         const double m = (p + q) / 2.0;
-        if (p > 0.0) left += p * log(p / m);               // rel_entr(0, m) = 0
-        if (q > 0.0) right += q * log(q / m);
+        // rel_entr(p,m) + rel_entr(q,m) of ONE node is >= 0 (log-sum inequality) while the two separate sums
+        // scipy forms cancel against each other: for near-identical distributions left ~ -right ~ 1e-3 and
+        // left + right ~ 1e-17, whose sign is rounding noise (sqrt of it can come out NaN).  The per-node sum
+        // goes into `left`; `right` stays 0, so left + right is the well-conditioned total.
+        double node = 0.0;
+        if (p > 0.0) node = p * log_ratio(p, m);           // rel_entr(0, m) = 0
+        if (q > 0.0) node += q * log_ratio(q, m);
+        left += node;
         if (p != p) left = p;                              // NaN normaliser (empty KDE) propagates
-        if (q != q) right = q;
+        if (q != q) left = q;
         if (z_out) { z_out[(size_t)s0 * G + k] = p; z_out[(size_t)s1 * G + k] = q; }
     }
     left = block_sum(left, s_w);
@@ -959,8 +973,9 @@ k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_
             const int bad = (rstat[wd.set[s0].rs_self].flags | rstat[wd.set[s0].rs_other].flags) & 1;
             if (out_lr) { out_lr[0] = L; out_lr[1] = Rr; }
             if (out_norm) { out_norm[0] = tp; out_norm[1] = tq; }
-            if (out_js) out_js[item_base + item] = bad ? __longlong_as_double(0x7ff8000000000000LL)
-                                                       : sqrt((L + Rr) / 2.0);
+            double js2 = (L + Rr) / 2.0;
+            if (js2 < 0.0) js2 = 0.0;          // rounding can leave -1e-20 where the exact value is +1e-20; NaN stays NaN
+            if (out_js) out_js[item_base + item] = bad ? __longlong_as_double(0x7ff8000000000000LL) : sqrt(js2);
             if (out_status) out_status[item_base + item] = bad ? 3 : 0;
             ticket[item] = 0;
         }

@@ -158,5 +158,7 @@ def row_sharded_discrepancy(df1, df2, gamma=1.0, eps=1e-12, log=False, *, resolu
     else:
         lr = np.zeros(2)
     parts = _all_gather_f64(lr, group, dev)
-    left, right = parts[:, 0].sum(), parts[:, 1].sum()
-    return np.float64(np.sqrt((left + right) / 2.0))
+    js2 = (parts[:, 0].sum() + parts[:, 1].sum()) / 2.0
+    if js2 < 0.0:            # rounding noise around an exact 0; NaN compares false and stays NaN
+        js2 = 0.0
+    return np.float64(np.sqrt(js2))

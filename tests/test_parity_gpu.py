@@ -504,3 +504,21 @@ def test_command_line_entry_point(pk, ko, tmp_path, capsys):
     out = capsys.readouterr().out.strip()
     assert out.startswith("js_distance_no_eps: ")
     assert rel(float(out.split(": ")[1]), ko.discrepancy(a, b, 0.25, 0.0)) < JS_RTOL_EXPECT
+
+
+def test_near_identical_distributions_and_wide_dynamic_range(pk, ko):
+    """Two regressions found by tools/stress.py.  (1) Almost identical clouds: scipy's left/right sums cancel to
+    ~1e-17 whose sign is noise (sqrt -> NaN or ~1e-9); the product sums rel_entr per node (>= 0) with log1p where
+    p ~ m and must return a small finite number.  (2) gamma = 3 spreads z over > 16 decades: q/m < 1e-16 must still
+    go through log(q/m)."""
+    rng = np.random.default_rng(33)
+    a = np.column_stack([rng.integers(1, 40, 29575) / 1e4, rng.integers(1, 60, 29575) / 100.0])
+    b = np.column_stack([rng.integers(1, 40, 8512) / 1e4, rng.integers(1, 60, 8512) / 100.0])
+    got = pk.KDE_JS_divergence(a, b, 1e-12, 1e-12, False, resolution=3, bandwidth=0.1)
+    assert np.isfinite(got) and 0.0 <= got < 3e-8
+    from oracle import workloads as wl
+
+    x, y = wl.synthetic_target(28000), wl.sim_S(5, 2000, 0.33, n=14000)
+    for gamma in (3.0, 2.0):
+        got = pk.KDE_JS_divergence(x, y, gamma, 0.0, False, resolution=300)
+        assert rel(got, ko.discrepancy(x, y, gamma, 0.0, False, resolution=300)) < 1e-9
