@@ -46,3 +46,19 @@ for trial in range(n_trials):
         assert err < 1e-9, (trial, n1, n2, R, h, gamma, eps, log, shape, got, want)
 print(f"stress ok: {n_trials} random configurations, worst relative error {worst:.2e}, NaN-consistent cases {nan_cases}, "
       f"{time.time() - t0:.0f} s")
+
+# ---- batches equal singles bitwise; dense fp32 kernel within its tolerance ---------------------------------
+t0 = time.time()
+for trial in range(12):
+    nobs = int(rng.integers(100, 20000))
+    obs = np.abs(rng.normal([0.002, 0.3], [3e-4, 0.05], (nobs, 2)))
+    sims = [np.abs(rng.normal([0.002, 0.3], [rng.uniform(1e-4, 6e-4), rng.uniform(0.01, 0.1)],
+                              (int(rng.integers(1, 15000)), 2))) for _ in range(int(rng.integers(1, 70)))]
+    R = int(rng.choice([50, 100, 128]))
+    out = pk.KDE_JS_divergence_batch(obs, sims, 0.25, 0.0, resolution=R)
+    for i in rng.choice(len(sims), size=min(4, len(sims)), replace=False):
+        single = pk.KDE_JS_divergence(obs, sims[i], 0.25, 0.0, resolution=R)
+        assert out[i] == single, (trial, i, out[i], single)
+        dense = pk.KDE_JS_divergence(obs, sims[i], 0.25, 0.0, resolution=R, algo="dense")
+        assert abs(dense - single) <= 1e-5 * single + 1e-7, (trial, i, dense, single)
+print(f"batch == singles bitwise and dense fp32 within 1e-5 on 12 random batches, {time.time() - t0:.0f} s")
