@@ -205,7 +205,7 @@ def _emit(real_fd, line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="kdejs", choices=["kdejs", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
