@@ -113,13 +113,13 @@ int get_ctx(int device, Ctx **out) {
             for (auto &s : c.slot) {
                 CU(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
                 CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-                OKR(s.tickets.ensure(sizeof(unsigned) * 2 * kMaxWaveSets));   // self-resetting tickets
+                OKR(s.tickets.ensure(sizeof(unsigned) * 3 * kMaxWaveSets));   // self-resetting tickets
                 CU(cudaMemset(s.tickets.p, 0, s.tickets.cap));
             }
             CU(cudaMalloc(&c.d_work, sizeof(unsigned long long)));
             CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
             CU(cudaFuncSetAttribute(k_scale_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSortWarps * kMaxCells * (int)sizeof(uint32_t)));
+                                    kSortWarps * kMaxCells * (int)sizeof(uint16_t)));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned, kDensThreads, 0));
             c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
             c.ready = true;
@@ -188,9 +188,14 @@ GridGeom make_geom(const Params &p) {
     g.inv_h = 1.0 / p.h;
     g.dh = g.step * g.inv_h;
     g.margin = 1e-9 * ext;
-    // culling cells: side >= h/2, at most kMaxRows cell rows per tile, at most 64 per side
+    // culling cells: side >= h/2 and at most 64 per side; on fine grids (a cell would span more than two tiles)
+    // side >= h/4 and up to 128 per side -- the sort's shared-memory histograms grow 4x, which only pays when the
+    // density kernel dominates; always at most kMaxRows cell rows per tile
     double reach = (kTile - 1) * g.step + 2.0 * p.h + 2.0 * g.margin;
-    int C = (int)std::floor(2.0 * ext / p.h);
+    int C = std::min((int)std::floor(2.0 * ext / p.h), 64);
+    if (ext / std::max(C, 1) > 2.0 * kTile * g.step && g.step > 0.0)
+        C = std::min((int)std::floor(4.0 * ext / p.h), kMaxCellsSide);
+    if (const char *e = getenv("KDEJS_CELLS")) C = atoi(e);
     C = std::min(C, (int)std::floor((kMaxRows - 2) * ext / reach));
     C = std::max(1, std::min(C, kMaxCellsSide));
     g.C = C;
@@ -281,6 +286,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
 
     unsigned *tk_minmax = sl.tickets.as<unsigned>();
     unsigned *tk_js = sl.tickets.as<unsigned>() + kMaxWaveSets;
+    unsigned *tk_scan = sl.tickets.as<unsigned>() + 2 * kMaxWaveSets;
 
     if (!io.identity_scaler) {
         KTimer t(c, 0, st);
@@ -289,6 +295,9 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     }
     if (binned) {
         const size_t smem = (size_t)kSortWarps * ncells * sizeof(uint16_t);
+        // one block per set scans <= 4096 cells over a few sort blocks fastest; otherwise one thread per cell
+        static const int force_wide = getenv("KDEJS_SCAN_WIDE") ? atoi(getenv("KDEJS_SCAN_WIDE")) : -1;
+        const bool wide_scan = force_wide >= 0 ? force_wide != 0 : (ncells > 4096 || nb_max > 32);
         {
             KTimer t(c, 1, st);
             k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
@@ -299,8 +308,13 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         }
         {
             KTimer t(c, 2, st);
-            k_scan<<<n_sets, 1024, 0, st>>>(wd, ncells, nb_max, sl.blockhist.as<uint32_t>(),
-                                            sl.cellstart.as<uint32_t>(), sl.counters.as<unsigned>());
+            if (wide_scan)
+                k_scan_wide<<<dim3((ncells + 1023) / 1024, n_sets), 1024, 0, st>>>(
+                    wd, ncells, nb_max, sl.blockhist.as<uint32_t>(), sl.cellstart.as<uint32_t>(),
+                    sl.counters.as<unsigned>(), tk_scan);
+            else
+                k_scan_narrow<<<n_sets, 1024, 0, st>>>(wd, ncells, nb_max, sl.blockhist.as<uint32_t>(),
+                                                       sl.cellstart.as<uint32_t>(), sl.counters.as<unsigned>());
         }
         {
             KTimer t(c, 3, st);
@@ -310,7 +324,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
                 io.identity_scaler ? 1 : 0, ncells, chw, nb_max, sl.cellid.as<uint16_t>(),
                 sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
-                sl.sorted.as<double2>());
+                wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>());
         }
         if (io.balance_world > 0) {
             // cut the tile rows into bands of equal estimated work; all ranks derive the same cuts

@@ -25,7 +25,7 @@ namespace kdejs {
 
 constexpr int kMaxWaveItems = 32;
 constexpr int kMaxWaveSets = 2 * kMaxWaveItems;
-constexpr int kMaxCellsSide = 64;                 // cells per side of the culling grid
+constexpr int kMaxCellsSide = 128;                // cells per side of the culling grid (64 unless the grid is fine)
 constexpr int kMaxCells = kMaxCellsSide * kMaxCellsSide;
 constexpr int kSortWarps = 4;
 constexpr int kSortThreads = kSortWarps * 32;
@@ -292,24 +292,29 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
 }
 
 // ------------------------------------------------------------------------------------------
-// k_scan: grid (n_sets), 1024 threads, 4 cells per thread.  Turns blockhist[set][b][c] into the
-// first sorted position of block b's points of cell c, and writes cellstart[set][0..ncells].
+// k_scan_narrow: grid (n_sets), 1024 threads, ncells <= 4096 (4 consecutive cells per thread).  Turns
+// blockhist[set][b][c] into the first sorted position of block b's points of cell c (absolute), and writes
+// cellstart[set][0..ncells].  Used for the 64x64-cell geometry, where a set has few sort blocks.
 __global__ void __launch_bounds__(1024)
-k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
-       uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart,
-       unsigned *__restrict__ counters) {
+k_scan_narrow(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
+              uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart,
+              unsigned *__restrict__ counters) {
     const int set = blockIdx.x;
     if (set == 0 && threadIdx.x < 16) counters[threadIdx.x] = 0u;  // work-list counters of this wave
     const int nb = wd.set[set].nb;
     uint32_t *bh = blockhist + (size_t)set * nb_max * ncells;
-    const int c0 = threadIdx.x * 4;
-    uint32_t tot[4] = {0u, 0u, 0u, 0u};
+    constexpr int CPT = 4;
+    const int c0 = threadIdx.x * CPT;
+    uint32_t tot[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) tot[k] = 0u;
     for (int b = 0; b < nb; ++b)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < CPT; ++k)
             if (c0 + k < ncells) tot[k] += bh[(size_t)b * ncells + c0 + k];
-    uint32_t tsum = tot[0] + tot[1] + tot[2] + tot[3];
-    // exclusive scan of tsum over the block
+    uint32_t tsum = 0u;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) tsum += tot[k];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t inc = tsum;
 #pragma unroll
@@ -332,9 +337,9 @@ k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
     __syncthreads();
     uint32_t run = s_w[w] + inc - tsum;
     uint32_t *cs = cellstart + (size_t)set * (ncells + 1);
-    uint32_t base[4];
+    uint32_t base[CPT];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < CPT; ++k) {
         base[k] = run;
         if (c0 + k < ncells) cs[c0 + k] = run;
         run += tot[k];
@@ -342,7 +347,7 @@ k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
     if (threadIdx.x == 0) cs[ncells] = (uint32_t)wd.set[set].n;
     for (int b = 0; b < nb; ++b)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < CPT; ++k)
             if (c0 + k < ncells) {
                 uint32_t t = bh[(size_t)b * ncells + c0 + k];
                 bh[(size_t)b * ncells + c0 + k] = base[k];
@@ -350,16 +355,95 @@ k_scan(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
             }
 }
 
+// k_scan_wide: grid (ceil(ncells/1024), n_sets), 1024 threads, one cell per thread (128x128 cells, or a set
+// with many sort blocks).  Turns blockhist[set][b][c]
+// into the number of cell-c points in EARLIER blocks of the set (one coalesced read+write pass), leaves the
+// cell totals in cellstart[set][c]; the last block of a set to finish (ticket) replaces those totals with
+// their exclusive scan and writes cellstart[set][ncells] = n.  Sorted position of a point =
+// cellstart[cell] + blockhist[block][cell] + warpprefix + rank (k_place).
+__global__ void __launch_bounds__(1024)
+k_scan_wide(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
+            uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart,
+            unsigned *__restrict__ counters, unsigned *__restrict__ ticket) {
+    const int set = blockIdx.y;
+    if (set == 0 && blockIdx.x == 0 && threadIdx.x < 16) counters[threadIdx.x] = 0u;  // work-list counters of this wave
+    const int nb = wd.set[set].nb;
+    uint32_t *cs = cellstart + (size_t)set * (ncells + 1);
+    const int c = blockIdx.x * 1024 + threadIdx.x;
+    if (c < ncells) {
+        uint32_t *bh = blockhist + (size_t)set * nb_max * ncells + c;
+        uint32_t run = 0u;
+        int b = 0;
+        for (; b + 4 <= nb; b += 4) {                      // four independent loads in flight
+            uint32_t t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = bh[(size_t)(b + u) * ncells];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { bh[(size_t)(b + u) * ncells] = run; run += t[u]; }
+        }
+        for (; b < nb; ++b) { const uint32_t t = bh[(size_t)b * ncells]; bh[(size_t)b * ncells] = run; run += t; }
+        cs[c] = run;
+    }
+    __shared__ bool s_last;
+    __shared__ uint32_t s_w[32];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();               // cumulative: orders the block's cs[] stores before the ticket
+        s_last = (atomicAdd(&ticket[set], 1u) == gridDim.x - 1);
+        __threadfence();
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // exclusive scan of the ncells totals: thread t owns cpt consecutive cells
+    constexpr int kCptMax = kMaxCells / 1024;
+    const int cpt = (ncells + 1023) / 1024;
+    const int c0 = threadIdx.x * cpt;
+    uint32_t tot[kCptMax];
+    uint32_t tsum = 0u;
+#pragma unroll
+    for (int k = 0; k < kCptMax; ++k) {
+        tot[k] = (k < cpt && c0 + k < ncells) ? __ldcg(cs + c0 + k) : 0u;
+        tsum += tot[k];
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t v = s_w[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_w[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = s_w[w] + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < kCptMax; ++k) {
+        if (k < cpt && c0 + k < ncells) cs[c0 + k] = run;
+        run += tot[k];
+    }
+    if (threadIdx.x == 0) { cs[ncells] = (uint32_t)wd.set[set].n; ticket[set] = 0u; }   // self-resetting
+}
+
 // ------------------------------------------------------------------------------------------
 // k_place: grid (ceil(n_max/256), n_sets), 256 threads, one point per thread.  The point's stable sorted
-// position is  block base (k_scan) + earlier warps of its block (k_scale_count) + its rank inside its
+// position is  cell start + earlier blocks (k_scan) + earlier warps of its block (k_scale_count) + its rank inside its
 // warp sub-chunk (k_scale_count); the scaled coordinates are re-derived from the raw point with the same
 // arithmetic as k_scale_count and written straight to that slot.  No shared memory, no ranking.
 __global__ void __launch_bounds__(256)
 k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, int log_flag, double eps,
         int identity_scaler, int ncells, int chw, int nb_max, const uint16_t *__restrict__ cellid,
         const uint16_t *__restrict__ rank16, const uint16_t *__restrict__ warpprefix,
-        const uint32_t *__restrict__ blockbase, double2 *__restrict__ sorted) {
+        const uint32_t *__restrict__ blockbase, const uint32_t *__restrict__ cellstart,
+        double2 *__restrict__ sorted) {
     const SetDesc sd = wd.set[blockIdx.y];
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= sd.n) return;
@@ -368,7 +452,9 @@ k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, 
     const uint32_t rank = rank16[sd.off + j];
     const int64_t wchunk = j / chw;                       // global warp sub-chunk index of the point
     const size_t row = (size_t)blockIdx.y * nb_max + (size_t)(wchunk / kSortWarps);
-    const uint32_t pos = blockbase[row * ncells + cell] +
+    // cellstart is null when k_scan_narrow left absolute positions in blockbase
+    const uint32_t pos = (cellstart ? cellstart[(size_t)blockIdx.y * (ncells + 1) + cell] : 0u) +
+                         blockbase[row * ncells + cell] +
                          warpprefix[(row * kSortWarps + (size_t)(wchunk % kSortWarps)) * ncells + cell] + rank;
     const Scaler sc = make_scaler(rstat, sd, identity_scaler);
     sorted[sd.off + pos] = scale_point(v, sc, log_flag, eps, identity_scaler);

@@ -125,7 +125,7 @@ def test_full_size_properties(pk, ko):
     assert js_aff == pytest.approx(js, rel=1e-9)
 
 
-@pytest.mark.parametrize("R", [1, 2, 3, 5, 17, 100, 129, 256, 511])
+@pytest.mark.parametrize("R", [1, 2, 3, 5, 17, 100, 129, 256, 511, 1024, 1500])     # >= 1024: 128x128 culling cells
 def test_resolutions(pk, ko, R):
     from oracle import workloads as wl
 
