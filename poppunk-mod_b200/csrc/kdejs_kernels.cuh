@@ -897,7 +897,9 @@ k_density_dense64(const __grid_constant__ WaveDesc wd, const GridGeom g,
 // ~1e-7.  Per pair: FFMA.SAT (t = sat(a_i - v_j^2): an exact ReLU because t <= 1) + FADD, i.e. 2
 // FMA-pipe lane-ops; 24 more per point per thread -> 152 per 64 pairs.  fp32 partial sums never run
 // longer than one slice; slices are folded in fp64 by k_dense_finish.
-// KERNEL 1 (gaussian): t = ex2(-(0.5 log2 e) d^2): FFMA + MUFU.EX2 + FADD per pair (SFU bound).
+// KERNEL 1 (gaussian): the term is separable, exp(-d^2/2) = ex_i * ey_j, so a point costs a thread 16
+// MUFU.EX2 and each pair ONE FFMA (acc += ex_i * ey_j) -- FMA-pipe bound like the Epanechnikov variant, not
+// SFU bound (an ex2 per pair would cap the kernel at 16 pairs/clk/SM, an eighth of the FFMA rate).
 constexpr int kD32Threads = 128;
 constexpr int kD32Patch = 8;
 constexpr int kD32TilesX = 16, kD32TilesY = 8;                 // threads per block along x / y
@@ -939,15 +941,16 @@ k_density_dense32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll
             for (int i = 0; i < kD32Patch; ++i) {
                 const float ux = (float)i * dh - u0;
-                a[i] = (KERNEL == 0) ? fmaf(-ux, ux, 1.0f) : -kexp * ux * ux;
-                v[i] = (float)i * dh - w0;
+                const float vy = (float)i * dh - w0;
+                a[i] = (KERNEL == 0) ? fmaf(-ux, ux, 1.0f) : exp2f(-kexp * ux * ux);
+                v[i] = (KERNEL == 0) ? vy : exp2f(-kexp * vy * vy);
             }
 #pragma unroll
             for (int i = 0; i < kD32Patch; ++i)
 #pragma unroll
                 for (int j = 0; j < kD32Patch; ++j) {
                     if (KERNEL == 0) acc[i][j] += __saturatef(fmaf(-v[j], v[j], a[i]));
-                    else acc[i][j] += exp2f(fmaf(-kexp * v[j], v[j], a[i]));
+                    else acc[i][j] = fmaf(a[i], v[j], acc[i][j]);
                 }
         }
     }
