@@ -227,6 +227,8 @@ def main():
     nat = pk._native
     L = nat.lib()
     rank, local_rank, world = rank_env()
+    # one process per GPU: run on (and allocate pinned staging memory from) the GPU's own NUMA node
+    numa_node = nat.bind_host_to_device(local_rank) if world > 1 else -1
     if world > 1:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -480,7 +482,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": (BATCH + 1) * N_PAIRS * 16, "d2h_bytes_per_step": BATCH * 12,
                 "steps": e2e_steps, "api": "KDE_JS_divergence_batch (ctypes -> kdejs_discrepancy_batch), "
-                                           "pinned host arrays"},
+                                           "pinned host arrays",
+                "host_numa_node": numa_node},
         "gpu_launches": int(n_launch.value),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -56,6 +56,10 @@ int kdejs_device_count(int *count);
 /* Create (idempotent) the context for `device`: streams, scratch.  Called lazily by every
  * compute entry point; exposed so callers can pay the ~100 ms context cost up front. */
 int kdejs_init(int device);
+/* NUMA node the GPU's PCIe root hangs off (sysfs), -1 when the platform does not say.  One-process-per-GPU
+ * callers bind themselves to that node BEFORE allocating pinned staging memory, so that eight ranks feeding
+ * eight GPUs do not cross the socket interconnect (the reference's fork pools have no such concern). */
+int kdejs_device_numa_node(int device, int *node);
 void kdejs_shutdown(void);
 const char *kdejs_last_error(void);
 

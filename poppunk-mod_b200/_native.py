@@ -30,6 +30,7 @@ _COMMON = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctyp
 _SIGNATURES = {
     "kdejs_version": (ctypes.c_int, []),
     "kdejs_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "kdejs_device_numa_node": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "kdejs_init": (ctypes.c_int, [ctypes.c_int]),
     "kdejs_shutdown": (None, []),
     "kdejs_last_error": (ctypes.c_char_p, []),
@@ -102,6 +103,39 @@ def device_count() -> int:
     n = ctypes.c_int(0)
     rc = lib().kdejs_device_count(ctypes.byref(n))
     return n.value if rc == KDEJS_OK else 0
+
+
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device(device: int) -> int:
+    """Pin the calling process to the CPUs of the NUMA node `device` hangs off, so that pinned staging
+    memory allocated afterwards (first touch) and the copy-engine traffic stay on the GPU's own socket.
+    Meant for one-process-per-GPU launches; returns the node, or -1 when nothing was changed (platform
+    does not expose the node, KDEJS_NUMA_BIND=0, or the affinity call is not permitted)."""
+    import os
+    if os.environ.get("KDEJS_NUMA_BIND", "1") == "0":
+        return -1
+    node = ctypes.c_int(-1)
+    if lib().kdejs_device_numa_node(int(device), ctypes.byref(node)) != KDEJS_OK or node.value < 0:
+        return -1
+    try:
+        with open(f"/sys/devices/system/node/node{node.value}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return -1
+        os.sched_setaffinity(0, cpus)
+    except (OSError, ValueError):
+        return -1
+    return node.value
 
 
 def as_points(x, name="array") -> np.ndarray:

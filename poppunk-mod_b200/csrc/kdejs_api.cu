@@ -8,6 +8,7 @@
 #include "kdejs_kernels.cuh"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -524,6 +525,22 @@ int kdejs_device_count(int *count) {
 int kdejs_init(int device) {
     Ctx *c;
     return get_ctx(device, &c);
+}
+
+int kdejs_device_numa_node(int device, int *node) {
+    if (!node) return fail(KDEJS_ERR_ARG, "node is null");
+    *node = -1;
+    char id[64] = {0};
+    cudaError_t e = cudaDeviceGetPCIBusId(id, (int)sizeof id - 1, device);
+    if (e != cudaSuccess) return fail(KDEJS_ERR_CUDA, cudaGetErrorString(e));
+    for (char *q = id; *q; ++q) *q = (char)tolower((unsigned char)*q);     // sysfs spells bus ids in lower case
+    const std::string path = std::string("/sys/bus/pci/devices/") + id + "/numa_node";
+    if (FILE *f = fopen(path.c_str(), "r")) {
+        int v = -1;
+        if (fscanf(f, "%d", &v) == 1) *node = v;
+        fclose(f);
+    }
+    return KDEJS_OK;
 }
 
 void kdejs_shutdown(void) {

@@ -133,3 +133,20 @@ def test_default_device_env(monkeypatch):
     assert pk.default_device() == 0
     monkeypatch.setenv("KDEJS_DEVICE", "3")
     assert pk.default_device() in (3, 3 % max(1, pk._native.device_count()))
+
+
+def test_cpulist_parser_and_numa_bind_opt_out(monkeypatch):
+    import os
+    import poppunk_mod_b200 as pk
+
+    nat = pk._native
+    assert nat._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert nat._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    monkeypatch.setenv("KDEJS_NUMA_BIND", "0")
+    assert nat.bind_host_to_device(0) == -1
+    monkeypatch.delenv("KDEJS_NUMA_BIND")
+    # without a GPU the node query fails: nothing may change
+    if not nat.device_count():
+        assert nat.bind_host_to_device(0) == -1
+        assert os.sched_getaffinity(0) == before

@@ -522,3 +522,18 @@ def test_near_identical_distributions_and_wide_dynamic_range(pk, ko):
     for gamma in (3.0, 2.0):
         got = pk.KDE_JS_divergence(x, y, gamma, 0.0, False, resolution=300)
         assert rel(got, ko.discrepancy(x, y, gamma, 0.0, False, resolution=300)) < 1e-9
+
+
+def test_numa_node_query_and_bind(pk):
+    import ctypes, os
+    nat = pk._native
+    node = ctypes.c_int(-5)
+    nat.check(nat.lib().kdejs_device_numa_node(0, ctypes.byref(node)))
+    assert node.value >= -1
+    before = os.sched_getaffinity(0)
+    try:
+        got = nat.bind_host_to_device(0)
+        assert got in (-1, node.value)
+        assert os.sched_getaffinity(0) <= before and os.sched_getaffinity(0)
+    finally:
+        os.sched_setaffinity(0, before)
