@@ -158,9 +158,10 @@ const char *kdejs_io_last_error(void);
 
 /* ---- measurement support (bench.py, tests) ------------------------------------------- */
 /* Per-kernel CUDA-event timing on the launching stream.  which: 0 minmax, 1 scale+count,
- * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence, 6 tile classification.
+ * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence, 6 tile classification,
+ * 7 cell moments (fine grids only).
  * Reading synchronises. */
-#define KDEJS_NUM_KERNELS 7
+#define KDEJS_NUM_KERNELS 8
 int kdejs_profile_enable(int device, int on);   /* 0 off, 1 every kernel, 2 the density kernel only */
 int kdejs_profile_read(int device, int which, double *ms_total, int64_t *launches);
 int kdejs_profile_reset(int device);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libkdejs.so")
 KDEJS_OK, KDEJS_ERR_CUDA, KDEJS_ERR_ARG, KDEJS_ERR_INF = 0, 1, 2, 3
 KERNELS = {"epanechnikov": 0, "gaussian": 1}
 ALGOS = {"binned": 0, "dense": 1, "dense64": 2}
-KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence", "classify")
+KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence", "classify", "moments")
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_dpp = ctypes.POINTER(ctypes.c_void_p)

@@ -52,7 +52,7 @@ struct DevBuf {
 };
 
 struct Slot {
-    DevBuf rawsims, scaled, sorted, cellid, blockhist, cellstart, dens, pz, zout, tilesum;
+    DevBuf rawsims, scaled, sorted, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
     DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, counters, totals, rank16, warpprefix;
     cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
 };
@@ -121,7 +121,7 @@ int get_ctx(int device, Ctx **out) {
             CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
             CU(cudaFuncSetAttribute(k_scale_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSortWarps * kMaxCells * (int)sizeof(uint16_t)));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned, kDensThreads, 0));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned<false>, kDensThreads, 0));
             c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
             c.ready = true;
         }
@@ -214,7 +214,16 @@ GridGeom make_geom(const Params &p) {
     g.tile_row_end = g.NT;
     g.heavy_log2 = 13;
     if (const char *e = getenv("KDEJS_HEAVY_LOG2")) g.heavy_log2 = std::max(6, std::min(30, atoi(e)));
-    g.pad2 = 0;
+    // Cells that lie wholly inside the support of every node of a tile enter through their moments.  A cell
+    // concentric with a tile qualifies up to a centre offset rho; worth its bookkeeping once that region is at
+    // least about two cells across (fine grids: R >= ~512 at h = 0.03; never at the headline R = 256).
+    {
+        const double half = 0.5 * ((kTile - 1) * g.step + g.cell_w);
+        const double rho = (p.h > half) ? std::sqrt(p.h * p.h - half * half) - half : -1.0;
+        // 1: eligible, run_wave() decides from the number of points per cell; 2: forced (KDEJS_MOMENTS=1)
+        g.use_moments = (p.kernel == KDEJS_KERNEL_EPANECHNIKOV && rho >= g.cell_w && C >= 4) ? 1 : 0;
+        if (const char *e = getenv("KDEJS_MOMENTS")) g.use_moments = (atoi(e) != 0 && p.kernel == KDEJS_KERNEL_EPANECHNIKOV && C >= 4) ? 2 : 0;
+    }
     return g;
 }
 
@@ -262,6 +271,9 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         wd.set[s].nb = (int)(((int64_t)wd.set[s].n + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps));
     const int ncells = g.C * g.C;
     const bool binned = (p.algo == KDEJS_ALGO_BINNED);
+    // a moment cell costs a tile as much as one point plus some per-row bookkeeping: it pays once cells hold
+    // hundreds of points (measured: -40 % density time at 1200 points per cell, +48 % at 49)
+    if (g.use_moments == 1 && P < (int64_t)128 * n_sets * ncells) g.use_moments = 0;
     const int nparts = binned ? g.NT * g.NT : (int)((G + 255) / 256);
 
     if (!binned) OKR(sl.scaled.ensure((size_t)P * sizeof(double2)));
@@ -281,6 +293,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         OKR(sl.warpprefix.ensure((size_t)n_sets * nb_max * kSortWarps * ncells * sizeof(uint16_t)));
         OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * ncells * sizeof(uint32_t)));
         OKR(sl.cellstart.ensure((size_t)n_sets * (ncells + 1) * sizeof(uint32_t)));
+        if (g.use_moments) OKR(sl.moments.ensure((size_t)n_sets * ncells * kMomentDoubles * sizeof(double)));
         OKR(sl.worklist.ensure((size_t)kNumClasses * n_sets * g.NT * g.NT * sizeof(uint32_t)));
         OKR(sl.counters.ensure(16 * sizeof(unsigned)));
     }
@@ -327,6 +340,11 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
                 wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>());
         }
+        if (g.use_moments) {
+            KTimer t(c, 7, st);
+            k_cell_moments<<<dim3((ncells + 3) / 4, n_sets), 128, 0, st>>>(
+                wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>());
+        }
         if (io.balance_world > 0) {
             // cut the tile rows into bands of equal estimated work; all ranks derive the same cuts
             OKR(c.misc.ensure(64 + sizeof(double) * (size_t)g.NT));
@@ -364,10 +382,16 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         if (tiles > 0) {
             KTimer t(c, 4, st);
             const int blocks = (int)std::min<int64_t>((int64_t)capacity, (int64_t)c.sm_count * c.dens_blocks_per_sm);
-            k_density_binned<<<blocks, kDensThreads, 0, st>>>(
-                wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.dens.as<double>(),
-                sl.pz.as<double>(), sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(),
-                sl.counters.as<unsigned>(), capacity);
+            if (g.use_moments)
+                k_density_binned<true><<<blocks, kDensThreads, 0, st>>>(
+                    wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
+                    sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
+                    sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity);
+            else
+                k_density_binned<false><<<blocks, kDensThreads, 0, st>>>(
+                    wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), nullptr,
+                    sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
+                    sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity);
         }
     } else {
         // dense fp64: scale only (C = 1: every point lands in cell 0, the histogram is unused)
@@ -550,7 +574,7 @@ void kdejs_shutdown(void) {
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
         for (auto &s : c.slot) {
-            for (DevBuf *b : {&s.rawsims, &s.scaled, &s.sorted, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
+            for (DevBuf *b : {&s.rawsims, &s.scaled, &s.sorted, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
                               &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart,
                               &s.dense_partial, &s.worklist, &s.counters, &s.totals, &s.rank16, &s.warpprefix}) {
                 if (b->p) cudaFree(b->p);

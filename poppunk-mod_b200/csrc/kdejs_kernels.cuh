@@ -61,7 +61,8 @@ struct GridGeom {
     double cell_w;                       // nominal cell side = extent / C
     double knorm, gamma, eps;
     int32_t tile_row_begin, tile_row_end;   // tile rows (index of column 0) this launch covers
-    int32_t heavy_log2, pad2;               // tiles with >= 2^heavy_log2 candidates are processed per block
+    int32_t heavy_log2, use_moments;        // tiles with >= 2^heavy_log2 candidates are processed per block;
+                                            // use_moments: cells wholly inside a tile's support go in as moments
 };
 
 __device__ __forceinline__ double pre_transform(double v, int log_flag, double eps) {
@@ -487,23 +488,45 @@ __device__ __forceinline__ TileCells tile_cells(const GridGeom &g, int ix0, int 
     t.cy_hi = cell_of(t.yhi + g.h + g.margin, g.cell_x0, g.cell_invw, g.C);
     return t;
 }
-// First sorted index and length of the candidate run of cell row cy (tc.cy_lo <= cy <= tc.cy_hi).
-__device__ __forceinline__ void tile_row_run(const GridGeom &g, const TileCells &tc,
-                                             const uint32_t *__restrict__ cs, int cy,
-                                             uint32_t &start, uint32_t &len) {
+// Candidates of cell row cy (tc.cy_lo <= cy <= tc.cy_hi): the cells [cx_lo, cx_hi] that can reach the tile.
+// With g.use_moments the cells [mlo, mlo+mcnt) in the middle of that range -- those whose EVERY point lies
+// within h of EVERY node of the tile -- are left out of the point runs: inside the support the Epanechnikov
+// term is a polynomial, so such a cell enters through its moments (accumulate_cell) at the cost of one
+// point.  What remains are two point runs (s1,l1) and (s2,l2) left and right of the moment cells.
+struct RowRuns { uint32_t s1, l1, s2, l2; int mlo, mcnt; };
+__device__ __forceinline__ RowRuns tile_row_runs(const GridGeom &g, const TileCells &tc,
+                                                 const uint32_t *__restrict__ cs, int cy, const bool moments) {
     // nominal y-interval of the row; the border rows also hold everything beyond the grid's extent, which
     // only lies farther from the tile than the nominal edge used here
     const double row_lo = g.cell_x0 + (double)cy * g.cell_w, row_hi = row_lo + g.cell_w;
     const double dy = fmax(fmax(row_lo - tc.yhi, tc.gy0 - row_hi) - g.margin, 0.0);
     const double rx2 = g.h * g.h - dy * dy;
-    start = 0u; len = 0u;
+    RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
     if (rx2 > 0.0) {
         const double rx = sqrt(rx2) + g.margin;
         const int cx_lo = cell_of(tc.gx0 - rx, g.cell_x0, g.cell_invw, g.C);
         const int cx_hi = cell_of(tc.xhi + rx, g.cell_x0, g.cell_invw, g.C);
-        start = cs[cy * g.C + cx_lo];
-        len = cs[cy * g.C + cx_hi + 1] - start;
+        int mlo = cx_hi + 1, mhi = cx_hi;                    // no moment cells
+        if (moments && cy > 0 && cy < g.C - 1) {             // border cells also hold out-of-extent points
+            // farthest a point of this row can be from a node of the tile in y, then the x-reach left for it
+            const double fy = fmax(tc.yhi - row_lo, row_hi - tc.gy0) + g.margin;
+            const double fx2 = g.h * g.h - fy * fy;
+            if (fx2 > 0.0) {
+                const double fx = sqrt(fx2) - g.margin;
+                // cell c = [x0 + c w, x0 + (c+1) w] qualifies iff  xhi - (x0 + c w) <= fx  and  x0 + (c+1) w - gx0 <= fx
+                const int lo = max(__double2int_ru((tc.xhi - fx - g.cell_x0) * g.cell_invw + 1e-9), max(cx_lo, 1));
+                const int hi = min(__double2int_rd((tc.gx0 + fx - g.cell_x0) * g.cell_invw - 1e-9) - 1, min(cx_hi, g.C - 2));
+                if (lo <= hi) { mlo = lo; mhi = hi; }
+            }
+        }
+        rr.s1 = cs[cy * g.C + cx_lo];
+        rr.l1 = cs[cy * g.C + mlo] - rr.s1;
+        rr.s2 = cs[cy * g.C + mhi + 1];
+        rr.l2 = cs[cy * g.C + cx_hi + 1] - rr.s2;
+        rr.mlo = mlo;
+        rr.mcnt = mhi - mlo + 1;
     }
+    return rr;
 }
 
 // Work-list layout.  Tiles are bucketed by candidate count so that the persistent density kernel can
@@ -542,9 +565,8 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const TileCells tc = tile_cells(g, ix0, iy0);
         const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
         for (int cy = tc.cy_lo + sub; cy <= tc.cy_hi; cy += kClassifyLanes) {
-            uint32_t s0, l0;
-            tile_row_run(g, tc, cs, cy, s0, l0);
-            total += l0;
+            const RowRuns rr = tile_row_runs(g, tc, cs, cy, g.use_moments != 0);
+            total += rr.l1 + rr.l2 + (uint32_t)rr.mcnt;
         }
     }
     total += __shfl_xor_sync(0xffffffffu, total, 1);
@@ -597,9 +619,8 @@ k_tile_rowwork(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
         uint32_t total = 0u;
         for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy) {
-            uint32_t s0, l0;
-            tile_row_run(g, tc, cs, cy, s0, l0);
-            total += l0;
+            const RowRuns rr = tile_row_runs(g, tc, cs, cy, g.use_moments != 0);
+            total += rr.l1 + rr.l2 + (uint32_t)rr.mcnt;
         }
         work += (double)total + (total ? 64.0 : 2.0);
     }
@@ -645,6 +666,63 @@ __device__ __forceinline__ void accumulate_point(const double2 p, const double g
     }
 }
 
+// One cell that lies wholly inside the support of all 16 nodes, through its moments about the cell centre
+// (units of h): m = {n, Sx, Sy, Sxx, Syy} with dx_k = (x_k - cx)/h.  For node (i,j) at u_i = (gx_i - cx)/h,
+// v_j = (gy_j - cy)/h:   sum_k [1 - (dx_k-u_i)^2 - (dy_k-v_j)^2] = A_i - B_j,
+//   A_i = (n - Sxx) + u_i (2 Sx - n u_i),   B_j = Syy - v_j (2 Sy - n v_j).
+constexpr int kMomentDoubles = 5;
+__device__ __forceinline__ void accumulate_cell(const double *__restrict__ m, const double cx, const double cy,
+                                                const double gx0, const double gy0, const double inv_h,
+                                                const double c1, const double c2, const double c3,
+                                                double (&acc)[kTile][kTile]) {
+    const double n = m[0];
+    if (n == 0.0) return;
+    const double sx2 = 2.0 * m[1], sy2 = 2.0 * m[2], nmxx = n - m[3], syy = m[4];
+    const double u0 = (gx0 - cx) * inv_h, v0 = (gy0 - cy) * inv_h;
+    const double u[kTile] = {u0, u0 + c1, u0 + c2, u0 + c3};
+    const double v[kTile] = {v0, v0 + c1, v0 + c2, v0 + c3};
+    double A[kTile], B[kTile];
+#pragma unroll
+    for (int i = 0; i < kTile; ++i) {
+        A[i] = fma(u[i], fma(-n, u[i], sx2), nmxx);
+        B[i] = fma(-v[i], fma(-n, v[i], sy2), syy);
+    }
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) acc[i][j] += A[i] - B[j];
+}
+__device__ __forceinline__ double cell_centre(const GridGeom &g, int c) {
+    return g.cell_x0 + ((double)c + 0.5) * g.cell_w;
+}
+
+// k_cell_moments: grid (ceil(ncells/4), n_sets), 128 threads, one warp per cell: the five moments
+// accumulate_cell() needs, summed lane-strided and folded with a fixed butterfly (bit-reproducible).
+__global__ void __launch_bounds__(128)
+k_cell_moments(const __grid_constant__ WaveDesc wd, const GridGeom g, const double2 *__restrict__ sorted,
+               const uint32_t *__restrict__ cellstart, double *__restrict__ moments) {
+    const int set = blockIdx.y, lane = threadIdx.x & 31;
+    const int ncells = g.C * g.C;
+    const int cell = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (cell >= ncells) return;
+    const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
+    const uint32_t b = cs[cell], e = cs[cell + 1];
+    const double cx = cell_centre(g, cell % g.C), cy = cell_centre(g, cell / g.C);
+    const double2 *__restrict__ pts = sorted + wd.set[set].off;
+    double sx = 0.0, sy = 0.0, sxx = 0.0, syy = 0.0;
+    for (uint32_t k = b + lane; k < e; k += 32) {
+        const double2 p = pts[k];
+        const double dx = (p.x - cx) * g.inv_h, dy = (p.y - cy) * g.inv_h;
+        sx += dx; sy += dy;
+        sxx = fma(dx, dx, sxx); syy = fma(dy, dy, syy);
+    }
+    sx = warp_sum(sx); sy = warp_sum(sy); sxx = warp_sum(sxx); syy = warp_sum(syy);
+    if (lane == 0) {
+        double *m = moments + ((size_t)set * ncells + cell) * kMomentDoubles;
+        m[0] = (double)(e - b); m[1] = sx; m[2] = sy; m[3] = sxx; m[4] = syy;
+    }
+}
+
 __device__ __forceinline__ uint32_t worklist_entry(const uint32_t *__restrict__ worklist, unsigned capacity,
                                                    unsigned item, const unsigned *s_cnt) {
     // item indexes the concatenation of classes 1..kNumClasses-1
@@ -663,14 +741,17 @@ __device__ __forceinline__ uint32_t worklist_entry(const uint32_t *__restrict__ 
 // Each phase ends a tile with a fixed-shape reduction through shared memory, the 16 node values,
 // their **gamma+eps and the tile's share of the normaliser.  Which warp or block processes a tile is
 // decided at run time (atomic tickets) but never changes a result.
+template <bool MOMENTS>
 __global__ void __launch_bounds__(kDensThreads, 6)
 k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
                  const double2 *__restrict__ sorted, const uint32_t *__restrict__ cellstart,
+                 const double *__restrict__ moments,
                  double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
                  const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
                  unsigned capacity) {
-    __shared__ uint32_t s_rs[kMaxRows];
-    __shared__ uint32_t s_cum[kMaxRows + 1];
+    __shared__ uint32_t s_rs[2 * kMaxRows];          // two point runs per cell row (left / right of the moment cells)
+    __shared__ uint32_t s_cum[2 * kMaxRows + 1];
+    __shared__ int s_mlo[kMaxRows], s_mcnt[kMaxRows], s_rows, s_cy0;
     __shared__ double s_red[kRedDoubles];
     __shared__ unsigned s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -702,20 +783,25 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
             const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
             const TileCells tc = tile_cells(g, ix0, iy0);
             const int rows = tc.cy_hi - tc.cy_lo + 1;       // <= kMaxRows by the host's choice of C
-            uint32_t s = 0u, len = 0u;
-            if (lane < rows) tile_row_run(g, tc, cs, tc.cy_lo + lane, s, len);
-            uint32_t inc = len;
+            RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
+            if (lane < rows) rr = tile_row_runs(g, tc, cs, tc.cy_lo + lane, MOMENTS);
+            const uint32_t both = rr.l1 + rr.l2;
+            uint32_t inc = both;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            s_rs[lane] = s;
-            s_cum[lane + 1] = inc;
-            if (lane == 0) s_cum[0] = 0u;
+            s_rs[2 * lane] = rr.s1;
+            s_rs[2 * lane + 1] = rr.s2;
+            s_cum[2 * lane + 1] = inc - both + rr.l1;
+            s_cum[2 * lane + 2] = inc;
+            s_mlo[lane] = rr.mlo;
+            s_mcnt[lane] = rr.mcnt;
+            if (lane == 0) { s_cum[0] = 0u; s_rows = rows; s_cy0 = tc.cy_lo; }
         }
         __syncthreads();
-        const uint32_t total = s_cum[kMaxRows];
+        const uint32_t total = s_cum[2 * kMaxRows];
         double acc[kTile][kTile];
 #pragma unroll
         for (int i = 0; i < kTile; ++i)
@@ -739,6 +825,18 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 pn = pts[s_rs[r] + (idx - s_cum[r])];
             }
             accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
+        }
+        if (MOMENTS) {
+            const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
+            const int rows = s_rows, cy0 = s_cy0;
+            for (int rr = 0; rr < rows; ++rr) {
+                const int mc = s_mcnt[rr], cy = cy0 + rr;
+                for (int k = threadIdx.x; k < mc; k += kDensThreads) {
+                    const int cx = s_mlo[rr] + k;
+                    accumulate_cell(mom + (size_t)(cy * g.C + cx) * kMomentDoubles, cell_centre(g, cx),
+                                    cell_centre(g, cy), gx0, gy0, g.inv_h, c1, c2, c3, acc);
+                }
+            }
         }
         // transpose through shared memory: 8 partial sums of 16 lanes per node, then a 3-step butterfly
 #pragma unroll
@@ -789,24 +887,37 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
         const TileCells tc = tile_cells(g, ix0, iy0);
         const int rows = tc.cy_hi - tc.cy_lo + 1;
-        uint32_t row_s = 0u, row_len = 0u;
-        if (lane < rows) tile_row_run(g, tc, cs, tc.cy_lo + lane, row_s, row_len);
+        RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
+        if (lane < rows) rr = tile_row_runs(g, tc, cs, tc.cy_lo + lane, MOMENTS);
         double acc[kTile][kTile];
 #pragma unroll
         for (int i = 0; i < kTile; ++i)
 #pragma unroll
             for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
+        constexpr int nparts = MOMENTS ? 2 : 1;        // without moment cells the second run is always empty
         for (int r = 0; r < rows; ++r) {
-            const uint32_t len = __shfl_sync(0xffffffffu, row_len, r);
-            const double2 *__restrict__ rp = pts + __shfl_sync(0xffffffffu, row_s, r);
-            uint32_t j = lane;
-            double2 pn = make_double2(0.0, 0.0);
-            if (j < len) pn = rp[j];
-            while (j < len) {
-                const double2 p = pn;
-                j += 32;
-                if (j < len) pn = rp[j];               // the lane's next candidate is in flight
-                accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
+#pragma unroll 1
+            for (int part = 0; part < nparts; ++part) {
+                const uint32_t len = __shfl_sync(0xffffffffu, part ? rr.l2 : rr.l1, r);
+                const double2 *__restrict__ rp = pts + __shfl_sync(0xffffffffu, part ? rr.s2 : rr.s1, r);
+                uint32_t j = lane;
+                double2 pn = make_double2(0.0, 0.0);
+                if (j < len) pn = rp[j];
+                while (j < len) {
+                    const double2 p = pn;
+                    j += 32;
+                    if (j < len) pn = rp[j];           // the lane's next candidate is in flight
+                    accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
+                }
+            }
+            if (MOMENTS) {
+                const int mc = __shfl_sync(0xffffffffu, rr.mcnt, r);
+                const int mlo = __shfl_sync(0xffffffffu, rr.mlo, r);
+                const int cy = tc.cy_lo + r;
+                const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
+                for (int k = lane; k < mc; k += 32)
+                    accumulate_cell(mom + (size_t)(cy * g.C + mlo + k) * kMomentDoubles, cell_centre(g, mlo + k),
+                                    cell_centre(g, cy), gx0, gy0, g.inv_h, c1, c2, c3, acc);
             }
         }
         // warp-level transpose: lane l sums 16 lanes' partials of node l/2, then one butterfly step

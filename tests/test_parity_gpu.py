@@ -537,3 +537,84 @@ def test_numa_node_query_and_bind(pk):
         assert os.sched_getaffinity(0) <= before and os.sched_getaffinity(0)
     finally:
         os.sched_setaffinity(0, before)
+
+
+# ---- cell moments (cells wholly inside a tile's support enter as five moments, fine grids) ---------------
+@pytest.mark.parametrize("R,cells", [(100, None), (256, None), (256, "128"), (511, None), (1024, None), (1200, "96")])
+def test_cell_moments_match_the_direct_sum(pk, ko, monkeypatch, R, cells):
+    from oracle import workloads as wl
+
+    a = wl.synthetic_target(30000, seed=5)
+    b = wl.sim_S(9, 2100, 0.33, n=20000)
+    if cells:
+        monkeypatch.setenv("KDEJS_CELLS", cells)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("KDEJS_MOMENTS", flag)
+        out[flag] = pk.KDE_distance._discrepancy(a, b, 0.25, 0.0, False, R, 0.03, "epanechnikov", None, None,
+                                                 want_z=True, want_density=True)
+    js_o, oz1, oz2, od1, od2 = ko.discrepancy(a, b, 0.25, 0.0, resolution=R, return_grids=True)
+    for flag in ("0", "1"):
+        js, z1, z2, d1, d2 = out[flag]
+        assert rel(js, js_o) < JS_RTOL_EXPECT
+        for got, want in ((d1, od1), (d2, od2)):
+            assert np.all(np.abs(got - want) <= 1e-9 * want + 1e-12 * want.max())
+            assert np.array_equal(got == 0, want == 0)
+    # the two paths agree far below the parity tolerance
+    assert np.max(np.abs(out["0"][3] - out["1"][3])) <= 1e-12 * od1.max()
+
+
+def test_cell_moments_row_sharded(pk, ko, monkeypatch):
+    """With the moments on (forced: the library only enables them by itself for >= 128 points per cell), the
+    row-sharded phases must agree with the single launch and with the direct sum."""
+    import ctypes
+
+    from oracle import workloads as wl
+
+    nat = pk._native
+    a = wl.synthetic_target(40000, seed=2)
+    b = wl.sim_S(4, 1500, 0.4, n=40000)
+    R = 1024
+    monkeypatch.setenv("KDEJS_MOMENTS", "0")
+    direct = pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R)
+    monkeypatch.setenv("KDEJS_MOMENTS", "1")
+    one = pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R)
+    assert rel(one, ko.discrepancy(a, b, 0.25, 0.0, resolution=R)) < JS_RTOL_EXPECT
+    assert rel(direct, one) < 1e-12       # different summation order, same number
+    bounds = [0, 300, 700, R]
+    common = (R, 0.03, 0.25, 0.0, 0, 0, 0)
+    norms, lrs = [], []
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        n = (ctypes.c_double * 2)()
+        nat.check(nat.lib().kdejs_shard_phase1(0, nat.ptr(a), len(a), nat.ptr(b), len(b), *common, lo, hi, n))
+        norms.append((n[0], n[1]))
+    tot = (ctypes.c_double * 2)(sum(x for x, _ in norms), sum(y for _, y in norms))
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        n = (ctypes.c_double * 2)()
+        lr = (ctypes.c_double * 2)()
+        nat.check(nat.lib().kdejs_shard_phase1(0, nat.ptr(a), len(a), nat.ptr(b), len(b), *common, lo, hi, n))
+        nat.check(nat.lib().kdejs_shard_phase2(0, tot, lr))
+        lrs.append((lr[0], lr[1]))
+    js = np.sqrt((sum(x for x, _ in lrs) + sum(y for _, y in lrs)) / 2.0)
+    assert js == pytest.approx(one, rel=1e-12)
+
+
+def test_cell_moments_switch_on_by_themselves_for_dense_cells(pk, ko):
+    """1.3 M points on a 512^2 grid (64^2 cells): >= 128 points per cell, so the library takes the moment path unasked
+    (profile slot 7 counts its launch) and still reproduces the oracle."""
+    import ctypes
+
+    from oracle import workloads as wl
+
+    nat = pk._native
+    L = nat.lib()
+    a = wl.synthetic_target(650_000, seed=8)
+    b = wl.sim_S(6, 1700, 0.37, n=650_000)
+    nat.check(L.kdejs_profile_reset(0))
+    nat.check(L.kdejs_profile_enable(0, 1))
+    got = pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=512)
+    ms, n = ctypes.c_double(), ctypes.c_int64()
+    nat.check(L.kdejs_profile_read(0, 7, ctypes.byref(ms), ctypes.byref(n)))
+    nat.check(L.kdejs_profile_enable(0, 0))
+    assert n.value == 1
+    assert rel(got, ko.discrepancy(a, b, 0.25, 0.0, resolution=512)) < JS_RTOL_EXPECT
