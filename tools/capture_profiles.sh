@@ -13,3 +13,8 @@ ncu --set full --clock-control none --import-source on -k regex:k_density_binned
 ncu --set full --clock-control none --import-source on -k regex:k_density_dense32 -c 1 -o $OUT/prof_dense32_${TAG} $CMD > $OUT/ncu_d.log 2>&1
 ncu --set full --clock-control none -k regex:"k_minmax|k_scale_count|k_scan|k_place|k_tile_classify|k_set_totals|k_js" -s 21 -c 7 -o $OUT/prof_small_${TAG} $CMD > $OUT/ncu_s.log 2>&1
 for f in ncu_b ncu_d ncu_s; do tail -n 1 $OUT/$f.log; done
+# fine-grid path (128x128 cells, cell moments): config C5 at 3 M + 3 M points, R = 1024
+C5CMD="python tools/c5_probe.py"
+C5_N=3000000 $C5CMD > $OUT/plain_c5_${TAG}.log 2>&1 || exit 3
+C5_N=3000000 ncu --set full --clock-control none --import-source on -k regex:"k_density_binned|k_cell_moments|k_scan_wide" -c 3 -o $OUT/prof_c5_${TAG} $C5CMD > $OUT/ncu_c5.log 2>&1
+tail -n 1 $OUT/ncu_c5.log

@@ -48,3 +48,30 @@ d = json.load(open(f"{G}/bench_{tag}_n1.json"))
 r = d["roofline"]
 print("value", d["value"], "e2e", d["e2e"]["value"], "frac", r["frac"], "fp64 util", r["fp64_pipe_utilisation"],
       "cpu", d["cpu_baseline"]["value"] if d.get("cpu_baseline") else None)
+
+# fine-grid capture (optional): 128x128 cells + cell moments
+import os  # noqa: E402
+
+if os.path.exists(f"{G}/prof_c5_{tag}.ncu-rep"):
+    full(f"{G}/prof_c5_{tag}.ncu-rep", f"profiles/{tag}_c5_fine_grid_full.txt",
+         "# C5_N=3000000 ncu --set full --clock-control none --import-source on "
+         "-k regex:'k_density_binned|k_cell_moments|k_scan_wide' -c 3 over tools/c5_probe.py\n"
+         "# fine-grid path: 3 M + 3 M points, R = 1024, 128x128 cells, cells inside the support summed from moments\n")
+
+# DRAM traffic of the dominant kernel per launch (bench.py's roofline.traffic reads this file)
+out = subprocess.run(["ncu", "-i", f"{G}/prof_binned_{tag}.ncu-rep", "--page", "raw", "--csv"],
+                     capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units, first = rows[0], rows[1], rows[2]
+
+
+def _bytes(key):
+    v = float(first[hdr.index(key)].replace(",", ""))
+    u = units[hdr.index(key)].lower()
+    return v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1.0)
+
+
+json.dump({"k_density_binned": {"dram_bytes_read": _bytes("dram__bytes_read.sum"),
+                                "dram_bytes_write": _bytes("dram__bytes_write.sum"), "evals_per_launch": 32,
+                                "source": f"profiles/{tag}_density_binned_full.txt (ncu --set full, launch 0)"}},
+          open("profiles/traffic.json", "w"), indent=1)

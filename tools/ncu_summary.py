@@ -36,6 +36,8 @@ def launches(src, dst):
     agg = collections.OrderedDict()
     for r in rows[1:]:
         name = r[ki].split("(")[0]
+        if name.startswith("void "):           # templated kernels are printed with their return type
+            name = name[5:]
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
         a = agg.setdefault(name, [0, 0.0])
