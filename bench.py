@@ -381,6 +381,8 @@ def main():
     roofline = {
         "bound": "fp64-pipe", "achieved": achieved, "peak": tf64.value, "unit": "TFLOP/s",
         "frac": achieved / tf64.value if tf64.value else None, "traffic": None,
+        "bound_note": "neither of the contract's two classes: the kernel is bound by the CUDA-core fp64 issue rate "
+                      "(contraction dimension 2 with a clamp: no tensor cores; DRAM at 5 % of peak, see hbm_* keys)",
         "kernel": "k_density_binned", "peak_source": "DFMA issue-rate microbenchmark run in this process "
         "(kdejs_peak_flops); MEASURED_PEAKS.json holds only HBM and bf16 tensor peaks",
         "algorithmic_flops_per_launch": alg_flops_per_launch,
