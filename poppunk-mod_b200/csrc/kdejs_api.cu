@@ -6,6 +6,7 @@
 // there is no descriptor staging buffer to race with asynchronous callers.
 #include "../../include/kdejs.h"
 #include "kdejs_kernels.cuh"
+#include "kdejs_stager.h"
 
 #include <algorithm>
 #include <cctype>
@@ -35,6 +36,31 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
         }                                                                                     \
     } while (0)
 #define OKR(call) do { int r_ = (call); if (r_ != KDEJS_OK) return r_; } while (0)
+
+// Host ranges of at least this size that are not page-locked go through the staging threads (kdejs_stager.h);
+// smaller ones are not worth waking them for.
+constexpr size_t kStageMinBytes = (size_t)4 << 20;
+
+// Upload several host ranges in order on `st`.  Page-locked sources are copied directly; pageable ones are
+// staged when together they are large enough.
+int h2d_ranges(int device, const std::vector<Stager::Range> &ranges, cudaStream_t st) {
+    std::vector<char> staged(ranges.size(), 0);
+    std::vector<Stager::Range> plan;
+    size_t pageable_bytes = 0;
+    for (size_t i = 0; i < ranges.size(); ++i)
+        if (ranges[i].bytes && Stager::pageable(ranges[i].src)) { staged[i] = 1; pageable_bytes += ranges[i].bytes; }
+    Stager *sg = (pageable_bytes >= kStageMinBytes) ? Stager::get(device) : nullptr;
+    if (sg) {
+        for (size_t i = 0; i < ranges.size(); ++i) if (staged[i]) plan.push_back(ranges[i]);
+        sg->plan(plan);
+    }
+    for (size_t i = 0; i < ranges.size(); ++i) {
+        if (!ranges[i].bytes) continue;
+        if (sg && staged[i]) CU(sg->issue_range(st));
+        else CU(cudaMemcpyAsync(ranges[i].dst, ranges[i].src, ranges[i].bytes, cudaMemcpyHostToDevice, st));
+    }
+    return KDEJS_OK;
+}
 
 struct DevBuf {
     void *p = nullptr;
@@ -630,10 +656,12 @@ int kdejs_discrepancy_pairs(int device, const double *const *sets, const int64_t
     std::vector<size_t> offs(n_sets);
     for (int s = 0; s < n_sets; ++s) { offs[s] = total; total += ((size_t)n_pts[s] * 16 + 255) / 256 * 256; }
     OKR(c->pool_raw.ensure(total));
+    std::vector<Stager::Range> up(n_sets);
     for (int s = 0; s < n_sets; ++s) {
-        CU(cudaMemcpyAsync((char *)c->pool_raw.p + offs[s], sets[s], (size_t)n_pts[s] * 16, cudaMemcpyHostToDevice, c->s_compute));
+        up[s] = Stager::Range{(char *)c->pool_raw.p + offs[s], sets[s], (size_t)n_pts[s] * 16};
         pool[s] = RawSet{(const double *)((char *)c->pool_raw.p + offs[s]), n_pts[s]};
     }
+    OKR(h2d_ranges(device, up, c->s_compute));
     OKR(c->js_out.ensure(sizeof(double) * (size_t)n_pairs));
     OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)n_pairs));
     OKR(ensure_host_results(*c, (size_t)n_pairs));
@@ -660,8 +688,8 @@ int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, 
     const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
     OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
     cudaStream_t st = c->s_compute;
-    CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, st));
+    OKR(h2d_ranges(device, {Stager::Range{c->pool_raw.p, a, (size_t)na * 16},
+                            Stager::Range{(char *)c->pool_raw.p + offb, b, (size_t)nb * 16}}, st));
     std::vector<RawSet> pool = {RawSet{(const double *)c->pool_raw.p, na},
                                 RawSet{(const double *)((char *)c->pool_raw.p + offb), nb}};
     OKR(c->js_out.ensure(sizeof(double)));
@@ -696,7 +724,6 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     OKR(c->pool_raw.ensure((size_t)n_obs * 16));
-    CU(cudaMemcpyAsync(c->pool_raw.p, obs, (size_t)n_obs * 16, cudaMemcpyHostToDevice, c->s_compute));
     OKR(c->js_out.ensure(sizeof(double) * (size_t)B));
     OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)B));
     OKR(ensure_host_results(*c, (size_t)B));
@@ -711,6 +738,25 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     const size_t sim_stride = ((size_t)nmax * 16 + 255) / 256 * 256;
     const int ring_items = (int)std::min<int64_t>(B, std::max<int64_t>(cap, (int64_t)(2.0e9 / (double)sim_stride)));
     OKR(c->sim_ring.ensure(sim_stride * (size_t)ring_items));
+    // Pageable sources (ordinary numpy arrays) are staged through pinned slots by worker threads that run ahead
+    // of this loop (kdejs_stager.h); page-locked sources are copied directly.
+    std::vector<char> staged(B + 1, 0);
+    Stager *sg = nullptr;
+    {
+        std::vector<Stager::Range> plan;
+        size_t pageable_bytes = 0;
+        if (Stager::pageable(obs)) { staged[B] = 1; pageable_bytes += (size_t)n_obs * 16; plan.push_back(Stager::Range{c->pool_raw.p, obs, (size_t)n_obs * 16}); }
+        for (int i = 0; i < B; ++i)
+            if (Stager::pageable(sims[i])) {
+                staged[i] = 1;
+                pageable_bytes += (size_t)n_sims[i] * 16;
+                plan.push_back(Stager::Range{(char *)c->sim_ring.p + sim_stride * (size_t)(i % ring_items), sims[i], (size_t)n_sims[i] * 16});
+            }
+        if (pageable_bytes >= kStageMinBytes) sg = Stager::get(device);
+        if (sg) sg->plan(plan);
+    }
+    if (sg && staged[B]) CU(sg->issue_range(c->s_compute));
+    else CU(cudaMemcpyAsync(c->pool_raw.p, obs, (size_t)n_obs * 16, cudaMemcpyHostToDevice, c->s_compute));
     int wave_size = std::min(cap, 16);
     if (const char *e = getenv("KDEJS_HOST_WAVE")) wave_size = std::max(1, std::min(cap, atoi(e)));
     std::vector<int> wave_of_item(B);
@@ -737,7 +783,9 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
             if (i >= ring_items)        // ring slot reuse: the evaluation that read it must have finished
                 if (cudaEventSynchronize(ev_done[wave_of_item[i - ring_items]]) != cudaSuccess) { rc = fail(KDEJS_ERR_CUDA, "event wait failed"); break; }
             char *dst = (char *)c->sim_ring.p + sim_stride * (size_t)(i % ring_items);
-            if (cudaMemcpyAsync(dst, sims[i], (size_t)n_sims[i] * 16, cudaMemcpyHostToDevice, c->s_copy) != cudaSuccess) {
+            const cudaError_t ce = (sg && staged[i]) ? sg->issue_range(c->s_copy)
+                                                     : cudaMemcpyAsync(dst, sims[i], (size_t)n_sims[i] * 16, cudaMemcpyHostToDevice, c->s_copy);
+            if (ce != cudaSuccess) {
                 rc = fail(KDEJS_ERR_CUDA, "H2D copy of a simulated set failed");
                 break;
             }
@@ -757,6 +805,7 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
             cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess)
             rc = fail(KDEJS_ERR_CUDA, "D2H copy of the results failed");
     }
+    if (sg && rc != KDEJS_OK) sg->abandon();
     cudaError_t se = cudaStreamSynchronize(c->s_compute);
     cudaStreamSynchronize(c->s_copy);
     for (auto e : ev_copied) c->free_plain_events.push_back(e);
@@ -892,8 +941,8 @@ int kdejs_shard_phase1(int device, const double *a, int64_t na, const double *b,
     std::lock_guard<std::mutex> lk(c->mu);
     const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
     OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
-    CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, c->s_compute));
-    CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, c->s_compute));
+    OKR(h2d_ranges(device, {Stager::Range{c->pool_raw.p, a, (size_t)na * 16},
+                            Stager::Range{(char *)c->pool_raw.p + offb, b, (size_t)nb * 16}}, c->s_compute));
     return shard_phase1_core(c, p, RawSet{(const double *)c->pool_raw.p, na},
                              RawSet{(const double *)((char *)c->pool_raw.p + offb), nb}, row_begin, row_end, out_norm);
 }
@@ -924,8 +973,8 @@ int kdejs_shard_phase1_balanced(int device, const double *a, int64_t na, const d
     if (!on_device) {
         const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
         OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
-        CU(cudaMemcpyAsync(c->pool_raw.p, a, (size_t)na * 16, cudaMemcpyHostToDevice, c->s_compute));
-        CU(cudaMemcpyAsync((char *)c->pool_raw.p + offb, b, (size_t)nb * 16, cudaMemcpyHostToDevice, c->s_compute));
+        OKR(h2d_ranges(device, {Stager::Range{c->pool_raw.p, a, (size_t)na * 16},
+                                Stager::Range{(char *)c->pool_raw.p + offb, b, (size_t)nb * 16}}, c->s_compute));
         ra.p = (const double *)c->pool_raw.p;
         rb.p = (const double *)((char *)c->pool_raw.p + offb);
     } else if ((((uintptr_t)a) | ((uintptr_t)b)) & 15) {

@@ -618,3 +618,34 @@ def test_cell_moments_switch_on_by_themselves_for_dense_cells(pk, ko):
     nat.check(L.kdejs_profile_enable(0, 0))
     assert n.value == 1
     assert rel(got, ko.discrepancy(a, b, 0.25, 0.0, resolution=512)) < JS_RTOL_EXPECT
+
+
+def test_pageable_inputs_go_through_the_staging_threads_and_change_nothing(pk):
+    """Ordinary numpy arrays (what the reference's callers pass) are staged through pinned slots by worker
+    threads; page-locked arrays are copied directly.  Same bits either way, for the batch, pairs and single paths,
+    including ragged sizes that split into several 2 MB chunks."""
+    from oracle import workloads as wl
+
+    nat = pk._native
+    rng = np.random.default_rng(3)
+    obs = wl.synthetic_target(100_000)
+    sizes = [100_000, 1, 131_072, 131_073, 262_145, 77, 50_000, 400_000] + [int(x) for x in rng.integers(1, 150_000, 40)]
+    sims = [wl.sim_S(10 + i, 1500 + 10 * i, 0.3 + 0.002 * i, n=n) for i, n in enumerate(sizes)]
+    pool = nat.PinnedPool()
+    pobs = pool.empty(obs.shape); pobs[:] = obs
+    psims = []
+    for s in sims:
+        b = pool.empty(s.shape); b[:] = s; psims.append(b)
+    want = pk.KDE_JS_divergence_batch(pobs, psims, 0.25, 0.0, resolution=128)
+    for _ in range(3):          # repeated calls reuse the slot ring
+        got = pk.KDE_JS_divergence_batch(obs, sims, 0.25, 0.0, resolution=128)
+        np.testing.assert_array_equal(got, want)
+    mixed = [psims[i] if i % 3 == 0 else sims[i] for i in range(len(sims))]
+    np.testing.assert_array_equal(pk.KDE_JS_divergence_batch(pobs, mixed, 0.25, 0.0, resolution=128), want)
+    pairs = [(0, 1), (3, 4), (7, 4), (2, 2)]
+    np.testing.assert_array_equal(pk.KDE_JS_divergence_pairs(sims[:8], pairs, gamma=0.25, eps=0.0, resolution=128),
+                                  pk.KDE_JS_divergence_pairs(psims[:8], pairs, gamma=0.25, eps=0.0, resolution=128))
+    big_a, big_b = wl.synthetic_target(700_001, seed=4), wl.sim_S(2, 1600, 0.35, n=333_333)
+    pa = pool.empty(big_a.shape); pa[:] = big_a
+    pb = pool.empty(big_b.shape); pb[:] = big_b
+    assert pk.KDE_JS_divergence(big_a, big_b, 0.25, 0.0, resolution=200) == pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=200)
