@@ -349,6 +349,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_sweep = world * sweep_n / float(t.item())
 
+    # ---- the same step from ordinary (pageable) numpy arrays: what a caller of the reference passes ------
+    e2e_pageable = None
+    if rank == 0 and world == 1:
+        pg = sims[:BATCH]
+        pk.KDE_JS_divergence_batch(target, pg, gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            res_pg = pk.KDE_JS_divergence_batch(target, pg, gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
+        e2e_pageable = 3 * BATCH / (time.perf_counter() - t0)
+        assert np.array_equal(res_pg, pk.KDE_JS_divergence_batch(h_target, h_sims[:BATCH], gamma=GAMMA, eps=EPS,
+                                                                 resolution=RES, algo=args.algo, devices=dev))
+
     # ---- single-call latency (BOLFI acquisition phase: batch of one) ------------------------------
     lat = []
     for s in range(8):
@@ -486,6 +498,9 @@ def main():
                 "steps": e2e_steps, "api": "KDE_JS_divergence_batch (ctypes -> kdejs_discrepancy_batch), "
                                            "pinned host arrays",
                 "host_numa_node": numa_node},
+        "e2e_pageable": {"value": e2e_pageable, "unit": UNIT,
+                         "note": "same step from ordinary numpy arrays (pageable memory), staged through pinned slots "
+                                 "by the library's worker threads (csrc/kdejs_stager.h); results bit-identical"},
         "gpu_launches": int(n_launch.value),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -39,7 +39,7 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 // Host ranges of at least this size that are not page-locked go through the staging threads (kdejs_stager.h);
 // smaller ones are not worth waking them for.
-constexpr size_t kStageMinBytes = (size_t)4 << 20;
+static const size_t kStageMinBytes = getenv("KDEJS_STAGE_MIN") ? (size_t)atoll(getenv("KDEJS_STAGE_MIN")) : ((size_t)4 << 20);
 
 // Upload several host ranges in order on `st`.  Page-locked sources are copied directly; pageable ones are
 // staged when together they are large enough.
