@@ -6,7 +6,8 @@
 //   k_minmax         joint NaN-ignoring min/max per raw point set (MinMaxScaler.fit, KDE_distance.py:81-82)
 //   k_scale_count    X*scale_+min_, NaN->0 (KDE_distance.py:85-86, :53): cell id and in-warp rank per point,
 //                    per-warp / per-block cell histograms
-//   k_scan           exclusive scan of the (cell, block) counts -> cell starts and block bases
+//   k_scan_*         exclusive scan of the (cell, block) counts -> cell starts and block bases
+//   k_cell_moments   (fine grids, dense cells) five moments per cell for cells wholly inside a tile's support
 //   k_place          stable counting-sort placement of the scaled points by cell (pure scatter)
 //   k_tile_classify  candidates per 4x4-node tile -> work list in ten weight classes; empty tiles finished here
 //   k_density_*      Epanechnikov sums on the R x R grid (get_kde + generate_samples, :48-64),
@@ -23,7 +24,7 @@
 
 namespace kdejs {
 
-constexpr int kMaxWaveItems = 32;
+constexpr int kMaxWaveItems = 64;
 constexpr int kMaxWaveSets = 2 * kMaxWaveItems;
 constexpr int kMaxCellsSide = 128;                // cells per side of the culling grid (64 unless the grid is fine)
 constexpr int kMaxCells = kMaxCellsSide * kMaxCellsSide;
@@ -45,7 +46,7 @@ struct SetDesc {           // one KDE to build: `rs_self` scaled jointly with `r
     int64_t off;                        // first point in the wave's scaled/sorted arrays
     double knorm_over_n;                // kernel normaliser / n: density = sum * knorm_over_n
 };
-struct WaveDesc {          // passed by value as a __grid_constant__ kernel parameter (< 4 KB)
+struct WaveDesc {          // passed by value as a __grid_constant__ kernel parameter (6 KB; CUDA >= 12.1 allows 32 KB)
     RawSet raw[kMaxWaveSets];
     SetDesc set[kMaxWaveSets];
     int32_t n_raw, n_sets;
