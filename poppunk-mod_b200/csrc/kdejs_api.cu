@@ -79,7 +79,7 @@ struct DevBuf {
 
 struct Slot {
     DevBuf rawsims, scaled, sorted, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
-    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, counters, totals, rank16, warpprefix;
+    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, counters, totals, rank16, warpprefix, tileflag;
     cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
 };
 
@@ -300,6 +300,12 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     // a moment cell costs a tile as much as one point plus some per-row bookkeeping: it pays once cells hold
     // hundreds of points (measured: -40 % density time at 1200 points per cell, +48 % at 49)
     if (g.use_moments == 1 && P < (int64_t)128 * n_sets * ncells) g.use_moments = 0;
+    // Plain discrepancies (no grids requested, one launch for the whole grid): tiles without candidates are only
+    // flagged and the divergence kernel reads the flag instead of 16 node values -- ~70 % of the grid is never
+    // written or read.
+    const bool lazy_empty = binned && !io.want_z && !io.density_only && !io.shard && io.balance_world == 0 &&
+                            g.tile_row_begin == 0 && g.tile_row_end == g.NT;
+    if (lazy_empty) OKR(sl.tileflag.ensure((size_t)n_sets * g.NT * g.NT));
     const int nparts = binned ? g.NT * g.NT : (int)((G + 255) / 256);
 
     if (!binned) OKR(sl.scaled.ensure((size_t)P * sizeof(double2)));
@@ -310,7 +316,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     const int mm_blocks = 64;
     OKR(sl.rpart.ensure(sizeof(RawStat) * kMaxWaveSets * mm_blocks));
     const int js_blocks = (int)((G + kJsNodesPerBlock - 1) / kJsNodesPerBlock);
-    OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)std::max(1, n_items) * js_blocks));
+    OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)std::max(1, n_items) * std::max(js_blocks, g.NT)));
     if (io.want_z) OKR(sl.zout.ensure((size_t)n_sets * G * sizeof(double)));
     if (binned) {
         OKR(sl.sorted.ensure((size_t)P * sizeof(double2)));
@@ -403,7 +409,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             k_tile_classify<<<dim3((tiles + 31) / 32, n_sets), 256, 0, st>>>(
                 wd, g, sl.cellstart.as<uint32_t>(), sl.dens.as<double>(), sl.pz.as<double>(),
                 sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity,
-                c.prof_on ? c.d_work : nullptr);
+                c.prof_on ? c.d_work : nullptr, lazy_empty ? sl.tileflag.as<uint8_t>() : nullptr);
         }
         if (tiles > 0) {
             KTimer t(c, 4, st);
@@ -472,6 +478,11 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             k_set_totals<<<n_sets, kJsThreads, 0, st>>>(nparts, sl.tilesum.as<double>(), sl.totals.as<double>());
         }
         KTimer t(c, 5, st);
+        if (lazy_empty)
+            k_js_tiles<<<dim3(g.NT, n_items), kJsThreads, 0, st>>>(
+                wd, g, sl.pz.as<double>(), sl.totals.as<double>(), sl.rstat.as<RawStat>(),
+                sl.tileflag.as<uint8_t>(), sl.jspart.as<double>(), tk_js, io.out_js, io.out_status, io.item_base);
+        else
         k_js<<<dim3(js_blocks, n_items), kJsThreads, 0, st>>>(
             wd, (int)G, nparts, 0, (int)G, sl.pz.as<double>(), sl.totals.as<double>(),
             sl.rstat.as<RawStat>(), io.want_z ? sl.zout.as<double>() : nullptr,
@@ -602,7 +613,7 @@ void kdejs_shutdown(void) {
         for (auto &s : c.slot) {
             for (DevBuf *b : {&s.rawsims, &s.scaled, &s.sorted, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
                               &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart,
-                              &s.dense_partial, &s.worklist, &s.counters, &s.totals, &s.rank16, &s.warpprefix}) {
+                              &s.dense_partial, &s.worklist, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag}) {
                 if (b->p) cudaFree(b->p);
                 b->p = nullptr; b->cap = 0;
             }
@@ -696,7 +707,7 @@ int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, 
     OKR(c->status_out.ensure(sizeof(int32_t)));
     OKR(ensure_host_results(*c, 1));
     const int32_t ia = 0, ib = 1;
-    const bool want_z = out_z1 || out_z2;
+    const bool want_z = out_z1 || out_z2 || out_d1 || out_d2;     // any grid output: every node value is materialised
     OKR(run_pairs_dev(*c, st, 0, p, pool, &ia, &ib, 1, c->js_out.as<double>(), c->status_out.as<int32_t>(), 0, want_z));
     CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

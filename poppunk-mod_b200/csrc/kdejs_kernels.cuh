@@ -34,7 +34,7 @@ constexpr int kTile = 4;                          // nodes per tile side (16 acc
 constexpr int kDensThreads = 128;
 constexpr int kMaxRows = 32;                      // cell rows a tile may have to visit
 constexpr int kJsThreads = 256;
-constexpr int kJsNodesPerBlock = 1024;
+constexpr int kJsNodesPerBlock = 2048;
 constexpr int kMinmaxThreads = 256;
 
 struct RawSet {            // a point set as the caller gave it: (n,2) interleaved fp64, device memory
@@ -494,6 +494,10 @@ __device__ __forceinline__ TileCells tile_cells(const GridGeom &g, int ix0, int 
 // within h of EVERY node of the tile -- are left out of the point runs: inside the support the Epanechnikov
 // term is a polynomial, so such a cell enters through its moments (accumulate_cell) at the cost of one
 // point.  What remains are two point runs (s1,l1) and (s2,l2) left and right of the moment cells.
+// Bounds of sqrt(x), x >= 0, from the fp32 unit: the cell ranges only have to be conservative, and an fp64
+// square root per cell row is a measurable part of the per-tile prologue (rel. error of the fp32 value <= 1.2e-7).
+__device__ __forceinline__ double sqrt_up(double x) { return (double)(sqrtf((float)x) * 1.000001f); }
+__device__ __forceinline__ double sqrt_down(double x) { return (double)(sqrtf((float)x) * 0.999999f); }
 struct RowRuns { uint32_t s1, l1, s2, l2; int mlo, mcnt; };
 __device__ __forceinline__ RowRuns tile_row_runs(const GridGeom &g, const TileCells &tc,
                                                  const uint32_t *__restrict__ cs, int cy, const bool moments) {
@@ -504,7 +508,7 @@ __device__ __forceinline__ RowRuns tile_row_runs(const GridGeom &g, const TileCe
     const double rx2 = g.h * g.h - dy * dy;
     RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
     if (rx2 > 0.0) {
-        const double rx = sqrt(rx2) + g.margin;
+        const double rx = sqrt_up(rx2) + g.margin;
         const int cx_lo = cell_of(tc.gx0 - rx, g.cell_x0, g.cell_invw, g.C);
         const int cx_hi = cell_of(tc.xhi + rx, g.cell_x0, g.cell_invw, g.C);
         int mlo = cx_hi + 1, mhi = cx_hi;                    // no moment cells
@@ -513,7 +517,7 @@ __device__ __forceinline__ RowRuns tile_row_runs(const GridGeom &g, const TileCe
             const double fy = fmax(tc.yhi - row_lo, row_hi - tc.gy0) + g.margin;
             const double fx2 = g.h * g.h - fy * fy;
             if (fx2 > 0.0) {
-                const double fx = sqrt(fx2) - g.margin;
+                const double fx = sqrt_down(fx2) - g.margin;
                 // cell c = [x0 + c w, x0 + (c+1) w] qualifies iff  xhi - (x0 + c w) <= fx  and  x0 + (c+1) w - gx0 <= fx
                 const int lo = max(__double2int_ru((tc.xhi - fx - g.cell_x0) * g.cell_invw + 1e-9), max(cx_lo, 1));
                 const int hi = min(__double2int_rd((tc.gx0 + fx - g.cell_x0) * g.cell_invw - 1e-9) - 1, min(cx_hi, g.C - 2));
@@ -553,7 +557,7 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 const uint32_t *__restrict__ cellstart, double *__restrict__ dens,
                 double *__restrict__ pz, double *__restrict__ tilesum, uint32_t *__restrict__ worklist,
                 unsigned *__restrict__ counters, unsigned capacity,
-                unsigned long long *__restrict__ work_counter) {
+                unsigned long long *__restrict__ work_counter, uint8_t *__restrict__ tileflag) {
     const int ntl = (g.tile_row_end - g.tile_row_begin) * g.NT;
     const int tl = blockIdx.x * (blockDim.x / kClassifyLanes) + threadIdx.x / kClassifyLanes;
     const int sub = threadIdx.x % kClassifyLanes;
@@ -575,10 +579,11 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
     total += __shfl_xor_sync(0xffffffffu, total, 4);
     if (live) {
         const int tile = tx * g.NT + ty;
+        if (tileflag && sub == 0) tileflag[(size_t)set * g.NT * g.NT + tile] = (total == 0u) ? 1 : 0;
         if (total == 0u) {
             const double P0 = gamma_eps(0.0, g);
 #pragma unroll
-            for (int k = sub; k < kTile * kTile; k += kClassifyLanes) {      // two nodes per lane
+            for (int k = sub; !tileflag && k < kTile * kTile; k += kClassifyLanes) {      // two nodes per lane
                 const int ix = ix0 + k / kTile, iy = iy0 + k % kTile;
                 if (ix < g.R && iy < g.R) {
                     const size_t n = (size_t)set * g.R * g.R + (size_t)ix * g.R + iy;
@@ -1137,9 +1142,15 @@ k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_
     double left = 0.0, right = 0.0;
     const int kb = k_begin + blockIdx.x * kJsNodesPerBlock;
     const int ke = min(kb + kJsNodesPerBlock, k_end);
+    const bool normal = (tp > 0.0) && (tq > 0.0);          // false for a zero or NaN normaliser (empty KDE)
     for (int k = kb + threadIdx.x; k < ke; k += kJsThreads) {
-        const double p = pz[(size_t)s0 * G + k] / tp;      // z /= z.sum()  KDE_distance.py:76
-        const double q = pz[(size_t)s1 * G + k] / tq;
+        const double a = pz[(size_t)s0 * G + k], b = pz[(size_t)s1 * G + k];
+        if (normal && a == 0.0 && b == 0.0) {              // both probabilities are exactly 0: nothing to add
+            if (z_out) { z_out[(size_t)s0 * G + k] = 0.0; z_out[(size_t)s1 * G + k] = 0.0; }
+            continue;
+        }
+        const double p = a / tp;                           // z /= z.sum()  KDE_distance.py:76
+        const double q = b / tq;
         const double m = (p + q) / 2.0;
         // rel_entr(p,m) + rel_entr(q,m) of ONE node is >= 0 (log-sum inequality) while the two separate sums
         // scipy forms cancel against each other: for near-identical distributions left ~ -right ~ 1e-3 and
@@ -1153,8 +1164,7 @@ k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_
         if (q != q) left = q;
         if (z_out) { z_out[(size_t)s0 * G + k] = p; z_out[(size_t)s1 * G + k] = q; }
     }
-    left = block_sum(left, s_w);
-    right = block_sum(right, s_w);
+    left = block_sum(left, s_w);                           // `right` is 0 in every thread
     if (threadIdx.x == 0) {
         jspart[((size_t)item * gridDim.x + blockIdx.x) * 2 + 0] = left;
         jspart[((size_t)item * gridDim.x + blockIdx.x) * 2 + 1] = right;
@@ -1175,6 +1185,74 @@ k_js(const __grid_constant__ WaveDesc wd, int G, int nparts, int k_begin, int k_
             if (out_lr) { out_lr[0] = L; out_lr[1] = Rr; }
             if (out_norm) { out_norm[0] = tp; out_norm[1] = tq; }
             double js2 = (L + Rr) / 2.0;
+            if (js2 < 0.0) js2 = 0.0;          // rounding can leave -1e-20 where the exact value is +1e-20; NaN stays NaN
+            if (out_js) out_js[item_base + item] = bad ? __longlong_as_double(0x7ff8000000000000LL) : sqrt(js2);
+            if (out_status) out_status[item_base + item] = bad ? 3 : 0;
+            ticket[item] = 0;
+        }
+    }
+}
+
+// k_js_tiles: the divergence of the binned path when nobody asked for the grids.  grid (NT tile rows, n_items),
+// 256 threads; a half-warp owns one 4x4-node tile at a time (its 16 nodes are four 32-byte segments of pz).
+// Tiles without candidates were only FLAGGED by k_tile_classify (tileflag = 1), their node values never written:
+// such a node's value is the constant gamma_eps(0), so neither kernel touches those ~70 % of the grid in memory.
+// Arithmetic per node and the last-block fold are k_js's.
+__global__ void __launch_bounds__(kJsThreads)
+k_js_tiles(const __grid_constant__ WaveDesc wd, const GridGeom g, const double *__restrict__ pz,
+           const double *__restrict__ totals, const RawStat *__restrict__ rstat,
+           const uint8_t *__restrict__ tileflag, double *__restrict__ jspart, unsigned *__restrict__ ticket,
+           double *__restrict__ out_js, int32_t *__restrict__ out_status, int item_base) {
+    __shared__ double s_w[32];
+    __shared__ bool s_last;
+    const int item = blockIdx.y;
+    const int s0 = 2 * item, s1 = 2 * item + 1;
+    const double tp = totals[s0], tq = totals[s1];
+    const bool normal = (tp > 0.0) && (tq > 0.0);
+    const double P0 = gamma_eps(0.0, g);
+    const size_t G = (size_t)g.R * g.R;
+    const int ntiles = g.NT * g.NT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x, ix = tx * kTile + ((lane & 15) >> 2), jj = lane & 3;
+    double left = 0.0;
+    if (ix < g.R) {
+        for (int ty = warp * 2 + (lane >> 4); ty < g.NT; ty += 2 * (kJsThreads / 32)) {
+            const int iy = ty * kTile + jj;
+            if (iy >= g.R) continue;
+            const int tile = tx * g.NT + ty;
+            const size_t k = (size_t)ix * g.R + iy;
+            const double a = tileflag[(size_t)s0 * ntiles + tile] ? P0 : pz[(size_t)s0 * G + k];
+            const double b = tileflag[(size_t)s1 * ntiles + tile] ? P0 : pz[(size_t)s1 * G + k];
+            if (normal && a == 0.0 && b == 0.0) continue;
+            const double p = a / tp;                           // z /= z.sum()  KDE_distance.py:76
+            const double q = b / tq;
+            const double m = (p + q) / 2.0;
+            double node = 0.0;
+            if (p > 0.0) node = p * log_ratio(p, m);           // rel_entr(0, m) = 0
+            if (q > 0.0) node += q * log_ratio(q, m);
+            left += node;
+            if (p != p) left = p;                              // NaN normaliser (empty KDE) propagates
+            if (q != q) left = q;
+        }
+    }
+    left = block_sum(left, s_w);
+    if (threadIdx.x == 0) {
+        jspart[((size_t)item * gridDim.x + blockIdx.x) * 2 + 0] = left;
+        jspart[((size_t)item * gridDim.x + blockIdx.x) * 2 + 1] = 0.0;
+        __threadfence();
+        unsigned t = atomicAdd(&ticket[item], 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {          // warp 0 of the last block folds the block partials, fixed shape
+        __threadfence();
+        const volatile double *vp = jspart + (size_t)item * gridDim.x * 2;
+        double L = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) L += vp[2 * i];
+        L = warp_sum(L);
+        if (threadIdx.x == 0) {
+            const int bad = (rstat[wd.set[s0].rs_self].flags | rstat[wd.set[s0].rs_other].flags) & 1;
+            double js2 = L / 2.0;
             if (js2 < 0.0) js2 = 0.0;          // rounding can leave -1e-20 where the exact value is +1e-20; NaN stays NaN
             if (out_js) out_js[item_base + item] = bad ? __longlong_as_double(0x7ff8000000000000LL) : sqrt(js2);
             if (out_status) out_status[item_base + item] = bad ? 3 : 0;
