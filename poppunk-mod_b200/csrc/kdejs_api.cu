@@ -313,7 +313,10 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     OKR(sl.pz.ensure((size_t)n_sets * G * sizeof(double)));
     OKR(sl.tilesum.ensure((size_t)n_sets * nparts * sizeof(double)));
     OKR(sl.rstat.ensure(sizeof(RawStat) * kMaxWaveSets));
-    const int mm_blocks = 64;
+    // blocks per raw set of the min/max pass: enough to fill the GPU about eight-fold over the whole wave, few enough
+    // that a block's reduction and ticket do not dominate its few hundred points
+    static const int mm_env = getenv("KDEJS_MM_BLOCKS") ? atoi(getenv("KDEJS_MM_BLOCKS")) : 0;
+    const int mm_blocks = mm_env > 0 ? std::min(mm_env, 64) : std::max(8, std::min(64, (8 * c.sm_count) / std::max(1, (int)wd.n_raw)));
     OKR(sl.rpart.ensure(sizeof(RawStat) * kMaxWaveSets * mm_blocks));
     const int js_blocks = (int)((G + kJsNodesPerBlock - 1) / kJsNodesPerBlock);
     OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)std::max(1, n_items) * std::max(js_blocks, g.NT)));
