@@ -238,6 +238,8 @@ GridGeom make_geom(const Params &p) {
     g.gamma_mode = (p.gamma == 1.0) ? 1 : (p.gamma == 0.5) ? 2 : (p.gamma == 0.25) ? 3 : 0;
     g.tile_row_begin = 0;
     g.tile_row_end = g.NT;
+    g.sets_per_group = kMaxWaveSets;      // one group until run_wave() knows the wave
+    g.pad3 = 0;
     g.heavy_log2 = 13;
     if (const char *e = getenv("KDEJS_HEAVY_LOG2")) g.heavy_log2 = std::max(6, std::min(30, atoi(e)));
     // Cells that lie wholly inside the support of every node of a tile enter through their moments.  A cell
@@ -329,8 +331,16 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * ncells * sizeof(uint32_t)));
         OKR(sl.cellstart.ensure((size_t)n_sets * (ncells + 1) * sizeof(uint32_t)));
         if (g.use_moments) OKR(sl.moments.ensure((size_t)n_sets * ncells * kMomentDoubles * sizeof(double)));
-        OKR(sl.worklist.ensure((size_t)kNumClasses * n_sets * g.NT * g.NT * sizeof(uint32_t)));
-        OKR(sl.counters.ensure(16 * sizeof(unsigned)));
+        // set groups of the work list: a group's sorted points (16 B each) should fit the L2 a few times over
+        {
+            const double group_bytes = 40.0e6;
+            int n_groups = (int)std::ceil((double)P * 16.0 / group_bytes);
+            n_groups = std::max(1, std::min(std::min(n_groups, kMaxGroups), n_sets));
+            if (const char *e = getenv("KDEJS_GROUPS")) n_groups = std::max(1, std::min(std::min(atoi(e), kMaxGroups), n_sets));
+            g.sets_per_group = (n_sets + n_groups - 1) / n_groups;
+        }
+        OKR(sl.worklist.ensure((size_t)kNumLists * g.sets_per_group * g.NT * g.NT * sizeof(uint32_t)));
+        OKR(sl.counters.ensure(kNumCounters * sizeof(unsigned)));
     }
 
     unsigned *tk_minmax = sl.tickets.as<unsigned>();
@@ -406,7 +416,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         }
         if (io.out_tile_rows) { io.out_tile_rows[0] = g.tile_row_begin; io.out_tile_rows[1] = g.tile_row_end; }
         const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
-        const unsigned capacity = (unsigned)tiles * (unsigned)n_sets;
+        const unsigned capacity = (unsigned)tiles * (unsigned)g.sets_per_group;      // entries per (group, class) list
         if (tiles > 0) {
             KTimer t(c, 6, st);
             k_tile_classify<<<dim3((tiles + 31) / 32, n_sets), 256, 0, st>>>(
@@ -416,7 +426,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         }
         if (tiles > 0) {
             KTimer t(c, 4, st);
-            const int blocks = (int)std::min<int64_t>((int64_t)capacity, (int64_t)c.sm_count * c.dens_blocks_per_sm);
+            const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * c.dens_blocks_per_sm);
             if (g.use_moments)
                 k_density_binned<true><<<blocks, kDensThreads, 0, st>>>(
                     wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),

@@ -72,6 +72,6 @@ def _bytes(key):
 
 
 json.dump({"k_density_binned": {"dram_bytes_read": _bytes("dram__bytes_read.sum"),
-                                "dram_bytes_write": _bytes("dram__bytes_write.sum"), "evals_per_launch": 32,
+                                "dram_bytes_write": _bytes("dram__bytes_write.sum"), "evals_per_launch": 64,
                                 "source": f"profiles/{tag}_density_binned_full.txt (ncu --set full, launch 0)"}},
           open("profiles/traffic.json", "w"), indent=1)
