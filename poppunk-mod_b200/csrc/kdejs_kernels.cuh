@@ -547,7 +547,7 @@ __device__ __forceinline__ RowRuns tile_row_runs(const GridGeom &g, const TileCe
 
 // Work-list layout.  Tiles are bucketed by candidate count so that the persistent density kernel can
 // hand them out heaviest first (longest-processing-time order keeps the tail short):
-//   class 0: >= 8192 candidates (one tile per block), class c in 1..9: [2^(13-c), 2^(14-c)) (per warp),
+//   class 0: >= 2^H candidates, H = heavy_log2 = 14 (one tile per block), class c in 1..9: [2^(H-c), 2^(H+1-c)) (per warp),
 //   class 9 also takes everything below 16.
 // counters: [group*10 + class] entries per list, then the block ticket and the warp ticket (zeroed by k_scan each wave).
 
@@ -760,7 +760,7 @@ __device__ __forceinline__ uint32_t list_entry(const uint32_t *__restrict__ work
 // contiguous run per cell row).  Lanes take candidates round-robin and keep the tile's 16 fp64 sums in
 // registers:  t = 1 - ux^2 - uy^2 in units of h, added when non-negative (strict dist < h,
 // sklearn:_binary_tree.pxi.tp:389-394; a zero term changes nothing).
-//   phase A  the few very heavy tiles (class 0, >= 8192 candidates): one tile per BLOCK
+//   phase A  the few very heavy tiles (class 0, >= 2^heavy_log2 candidates): one tile per BLOCK
 //   phase B  everything else: one tile per WARP, no block-level synchronisation at all
 // Each phase ends a tile with a fixed-shape reduction through shared memory, the 16 node values,
 // their **gamma+eps and the tile's share of the normaliser.  Which warp or block processes a tile is
