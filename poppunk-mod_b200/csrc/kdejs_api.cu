@@ -240,7 +240,7 @@ GridGeom make_geom(const Params &p) {
     g.tile_row_end = g.NT;
     g.sets_per_group = kMaxWaveSets;      // one group until run_wave() knows the wave
     g.pad3 = 0;
-    g.heavy_log2 = 14;
+    g.heavy_log2 = 13;
     if (const char *e = getenv("KDEJS_HEAVY_LOG2")) g.heavy_log2 = std::max(6, std::min(30, atoi(e)));
     // Cells that lie wholly inside the support of every node of a tile enter through their moments.  A cell
     // concentric with a tile qualifies up to a centre offset rho; worth its bookkeeping once that region is at

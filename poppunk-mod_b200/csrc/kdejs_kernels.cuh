@@ -547,7 +547,7 @@ __device__ __forceinline__ RowRuns tile_row_runs(const GridGeom &g, const TileCe
 
 // Work-list layout.  Tiles are bucketed by candidate count so that the persistent density kernel can
 // hand them out heaviest first (longest-processing-time order keeps the tail short):
-//   class 0: >= 2^H candidates, H = heavy_log2 = 14 (one tile per block), class c in 1..9: [2^(H-c), 2^(H+1-c)) (per warp),
+//   class 0: >= 2^H candidates, H = heavy_log2 = 13 (one tile per block), class c in 1..9: [2^(H-c), 2^(H+1-c)) (per warp),
 //   class 9 also takes everything below 16.
 // counters: [group*10 + class] entries per list, then the block ticket and the warp ticket (zeroed by k_scan each wave).
 
@@ -828,46 +828,37 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
             const int rows = tc.cy_hi - tc.cy_lo + 1;       // <= kMaxRows by the host's choice of C
             RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
             if (lane < rows) rr = tile_row_runs(g, tc, cs, tc.cy_lo + lane, MOMENTS);
-            const uint32_t both = rr.l1 + rr.l2;
-            uint32_t inc = both;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
             s_rs[2 * lane] = rr.s1;
             s_rs[2 * lane + 1] = rr.s2;
-            s_cum[2 * lane + 1] = inc - both + rr.l1;
-            s_cum[2 * lane + 2] = inc;
+            s_cum[2 * lane] = rr.l1;                         // run LENGTHS (the name is historic)
+            s_cum[2 * lane + 1] = rr.l2;
             s_mlo[lane] = rr.mlo;
             s_mcnt[lane] = rr.mcnt;
-            if (lane == 0) { s_cum[0] = 0u; s_rows = rows; s_cy0 = tc.cy_lo; }
+            if (lane == 0) { s_rows = rows; s_cy0 = tc.cy_lo; }
         }
         __syncthreads();
-        const uint32_t total = s_cum[2 * kMaxRows];
         double acc[kTile][kTile];
 #pragma unroll
         for (int i = 0; i < kTile; ++i)
 #pragma unroll
             for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
         const double2 *__restrict__ pts = sorted + sd.off;
-        int r = 0;
-        uint32_t idx = threadIdx.x;
-        bool more = idx < total;
-        double2 pn = make_double2(0.0, 0.0);
-        if (more) {
-            while (idx >= s_cum[r + 1]) ++r;
-            pn = pts[s_rs[r] + (idx - s_cum[r])];
-        }
-        while (more) {
-            const double2 p = pn;
-            idx += kDensThreads;                            // the lane's next candidate is in flight
-            more = idx < total;
-            if (more) {
-                while (idx >= s_cum[r + 1]) ++r;
-                pn = pts[s_rs[r] + (idx - s_cum[r])];
+        // run by run, the block's 128 threads stride through the candidates: the same loop as phase B (no
+        // per-candidate run lookup; a heavy tile's runs are long, so the ragged last 128 cost a few per cent)
+        const int nruns = (MOMENTS ? 2 : 1) * s_rows;
+        for (int k = 0; k < nruns; ++k) {
+            const int e = MOMENTS ? k : 2 * k;               // without moment cells only the even entries are used
+            const uint32_t len = s_cum[e];
+            const double2 *__restrict__ rp = pts + s_rs[e];
+            uint32_t j = threadIdx.x;
+            double2 pn = make_double2(0.0, 0.0);
+            if (j < len) pn = rp[j];
+            while (j < len) {
+                const double2 p = pn;
+                j += kDensThreads;
+                if (j < len) pn = rp[j];                     // the lane's next candidate is in flight
+                accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
             }
-            accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
         }
         if (MOMENTS) {
             const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
