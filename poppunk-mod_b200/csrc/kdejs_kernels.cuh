@@ -776,6 +776,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
     __shared__ uint32_t s_rs[2 * kMaxRows];          // two point runs per cell row (left / right of the moment cells)
     __shared__ uint32_t s_cum[2 * kMaxRows + 1];
     __shared__ int s_mlo[kMaxRows], s_mcnt[kMaxRows], s_rows, s_cy0;
+    __shared__ uint8_t s_base[2 * kMaxRows];
     __shared__ double s_red[kRedDoubles];
     __shared__ unsigned s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -832,6 +833,16 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
             s_rs[2 * lane + 1] = rr.s2;
             s_cum[2 * lane] = rr.l1;                         // run LENGTHS (the name is historic)
             s_cum[2 * lane + 1] = rr.l2;
+            // 32-candidate chunks are dealt to the four warps round-robin ACROSS runs: s_base = chunks before a run
+            const uint32_t c1n = (rr.l1 + 31u) >> 5, c2n = (rr.l2 + 31u) >> 5;
+            uint32_t cinc = c1n + c2n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, cinc, o);
+                if (lane >= o) cinc += t;
+            }
+            s_base[2 * lane] = (uint8_t)((cinc - c1n - c2n) & 3u);
+            s_base[2 * lane + 1] = (uint8_t)((cinc - c2n) & 3u);
             s_mlo[lane] = rr.mlo;
             s_mcnt[lane] = rr.mcnt;
             if (lane == 0) { s_rows = rows; s_cy0 = tc.cy_lo; }
@@ -843,14 +854,14 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll
             for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
         const double2 *__restrict__ pts = sorted + sd.off;
-        // run by run, the block's 128 threads stride through the candidates: the same loop as phase B (no
-        // per-candidate run lookup; a heavy tile's runs are long, so the ragged last 128 cost a few per cent)
+        // run by run, each warp strides through every fourth 32-candidate chunk: the same loop as phase B (no
+        // per-candidate run lookup), and only the last chunk of a run is ragged
         const int nruns = (MOMENTS ? 2 : 1) * s_rows;
         for (int k = 0; k < nruns; ++k) {
             const int e = MOMENTS ? k : 2 * k;               // without moment cells only the even entries are used
             const uint32_t len = s_cum[e];
             const double2 *__restrict__ rp = pts + s_rs[e];
-            uint32_t j = threadIdx.x;
+            uint32_t j = (((uint32_t)warp - s_base[e]) & 3u) * 32u + lane;
             double2 pn = make_double2(0.0, 0.0);
             if (j < len) pn = rp[j];
             while (j < len) {
