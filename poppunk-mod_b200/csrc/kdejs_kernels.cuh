@@ -757,11 +757,14 @@ __device__ __forceinline__ uint32_t list_entry(const uint32_t *__restrict__ work
 
 // k_density_binned: persistent, (#SM x resident) blocks of 128 threads pulling 4x4-node tiles from
 // the work list.  A tile's candidates are the sorted points of the cells that can reach it (one
-// contiguous run per cell row).  Lanes take candidates round-robin and keep the tile's 16 fp64 sums in
-// registers:  t = 1 - ux^2 - uy^2 in units of h, added when non-negative (strict dist < h,
-// sklearn:_binary_tree.pxi.tp:389-394; a zero term changes nothing).
-//   phase A  the few very heavy tiles (class 0, >= 2^heavy_log2 candidates): one tile per BLOCK
+// contiguous run per cell row; with MOMENTS two runs around the cells that enter through their moments).
+// Lanes take candidates round-robin and keep the tile's 16 fp64 sums in registers:  t = 1 - ux^2 - uy^2 in
+// units of h, added when non-negative (strict dist < h, sklearn:_binary_tree.pxi.tp:389-394; a zero term
+// changes nothing).
+//   phase A  the few very heavy tiles (class 0, >= 2^heavy_log2 candidates): one tile per BLOCK, the 32-candidate
+//            chunks of its runs dealt to the four warps round-robin
 //   phase B  everything else: one tile per WARP, no block-level synchronisation at all
+// Both phases walk the work list in (set group, class) order -- see kMaxGroups.
 // Each phase ends a tile with a fixed-shape reduction through shared memory, the 16 node values,
 // their **gamma+eps and the tile's share of the normaliser.  Which warp or block processes a tile is
 // decided at run time (atomic tickets) but never changes a result.
@@ -774,7 +777,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
                  const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
                  unsigned capacity) {
     __shared__ uint32_t s_rs[2 * kMaxRows];          // two point runs per cell row (left / right of the moment cells)
-    __shared__ uint32_t s_cum[2 * kMaxRows + 1];
+    __shared__ uint32_t s_len[2 * kMaxRows];         // their lengths
     __shared__ int s_mlo[kMaxRows], s_mcnt[kMaxRows], s_rows, s_cy0;
     __shared__ uint8_t s_base[2 * kMaxRows];
     __shared__ double s_red[kRedDoubles];
@@ -785,7 +788,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
     __shared__ unsigned s_preA[kMaxGroups + 1], s_preB[kMaxGroups * (kNumClasses - 1) + 1];
     __shared__ uint8_t s_listA[kMaxGroups], s_listB[kMaxGroups * (kNumClasses - 1)];
     __shared__ unsigned s_cnt[kNumLists];
-    if (threadIdx.x < kNumLists) s_cnt[threadIdx.x] = counters[threadIdx.x];     // one round trip, not eighty
+    if (threadIdx.x < kNumLists) s_cnt[threadIdx.x] = counters[threadIdx.x];     // one round trip for all lists
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned a = 0u, b = 0u;
@@ -831,8 +834,8 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
             if (lane < rows) rr = tile_row_runs(g, tc, cs, tc.cy_lo + lane, MOMENTS);
             s_rs[2 * lane] = rr.s1;
             s_rs[2 * lane + 1] = rr.s2;
-            s_cum[2 * lane] = rr.l1;                         // run LENGTHS (the name is historic)
-            s_cum[2 * lane + 1] = rr.l2;
+            s_len[2 * lane] = rr.l1;
+            s_len[2 * lane + 1] = rr.l2;
             // 32-candidate chunks are dealt to the four warps round-robin ACROSS runs: s_base = chunks before a run
             const uint32_t c1n = (rr.l1 + 31u) >> 5, c2n = (rr.l2 + 31u) >> 5;
             uint32_t cinc = c1n + c2n;
@@ -859,7 +862,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int nruns = (MOMENTS ? 2 : 1) * s_rows;
         for (int k = 0; k < nruns; ++k) {
             const int e = MOMENTS ? k : 2 * k;               // without moment cells only the even entries are used
-            const uint32_t len = s_cum[e];
+            const uint32_t len = s_len[e];
             const double2 *__restrict__ rp = pts + s_rs[e];
             uint32_t j = (((uint32_t)warp - s_base[e]) & 3u) * 32u + lane;
             double2 pn = make_double2(0.0, 0.0);
@@ -911,7 +914,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         __syncthreads();
         if (threadIdx.x == 0)
             tilesum[(size_t)set * g.NT * g.NT + tile] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-        __syncthreads();                               // s_item, s_rs, s_cum, s_red free for the next tile
+        __syncthreads();                               // s_item, s_rs, s_len, s_red free for the next tile
     }
 
     // ---------------- phase B: warp per tile ----------------
