@@ -129,3 +129,23 @@ def test_live_reference_agrees_with_golden_and_port(golden):
         assert float(ref_port.js_port(a, b, resolution=case["R"], **case_kwargs(case))) == raw
         masked, _, _ = ref_shim.js_masked(a, b, R=case["R"], **case_kwargs(case))
         assert rel(ko.discrepancy(a, b, resolution=case["R"], **case_kwargs(case)), float(masked)) < 1e-11
+
+
+def test_cell_moment_identity_used_by_the_fine_grid_path():
+    """for points that all lie inside the support of a node, the Epanechnikov sum is a polynomial in
+    five moments of the cell -- n, Sx, Sy, Sxx, Syy about the cell centre, in units of h:
+        sum_k [1 - (dx_k-u)^2 - (dy_k-v)^2] = (n - Sxx) + u (2 Sx - n u) - [Syy - v (2 Sy - n v)].
+    The CUDA kernel (accumulate_cell) evaluates exactly this expression; here it is checked against the direct sum."""
+    rng = np.random.default_rng(7)
+    h = 0.03
+    cx, cy, w = 0.4375, 0.71875, 1.0 / 128
+    pts = np.column_stack([cx + (rng.random(500) - 0.5) * w, cy + (rng.random(500) - 0.5) * w])
+    dx, dy = (pts[:, 0] - cx) / h, (pts[:, 1] - cy) / h
+    n, sx, sy, sxx, syy = len(pts), dx.sum(), dy.sum(), (dx * dx).sum(), (dy * dy).sum()
+    for gx, gy in [(0.43, 0.72), (0.45, 0.705), (cx, cy), (0.4375 + 0.012, 0.71875 - 0.015)]:
+        d2 = ((pts[:, 0] - gx) ** 2 + (pts[:, 1] - gy) ** 2) / h ** 2
+        assert d2.max() < 1.0                                   # the cell is wholly inside this node's support
+        direct = (1.0 - d2).sum()
+        u, v = (gx - cx) / h, (gy - cy) / h
+        via_moments = ((n - sxx) + u * (2 * sx - n * u)) - (syy - v * (2 * sy - n * v))
+        assert abs(via_moments - direct) <= 1e-12 * direct
