@@ -80,7 +80,9 @@ int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, 
 /* One target against B simulated sets: B independent KDE_JS_divergence(obs, sims[i], ...)
  * calls (the per-simulation call at poppunk_mod.py:373 over a BOLFI batch; the
  * Pool.imap loops at scripts/distance_to_gridsearch.py:109-110).  HOST pointers; sims
- * in pinned memory (kdejs_host_alloc) are copied asynchronously and overlap compute.
+ * in pinned memory (kdejs_host_alloc) are copied asynchronously and overlap compute;
+ * pageable sims (ordinary numpy arrays) are staged through pinned slots by the library's own
+ * threads (KDEJS_STAGE_THREADS, default 4) and reach ~85 % of the pinned rate.
  * out_js: B doubles.  If some sets contain infinity their out_js is NaN and the call
  * returns KDEJS_ERR_INF after finishing the others. */
 int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs,
