@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- KDE discrepancy evaluations/s on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--algo binned|binned32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config C2 of SURVEY.md 8d, batched as C3): every step each GPU evaluates BATCH=64
-independent discrepancies KDE_JS_divergence(target, sim_i, gamma=0.25, eps=0) with a 100 000-pair
-target, 100 000-pair simulated sets, a 256x256 grid, bandwidth 0.03, Epanechnikov kernel.
-Sims are distinct per step and per rank (a resident pool larger than L2 is rotated).
+Workload (config C2 of SURVEY.md 8d, batched as C3): every step each GPU evaluates BATCH=64 independent
+discrepancies KDE_JS_divergence(target, sim_i, gamma=0.25, eps=0) with the reference's 100 000-pair example
+target (tests/golden/example_target.npz), 100 000-pair simulated sets, a 256x256 grid, bandwidth 0.03,
+Epanechnikov kernel.  Sims are distinct per step and per rank (a resident pool larger than L2 is rotated).
 
 value  : evaluations/s, device-resident inputs, CUDA-event timed on the launching stream, max over ranks
-e2e    : evaluations/s through the public Python API (KDE_JS_divergence_batch) from pinned HOST
-         buffers, H2D of every input and D2H of the results inside the timed region
-roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
+e2e    : evaluations/s through the public Python API (KDE_JS_divergence_batch) from pinned HOST buffers, H2D of
+         every input and D2H of the results inside the timed region
+Extra keys: c4_sweep (>= 10 000 parameter sets in one call), c5_row_sharded (one 10 M + 10 M evaluation on a
+1024^2 grid, node rows sharded over the ranks), r100 (the reference's own 100x100 grid), algos (both culled
+kernels), roofline / cpu_baseline / clocks: see DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
@@ -39,9 +41,21 @@ BATCH = 64
 POOL = 192          # resident sims per GPU: 192 x 1.6 MB = 307 MB > 126 MB L2
 METRIC = "kde_discrepancy_evals_per_sec"
 UNIT = "evals/s"
-def workload():
-    return (f"C2 single discrepancy 100k sim pairs vs 100k target pairs, {RES}x{RES} grid, gamma=0.25, eps=0, "
-            f"epanechnikov h=0.03; one step = {BATCH} such evaluations per GPU (distinct sims, one target)")
+REFERENCE_BUDGET_S = 240.0
+
+
+def bench_config(res):
+    """The `config` object of the JSON line -- the SAME dict in both arms (the driver compares them)."""
+    return {
+        "workload": (f"C2 single discrepancy: 100k simulated pairs vs the reference's 100k-pair example target, "
+                     f"{res}x{res} grid, gamma=0.25, eps=0, epanechnikov h=0.03; one step = {BATCH} such evaluations "
+                     "per GPU (distinct sims, one target)"),
+        "resolution": res, "pairs": N_PAIRS, "gamma": GAMMA, "eps": EPS, "bandwidth": BANDWIDTH,
+        "kernel": "epanechnikov", "evals_per_step_per_gpu": BATCH,
+        "target": "example_input/core_mu_1e-5_rate_genes1_1e-3_prop_genes2_0.125.tsv (tests/golden/example_target.npz)",
+        "l2": f"resident pool of {POOL} sims ({POOL * N_PAIRS * 16 / 1e6:.0f} MB) rotated: inputs larger than the "
+              "126 MB L2 between reuse",
+    }
 
 
 def rank_env():
@@ -121,68 +135,108 @@ def in_support_pairs(a, b, R, h):
 
 
 def make_inputs(rank, n_sims):
-    from oracle import workloads as wl      # seeded numpy generators only (no oracle code runs here)
+    from oracle import workloads as wl      # seeded numpy generators and the committed target fixture only
 
-    target = wl.synthetic_target(N_PAIRS)
+    target = wl.example_target()
     sims = [wl.sim_batch_member(100_000 * rank + s, n=N_PAIRS) for s in range(n_sims)]
     return target, sims
 
 
-def cpu_reference_rate(target, sims, processes, node_stride=1):
-    """The reference's CPU arithmetic (sklearn ball-tree KDE + scipy JS) on the host cores."""
-    from oracle import ref_port
+# ---- reference arm ------------------------------------------------------------------------------------
+def _ref_job(args):
+    from oracle import ref_shim
 
-    pairs = [(target, s) for s in sims]
-    kw = dict(gamma=GAMMA, eps=EPS, log=False, resolution=RES, bandwidth=BANDWIDTH, node_stride=node_stride)
+    a, b, res = args
+    return ref_shim.js(a, b, GAMMA, EPS, False, R=res)
+
+
+def cpu_reference_rate(target, sims, processes, res, node_stride=1, use_reference=False):
+    """The reference's CPU arithmetic (sklearn ball-tree KDE + scipy JS) on the host cores: the unmodified
+    reference module when it is staged under oracle/_ref (use_reference), else its port on the same wheels."""
     t0 = time.perf_counter()
-    vals = ref_port.js_port_many(pairs, processes=processes, **kw)
+    if use_reference:
+        import multiprocessing as mp
+
+        jobs = [(target, s, res) for s in sims]
+        if processes <= 1:
+            vals = np.array([_ref_job(j) for j in jobs])
+        else:
+            with mp.get_context("fork").Pool(processes) as pool:
+                vals = np.array(pool.map(_ref_job, jobs))
+    else:
+        from oracle import ref_port
+
+        pairs = [(target, s) for s in sims]
+        kw = dict(gamma=GAMMA, eps=EPS, log=False, resolution=res, bandwidth=BANDWIDTH, node_stride=node_stride)
+        vals = ref_port.js_port_many(pairs, processes=processes, **kw)
     dt = time.perf_counter() - t0
-    return len(pairs) / dt, dt, vals
+    return len(sims) / dt, dt, vals
 
 
-REFERENCE_BUDGET_S = 240.0
+def reference_available():
+    from oracle import ref_shim
+
+    return ref_shim.available()
 
 
 def run_reference(args, real_stdout):
-    """Reference arm: the reference's own CPU implementation of the path (its call sequence on the
-    sklearn/scipy wheels, oracle/ref_port.py -- /root/reference itself is not on the GPU box), one
-    evaluation per host core per step through a fork pool, the reference's scaling mechanism."""
+    """Reference arm: the reference's own CPU implementation of the path -- the unmodified KDE_distance.py staged
+    under oracle/_ref by oracle/stage_ref.py (kind "reference"), or, when that copy is absent, its call sequence
+    on the same sklearn/scipy wheels (oracle/ref_port.py, kind "port").  One evaluation per host core per step
+    through a fork pool, the reference's own scaling mechanism."""
     rank, _, world = rank_env()
     if rank != 0:
         return 0
+    res = args.resolution
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     target, sims = make_inputs(0, procs)
-    # one full step to size the run; if K+W full steps do not fit the budget, later steps score every
-    # s-th grid node only and are converted with the measured full/sampled cost ratio
-    _, t_full, _ = cpu_reference_rate(target, sims, procs)
+    use_ref = reference_available()
     total_steps = args.warmup + args.steps
-    stride, ratio = 1, 1.0
-    if t_full * total_steps > REFERENCE_BUDGET_S:
-        stride = int(np.ceil(t_full * total_steps / (0.7 * REFERENCE_BUDGET_S)))
-        _, t_s, _ = cpu_reference_rate(target, sims, procs, stride)
-        ratio = t_full / t_s                      # full-evaluation equivalents per sampled evaluation
-    times = []
-    for it in range(total_steps):
-        _, dt, _ = cpu_reference_rate(target, sims, procs, stride)
-        if it >= args.warmup:
-            times.append(dt * ratio)              # time the same step would take at full size
-    t = float(np.sum(times))
-    value = procs * args.steps / t
-    sample = (f"{procs} evaluations per step, one per process (fork pool), the reference's call sequence on "
-              "sklearn/scipy (oracle/ref_port.py)")
-    if stride > 1:
-        sample += (f"; to fit {REFERENCE_BUDGET_S:.0f} s each step scores every {stride}th grid node and is scaled by "
-                   f"the measured full/sampled time ratio {ratio:.2f} (full step {t_full:.2f} s)")
+    _, t_full, _ = cpu_reference_rate(target, sims, procs, res, use_reference=use_ref)     # sizes the run
+    times, note = [], ""
+    if use_ref:
+        # the unmodified reference cannot be sub-sampled: run full steps until the time budget is used up
+        t_start = time.perf_counter() - t_full
+        for it in range(total_steps):
+            if times and (time.perf_counter() - t_start) + t_full > REFERENCE_BUDGET_S:
+                break
+            _, dt, _ = cpu_reference_rate(target, sims, procs, res, use_reference=True)
+            if it >= args.warmup:
+                times.append(dt)
+        if len(times) < args.steps:
+            note = (f"; {len(times)} of the {args.steps} requested steps were executed (a full step takes "
+                    f"{t_full:.1f} s; budget {REFERENCE_BUDGET_S:.0f} s), ms_per_step is their mean")
+        t_step = float(np.mean(times)) if times else t_full
+    else:
+        # later steps may score every s-th grid node only, converted with the measured full/sampled cost ratio
+        stride, ratio = 1, 1.0
+        if t_full * total_steps > REFERENCE_BUDGET_S:
+            stride = int(np.ceil(t_full * total_steps / (0.7 * REFERENCE_BUDGET_S)))
+            _, t_s, _ = cpu_reference_rate(target, sims, procs, res, stride)
+            ratio = t_full / t_s
+        for it in range(total_steps):
+            _, dt, _ = cpu_reference_rate(target, sims, procs, res, stride)
+            if it >= args.warmup:
+                times.append(dt * ratio)
+        t_step = float(np.mean(times)) if times else t_full
+        if stride > 1:
+            note = (f"; to fit {REFERENCE_BUDGET_S:.0f} s each step scores every {stride}th grid node and is scaled "
+                    f"by the measured full/sampled time ratio {ratio:.2f} (full step {t_full:.2f} s)")
+    value = procs / t_step
+    sample = (f"{procs} evaluations per step, one per process (fork pool), " +
+              ("the UNMODIFIED reference KDE_distance.KDE_JS_divergence (oracle/_ref, staged by oracle/stage_ref.py; "
+               "grid size through its own get_grid)" if use_ref else
+               "the reference's call sequence on sklearn/scipy (oracle/ref_port.py)") + note)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload(), "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
-                   "evals_per_step": procs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "config": bench_config(res),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference" if use_ref else "port",
+                         "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "steps_executed": len(times),
     }
     _emit(real_stdout, line)
     return 0
@@ -202,6 +256,63 @@ def _emit(real_fd, line):
     os.write(real_fd, (json.dumps(line) + "\n").encode())
 
 
+# ---- our arm ------------------------------------------------------------------------------------------
+class DeviceBench:
+    """Device-resident steps through kdejs_discrepancy_batch_dev on a dedicated torch stream."""
+
+    def __init__(self, torch, nat, dev, target, sims):
+        self.torch, self.nat, self.L, self.dev = torch, nat, nat.lib(), dev
+        self.d_target = torch.from_numpy(target).cuda()
+        self.d_sims = [torch.from_numpy(s).cuda() for s in sims]
+        self.d_out = torch.zeros(BATCH, dtype=torch.float64, device="cuda")
+        self.d_status = torch.zeros(BATCH, dtype=torch.int32, device="cuda")
+        # a real (non-default) stream: the C ABI treats a NULL stream as "the library's own", and torch's default
+        # stream handle is NULL -- events must be recorded on the stream the kernels use
+        self.stream = torch.cuda.Stream()
+        self.cnt = (ctypes.c_int64 * BATCH)(*([N_PAIRS] * BATCH))
+
+    def step(self, s, res, algo, batch=BATCH):
+        first = (s * batch) % POOL
+        ptrs = (ctypes.c_void_p * batch)(*[self.d_sims[(first + k) % POOL].data_ptr() for k in range(batch)])
+        self.nat.check(self.L.kdejs_discrepancy_batch_dev(
+            self.dev, self.d_target.data_ptr(), N_PAIRS, ptrs, self.cnt, batch, res, BANDWIDTH, GAMMA, EPS, 0, 0,
+            self.nat.ALGOS[algo], self.d_out.data_ptr(), self.d_status.data_ptr(), self.stream.cuda_stream))
+
+    def timed(self, res, algo, steps, warmup, barrier, first=0):
+        torch = self.torch
+        for s in range(warmup):
+            self.step(first + s, res, algo)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for s in range(steps):
+            self.step(first + warmup + s, res, algo)
+        e1.record(self.stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
+
+def h2d_probe(torch, barrier, sizes=(1.6e6, 25.6e6)):
+    """Pinned host -> device copy rate of this rank with ALL ranks copying at once: the ceiling the end-to-end
+    number can approach on this host (tools/h2d_probe.py sweeps more sizes and rank counts)."""
+    x = torch.empty(64 * 1024 * 1024 // 8, dtype=torch.float64).pin_memory()
+    d = torch.empty_like(x, device="cuda")
+    out = {}
+    for n in sizes:
+        k = int(n // 8)
+        reps = max(4, int(256e6 // n))
+        for _ in range(3):
+            d[:k].copy_(x[:k], non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            d[:k].copy_(x[:k], non_blocking=True)
+        torch.cuda.synchronize()
+        out[f"{n / 1e6:.1f}MB"] = n * reps / (time.perf_counter() - t0) / 1e9
+        barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,12 +320,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="kdejs", choices=["kdejs", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--algo", default="binned", choices=["binned", "dense", "dense64"])
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only (profiling runs)")
+    ap.add_argument("--algo", default=None, choices=["binned", "binned32", "dense", "dense64"],
+                    help="density algorithm of the headline (default: the package's default)")
     ap.add_argument("--resolution", type=int, default=RES,
                     help="grid nodes per axis (headline: 256; the reference's hard-coded default is 100)")
+    ap.add_argument("--c5-pairs", type=int, default=10_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "kdejs" else args.warmup
-    globals()["RES"] = args.resolution
+    res = args.resolution
     real_stdout = _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args, real_stdout)
@@ -223,6 +337,7 @@ def main():
     import torch.distributed as dist
 
     import poppunk_mod_b200 as pk
+    from poppunk_mod_b200 import distributed as D
 
     nat = pk._native
     L = nat.lib()
@@ -236,35 +351,26 @@ def main():
     torch.cuda.set_device(dev)
     os.environ["KDEJS_DEVICE"] = str(dev)
     nat.check(L.kdejs_init(dev))
-
-    target, sims = make_inputs(rank, POOL)
-    algo = nat.ALGOS[args.algo]
-    common = (RES, BANDWIDTH, GAMMA, EPS, 0, 0, algo)
-
-    # ---- device-resident inputs --------------------------------------------------------------
-    d_target = torch.from_numpy(target).cuda()
-    d_sims = [torch.from_numpy(s).cuda() for s in sims]
-    d_out = torch.zeros(BATCH, dtype=torch.float64, device="cuda")
-    d_status = torch.zeros(BATCH, dtype=torch.int32, device="cuda")
-    # a real (non-default) stream: the C ABI treats a NULL stream as "the library's own", and
-    # torch's default stream handle is NULL -- events must be recorded on the stream the kernels use
-    stream = torch.cuda.Stream()
-    cnt = (ctypes.c_int64 * BATCH)(*([N_PAIRS] * BATCH))
-
-    def step_dev(s):
-        first = (s * BATCH) % POOL
-        idx = [(first + k) % POOL for k in range(BATCH)]
-        ptrs = (ctypes.c_void_p * BATCH)(*[d_sims[i].data_ptr() for i in idx])
-        nat.check(L.kdejs_discrepancy_batch_dev(dev, d_target.data_ptr(), N_PAIRS, ptrs, cnt, BATCH, *common,
-                                                d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream))
+    algo = args.algo or pk.KDE_distance.DEFAULT_ALGO
+    other_algo = {"binned": "binned32", "binned32": "binned"}.get(algo)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    target, sims = make_inputs(rank, POOL)
+    db = DeviceBench(torch, nat, dev, target, sims)
+
+    # ---- device-resident headline -------------------------------------------------------------------
     for s in range(args.warmup):
-        step_dev(s)
+        db.step(s, res, algo)
     barrier()
     nat.check(L.kdejs_profile_reset(dev))
     nat.check(L.kdejs_profile_enable(dev, 2))      # timed region: events around the dominant kernel only
@@ -276,10 +382,10 @@ def main():
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record(stream)
+    e0.record(db.stream)
     for s in range(args.steps):
-        step_dev(args.warmup + s)
-    e1.record(stream)
+        db.step(args.warmup + s, res, algo)
+    e1.record(db.stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
@@ -294,81 +400,113 @@ def main():
     nat.check(L.kdejs_profile_enable(dev, 1))
     prof_steps = min(args.steps, 20)
     for s in range(prof_steps):
-        step_dev(args.warmup + args.steps + s)
+        db.step(args.warmup + args.steps + s, res, algo)
     torch.cuda.synchronize()
     prof = {}
     for k, nm in enumerate(nat.KERNEL_NAMES):
         nat.check(L.kdejs_profile_read(dev, k, ctypes.byref(pm), ctypes.byref(pn)))
         prof[nm] = (pm.value, pn.value)
     nat.check(L.kdejs_profile_enable(dev, 0))
-    js_last = d_out.cpu().numpy().copy()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    js_last = db.d_out.cpu().numpy().copy()
+    ms_max = max_over_ranks(ms)
     value = world * args.steps * BATCH / (ms_max * 1e-3)
 
     # ---- end to end through the public API, pinned host inputs ----------------------------------
+    probe = h2d_probe(torch, barrier)
     pool = nat.PinnedPool()
     h_target = pool.empty((N_PAIRS, 2)); h_target[:] = target
-    h_sims = []
-    for s in sims[:2 * BATCH]:
-        buf = pool.empty((N_PAIRS, 2)); buf[:] = s
-        h_sims.append(buf)
+    h_sims = pool.empty_batch(2 * BATCH, (N_PAIRS, 2))      # one page-locked arena: a wave uploads with one copy
+    for buf, s in zip(h_sims, sims):
+        buf[:] = s
     e2e_steps = max(3, min(args.steps, 10))
+    api_kw = dict(gamma=GAMMA, eps=EPS, resolution=res, algo=algo, devices=dev)
 
     def step_e2e(s):
         first = (s % 2) * BATCH
-        return pk.KDE_JS_divergence_batch(h_target, h_sims[first:first + BATCH], gamma=GAMMA, eps=EPS,
-                                          resolution=RES, algo=args.algo, devices=dev)
+        return pk.KDE_JS_divergence_batch(h_target, h_sims[first:first + BATCH], **api_kw)
 
     for s in range(2):
         step_e2e(s)
     barrier()
     t0 = time.perf_counter()
     for s in range(e2e_steps):
-        res = step_e2e(s)
+        res_e2e = step_e2e(s)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * BATCH / float(t.item())
-    assert np.all(np.isfinite(res)) and np.all(res > 0) and np.all(res < 0.8326)
+    e2e_dt = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * e2e_steps * BATCH / e2e_dt
+    assert np.all(np.isfinite(res_e2e)) and np.all(res_e2e > 0) and np.all(res_e2e < 0.8326)
+    h2d_bytes_step = (BATCH + 1) * N_PAIRS * 16
+    e2e_h2d_gbs = h2d_bytes_step * e2e_steps / e2e_dt / 1e9          # per rank
+    ceiling = max(probe.values())
 
-    # ---- one long sweep call (config C4 shape: many parameter sets per call, pipeline fill amortised) ---
-    sweep_n = 512
+    # ---- config C4: one Latin-hypercube-sized sweep, >= 10 000 parameter sets ---------------------------
+    sweep_n = 10_000 if not args.no_extras else 512
     sweep_list = [h_sims[k % len(h_sims)] for k in range(sweep_n)]
-    # warm-up with the full list: the library grows its device ring for 512 sets once (a cudaMalloc of 0.8 GB)
-    pk.KDE_JS_divergence_batch(h_target, sweep_list, gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
+    if world == 1:
+        run_sweep = lambda: pk.KDE_JS_divergence_batch(h_target, sweep_list, **api_kw)
+    else:       # every rank evaluates items rank, rank+world, ...; only the scalars are gathered (NCCL)
+        run_sweep = lambda: D.batch_discrepancy_sharded(h_target, sweep_list, GAMMA, EPS, False, resolution=res,
+                                                        algo=algo, devices=dev)
+    pk.KDE_JS_divergence_batch(h_target, sweep_list[:640], **api_kw)     # grows the device ring once
     barrier()
     t0 = time.perf_counter()
-    pk.KDE_JS_divergence_batch(h_target, sweep_list, gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
+    sweep_res = run_sweep()
     torch.cuda.synchronize()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_sweep = world * sweep_n / float(t.item())
+    sweep_dt = max_over_ranks(time.perf_counter() - t0)
+    assert sweep_res.shape == (sweep_n,) and np.all(np.isfinite(sweep_res))
+    c4 = {"value": sweep_n / sweep_dt, "unit": UNIT, "evals": sweep_n, "seconds": sweep_dt, "n_gpus": world,
+          "api": "KDE_JS_divergence_batch, one call" if world == 1 else
+                 "distributed.batch_discrepancy_sharded (items dealt to ranks, B scalars all-gathered)",
+          "note": f"{sweep_n} parameter sets x 100k pairs against one target from pinned host memory (H2D inside); "
+                  f"the list cycles {len(h_sims)} distinct sims per rank"}
 
+    extras = not args.no_extras
     # ---- the same step from ordinary (pageable) numpy arrays: what a caller of the reference passes ------
     e2e_pageable = None
-    if rank == 0 and world == 1:
-        pg = sims[:BATCH]
-        pk.KDE_JS_divergence_batch(target, pg, gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            res_pg = pk.KDE_JS_divergence_batch(target, pg, gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, devices=dev)
-        e2e_pageable = 3 * BATCH / (time.perf_counter() - t0)
-        assert np.array_equal(res_pg, pk.KDE_JS_divergence_batch(h_target, h_sims[:BATCH], gamma=GAMMA, eps=EPS,
-                                                                 resolution=RES, algo=args.algo, devices=dev))
+    single_ms = None
+    if extras:
+        if rank == 0 and world == 1:
+            pg = sims[:BATCH]
+            pk.KDE_JS_divergence_batch(target, pg, **api_kw)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                res_pg = pk.KDE_JS_divergence_batch(target, pg, **api_kw)
+            e2e_pageable = 3 * BATCH / (time.perf_counter() - t0)
+            assert np.array_equal(res_pg, pk.KDE_JS_divergence_batch(h_target, h_sims[:BATCH], **api_kw))
+        # single-call latency (BOLFI acquisition phase: batch of one)
+        lat = []
+        for s in range(8):
+            t0 = time.perf_counter()
+            pk.KDE_JS_divergence(h_target, h_sims[s], gamma=GAMMA, eps=EPS, resolution=res, algo=algo, device=dev)
+            lat.append(time.perf_counter() - t0)
+        single_ms = 1e3 * float(np.median(lat[2:]))
 
-    # ---- single-call latency (BOLFI acquisition phase: batch of one) ------------------------------
-    lat = []
-    for s in range(8):
+    # ---- the other culled kernel and the reference's own 100x100 grid (short device-resident runs) --------
+    algos, r100 = None, None
+    if extras and other_algo:
+        ms_o = max_over_ranks(db.timed(res, other_algo, 40, 5, barrier))
+        db.step(0, res, algo); torch.cuda.synchronize(); ja = db.d_out.cpu().numpy().copy()
+        db.step(0, res, other_algo); torch.cuda.synchronize(); jb = db.d_out.cpu().numpy().copy()
+        algos = {algo: {"value": value, "unit": UNIT, "headline": True},
+                 other_algo: {"value": world * 40 * BATCH / (ms_o * 1e-3), "unit": UNIT, "steps": 40},
+                 "max_rel_gap_between_them": float(np.max(np.abs(ja - jb) / jb)),
+                 "note": "binned = fp64 culled sum (exact); binned32 = fp32 terms on the FP32 pipe, exact zeros kept, "
+                         "uncertified nodes redone in fp64 (DESIGN.md 2.7)"}
+    if extras and res != 100:
+        ms_r = max_over_ranks(db.timed(100, algo, 60, 5, barrier))
         t0 = time.perf_counter()
-        pk.KDE_JS_divergence(h_target, h_sims[s], gamma=GAMMA, eps=EPS, resolution=RES, algo=args.algo, device=dev)
-        lat.append(time.perf_counter() - t0)
-    single_ms = 1e3 * float(np.median(lat[2:]))
+        for s in range(3):
+            pk.KDE_JS_divergence_batch(h_target, h_sims[:BATCH], gamma=GAMMA, eps=EPS, resolution=100, algo=algo,
+                                       devices=dev)
+        dt_r = max_over_ranks(time.perf_counter() - t0)
+        r100 = {"value": world * 60 * BATCH / (ms_r * 1e-3), "unit": UNIT, "resolution": 100,
+                "e2e": world * 3 * BATCH / dt_r,
+                "note": "the reference's hard-coded grid (KDE_distance.py:89), same inputs, 60 device-resident steps"}
+
+    # ---- config C5: one 10 M + 10 M evaluation on a 1024^2 grid, node rows sharded over the ranks ---------
+    c5 = None
+    if extras:
+        c5 = run_c5(torch, dist, pk, D, nat, rank, world, dev, args.c5_pairs, barrier, max_over_ranks)
 
     if rank != 0:
         if world > 1:
@@ -382,7 +520,7 @@ def main():
     nat.check(L.kdejs_peak_flops(dev, 0, ctypes.byref(tf32), ctypes.byref(mhz)))
     dens_ms, dens_n = dens_timed
     evals_timed = args.steps * BATCH
-    sample = [in_support_pairs(target, sims[i], RES, BANDWIDTH) for i in (0, 7, 19)]
+    sample = [in_support_pairs(target, sims[i], res, BANDWIDTH) for i in (0, 7, 19)]
     pairs_per_eval = float(np.mean(sample))
     flop_per_pair = 8.0            # 2 sub, 2 mul+add, max, add
     evals_per_launch = evals_timed / max(dens_n, 1)
@@ -391,33 +529,40 @@ def main():
     achieved = alg_flops_per_launch / avg_launch_s / 1e12 if dens_n else 0.0
     total_kernel_ms = sum(v[0] for v in prof.values())
     dens_share = prof["density"][0] / total_kernel_ms if total_kernel_ms else None
+    fp32 = algo == "binned32"
+    peak = tf32.value if fp32 else tf64.value
+    # pipe lane-ops per executed pair test: fp64 kernel 46 fp64 instructions per candidate and 16 nodes;
+    # fp32 kernel 12 + 16 FFMA and 8 packed FADD2 (two lanes of work each) = 44 FMA-pipe lane-ops
+    lane_ops = (44.0 if fp32 else 46.0) / 16.0
     roofline = {
-        "bound": "fp64-pipe", "achieved": achieved, "peak": tf64.value, "unit": "TFLOP/s",
-        "frac": achieved / tf64.value if tf64.value else None, "traffic": None,
-        "bound_note": "neither of the contract's two classes: the kernel is bound by the CUDA-core fp64 issue rate "
-                      "(contraction dimension 2 with a clamp: no tensor cores; DRAM at 5 % of peak, see hbm_* keys)",
-        "kernel": "k_density_binned", "peak_source": "DFMA issue-rate microbenchmark run in this process "
+        "bound": "fp32-pipe" if fp32 else "fp64-pipe", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak if peak else None, "traffic": None,
+        "bound_note": "neither of the contract's two classes: the kernel is bound by the CUDA-core "
+                      + ("FP32 (FMA-pipe) issue rate" if fp32 else "fp64 issue rate") +
+                      " (contraction dimension 2 with a clamp: no tensor cores; DRAM a few % of peak, see hbm_* keys)",
+        "kernel": "k_density_binned32" if fp32 else "k_density_binned",
+        "peak_source": ("FFMA" if fp32 else "DFMA") + " issue-rate microbenchmark run in this process "
         "(kdejs_peak_flops); MEASURED_PEAKS.json holds only HBM and bf16 tensor peaks",
         "algorithmic_flops_per_launch": alg_flops_per_launch,
         "in_support_pairs_per_eval": pairs_per_eval,
         "executed_pair_tests_per_eval": w.value / evals_timed if evals_timed else None,
-        "dense_equivalent_pairs_per_eval": 2.0 * N_PAIRS * RES * RES,
+        "dense_equivalent_pairs_per_eval": 2.0 * N_PAIRS * res * res,
         "avg_launch_ms": 1e3 * avg_launch_s, "launches": dens_n,
         "kernel_share_of_step": dens_share,
-        "fp32_ffma_peak_tflops": tf32.value,
-        "fp64_pipe_lane_ops_per_pair_test": 46.0 / 16.0,
-        "fp64_pipe_utilisation": ((w.value / max(dens_n, 1)) * (46.0 / 16.0) / avg_launch_s) / (tf64.value * 1e12 / 2.0)
+        "fp32_ffma_peak_tflops": tf32.value, "fp64_dfma_peak_tflops": tf64.value,
+        "pipe_lane_ops_per_pair_test": lane_ops,
+        "pipe_utilisation": ((w.value / max(dens_n, 1)) * lane_ops / avg_launch_s) / (peak * 1e12 / 2.0)
         if dens_n else None,
         "per_kernel_us_per_eval": {k: 1e3 * v[0] / (prof_steps * BATCH) for k, v in prof.items()},
         "per_kernel_note": f"separate pass of {prof_steps} steps with CUDA events around every launch",
     }
-    try:      # DRAM traffic of the dominant kernel from the committed ncu --set full capture (cannot be measured live)
+    try:      # DRAM traffic of the dominant kernel: not measurable live, taken from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tr = json.load(f)["k_density_binned"]
+            tr = json.load(f)[roofline["kernel"]]
         scale = evals_per_launch / tr["evals_per_launch"]
         roofline["traffic"] = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * scale
-        roofline["traffic_source"] = tr["source"]
-        roofline["traffic_algorithmic_bytes"] = evals_per_launch * (2 * N_PAIRS * 16 + 2 * RES * RES * 16)
+        roofline["traffic_source"] = "from committed capture: " + tr["source"]
+        roofline["traffic_algorithmic_bytes"] = evals_per_launch * (2 * N_PAIRS * (8 if fp32 else 16) + 2 * res * res * 16)
     except (OSError, ValueError, KeyError):
         pass
     hbm_bytes = (2 * N_PAIRS * 16) * evals_timed     # every input point read once per evaluation
@@ -432,72 +577,71 @@ def main():
 
     # ---- the dense fp32 brute-force kernel (north-star kernel), a short side measurement ----------
     dense = None
-    if args.algo == "binned":
+    if extras and algo in ("binned", "binned32"):
         nd = 8
-        dptrs = (ctypes.c_void_p * nd)(*[d_sims[i].data_ptr() for i in range(nd)])
-        dcnt = (ctypes.c_int64 * nd)(*([N_PAIRS] * nd))
-        dcommon = (RES, BANDWIDTH, GAMMA, EPS, 0, 0, nat.ALGOS["dense"])
-
-        def step_dense():
-            nat.check(L.kdejs_discrepancy_batch_dev(dev, d_target.data_ptr(), N_PAIRS, dptrs, dcnt, nd, *dcommon,
-                                                    d_out.data_ptr(), d_status.data_ptr(), stream.cuda_stream))
-        step_dense()
         torch.cuda.synchronize()
         nat.check(L.kdejs_profile_reset(dev))
         nat.check(L.kdejs_profile_enable(dev, 1))
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record(stream)
-        for _ in range(3):
-            step_dense()
-        d1.record(stream)
+        db.step(0, res, "dense", batch=nd)
         torch.cuda.synchronize()
-        pm, pn = ctypes.c_double(), ctypes.c_int64()
+        nat.check(L.kdejs_profile_reset(dev))
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(db.stream)
+        for _ in range(3):
+            db.step(0, res, "dense", batch=nd)
+        d1.record(db.stream)
+        torch.cuda.synchronize()
         nat.check(L.kdejs_profile_read(dev, 4, ctypes.byref(pm), ctypes.byref(pn)))
         nat.check(L.kdejs_profile_enable(dev, 0))
-        dense_js = d_out.cpu().numpy()[:nd].copy()
-        step_dev(0)
+        dense_js = db.d_out.cpu().numpy()[:nd].copy()
+        db.step(0, res, "binned", batch=nd)
         torch.cuda.synchronize()
-        exact_js = d_out.cpu().numpy()[:nd].copy()
+        exact_js = db.d_out.cpu().numpy()[:nd].copy()
         dms = d0.elapsed_time(d1)
-        dpairs = 2.0 * N_PAIRS * RES * RES * nd * 3          # pair evaluations in the 3 timed steps
+        dpairs = 2.0 * N_PAIRS * res * res * nd * 3          # pair evaluations in the 3 timed steps
         dens_s = pm.value * 1e-3                             # density (+finish) launches only
+        util = (dpairs * 152.0 / 64.0 / dens_s) / (tf32.value * 1e12 / 2.0)
         dense = {
             "kernel": "k_density_dense32", "bound": "fp32-pipe", "evals_per_s": 3 * nd / (dms * 1e-3),
-            "pairs_per_s": dpairs / dens_s, "achieved": dpairs * 8.0 / dens_s / 1e12, "peak": tf32.value,
-            "unit": "TFLOP/s", "frac": dpairs * 8.0 / dens_s / 1e12 / tf32.value, "flop_per_pair": 8.0,
-            "fma_pipe_lane_ops_per_pair": 152.0 / 64.0,
-            "fma_pipe_utilisation": (dpairs * 152.0 / 64.0 / dens_s) / (tf32.value * 1e12 / 2.0),
+            "pairs_per_s": dpairs / dens_s, "frac": util, "peak": tf32.value, "unit": "TFLOP/s",
+            "frac_definition": "FMA-pipe utilisation: issued FMA-pipe lane-ops (152 per 64 pairs: FFMA.SAT fuses "
+                               "multiply, add and clamp; coordinate work amortised over 8x8 patches) / FFMA issue peak",
+            "canonical_flop_rate_tflops": dpairs * 8.0 / dens_s / 1e12,
+            "canonical_note": "SURVEY.md 8d counts 8 flop per pair; at 2.375 issued lane-ops per pair that rate can "
+                              "exceed the FFMA peak, so it is reported as a rate, not as a fraction",
             "max_rel_gap_to_fp64_path": float(np.max(np.abs(dense_js - exact_js) / exact_js)),
-            "note": "frac uses SURVEY.md 8d's canonical 8 flop/pair; the kernel issues 2.375 FMA-pipe lane-ops per "
-                    "pair (FFMA.SAT fuses multiply, add and clamp; coordinate work is amortised over 8x8 patches), so "
-                    "fma_pipe_utilisation is the pipe-occupancy figure",
         }
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         n_cpu = 4
-        rate, cdt, vals = cpu_reference_rate(target, sims[:n_cpu], 1)
-        gpu_vals = pk.KDE_JS_divergence_batch(target, sims[:n_cpu], gamma=GAMMA, eps=EPS, resolution=RES, devices=dev)
-        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"{n_cpu} of the step's evaluations, sequential, one process ({cdt:.1f} s): the "
-                                  "reference's call sequence on sklearn/scipy (oracle/ref_port.py)",
+        use_ref = reference_available()
+        rate, cdt, vals = cpu_reference_rate(target, sims[:n_cpu], 1, res, use_reference=use_ref)
+        gpu_vals = pk.KDE_JS_divergence_batch(target, sims[:n_cpu], gamma=GAMMA, eps=EPS, resolution=res, devices=dev,
+                                              algo=algo)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference" if use_ref else "port",
+                        "sample": f"{n_cpu} of the step's evaluations, sequential, one process ({cdt:.1f} s): " +
+                                  ("the unmodified reference module staged under oracle/_ref" if use_ref else
+                                   "the reference's call sequence on sklearn/scipy (oracle/ref_port.py)"),
                         "max_rel_gap_to_gpu": float(np.max(np.abs(vals - gpu_vals) / gpu_vals)),
                         "gap_note": "the gap is the reference's ball-tree residue amplified by gamma=0.25 "
-                                    "(SURVEY.md 0.3); against the exact oracle the GPU agrees to ~1e-13"}
+                                    "(SURVEY.md 0.3, INTEGRATION.md 5); against the exact oracle the GPU agrees to ~1e-13 "
+                                    "(binned) / ~1e-8 (binned32)"}
 
+    cfg = bench_config(res)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload(), "resolution": RES, "pairs": N_PAIRS, "gamma": GAMMA,
-                   "evals_per_step_per_gpu": BATCH, "algo": args.algo,
-                   "l2": f"resident pool of {POOL} sims ({POOL * N_PAIRS * 16 / 1e6:.0f} MB) rotated: inputs "
-                         "larger than the 126 MB L2 between reuse"},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 terms, f64 accumulation" if fp32 else "f64",
+        "data": "synthetic", "config": cfg, "algo": algo,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
-                "h2d_bytes_per_step": (BATCH + 1) * N_PAIRS * 16, "d2h_bytes_per_step": BATCH * 12,
+                "h2d_bytes_per_step": h2d_bytes_step, "d2h_bytes_per_step": BATCH * 12,
                 "steps": e2e_steps, "api": "KDE_JS_divergence_batch (ctypes -> kdejs_discrepancy_batch), "
-                                           "pinned host arrays",
+                                           "pinned host arrays in one arena (PinnedPool.empty_batch)",
+                "h2d_gbs_per_rank": e2e_h2d_gbs, "h2d_probe_gbs_per_rank": probe,
+                "frac_of_h2d_ceiling": e2e_h2d_gbs / ceiling if ceiling else None,
+                "ceiling_note": f"pinned-memory copy rate measured in this run with all {world} rank(s) copying at once",
                 "host_numa_node": numa_node},
         "e2e_pageable": {"value": e2e_pageable, "unit": UNIT,
                          "note": "same step from ordinary numpy arrays (pageable memory), staged through pinned slots "
@@ -505,8 +649,10 @@ def main():
         "gpu_launches": int(n_launch.value),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
-        "e2e_sweep_call": {"value": e2e_sweep, "unit": UNIT, "evals_per_call": sweep_n,
-                           "note": "one KDE_JS_divergence_batch call over 512 pinned host sims (H2D inside)"},
+        "c4_sweep": c4,
+        "c5_row_sharded": c5,
+        "r100": r100,
+        "algos": algos,
         "single_call_latency_ms": single_ms,
         "dense_fp32": dense,
         "js_sample": [float(x) for x in js_last[:3]],
@@ -515,6 +661,84 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_c5(torch, dist, pk, D, nat, rank, world, dev, n_pairs, barrier, max_over_ranks):
+    """Config C5.  Every rank holds a contiguous 1/world slice of each table (the target and the simulated set).
+    Timed: (a) slices already on the device, (b) slices in pinned host memory (upload inside).  Compared with the
+    same evaluation on ONE GPU (rank 0 alone), and at a reduced size (1 M pairs, R = 512) with the CPU oracle."""
+    from oracle import kde_oracle
+    from oracle import workloads as wl
+
+    R5 = 1024
+    out = {"pairs": n_pairs, "resolution": R5, "n_gpus": world,
+           "workload": f"C5: target = {n_pairs} rows bootstrap-resampled with jitter from the reference's example "
+                       f"target, sim = {n_pairs} rows from S stretched to its range, {R5}x{R5} grid, gamma=0.25"}
+    # reduced size against the oracle (seconds on the host cores)
+    a_s, b_s = wl.c5_inputs(1_000_000, seed=9)
+    cut = lambda x: x[len(x) * rank // world: len(x) * (rank + 1) // world]
+    js_small = D.row_sharded_discrepancy(cut(a_s), cut(b_s), GAMMA, EPS, resolution=512, sliced=True, device=dev)
+    if rank == 0:
+        want = kde_oracle.discrepancy(a_s, b_s, GAMMA, EPS, resolution=512)
+        out["reduced_1M_R512"] = {"value": float(js_small), "oracle": float(want),
+                                  "rel_gap_to_oracle": abs(js_small - want) / want}
+    a, b = wl.c5_inputs(n_pairs, seed=5)
+    pool = nat.PinnedPool()
+    ha = pool.empty(cut(a).shape); ha[:] = cut(a)
+    hb = pool.empty(cut(b).shape); hb[:] = cut(b)
+    kw = dict(resolution=R5, sliced=True, device=dev)
+    times_h, times_d = [], []
+    for it in range(4):
+        barrier()
+        t0 = time.perf_counter()
+        js_h = D.row_sharded_discrepancy(ha, hb, GAMMA, EPS, **kw)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if it:
+            times_h.append(dt)
+    da, db_ = torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
+    for it in range(4):
+        barrier()
+        t0 = time.perf_counter()
+        js_d = D.row_sharded_discrepancy(da, db_, GAMMA, EPS, **kw)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        if it:
+            times_d.append(dt)
+    out.update({"ms_from_host": 1e3 * min(times_h), "ms_device_resident": 1e3 * min(times_d), "value": float(js_h),
+                "same_result_host_and_device_slices": bool(js_h == js_d), "api": "distributed.row_sharded_discrepancy"})
+    del da, db_
+    # the same evaluation on one GPU (rank 0 alone; the other ranks wait at the barrier)
+    if rank == 0:
+        pa = pool.empty(a.shape); pa[:] = a
+        pb = pool.empty(b.shape); pb[:] = b
+        one = []
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            js_1 = pk.KDE_JS_divergence(pa, pb, GAMMA, EPS, resolution=R5, device=dev)
+            if it:
+                one.append(time.perf_counter() - t0)
+        ta, tb = torch.from_numpy(pa).cuda(), torch.from_numpy(pb).cuda()
+        o = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ptr = (ctypes.c_void_p * 1)(tb.data_ptr())
+        cnt = (ctypes.c_int64 * 1)(len(b))
+        st = torch.cuda.current_stream().cuda_stream
+        oned = []
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nat.check(nat.lib().kdejs_discrepancy_batch_dev(dev, ta.data_ptr(), len(a), ptr, cnt, 1, R5, BANDWIDTH,
+                                                            GAMMA, EPS, 0, 0, nat.ALGOS[pk.KDE_distance.DEFAULT_ALGO],
+                                                            o.data_ptr(), None, st))
+            torch.cuda.synchronize()
+            if it:
+                oned.append(time.perf_counter() - t0)
+        out.update({"single_gpu_ms_from_host": 1e3 * min(one), "single_gpu_ms_device_resident": 1e3 * min(oned),
+                    "single_gpu_value": float(js_1), "rel_gap_to_single_gpu": abs(js_h - js_1) / js_1,
+                    "speedup_from_host": min(one) / min(times_h), "speedup_device_resident": min(oned) / min(times_d)})
+    barrier()
+    return out
 
 
 if __name__ == "__main__":

@@ -49,6 +49,12 @@ extern "C" {
 #define KDEJS_ALGO_DENSE 1    /* fp32 terms / fp64 accumulation brute force over all       */
                               /* N x G pairs (the north-star kernel; FP32-pipe roofline)   */
 #define KDEJS_ALGO_DENSE64 2  /* fp64 brute force (cross-check; gaussian parity)           */
+#define KDEJS_ALGO_BINNED32 3 /* the culled sum with fp32 terms on the FP32 pipe (sorted     */
+                              /* points as 32-bit fixed point, fp64 accumulation across      */
+                              /* lanes): exact zeros stay exact, non-zero node densities     */
+                              /* agree with BINNED to ~1e-7 relative; nodes it cannot        */
+                              /* certify are redone in fp64.  Geometries its fixed-point     */
+                              /* format does not cover fall back to BINNED.                  */
 
 /* ---- life cycle -------------------------------------------------------------------- */
 int kdejs_version(void);
@@ -161,9 +167,9 @@ const char *kdejs_io_last_error(void);
 /* ---- measurement support (bench.py, tests) ------------------------------------------- */
 /* Per-kernel CUDA-event timing on the launching stream.  which: 0 minmax, 1 scale+count,
  * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence, 6 tile classification,
- * 7 cell moments (fine grids only).
+ * 7 cell moments (fine grids only), 8 fp64 redo pass of KDEJS_ALGO_BINNED32, 9 summary vector.
  * Reading synchronises. */
-#define KDEJS_NUM_KERNELS 8
+#define KDEJS_NUM_KERNELS 10
 int kdejs_profile_enable(int device, int on);   /* 0 off, 1 every kernel, 2 the density kernel only */
 int kdejs_profile_read(int device, int which, double *ms_total, int64_t *launches);
 int kdejs_profile_reset(int device);

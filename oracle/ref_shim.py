@@ -6,9 +6,10 @@ stub modules are registered before the import so the file loads unchanged.  The 
 hard-coded to 100x100 (KDE_distance.py:89) but `get_grid` is resolved through module
 globals, so other resolutions are obtained by rebinding that name -- no edits.
 
-/root/reference does not exist on the GPU box: nothing under tests -m gpu, smoke() or
-bench.py may import this file.  It is used by oracle/make_golden.py (fixtures) and by
-CPU-side tests that skip when the reference is absent.
+/root/reference does not exist on the GPU box.  oracle/stage_ref.py stages a byte-identical copy of
+that one file under oracle/_ref/ (git-ignored, travels with the snapshot); this module loads the
+reference tree when it is present and the staged copy otherwise.  Users: oracle/make_golden.py
+(fixtures), CPU-side tests, and bench.py's `--impl reference` / cpu_baseline legs.
 """
 from __future__ import annotations
 
@@ -18,10 +19,20 @@ import sys
 import types
 
 REFERENCE_DIR = os.environ.get("KDEJS_REFERENCE_DIR", "/root/reference")
+STAGED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_file():
+    """Path of the reference's KDE_distance.py: the reference tree, else the staged copy, else None."""
+    for d in (REFERENCE_DIR, STAGED_DIR):
+        f = os.path.join(d, "KDE_distance.py")
+        if os.path.exists(f):
+            return f
+    return None
 
 
 def available() -> bool:
-    return os.path.exists(os.path.join(REFERENCE_DIR, "KDE_distance.py"))
+    return reference_file() is not None
 
 
 def load():
@@ -30,7 +41,7 @@ def load():
     if name in sys.modules:
         return sys.modules[name]
     if not available():
-        raise FileNotFoundError(f"reference not present at {REFERENCE_DIR}")
+        raise FileNotFoundError(f"reference not present at {REFERENCE_DIR} nor staged under {STAGED_DIR}")
     try:
         import matplotlib.pyplot  # noqa: F401
     except Exception:
@@ -41,7 +52,7 @@ def load():
         sys.modules.setdefault("matplotlib.pyplot", plt)
     import importlib.util
 
-    spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_DIR, "KDE_distance.py"))
+    spec = importlib.util.spec_from_file_location(name, reference_file())
     mod = importlib.util.module_from_spec(spec)
     sys.modules[name] = mod
     spec.loader.exec_module(mod)

@@ -50,6 +50,22 @@ def example_target():
         return f["target"].astype(np.float64)
 
 
+def c5_inputs(n=10_000_000, seed=5):
+    """Config C5 of SURVEY.md 8(d): a target of n real-genome-shaped pairs, bootstrap-resampled with jitter
+    N(0, (1e-4 * range)^2) from real rows (the reference's example target -- the committed fixture that travels
+    to the GPU box; distances/2_column is only in the build container), and a simulated set of n pairs from the
+    S generator stretched to the target's range."""
+    base = example_target()
+    r = np.random.default_rng(seed)
+    span = base.max(0) - base.min(0)
+    idx = r.integers(0, len(base), n)
+    target = base[idx] + r.standard_normal((n, 2)) * (1e-4 * span)
+    sim = sim_S(seed + 1, 1800.0, 0.36, n=n)
+    lo, hi = sim.min(0), sim.max(0)
+    sim = (sim - lo) / (hi - lo) * span + base.min(0)
+    return np.ascontiguousarray(target), np.ascontiguousarray(sim)
+
+
 def g1_inputs():
     """SURVEY.md 8(c) golden case G1 (same generator, drawn in this order)."""
     rng = np.random.default_rng(0)

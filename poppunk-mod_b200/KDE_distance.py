@@ -47,6 +47,9 @@ __all__ = ["get_grid", "scale_KDE", "KDE_JS_divergence", "KDE_KL_divergence", "K
 
 _DEFAULT_RESOLUTION = 100      # KDE_distance.py:89
 _DEFAULT_BANDWIDTH = 0.03      # KDE_distance.py:50
+# Density algorithm used when a caller does not name one (Epanechnikov kernel): "binned" = fp64 culled sum,
+# "binned32" = the same sum with fp32 terms on the FP32 pipe (exact zeros kept, ~1e-8 on the JS value).
+DEFAULT_ALGO = os.environ.get("KDEJS_DEFAULT_ALGO", "binned")
 
 
 def default_device() -> int:
@@ -71,7 +74,7 @@ def _common(resolution, bandwidth, gamma, eps, log, kernel, algo):
     if kernel not in nat.KERNELS:
         raise ValueError(f"kernel must be one of {sorted(nat.KERNELS)}; got {kernel!r}")
     if algo is None:
-        algo = "binned" if kernel == "epanechnikov" else "dense64"
+        algo = DEFAULT_ALGO if kernel == "epanechnikov" else "dense64"
     if algo not in nat.ALGOS:
         raise ValueError(f"algo must be one of {sorted(nat.ALGOS)}; got {algo!r}")
     return (int(resolution), float(bandwidth), float(gamma), float(eps), int(bool(log)),

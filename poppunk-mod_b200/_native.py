@@ -13,8 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libkdejs.so")
 
 KDEJS_OK, KDEJS_ERR_CUDA, KDEJS_ERR_ARG, KDEJS_ERR_INF = 0, 1, 2, 3
 KERNELS = {"epanechnikov": 0, "gaussian": 1}
-ALGOS = {"binned": 0, "dense": 1, "dense64": 2}
-KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence", "classify", "moments")
+ALGOS = {"binned": 0, "dense": 1, "dense64": 2, "binned32": 3}
+KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence", "classify", "moments",
+                "redo64", "summary")
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_dpp = ctypes.POINTER(ctypes.c_void_p)
@@ -175,6 +176,13 @@ class PinnedPool:
         self._ptrs.append(p)
         buf = (ctypes.c_char * max(nbytes, 1)).from_address(p)
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def empty_batch(self, count, shape, dtype=np.float64):
+        """`count` arrays of `shape` carved out of ONE page-locked arena, back to back: kdejs_discrepancy_batch
+        then uploads a whole wave of them with a single copy instead of one per array."""
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        arena = self.empty((int(count),) + shape, dtype)
+        return [arena[i] for i in range(int(count))]
 
     def close(self):
         for p in self._ptrs:

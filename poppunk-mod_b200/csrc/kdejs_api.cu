@@ -1,14 +1,18 @@
 // kdejs_api.cu -- C ABI (include/kdejs.h) over the sm_100a kernels in kdejs_kernels.cuh.
 //
-// Host-side structure: one lazily created context per device (two streams, two workspace slots so
-// the H2D copy of wave k+1 overlaps the kernels of wave k).  Evaluations are grouped into waves of
+// Host-side structure: one lazily created context per device: a compute stream, a copy stream and ONE set of
+// scratch buffers (the waves of a call are ordered on the compute stream anyway; the H2D copies of later waves
+// run ahead on the copy stream into a ring of raw-input buffers).  Evaluations are grouped into waves of
 // up to kMaxWaveItems; a wave's descriptors travel as a __grid_constant__ kernel parameter, so
-// there is no descriptor staging buffer to race with asynchronous callers.
+// there is no descriptor staging buffer to race with asynchronous callers.  Entry points that enqueue on a
+// caller's stream and return without synchronising (*_dev) leave an event behind that every later user of the
+// scratch waits for (see Ctx::scratch_busy).
 #include "../../include/kdejs.h"
 #include "kdejs_kernels.cuh"
 #include "kdejs_stager.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -67,7 +71,12 @@ struct DevBuf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return KDEJS_OK;
-        if (p) CU(cudaFree(p));      // cudaFree waits for outstanding work on the device
+        if (p) {
+            // Work from ANY stream (a caller's stream of a *_dev entry point included) may still be using the old
+            // block: drain the device before it is released.  Growth is rare (first calls, larger problems).
+            CU(cudaDeviceSynchronize());
+            CU(cudaFree(p));
+        }
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 4 + 256;
         CU(cudaMalloc(&p, want));
@@ -78,9 +87,8 @@ struct DevBuf {
 };
 
 struct Slot {
-    DevBuf rawsims, scaled, sorted, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
-    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, counters, totals, rank16, warpprefix, tileflag;
-    cudaEvent_t ev_copied = nullptr, ev_done = nullptr;
+    DevBuf scaled, sorted, sorted_q, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
+    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, redo, counters, totals, rank16, warpprefix, tileflag;
 };
 
 struct Params {
@@ -92,12 +100,17 @@ struct Pending { int kind; cudaEvent_t e0, e1; };
 
 struct Ctx {
     int dev = -1;
-    bool ready = false;
+    std::atomic<bool> ready{false};
     int sm_count = 0;
-    int dens_blocks_per_sm = 1;
+    int dens_blocks_per_sm = 1, dens32_blocks_per_sm = 1;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    Slot slot[2];
-    DevBuf pool_raw, js_out, status_out, misc, sim_ring;
+    Slot slot;
+    // Cross-stream ordering of the scratch (slot, tickets, counters, rstat): an entry point that returns with work
+    // still enqueued on `scratch_stream` records `scratch_busy` there; the next user on a DIFFERENT stream waits for it.
+    cudaEvent_t scratch_busy = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_pending = false;
+    DevBuf pool_raw, js_out, status_out, misc, sim_ring, summary;
     std::vector<cudaEvent_t> free_plain_events;
     double *h_js = nullptr; int32_t *h_status = nullptr; size_t h_cap = 0;   // pinned results
     std::mutex mu;
@@ -119,12 +132,73 @@ constexpr int kMaxDevices = 64;
 Ctx g_ctx[kMaxDevices];
 std::mutex g_init_mu;
 
+int init_ctx(Ctx &c) {
+    CU(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.s_copy, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c.scratch_busy, cudaEventDisableTiming));
+    OKR(c.slot.tickets.ensure(sizeof(unsigned) * 3 * kMaxWaveSets));   // self-resetting tickets
+    CU(cudaMemset(c.slot.tickets.p, 0, c.slot.tickets.cap));
+    CU(cudaMalloc(&c.d_work, sizeof(unsigned long long)));
+    CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
+    CU(cudaFuncSetAttribute(k_scale_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            kSortWarps * kMaxCells * (int)sizeof(uint16_t)));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned<false>, kDensThreads, 0));
+    c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens32_blocks_per_sm, k_density_binned32<false>, kDensThreads, 0));
+    c.dens32_blocks_per_sm = std::max(1, c.dens32_blocks_per_sm);
+    return KDEJS_OK;
+}
+
+// Release everything a context owns (shutdown, or a failed init).  The caller holds g_init_mu.
+void destroy_ctx(Ctx &c) {
+    Slot &s = c.slot;
+    for (DevBuf *b : {&s.scaled, &s.sorted, &s.sorted_q, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
+                      &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart, &s.dense_partial,
+                      &s.worklist, &s.redo, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag,
+                      &c.pool_raw, &c.js_out, &c.status_out, &c.misc, &c.sim_ring, &c.summary}) {
+        if (b->p) cudaFree(b->p);
+        b->p = nullptr; b->cap = 0;
+    }
+    for (auto e : c.free_plain_events) cudaEventDestroy(e);
+    c.free_plain_events.clear();
+    if (c.h_js) { cudaFreeHost(c.h_js); cudaFreeHost(c.h_status); c.h_js = nullptr; c.h_status = nullptr; c.h_cap = 0; }
+    for (auto &pd : c.pending) { cudaEventDestroy(pd.e0); cudaEventDestroy(pd.e1); }
+    c.pending.clear();
+    for (auto e : c.free_events) cudaEventDestroy(e);
+    c.free_events.clear();
+    if (c.d_work) { cudaFree(c.d_work); c.d_work = nullptr; }
+    if (c.scratch_busy) { cudaEventDestroy(c.scratch_busy); c.scratch_busy = nullptr; }
+    if (c.s_compute) { cudaStreamDestroy(c.s_compute); c.s_compute = nullptr; }
+    if (c.s_copy) { cudaStreamDestroy(c.s_copy); c.s_copy = nullptr; }
+    c.scratch_pending = false;
+    c.scratch_stream = nullptr;
+    c.shard_valid = false;
+}
+
+// Every user of the scratch calls this first with the stream it is about to enqueue on.
+int acquire_scratch(Ctx &c, cudaStream_t st) {
+    if (c.scratch_pending && c.scratch_stream != st) CU(cudaStreamWaitEvent(st, c.scratch_busy, 0));
+    return KDEJS_OK;
+}
+// ... and this last: `synced` = the entry point synchronised `st` before returning (nothing is left in flight).
+int release_scratch(Ctx &c, cudaStream_t st, bool synced) {
+    if (synced) {
+        // a wait on scratch_busy was enqueued before our work, so whatever recorded it has finished too
+        c.scratch_pending = false;
+        return KDEJS_OK;
+    }
+    CU(cudaEventRecord(c.scratch_busy, st));
+    c.scratch_pending = true;
+    c.scratch_stream = st;
+    return KDEJS_OK;
+}
+
 int get_ctx(int device, Ctx **out) {
     if (device < 0 || device >= kMaxDevices) return fail(KDEJS_ERR_ARG, "device index out of range");
     Ctx &c = g_ctx[device];
-    if (!c.ready) {
+    if (!c.ready.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lk(g_init_mu);
-        if (!c.ready) {
+        if (!c.ready.load(std::memory_order_relaxed)) {
             int n = 0;
             CU(cudaGetDeviceCount(&n));
             if (device >= n) return fail(KDEJS_ERR_CUDA, "no such CUDA device (kdejs has no CPU fallback)");
@@ -135,21 +209,9 @@ int get_ctx(int device, Ctx **out) {
                 return fail(KDEJS_ERR_CUDA, std::string("kdejs is built for sm_100a only; device is ") + prop.name);
             c.dev = device;
             c.sm_count = prop.multiProcessorCount;
-            CU(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
-            CU(cudaStreamCreateWithFlags(&c.s_copy, cudaStreamNonBlocking));
-            for (auto &s : c.slot) {
-                CU(cudaEventCreateWithFlags(&s.ev_copied, cudaEventDisableTiming));
-                CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-                OKR(s.tickets.ensure(sizeof(unsigned) * 3 * kMaxWaveSets));   // self-resetting tickets
-                CU(cudaMemset(s.tickets.p, 0, s.tickets.cap));
-            }
-            CU(cudaMalloc(&c.d_work, sizeof(unsigned long long)));
-            CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
-            CU(cudaFuncSetAttribute(k_scale_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSortWarps * kMaxCells * (int)sizeof(uint16_t)));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned<false>, kDensThreads, 0));
-            c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
-            c.ready = true;
+            const int rc = init_ctx(c);
+            if (rc != KDEJS_OK) { destroy_ctx(c); return rc; }       // a failed init leaves nothing behind for the retry
+            c.ready.store(true, std::memory_order_release);
         }
     }
     CU(cudaSetDevice(device));
@@ -196,9 +258,10 @@ int check_params(const Params &p) {
     if (!(p.gmax > p.gmin)) return fail(KDEJS_ERR_ARG, "grid maximum must exceed grid minimum");
     if (p.kernel != KDEJS_KERNEL_EPANECHNIKOV && p.kernel != KDEJS_KERNEL_GAUSSIAN)
         return fail(KDEJS_ERR_ARG, "unknown kernel");
-    if (p.algo != KDEJS_ALGO_BINNED && p.algo != KDEJS_ALGO_DENSE && p.algo != KDEJS_ALGO_DENSE64)
+    if (p.algo != KDEJS_ALGO_BINNED && p.algo != KDEJS_ALGO_DENSE && p.algo != KDEJS_ALGO_DENSE64 &&
+        p.algo != KDEJS_ALGO_BINNED32)
         return fail(KDEJS_ERR_ARG, "unknown algorithm");
-    if (p.kernel == KDEJS_KERNEL_GAUSSIAN && p.algo == KDEJS_ALGO_BINNED)
+    if (p.kernel == KDEJS_KERNEL_GAUSSIAN && (p.algo == KDEJS_ALGO_BINNED || p.algo == KDEJS_ALGO_BINNED32))
         return fail(KDEJS_ERR_ARG, "the gaussian kernel has unbounded support: use a dense algorithm");
     if (std::isnan(p.gamma) || std::isnan(p.eps)) return fail(KDEJS_ERR_ARG, "gamma/eps must not be NaN");
     return KDEJS_OK;
@@ -252,6 +315,22 @@ GridGeom make_geom(const Params &p) {
         g.use_moments = (p.kernel == KDEJS_KERNEL_EPANECHNIKOV && rho >= g.cell_w && C >= 4) ? 1 : 0;
         if (const char *e = getenv("KDEJS_MOMENTS")) g.use_moments = (atoi(e) != 0 && p.kernel == KDEJS_KERNEL_EPANECHNIKOV && C >= 4) ? 2 : 0;
     }
+    // fp32 path: sorted points as 32-bit fixed point in units of h * 2^-q_shift, modulo 2^32.  The largest
+    // coordinate difference between a tile's first node and one of its candidates (clamped to 2h beyond the grid)
+    // must stay below 2^31 units: left of the node h + one cell (+ 2h when clamped), right of it tile side + h + cell.
+    {
+        const double cw_h = g.cell_w / p.h, tile_h = (kTile - 1) * g.dh;
+        const double maxdiff_h = std::max(3.0 + cw_h, tile_h + 1.0 + cw_h) + 0.01;
+        int shift = (int)std::floor(std::log2(2147483648.0 / maxdiff_h));
+        shift = std::min(shift, 29);                  // the padding candidate sits 2^30 units (>= 2 h) left of the node
+        g.q_shift = (shift >= 26 && p.kernel == KDEJS_KERNEL_EPANECHNIKOV && p.R > 1) ? shift : 0;
+        g.q_pad = 0;
+        g.q_scale = std::ldexp(g.inv_h, shift);
+        g.q_lo = p.gmin - 2.0 * p.h;
+        g.q_hi = p.gmax + 2.0 * p.h;
+        g.q_unit = (float)std::ldexp(1.0, -shift);
+        g.q_dh = (float)g.dh;
+    }
     return g;
 }
 
@@ -298,7 +377,10 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     for (int s = 0; s < n_sets; ++s)
         wd.set[s].nb = (int)(((int64_t)wd.set[s].n + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps));
     const int ncells = g.C * g.C;
-    const bool binned = (p.algo == KDEJS_ALGO_BINNED);
+    const bool binned = (p.algo == KDEJS_ALGO_BINNED || p.algo == KDEJS_ALGO_BINNED32);
+    // the fp32 kernel needs a geometry its fixed-point format covers; otherwise the fp64 kernel does the work
+    static const int force32 = getenv("KDEJS_FP32") ? atoi(getenv("KDEJS_FP32")) : -1;
+    const bool fast32 = binned && g.q_shift > 0 && (force32 >= 0 ? force32 != 0 : p.algo == KDEJS_ALGO_BINNED32);
     // a moment cell costs a tile as much as one point plus some per-row bookkeeping: it pays once cells hold
     // hundreds of points (measured: -40 % density time at 1200 points per cell, +48 % at 49)
     if (g.use_moments == 1 && P < (int64_t)128 * n_sets * ncells) g.use_moments = 0;
@@ -340,7 +422,11 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             g.sets_per_group = (n_sets + n_groups - 1) / n_groups;
         }
         OKR(sl.worklist.ensure((size_t)kNumLists * g.sets_per_group * g.NT * g.NT * sizeof(uint32_t)));
-        OKR(sl.counters.ensure(kNumCounters * sizeof(unsigned)));
+        OKR(sl.counters.ensure(kAllCounters * sizeof(unsigned)));
+        if (fast32) {
+            OKR(sl.sorted_q.ensure((size_t)P * sizeof(uint2)));
+            OKR(sl.redo.ensure((size_t)kNumLists * g.sets_per_group * g.NT * g.NT * sizeof(uint32_t)));
+        }
     }
 
     unsigned *tk_minmax = sl.tickets.as<unsigned>();
@@ -383,7 +469,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
                 io.identity_scaler ? 1 : 0, ncells, chw, nb_max, sl.cellid.as<uint16_t>(),
                 sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
-                wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>());
+                wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>(),
+                fast32 ? sl.sorted_q.as<uint2>() : nullptr, g);
         }
         if (g.use_moments) {
             KTimer t(c, 7, st);
@@ -424,7 +511,36 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity,
                 c.prof_on ? c.d_work : nullptr, lazy_empty ? sl.tileflag.as<uint8_t>() : nullptr);
         }
-        if (tiles > 0) {
+        if (tiles > 0 && fast32) {
+            {
+                KTimer t(c, 4, st);
+                const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * c.dens32_blocks_per_sm);
+                if (g.use_moments)
+                    k_density_binned32<true><<<blocks, kDensThreads, 0, st>>>(
+                        wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
+                        sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
+                        sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>());
+                else
+                    k_density_binned32<false><<<blocks, kDensThreads, 0, st>>>(
+                        wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), nullptr,
+                        sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
+                        sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>());
+            }
+            // tiles with a node the fp32 arithmetic could not certify (a nearest candidate within ~1e-6 of the
+            // support's edge): the fp64 kernel on the redo list -- usually empty, a few tiles per evaluation at most
+            KTimer t(c, 8, st);
+            const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * 2);
+            if (g.use_moments)
+                k_density_binned<true><<<blocks, kDensThreads, 0, st>>>(
+                    wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
+                    sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
+                    sl.redo.as<uint32_t>(), sl.counters.as<unsigned>() + kRedoBase, capacity);
+            else
+                k_density_binned<false><<<blocks, kDensThreads, 0, st>>>(
+                    wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), nullptr,
+                    sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
+                    sl.redo.as<uint32_t>(), sl.counters.as<unsigned>() + kRedoBase, capacity);
+        } else if (tiles > 0) {
             KTimer t(c, 4, st);
             const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * c.dens_blocks_per_sm);
             if (g.use_moments)
@@ -524,8 +640,8 @@ int wave_capacity(const Params &p, int64_t pts_per_item) {
     return std::min(cap, kMaxWaveItems);
 }
 
-// Pairs over a pool of raw DEVICE sets; items [0, n_items): (ia[i], ib[i]).  Runs on `st`, one slot.
-int run_pairs_dev(Ctx &c, cudaStream_t st, int slot_idx, const Params &p, const std::vector<RawSet> &pool,
+// Pairs over a pool of raw DEVICE sets; items [0, n_items): (ia[i], ib[i]).  Runs on `st`.
+int run_pairs_dev(Ctx &c, cudaStream_t st, const Params &p, const std::vector<RawSet> &pool,
                   const int32_t *ia, const int32_t *ib, int64_t n_items, double *out_js_dev,
                   int32_t *status_dev, int64_t out_base, bool want_z) {
     GridGeom g = make_geom(p);
@@ -558,7 +674,7 @@ int run_pairs_dev(Ctx &c, cudaStream_t st, int slot_idx, const Params &p, const 
         wd.n_sets = 2 * items;
         WaveIO io;
         io.out_js = out_js_dev; io.out_status = status_dev; io.item_base = (int)(out_base + i); io.want_z = want_z;
-        OKR(run_wave(c, c.slot[slot_idx], st, p, g, wd, io));
+        OKR(run_wave(c, c.slot, st, p, g, wd, io));
         i += items;
     }
     return KDEJS_OK;
@@ -620,35 +736,12 @@ int kdejs_device_numa_node(int device, int *node) {
 void kdejs_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_init_mu);
     for (auto &c : g_ctx) {
-        if (!c.ready) continue;
+        if (!c.ready.load(std::memory_order_acquire)) continue;
+        std::lock_guard<std::mutex> lc(c.mu);          // no entry point is inside this context while it is torn down
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
-        for (auto &s : c.slot) {
-            for (DevBuf *b : {&s.rawsims, &s.scaled, &s.sorted, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
-                              &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart,
-                              &s.dense_partial, &s.worklist, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag}) {
-                if (b->p) cudaFree(b->p);
-                b->p = nullptr; b->cap = 0;
-            }
-            cudaEventDestroy(s.ev_copied);
-            cudaEventDestroy(s.ev_done);
-        }
-        for (auto e : c.free_plain_events) cudaEventDestroy(e);
-        c.free_plain_events.clear();
-        for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.misc, &c.sim_ring}) {
-            if (b->p) cudaFree(b->p);
-            b->p = nullptr; b->cap = 0;
-        }
-        if (c.h_js) { cudaFreeHost(c.h_js); cudaFreeHost(c.h_status); c.h_js = nullptr; c.h_status = nullptr; c.h_cap = 0; }
-        for (auto &pd : c.pending) { cudaEventDestroy(pd.e0); cudaEventDestroy(pd.e1); }
-        c.pending.clear();
-        for (auto e : c.free_events) cudaEventDestroy(e);
-        c.free_events.clear();
-        cudaFree(c.d_work);
-        cudaStreamDestroy(c.s_compute);
-        cudaStreamDestroy(c.s_copy);
-        c.shard_valid = false;
-        c.ready = false;
+        destroy_ctx(c);
+        c.ready.store(false, std::memory_order_release);
     }
 }
 
@@ -674,6 +767,7 @@ int kdejs_discrepancy_pairs(int device, const double *const *sets, const int64_t
     Ctx *c;
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
+    OKR(acquire_scratch(*c, c->s_compute));
     // upload the pool once
     std::vector<RawSet> pool(n_sets);
     size_t total = 0;
@@ -689,11 +783,12 @@ int kdejs_discrepancy_pairs(int device, const double *const *sets, const int64_t
     OKR(c->js_out.ensure(sizeof(double) * (size_t)n_pairs));
     OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)n_pairs));
     OKR(ensure_host_results(*c, (size_t)n_pairs));
-    OKR(run_pairs_dev(*c, c->s_compute, 0, p, pool, ia, ib, n_pairs, c->js_out.as<double>(),
+    OKR(run_pairs_dev(*c, c->s_compute, p, pool, ia, ib, n_pairs, c->js_out.as<double>(),
                       c->status_out.as<int32_t>(), 0, false));
     CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c->s_compute));
     CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)n_pairs, cudaMemcpyDeviceToHost, c->s_compute));
     CU(cudaStreamSynchronize(c->s_compute));
+    release_scratch(*c, c->s_compute, true);
     memcpy(out_js, c->h_js, sizeof(double) * (size_t)n_pairs);
     return finish_status(c->h_status, n_pairs);
 }
@@ -712,6 +807,7 @@ int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, 
     const size_t offb = ((size_t)na * 16 + 255) / 256 * 256;
     OKR(c->pool_raw.ensure(offb + (size_t)nb * 16));
     cudaStream_t st = c->s_compute;
+    OKR(acquire_scratch(*c, st));
     OKR(h2d_ranges(device, {Stager::Range{c->pool_raw.p, a, (size_t)na * 16},
                             Stager::Range{(char *)c->pool_raw.p + offb, b, (size_t)nb * 16}}, st));
     std::vector<RawSet> pool = {RawSet{(const double *)c->pool_raw.p, na},
@@ -721,16 +817,17 @@ int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, 
     OKR(ensure_host_results(*c, 1));
     const int32_t ia = 0, ib = 1;
     const bool want_z = out_z1 || out_z2 || out_d1 || out_d2;     // any grid output: every node value is materialised
-    OKR(run_pairs_dev(*c, st, 0, p, pool, &ia, &ib, 1, c->js_out.as<double>(), c->status_out.as<int32_t>(), 0, want_z));
+    OKR(run_pairs_dev(*c, st, p, pool, &ia, &ib, 1, c->js_out.as<double>(), c->status_out.as<int32_t>(), 0, want_z));
     CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     const size_t G = (size_t)resolution * resolution;
-    Slot &sl = c->slot[0];
+    Slot &sl = c->slot;
     if (out_z1) CU(cudaMemcpyAsync(out_z1, sl.zout.as<double>(), G * 8, cudaMemcpyDeviceToHost, st));
     if (out_z2) CU(cudaMemcpyAsync(out_z2, sl.zout.as<double>() + G, G * 8, cudaMemcpyDeviceToHost, st));
     if (out_d1) CU(cudaMemcpyAsync(out_d1, sl.dens.as<double>(), G * 8, cudaMemcpyDeviceToHost, st));
     if (out_d2) CU(cudaMemcpyAsync(out_d2, sl.dens.as<double>() + G, G * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    release_scratch(*c, st, true);
     *out_js = c->h_js[0];
     return finish_status(c->h_status, 1);
 }
@@ -747,6 +844,7 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     Ctx *c;
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
+    OKR(acquire_scratch(*c, c->s_compute));
     OKR(c->pool_raw.ensure((size_t)n_obs * 16));
     OKR(c->js_out.ensure(sizeof(double) * (size_t)B));
     OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)B));
@@ -783,6 +881,7 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     else CU(cudaMemcpyAsync(c->pool_raw.p, obs, (size_t)n_obs * 16, cudaMemcpyHostToDevice, c->s_compute));
     int wave_size = std::min(cap, 16);
     if (const char *e = getenv("KDEJS_HOST_WAVE")) wave_size = std::max(1, std::min(cap, atoi(e)));
+    static const bool merge_copies = !(getenv("KDEJS_MERGE_COPIES") && atoi(getenv("KDEJS_MERGE_COPIES")) == 0);
     std::vector<int> wave_of_item(B);
     std::vector<cudaEvent_t> ev_copied, ev_done;
     auto new_event = [&](cudaEvent_t &e) -> int {
@@ -807,19 +906,34 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
             if (i >= ring_items)        // ring slot reuse: the evaluation that read it must have finished
                 if (cudaEventSynchronize(ev_done[wave_of_item[i - ring_items]]) != cudaSuccess) { rc = fail(KDEJS_ERR_CUDA, "event wait failed"); break; }
             char *dst = (char *)c->sim_ring.p + sim_stride * (size_t)(i % ring_items);
-            const cudaError_t ce = (sg && staged[i]) ? sg->issue_range(c->s_copy)
-                                                     : cudaMemcpyAsync(dst, sims[i], (size_t)n_sims[i] * 16, cudaMemcpyHostToDevice, c->s_copy);
-            if (ce != cudaSuccess) {
-                rc = fail(KDEJS_ERR_CUDA, "H2D copy of a simulated set failed");
-                break;
-            }
             pool[k + 1] = RawSet{(const double *)dst, n_sims[i]};
             ib[k] = k + 1;
         }
         if (rc != KDEJS_OK) break;
+        // One cudaMemcpyAsync per run of sims that are contiguous on the host AND land contiguously in the ring
+        // (a caller that carved its sims out of one pinned arena, PinnedPool.empty_batch): a 1.6 MB copy reaches
+        // ~2/3 of the link rate, a 26 MB one all of it.  Anything else: one copy per sim, as before.
+        for (int k = 0; k < items && rc == KDEJS_OK;) {
+            const int i = i0 + k;
+            char *dst = (char *)c->sim_ring.p + sim_stride * (size_t)(i % ring_items);
+            size_t bytes = (size_t)n_sims[i] * 16;
+            int m = 1;
+            if (!(sg && staged[i]) && merge_copies)
+                while (k + m < items && !(sg && staged[i + m]) && bytes == sim_stride * (size_t)m &&
+                       (const char *)sims[i + m] == (const char *)sims[i] + bytes &&
+                       (i + m) % ring_items == (i % ring_items) + m) {
+                    bytes += (size_t)n_sims[i + m] * 16;
+                    ++m;
+                }
+            const cudaError_t ce = (sg && staged[i]) ? sg->issue_range(c->s_copy)
+                                                     : cudaMemcpyAsync(dst, sims[i], bytes, cudaMemcpyHostToDevice, c->s_copy);
+            if (ce != cudaSuccess) rc = fail(KDEJS_ERR_CUDA, "H2D copy of a simulated set failed");
+            k += m;
+        }
+        if (rc != KDEJS_OK) break;
         cudaEventRecord(ec, c->s_copy);
         cudaStreamWaitEvent(c->s_compute, ec, 0);
-        rc = run_pairs_dev(*c, c->s_compute, 0, p, pool, ia.data(), ib.data(), items,
+        rc = run_pairs_dev(*c, c->s_compute, p, pool, ia.data(), ib.data(), items,
                            c->js_out.as<double>(), c->status_out.as<int32_t>(), i0, false);
         cudaEventRecord(ed, c->s_compute);
         i0 += items;
@@ -832,6 +946,7 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     if (sg && rc != KDEJS_OK) sg->abandon();
     cudaError_t se = cudaStreamSynchronize(c->s_compute);
     cudaStreamSynchronize(c->s_copy);
+    release_scratch(*c, c->s_compute, true);
     for (auto e : ev_copied) c->free_plain_events.push_back(e);
     for (auto e : ev_done) c->free_plain_events.push_back(e);
     if (rc != KDEJS_OK) return rc;
@@ -858,11 +973,16 @@ int kdejs_discrepancy_batch_dev(int device, const double *obs_dev, int64_t n_obs
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    OKR(acquire_scratch(*c, st));
     std::vector<RawSet> pool(B + 1);
     pool[0] = RawSet{obs_dev, n_obs};
     std::vector<int32_t> ia(B, 0), ib(B);
     for (int i = 0; i < B; ++i) { pool[i + 1] = RawSet{sims_dev[i], n_sims[i]}; ib[i] = i + 1; }
-    return run_pairs_dev(*c, st, 0, p, pool, ia.data(), ib.data(), B, out_js_dev, status_dev, 0, false);
+    const int rc = run_pairs_dev(*c, st, p, pool, ia.data(), ib.data(), B, out_js_dev, status_dev, 0, false);
+    // the call returns with work in flight on the caller's stream: the next user of the scratch -- this stream or
+    // another -- is ordered behind it through the event (same-stream users are ordered by the stream itself)
+    const int rr = release_scratch(*c, st, false);
+    return rc != KDEJS_OK ? rc : rr;
 }
 
 int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, double gmax, int resolution,
@@ -876,6 +996,7 @@ int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, dou
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t st = c->s_compute;
+    OKR(acquire_scratch(*c, st));
     OKR(c->pool_raw.ensure((size_t)n * 16));
     CU(cudaMemcpyAsync(c->pool_raw.p, pts, (size_t)n * 16, cudaMemcpyHostToDevice, st));
     GridGeom g = make_geom(p);
@@ -886,9 +1007,10 @@ int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, dou
     wd.set[0].rs_self = 0; wd.set[0].rs_other = 0; wd.set[0].n = (int32_t)n;
     WaveIO io;
     io.density_only = true; io.identity_scaler = true;
-    OKR(run_wave(*c, c->slot[0], st, p, g, wd, io));
-    CU(cudaMemcpyAsync(out_dens, c->slot[0].dens.p, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost, st));
+    OKR(run_wave(*c, c->slot, st, p, g, wd, io));
+    CU(cudaMemcpyAsync(out_dens, c->slot.dens.p, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    release_scratch(*c, st, true);
     return KDEJS_OK;
 }
 
@@ -897,6 +1019,7 @@ static int shard_phase1_core(Ctx *c, const Params &p, RawSet ra, RawSet rb, int 
                              int *out_rows = nullptr) {
     c->shard_valid = false;
     cudaStream_t st = c->s_compute;
+    OKR(acquire_scratch(*c, st));
     GridGeom g = make_geom(p);
     g.tile_row_begin = row_begin / kTile;
     g.tile_row_end = (row_end + kTile - 1) / kTile;
@@ -912,7 +1035,7 @@ static int shard_phase1_core(Ctx *c, const Params &p, RawSet ra, RawSet rb, int 
     int tile_rows[2] = {g.tile_row_begin, g.tile_row_end};
     io.out_tile_rows = tile_rows;
     if (balance_world > 0) { io.balance_rank = balance_rank; io.balance_world = balance_world; }
-    Slot &sl = c->slot[0];
+    Slot &sl = c->slot;
     OKR(run_wave(*c, sl, st, p, g, wd, io));
     g.tile_row_begin = tile_rows[0];
     g.tile_row_end = tile_rows[1];
@@ -931,6 +1054,7 @@ static int shard_phase1_core(Ctx *c, const Params &p, RawSet ra, RawSet rb, int 
     CU(cudaMemcpyAsync(c->h_status, &sl.rstat.as<RawStat>()[0].flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_status + 1, &sl.rstat.as<RawStat>()[1].flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    release_scratch(*c, st, true);
     if ((c->h_status[0] | c->h_status[1]) & 1)
         return fail(KDEJS_ERR_INF, "Input X contains infinity or a value too large for dtype('float64').");
     out_norm[0] = c->h_js[0];
@@ -947,7 +1071,8 @@ static int shard_check(const Params &p, const double *a, int64_t na, const doubl
     OKR(check_params(p));
     OKR(check_set(a, na, "df1"));
     OKR(check_set(b, nb, "df2"));
-    if (p.algo != KDEJS_ALGO_BINNED) return fail(KDEJS_ERR_ARG, "row sharding is implemented for the binned algorithm");
+    if (p.algo != KDEJS_ALGO_BINNED && p.algo != KDEJS_ALGO_BINNED32)
+        return fail(KDEJS_ERR_ARG, "row sharding is implemented for the binned algorithms");
     if (row_begin < 0 || row_end > p.R || row_begin >= row_end) return fail(KDEJS_ERR_ARG, "bad row range");
     if (row_begin % kTile != 0 || (row_end % kTile != 0 && row_end != p.R))
         return fail(KDEJS_ERR_ARG, "row range must be aligned to 4 rows (or end at the last row)");
@@ -1014,7 +1139,8 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->shard_valid) return fail(KDEJS_ERR_ARG, "kdejs_shard_phase2 called without a successful phase 1");
     cudaStream_t st = c->s_compute;
-    Slot &sl = c->slot[0];
+    OKR(acquire_scratch(*c, st));
+    Slot &sl = c->slot;
     const GridGeom &g = c->shard_geom;
     const int G = g.R * g.R;
     double *d = c->misc.as<double>();      // [0,1] totals in, [2,3] (left,right) out
@@ -1034,6 +1160,7 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
     OKR(ensure_host_results(*c, 4));
     CU(cudaMemcpyAsync(c->h_js, d + 2, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    release_scratch(*c, st, true);
     out_lr[0] = c->h_js[0];
     out_lr[1] = c->h_js[1];
     return KDEJS_OK;

@@ -43,6 +43,8 @@ constexpr int kMaxGroups = 4;      // measured: 4 groups bring the kernel's DRAM
 constexpr int kNumLists = kMaxGroups * kNumClasses;
 constexpr int kTicketA = kNumLists, kTicketB = kNumLists + 1;
 constexpr int kNumCounters = kNumLists + 2;
+constexpr int kRedoBase = kNumCounters;           // counters[kRedoBase ...]: the same layout again for the redo list
+constexpr int kAllCounters = 2 * kNumCounters;
 constexpr int kJsThreads = 256;
 constexpr int kJsNodesPerBlock = 2048;
 constexpr int kMinmaxThreads = 256;
@@ -75,6 +77,11 @@ struct GridGeom {
     int32_t sets_per_group, pad3;           // work-list locality: sets [k*spg, (k+1)*spg) form group k (see kMaxGroups)
     int32_t heavy_log2, use_moments;        // tiles with >= 2^heavy_log2 candidates are processed per block;
                                             // use_moments: cells wholly inside a tile's support go in as moments
+    // fp32 path (k_density_binned32): sorted points are also kept as 32-bit fixed point in units of h * 2^-q_shift
+    // (modulo 2^32: only differences to a tile's first node are ever used, and those stay below 2^31)
+    int32_t q_shift, q_pad;                 // 0: geometry not eligible (reach too long for the format), fp64 path is used
+    double q_scale, q_lo, q_hi;             // q = (u32)(i64)rint((clamp(x, q_lo, q_hi) - gmin) * q_scale)
+    float q_unit, q_dh;                     // 2^-q_shift; dh as float
 };
 
 __device__ __forceinline__ double pre_transform(double v, int log_flag, double eps) {
@@ -313,7 +320,7 @@ k_scan_narrow(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
               uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart,
               unsigned *__restrict__ counters) {
     const int set = blockIdx.x;
-    if (set == 0 && threadIdx.x < kNumCounters) counters[threadIdx.x] = 0u;  // work-list counters of this wave
+    if (set == 0 && threadIdx.x < kAllCounters) counters[threadIdx.x] = 0u;  // work-list (+ redo) counters of this wave
     const int nb = wd.set[set].nb;
     uint32_t *bh = blockhist + (size_t)set * nb_max * ncells;
     constexpr int CPT = 4;
@@ -379,7 +386,7 @@ k_scan_wide(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
             uint32_t *__restrict__ blockhist, uint32_t *__restrict__ cellstart,
             unsigned *__restrict__ counters, unsigned *__restrict__ ticket) {
     const int set = blockIdx.y;
-    if (set == 0 && blockIdx.x == 0 && threadIdx.x < kNumCounters) counters[threadIdx.x] = 0u;  // work-list counters of this wave
+    if (set == 0 && blockIdx.x == 0 && threadIdx.x < kAllCounters) counters[threadIdx.x] = 0u;  // work-list (+ redo) counters of this wave
     const int nb = wd.set[set].nb;
     uint32_t *cs = cellstart + (size_t)set * (ncells + 1);
     const int c = blockIdx.x * 1024 + threadIdx.x;
@@ -446,6 +453,13 @@ k_scan_wide(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
     if (threadIdx.x == 0) { cs[ncells] = (uint32_t)wd.set[set].n; ticket[set] = 0u; }   // self-resetting
 }
 
+// 32-bit fixed-point copy of a scaled coordinate for the fp32 path.  Coordinates beyond [q_lo, q_hi] (2h outside the
+// grid's extent: they cannot be within h of any node) are clamped so that differences to in-reach nodes never wrap.
+__device__ __forceinline__ uint32_t quantise(double x, const GridGeom &g) {
+    const double c = fmin(fmax(x, g.q_lo), g.q_hi);
+    return (uint32_t)(long long)__double2ll_rn((c - g.gmin) * g.q_scale);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_place: grid (ceil(n_max/256), n_sets), 256 threads, one point per thread.  The point's stable sorted
 // position is  cell start + earlier blocks (k_scan) + earlier warps of its block (k_scale_count) + its rank inside its
@@ -456,7 +470,7 @@ k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, 
         int identity_scaler, int ncells, int chw, int nb_max, const uint16_t *__restrict__ cellid,
         const uint16_t *__restrict__ rank16, const uint16_t *__restrict__ warpprefix,
         const uint32_t *__restrict__ blockbase, const uint32_t *__restrict__ cellstart,
-        double2 *__restrict__ sorted) {
+        double2 *__restrict__ sorted, uint2 *__restrict__ sorted_q, const GridGeom g) {
     const SetDesc sd = wd.set[blockIdx.y];
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= sd.n) return;
@@ -470,7 +484,9 @@ k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, 
                          blockbase[row * ncells + cell] +
                          warpprefix[(row * kSortWarps + (size_t)(wchunk % kSortWarps)) * ncells + cell] + rank;
     const Scaler sc = make_scaler(rstat, sd, identity_scaler);
-    sorted[sd.off + pos] = scale_point(v, sc, log_flag, eps, identity_scaler);
+    const double2 X = scale_point(v, sc, log_flag, eps, identity_scaler);
+    sorted[sd.off + pos] = X;
+    if (sorted_q) sorted_q[sd.off + pos] = make_uint2(quantise(X.x, g), quantise(X.y, g));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -754,6 +770,19 @@ __device__ __forceinline__ uint32_t list_entry(const uint32_t *__restrict__ work
     }
     return worklist[(size_t)s_list[lo] * capacity + (item - s_pre[lo])];
 }
+// The same, also returning which list the item came from (the fp32 path re-queues a tile on the same list of the
+// redo set when it cannot certify a node).
+__device__ __forceinline__ uint32_t list_entry_ex(const uint32_t *__restrict__ worklist, unsigned capacity,
+                                                  unsigned item, const unsigned *s_pre, const uint8_t *s_list,
+                                                  int n_lists, int &list) {
+    int lo = 0, hi = n_lists - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_pre[mid] <= item) lo = mid; else hi = mid - 1;
+    }
+    list = s_list[lo];
+    return worklist[(size_t)s_list[lo] * capacity + (item - s_pre[lo])];
+}
 
 // k_density_binned: persistent, (#SM x resident) blocks of 128 threads pulling 4x4-node tiles from
 // the work list.  A tile's candidates are the sorted points of the cells that can reach it (one
@@ -990,6 +1019,338 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         }
 #pragma unroll
         for (int o = 2; o < 32; o <<= 1) P += __shfl_xor_sync(0xffffffffu, P, o);   // 16 node values, fixed tree
+        if (lane == 0) tilesum[(size_t)set * g.NT * g.NT + tile] = P;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// k_density_binned32: the culled sum on the FP32 pipe.  Same work list, same cell runs, same tile shape as
+// k_density_binned; the candidates come from the 32-bit fixed-point copy of the sorted points (k_place), 8 bytes
+// each.  Per candidate and lane: two integer subtractions against the tile's first node (exact), two I2FP, eight
+// FFMA/FMUL for the node offsets in units of h, four FFMA for a_i = 1 - ux_i^2, then per node
+//     t = sat(a_i - uy_j^2)        FFMA.SAT: multiply, add and an exact ReLU in one instruction (t <= 1 always)
+//     acc_ij += t                  FADD2 (packed f32x2: one issue slot for two nodes)
+// i.e. 44 FMA-pipe cycles and ~48 issue slots where the fp64 kernel spends 92 fp64-pipe cycles.  fp32 partial sums
+// are folded into per-lane fp64 sums every kFlushTrips candidates, so the accumulation error does not grow with
+// the tile's weight; the cross-lane reduction is fp64 and fixed-shape (bit-reproducible like the fp64 path).
+//
+// Exact zeros stay exact zeros.  The error of a computed t is below kBias32/2 (coordinates: 2^-29 h quantisation,
+// one I2FP rounding of |u| <= 2.5, fp32 node offsets), so
+//   * a node whose sum reaches  thr = kBias32 * max(candidates, 1024)  certainly has an in-support point;
+//   * otherwise the tile is walked a second time with every a_i raised by kBias32: a node whose biased sum is still
+//     exactly 0 certainly has none (every true t <= -kBias32/2) and is written as the exact 0;
+//   * a node that is neither (0 < true |t| of its nearest candidate < ~1e-6: a handful per evaluation) sends its
+//     tile to the redo list, which k_density_binned (fp64) processes right after this kernel.
+// Phase A (heavy tiles, block per tile) skips the biased walk and re-queues directly; it practically never happens.
+constexpr int kFlushTrips = 16;
+constexpr float kBias32 = 9.5367431640625e-07f;       // 2^-20
+constexpr uint32_t kFarQ = 0x40000000u;               // a padding candidate 2^30 units (>= 2 h, q_shift <= 29) LEFT of the
+                                                      // tile's first node: out of every node's support, adds exactly 0
+
+__device__ __forceinline__ void accumulate_point32(const uint2 q, const uint32_t gxq, const uint32_t gyq,
+                                                   const float unit, const float c1, const float c2, const float c3,
+                                                   const float one, float (&acc)[kTile][kTile]) {
+    const float fx = (float)(int)(q.x - gxq), fy = (float)(int)(q.y - gyq);
+    const float u0 = fx * unit, v0 = fy * unit;                       // offsets from the tile's first node, units of h
+    const float u1 = fmaf(fx, unit, -c1), u2 = fmaf(fx, unit, -c2), u3 = fmaf(fx, unit, -c3);
+    const float v1 = fmaf(fy, unit, -c1), v2 = fmaf(fy, unit, -c2), v3 = fmaf(fy, unit, -c3);
+    const float a[kTile] = {fmaf(-u0, u0, one), fmaf(-u1, u1, one), fmaf(-u2, u2, one), fmaf(-u3, u3, one)};
+    const float v[kTile] = {v0, v1, v2, v3};
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; j += 2) {
+            const float2 t = make_float2(__saturatef(fmaf(-v[j], v[j], a[i])),
+                                         __saturatef(fmaf(-v[j + 1], v[j + 1], a[i])));
+            const float2 r = __fadd2_rn(make_float2(acc[i][j], acc[i][j + 1]), t);
+            acc[i][j] = r.x;
+            acc[i][j + 1] = r.y;
+        }
+}
+__device__ __forceinline__ void flush32(float (&a32)[kTile][kTile], double (&a64)[kTile][kTile]) {
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) { a64[i][j] += (double)a32[i][j]; a32[i][j] = 0.f; }
+}
+
+template <bool MOMENTS>
+__global__ void __launch_bounds__(kDensThreads, 5)
+k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
+                   const uint2 *__restrict__ sorted_q, const uint32_t *__restrict__ cellstart,
+                   const double *__restrict__ moments,
+                   double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
+                   const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
+                   unsigned capacity, uint32_t *__restrict__ redo_list) {
+    __shared__ uint32_t s_rs[2 * kMaxRows];
+    __shared__ uint32_t s_len[2 * kMaxRows];
+    __shared__ int s_mlo[kMaxRows], s_mcnt[kMaxRows], s_rows, s_cy0;
+    __shared__ uint8_t s_base[2 * kMaxRows];
+    __shared__ double s_red[kRedDoubles];
+    __shared__ unsigned s_item;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncells = g.C * g.C;
+    __shared__ unsigned s_preA[kMaxGroups + 1], s_preB[kMaxGroups * (kNumClasses - 1) + 1];
+    __shared__ uint8_t s_listA[kMaxGroups], s_listB[kMaxGroups * (kNumClasses - 1)];
+    __shared__ unsigned s_cnt[kNumLists];
+    if (threadIdx.x < kNumLists) s_cnt[threadIdx.x] = counters[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned a = 0u, b = 0u;
+        int nb_lists = 0;
+#pragma unroll 1
+        for (int grp = 0; grp < kMaxGroups; ++grp) {
+            s_preA[grp] = a; s_listA[grp] = (uint8_t)(grp * kNumClasses);
+            a += s_cnt[grp * kNumClasses];
+#pragma unroll 1
+            for (int c = 1; c < kNumClasses; ++c) {
+                s_preB[nb_lists] = b; s_listB[nb_lists] = (uint8_t)(grp * kNumClasses + c);
+                b += s_cnt[grp * kNumClasses + c];
+                ++nb_lists;
+            }
+        }
+        s_preA[kMaxGroups] = a;
+        s_preB[nb_lists] = b;
+    }
+    __syncthreads();
+    const unsigned n0 = s_preA[kMaxGroups];
+    const unsigned nB = s_preB[kMaxGroups * (kNumClasses - 1)];
+    const double c1 = g.dh, c2 = 2.0 * g.dh, c3 = 3.0 * g.dh;
+    const float f1 = g.q_dh, f2 = 2.0f * g.q_dh, f3 = 3.0f * g.q_dh;
+    const float unit = g.q_unit;
+    const size_t G = (size_t)g.R * g.R;
+    unsigned *__restrict__ redo_counters = counters + kRedoBase;
+
+    // ---------------- phase A: block per tile ----------------
+    for (;;) {
+        if (n0 == 0u) break;
+        if (threadIdx.x == 0) s_item = atomicAdd(&counters[kTicketA], 1u);
+        __syncthreads();
+        const unsigned item = s_item;
+        if (item >= n0) break;
+        int list;
+        const uint32_t entry = list_entry_ex(worklist, capacity, item, s_preA, s_listA, kMaxGroups, list);
+        const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
+        const SetDesc sd = wd.set[set];
+        const int tx = tile / g.NT, ty = tile % g.NT;
+        const int ix0 = tx * kTile, iy0 = ty * kTile;
+        const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
+        const uint32_t gxq = quantise(gx0, g), gyq = quantise(gy0, g);
+        if (warp == 0) {
+            const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
+            const TileCells tc = tile_cells(g, ix0, iy0);
+            const int rows = tc.cy_hi - tc.cy_lo + 1;
+            RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
+            if (lane < rows) rr = tile_row_runs(g, tc, cs, tc.cy_lo + lane, MOMENTS);
+            s_rs[2 * lane] = rr.s1;
+            s_rs[2 * lane + 1] = rr.s2;
+            s_len[2 * lane] = rr.l1;
+            s_len[2 * lane + 1] = rr.l2;
+            const uint32_t c1n = (rr.l1 + 31u) >> 5, c2n = (rr.l2 + 31u) >> 5;
+            uint32_t cinc = c1n + c2n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, cinc, o);
+                if (lane >= o) cinc += t;
+            }
+            s_base[2 * lane] = (uint8_t)((cinc - c1n - c2n) & 3u);
+            s_base[2 * lane + 1] = (uint8_t)((cinc - c2n) & 3u);
+            s_mlo[lane] = rr.mlo;
+            s_mcnt[lane] = rr.mcnt;
+            if (lane == 0) { s_rows = rows; s_cy0 = tc.cy_lo; }
+        }
+        __syncthreads();
+        float acc[kTile][kTile];
+        double acc64[kTile][kTile];
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) { acc[i][j] = 0.f; acc64[i][j] = 0.0; }
+        const uint2 *__restrict__ pts = sorted_q + sd.off;
+        const int nruns = (MOMENTS ? 2 : 1) * s_rows;
+        int budget = kFlushTrips;
+        uint32_t ncand = 0u;
+        for (int k = 0; k < nruns; ++k) {
+            const int e = MOMENTS ? k : 2 * k;
+            const uint32_t len = s_len[e];
+            ncand += len;
+            const uint2 *__restrict__ rp = pts + s_rs[e];
+            const uint32_t nch = (len + 31u) >> 5, first = ((uint32_t)warp - s_base[e]) & 3u;
+            const uint32_t trips = first < nch ? (nch - first + 3u) >> 2 : 0u;      // warp-uniform
+            uint32_t j = first * 32u + lane;
+            uint2 pn = make_uint2(gxq - kFarQ, gyq);
+            if (j < len) pn = rp[j];
+            for (uint32_t t = 0; t < trips; ++t) {
+                const uint2 p = pn;
+                j += kDensThreads;
+                pn = make_uint2(gxq - kFarQ, gyq);
+                if (j < len) pn = rp[j];
+                accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, 1.0f, acc);
+                if (--budget == 0) { flush32(acc, acc64); budget = kFlushTrips; }
+            }
+        }
+        flush32(acc, acc64);
+        if (MOMENTS) {
+            const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
+            const int rows = s_rows, cy0 = s_cy0;
+            for (int rr = 0; rr < rows; ++rr) {
+                const int mc = s_mcnt[rr], cy = cy0 + rr;
+                ncand += (uint32_t)mc;
+                for (int k = threadIdx.x; k < mc; k += kDensThreads) {
+                    const int cx = s_mlo[rr] + k;
+                    accumulate_cell(mom + (size_t)(cy * g.C + cx) * kMomentDoubles, cell_centre(g, cx),
+                                    cell_centre(g, cy), gx0, gy0, g.inv_h, c1, c2, c3, acc64);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) s_red[(i * kTile + j) * kRedStride + threadIdx.x] = acc64[i][j];
+        __syncthreads();
+        const int node = threadIdx.x >> 3, part = threadIdx.x & 7;
+        double S = 0.0;
+#pragma unroll
+        for (int k = 0; k < kDensThreads / 8; ++k) S += s_red[node * kRedStride + part + 8 * k];
+        S += __shfl_xor_sync(0xffffffffu, S, 1);
+        S += __shfl_xor_sync(0xffffffffu, S, 2);
+        S += __shfl_xor_sync(0xffffffffu, S, 4);
+        const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
+        const bool valid = ix < g.R && iy < g.R;
+        const double thr = (double)kBias32 * (double)max(ncand, 1024u);
+        const int low = __syncthreads_or(valid && S < thr);      // also: everyone is done reading s_red
+        if (low) {                                               // cannot certify a node here: fp64 does this tile
+            if (threadIdx.x == 0) {
+                const unsigned slot = atomicAdd(&redo_counters[list], 1u);
+                redo_list[(size_t)list * capacity + slot] = entry;
+            }
+            continue;
+        }
+        double P = 0.0;
+        if (part == 0 && valid) {
+            const double d = S * sd.knorm_over_n;
+            P = gamma_eps(d, g);
+            dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
+            pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
+        }
+        P += __shfl_xor_sync(0xffffffffu, P, 8);
+        P += __shfl_xor_sync(0xffffffffu, P, 16);
+        if (lane == 0) s_red[warp] = P;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            tilesum[(size_t)set * g.NT * g.NT + tile] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+        __syncthreads();
+    }
+
+    // ---------------- phase B: warp per tile ----------------
+    double *__restrict__ wred = s_red + warp * (kTile * kTile * kWarpRedStride);
+    __syncthreads();
+    for (;;) {
+        unsigned item = 0u;
+        if (lane == 0) item = atomicAdd(&counters[kTicketB], 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nB) break;
+        int list;
+        const uint32_t entry = list_entry_ex(worklist, capacity, item, s_preB, s_listB,
+                                             kMaxGroups * (kNumClasses - 1), list);
+        const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
+        const double knorm_over_n = wd.set[set].knorm_over_n;
+        const uint2 *__restrict__ pts = sorted_q + wd.set[set].off;
+        const int tx = tile / g.NT, ty = tile % g.NT;
+        const int ix0 = tx * kTile, iy0 = ty * kTile;
+        const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
+        const uint32_t gxq = quantise(gx0, g), gyq = quantise(gy0, g);
+        const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
+        const TileCells tc = tile_cells(g, ix0, iy0);
+        const int rows = tc.cy_hi - tc.cy_lo + 1;
+        RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
+        if (lane < rows) rr = tile_row_runs(g, tc, cs, tc.cy_lo + lane, MOMENTS);
+        uint32_t ncand = rr.l1 + rr.l2 + (uint32_t)rr.mcnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+        const double thr = (double)kBias32 * (double)max(ncand, 1024u);
+        const int node = lane >> 1, half = lane & 1;
+        const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
+        const bool valid = ix < g.R && iy < g.R;
+        float one = 1.0f;
+        double S = 0.0, S1 = 0.0;
+        bool requeue = false;
+#pragma unroll 1
+        for (int pass = 0;; ++pass) {
+            float acc[kTile][kTile];
+            double acc64[kTile][kTile];
+#pragma unroll
+            for (int i = 0; i < kTile; ++i)
+#pragma unroll
+                for (int j = 0; j < kTile; ++j) { acc[i][j] = 0.f; acc64[i][j] = 0.0; }
+            constexpr int nparts = MOMENTS ? 2 : 1;
+            int budget = kFlushTrips;
+            for (int r = 0; r < rows; ++r) {
+#pragma unroll 1
+                for (int part = 0; part < nparts; ++part) {
+                    const uint32_t len = __shfl_sync(0xffffffffu, part ? rr.l2 : rr.l1, r);
+                    const uint2 *__restrict__ rp = pts + __shfl_sync(0xffffffffu, part ? rr.s2 : rr.s1, r);
+                    const uint32_t trips = (len + 31u) >> 5;
+                    uint32_t j = lane;
+                    uint2 pn = make_uint2(gxq - kFarQ, gyq);
+                    if (j < len) pn = rp[j];
+                    for (uint32_t t = 0; t < trips; ++t) {
+                        const uint2 p = pn;
+                        j += 32;
+                        pn = make_uint2(gxq - kFarQ, gyq);
+                        if (j < len) pn = rp[j];
+                        accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, one, acc);
+                        if (--budget == 0) { flush32(acc, acc64); budget = kFlushTrips; }
+                    }
+                }
+                if (MOMENTS) {
+                    const int mc = __shfl_sync(0xffffffffu, rr.mcnt, r);
+                    const int mlo = __shfl_sync(0xffffffffu, rr.mlo, r);
+                    const int cy = tc.cy_lo + r;
+                    const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
+                    for (int k = lane; k < mc; k += 32)
+                        accumulate_cell(mom + (size_t)(cy * g.C + mlo + k) * kMomentDoubles, cell_centre(g, mlo + k),
+                                        cell_centre(g, cy), gx0, gy0, g.inv_h, c1, c2, c3, acc64);
+                }
+            }
+            flush32(acc, acc64);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < kTile; ++i)
+#pragma unroll
+                for (int j = 0; j < kTile; ++j) wred[(i * kTile + j) * kWarpRedStride + lane] = acc64[i][j];
+            __syncwarp();
+            S = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) S += wred[node * kWarpRedStride + half + 2 * k];
+            S += __shfl_xor_sync(0xffffffffu, S, 1);
+            if (pass == 0) {
+                if (!__any_sync(0xffffffffu, valid && S < thr)) break;      // every node certainly non-zero
+                S1 = S;
+                one = 1.0f + kBias32;                                       // second walk, every a_i raised by the bias
+            } else {
+                requeue = __any_sync(0xffffffffu, valid && S1 < thr && S > 0.0);
+                S = (S1 < thr) ? 0.0 : S1;                                  // biased sum exactly 0: certainly no in-support point
+                break;
+            }
+        }
+        if (requeue) {
+            if (lane == 0) {
+                const unsigned slot = atomicAdd(&redo_counters[list], 1u);
+                redo_list[(size_t)list * capacity + slot] = entry;
+            }
+            continue;
+        }
+        double P = 0.0;
+        if (half == 0 && valid) {
+            const double d = S * knorm_over_n;
+            P = gamma_eps(d, g);
+            dens[(size_t)set * G + (size_t)ix * g.R + iy] = d;
+            pz[(size_t)set * G + (size_t)ix * g.R + iy] = P;
+        }
+#pragma unroll
+        for (int o = 2; o < 32; o <<= 1) P += __shfl_xor_sync(0xffffffffu, P, o);
         if (lane == 0) tilesum[(size_t)set * g.NT * g.NT + tile] = P;
     }
 }

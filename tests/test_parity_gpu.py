@@ -125,7 +125,8 @@ def test_full_size_properties(pk, ko):
     assert js_aff == pytest.approx(js, rel=1e-9)
 
 
-@pytest.mark.parametrize("R", [1, 2, 3, 5, 17, 100, 129, 256, 511, 1024, 1500])     # >= 1024: 128x128 culling cells
+# 50, 99, 104: resolutions where (R-1) * fl(1/(R-1)) != 1.0 while numpy.linspace forces the last node to the maximum
+@pytest.mark.parametrize("R", [1, 2, 3, 5, 17, 50, 99, 100, 104, 129, 256, 511, 1024, 1500])     # >= 1024: 128x128 culling cells
 def test_resolutions(pk, ko, R):
     from oracle import workloads as wl
 
@@ -649,3 +650,42 @@ def test_pageable_inputs_go_through_the_staging_threads_and_change_nothing(pk):
     pa = pool.empty(big_a.shape); pa[:] = big_a
     pb = pool.empty(big_b.shape); pb[:] = big_b
     assert pk.KDE_JS_divergence(big_a, big_b, 0.25, 0.0, resolution=200) == pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=200)
+
+
+def test_dev_entry_interleaved_with_host_calls_without_sync(pk):
+    """kdejs_discrepancy_batch_dev returns with its wave still running on the caller's stream; host entry points
+    (library stream) and a second caller stream reuse the same scratch right away.  The library orders them through
+    an event; no result may change."""
+    import ctypes
+
+    import torch
+
+    from oracle import workloads as wl
+
+    nat = pk._native
+    obs = wl.synthetic_target(60000)
+    sims = [wl.sim_batch_member(s, n=50000) for s in range(24)]
+    other = [wl.sim_batch_member(100 + s, n=7000) for s in range(6)]
+    want_dev = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0, resolution=256)
+    want_host = pk.KDE_JS_divergence_batch(obs[:9000], other, gamma=0.5, eps=1e-12, resolution=64)
+    dobs = torch.from_numpy(obs).cuda()
+    dsims = [torch.from_numpy(s).cuda() for s in sims]
+    ptrs = (ctypes.c_void_p * 24)(*[t.data_ptr() for t in dsims])
+    cnt = (ctypes.c_int64 * 24)(*[t.shape[0] for t in dsims])
+    torch.cuda.synchronize()
+    for rep in range(3):
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        out1 = torch.zeros(24, dtype=torch.float64, device="cuda")
+        out2 = torch.zeros(24, dtype=torch.float64, device="cuda")
+        call = lambda out, st: nat.check(nat.lib().kdejs_discrepancy_batch_dev(
+            0, dobs.data_ptr(), len(obs), ptrs, cnt, 24, 256, 0.03, 0.25, 0.0, 0, 0, 0, out.data_ptr(), None,
+            st.cuda_stream))
+        call(out1, s1)                                               # in flight on s1 ...
+        got_host = pk.KDE_JS_divergence_batch(obs[:9000], other, gamma=0.5, eps=1e-12, resolution=64)   # ... library stream
+        call(out2, s2)                                               # ... and a different caller stream
+        single = pk.KDE_JS_divergence(obs, sims[3], gamma=0.25, eps=0.0, resolution=256)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out1.cpu().numpy(), want_dev)
+        np.testing.assert_array_equal(out2.cpu().numpy(), want_dev)
+        np.testing.assert_array_equal(got_host, want_host)
+        assert single == want_dev[3]
