@@ -96,6 +96,18 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs,
                             int resolution, double bandwidth, double gamma, double eps,
                             int log_flag, int kernel, int algo, double *out_js);
 
+/* process_result's summary vector for a batch of simulations, and the two ELFI nodes built on it, fused behind
+ * the discrepancies (poppunk_mod.py:351-382 with calculate_gene_freqs :285-291; Distance("euclidean") and
+ * Operation(np.log) :571-572 against the observed vector [0, fc, fi, fr] of :494).  obs/sims as in
+ * kdejs_discrepancy_batch; freqs[i] = the simulation's gene-frequency vector (n_freqs[i] doubles, HOST).
+ * out_summary: B x 4 = [JS, freq_core, freq_intermediate, freq_rare]; out_d / out_log_d (nullable): B each.
+ * The frequencies travel in one upload, one kernel runs behind the last wave, results come back in one copy. */
+int kdejs_summary_batch(int device, const double *obs, int64_t n_obs, const double *const *sims,
+                        const int64_t *n_sims, const double *const *freqs, const int64_t *n_freqs, int B,
+                        double core_threshold, double rare_threshold, const double observed[4], int resolution,
+                        double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                        double *out_summary, double *out_d, double *out_log_d);
+
 /* General pairs: out_js[i] = KDE_JS_divergence(sets[ia[i]], sets[ib[i]]) over a pool of
  * n_sets HOST point sets, each uploaded once (the itertools.combinations loop at
  * scripts/pairwise_2D_distance.py:112-118). */
@@ -146,6 +158,46 @@ int kdejs_shard_phase1_balanced(int device, const double *a, int64_t na, const d
                                 double out_norm[2], int out_rows[2]);
 int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2]);
 
+/* ---- one huge evaluation with the POINTS sharded too (band mode) ----------------
+ * Replaces the single serial node loop of KDE_distance.py:58-64 over a table no rank holds completely.  Every rank
+ * holds a contiguous slice of each table ON ITS DEVICE (rank order = row order) and ends up owning a band of tile
+ * columns (4 nodes of grid column 1 each) chosen so that the bands carry equal estimated work.  Only what a band
+ * needs crosses NVLink: the points of the cell rows within h of it.  All entry points enqueue on `stream` (NULL = the
+ * library's stream); only kdejs_band_plan synchronises.  The caller (poppunk-mod_b200/distributed.py) runs the three
+ * small all-gathers and the one all-to-all between the steps:
+ *
+ *   kdejs_band_minmax_dev   extrema of the own slices                          -> all-gather (10 doubles per rank)
+ *   kdejs_band_sort_dev     joint scaler from all extrema (KDE_distance.py:81-86), own slices scaled and counting-sorted
+ *                           by cell; out_sorted_dev = (na + nb, 2) scaled points, set 1 after set 0;
+ *                           out_block_dev = the rank's count block                 -> all-gather (block_u32 per rank)
+ *   kdejs_band_plan         (host sync) work per tile column from the global counts -> kdejs_band_cuts,
+ *                           every rank's row starts (sizes of the exchange), moment-cell decision
+ *   kdejs_band_cuts / kdejs_band_cell_rows   (pure host) equal-work bands; cell rows a band needs
+ *                           -> all-to-all: rank s sends rank d its sorted points of d's cell rows, per set
+ *   kdejs_band_phase1_dev   received slices (source after source) merged per cell in rank order = original order,
+ *                           density of the band's tiles, partial normalisers       -> all-gather (2 doubles)
+ *   kdejs_band_phase2_dev   normalisers folded in rank order, rel_entr partials of the band -> all-gather (3 doubles);
+ *                           JS = sqrt(max(0, sum of out_lr[0] + out_lr[1]) / 2); out_lr[2] != 0: an input held infinity.
+ * A rank's count block (u32): cellstart[2][C*C + 1] of its sorted slices, then rowstart[2][C + 1]. */
+int kdejs_band_geometry(int resolution, double bandwidth, int kernel, int out[4]);   /* C, NT, block_u32, moments eligible */
+int kdejs_band_minmax_dev(int device, const double *a_dev, int64_t na, const double *b_dev, int64_t nb,
+                          int log_flag, double eps, double *out_stats_dev, void *stream);
+int kdejs_band_sort_dev(int device, const double *a_dev, int64_t na, const double *b_dev, int64_t nb, int resolution,
+                        double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                        const double *stats_all_dev, int world, double *out_sorted_dev, uint32_t *out_block_dev,
+                        void *stream);
+int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int resolution, double bandwidth,
+                    double gamma, double eps, int log_flag, int kernel, int algo, double *out_colwork,
+                    uint32_t *out_rowstart, int *out_use_moments, void *stream);
+int kdejs_band_cuts(const double *colwork, int nt, int world, int *cuts);
+int kdejs_band_cell_rows(int resolution, double bandwidth, int ty_begin, int ty_end, int out_cy[2]);
+int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, const double *stage_b_dev, int64_t nb,
+                          int64_t na_total, int64_t nb_total, const uint32_t *blocks_all_dev, int world,
+                          const double *stats_all_dev, int resolution, double bandwidth, double gamma, double eps,
+                          int log_flag, int kernel, int algo, int ty_begin, int ty_end, int cy_lo, int cy_hi,
+                          int use_moments, double *out_norm_dev, void *stream);
+int kdejs_band_phase2_dev(int device, const double *norms_all_dev, int world, double *out_lr_dev, void *stream);
+
 /* ---- host memory --------------------------------------------------------------------- */
 void *kdejs_host_alloc(size_t bytes);   /* pinned (page-locked) host memory, NULL on failure */
 void kdejs_host_free(void *p);
@@ -178,6 +230,14 @@ int kdejs_launch_count(int device, int64_t *count, int reset);
 /* Work counters of the density launches since the last reset: pair_tests = (point, node)
  * kernel evaluations executed; in_support is filled only by the CPU-side estimate (0 here). */
 int kdejs_work_counters(int device, double *pair_tests, int reset);
+/* KDEJS_ALGO_BINNED32 bookkeeping since the last reset, filled only while profiling is enabled: out[0] tiles,
+ * [1] tiles walked a second time (a node's fp32 sum below the certification threshold), [2] / [3] warp trips of
+ * the first / second walks, [4] tiles re-queued for the fp64 kernel. */
+int kdejs_fp32_stats(int device, double out[5], int reset);
+/* The candidate loops of the two culled density kernels over an L1-resident run, no per-tile work: (point, node)
+ * pair tests per second.  which: 0 fp64 loop (k_density_binned), 1 fp32 loop without, 2 with the periodic fold of
+ * the fp32 partial sums into fp64 (k_density_binned32).  The ceiling the kernels' candidate work can approach. */
+int kdejs_loop_peak(int device, int which, double *pair_tests_per_s);
 /* Issue-rate microbenchmarks used as roofline denominators.  which: 0 FFMA fp32,
  * 1 DFMA fp64, 2 packed FFMA2 (f32x2), 3 / 4 DFMA interleaved with one / two independent ALU-pipe
  * instructions per DFMA (reports the DFMA rate only: does a co-issued instruction slow the fp64 pipe?).

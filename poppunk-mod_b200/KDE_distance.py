@@ -43,7 +43,7 @@ except ImportError:  # used as a top-level drop-in module: `sys.path.insert(0, "
     _spec.loader.exec_module(nat)
 
 __all__ = ["get_grid", "scale_KDE", "KDE_JS_divergence", "KDE_KL_divergence", "KDE_JS_divergence_batch",
-           "KDE_JS_divergence_pairs", "kde_density", "default_device", "main"]
+           "KDE_JS_divergence_pairs", "kde_density", "summary_batch", "rule_bandwidth", "default_device", "main"]
 
 _DEFAULT_RESOLUTION = 100      # KDE_distance.py:89
 _DEFAULT_BANDWIDTH = 0.03      # KDE_distance.py:50
@@ -70,6 +70,28 @@ def get_grid(minimum, maximum, resolution):
     return xx, yy, xy
 
 
+def rule_bandwidth(rule, n_samples, n_features=2):
+    """sklearn's bandwidth rules (sklearn:neighbors/_kde.py:223-229): "scott" = n**(-1/(d+4)),
+    "silverman" = (n (d+2) / 4)**(-1/(d+4)); no covariance factor.  For d = 2 the two coincide."""
+    if rule == "scott":
+        return float(n_samples) ** (-1.0 / (n_features + 4))
+    if rule == "silverman":
+        return (float(n_samples) * (n_features + 2) / 4.0) ** (-1.0 / (n_features + 4))
+    raise ValueError(f"bandwidth must be a positive number, 'scott' or 'silverman'; got {rule!r}")
+
+
+def _bandwidth(bandwidth, *sets):
+    """A number passes through; a rule name is resolved from the sample count like sklearn does at fit() time.
+    The kernels use one bandwidth per evaluation, so with a rule all sets of the call must have the same size."""
+    if not isinstance(bandwidth, str):
+        return float(bandwidth)
+    sizes = {int(np.shape(x)[0]) for x in sets}
+    if len(sizes) != 1:
+        raise ValueError(f"bandwidth={bandwidth!r} needs point sets of equal size in one call (sklearn fits the rule "
+                         f"per set; sizes here: {sorted(sizes)}); pass a number instead")
+    return rule_bandwidth(bandwidth, sizes.pop())
+
+
 def _common(resolution, bandwidth, gamma, eps, log, kernel, algo):
     if kernel not in nat.KERNELS:
         raise ValueError(f"kernel must be one of {sorted(nat.KERNELS)}; got {kernel!r}")
@@ -85,7 +107,7 @@ def _discrepancy(df1, df2, gamma, eps, log, resolution, bandwidth, kernel, algo,
                  want_density=False):
     a = nat.as_points(df1, "df1")
     b = nat.as_points(df2, "df2")
-    common = _common(resolution, bandwidth, gamma, eps, log, kernel, algo)
+    common = _common(resolution, _bandwidth(bandwidth, a, b), gamma, eps, log, kernel, algo)
     G = int(resolution) * int(resolution)
     out = ctypes.c_double()
     z1 = z2 = d1 = d2 = None
@@ -137,7 +159,7 @@ def KDE_JS_divergence_batch(obs, sims, gamma=1.0, eps=1e-12, log=False, *,
     sims are dealt round-robin, one host thread per device, and only the B scalars come back."""
     o = nat.as_points(obs, "obs")
     arrays = [nat.as_points(s, f"sims[{i}]") for i, s in enumerate(sims)]
-    common = _common(resolution, bandwidth, gamma, eps, log, kernel, algo)
+    common = _common(resolution, _bandwidth(bandwidth, o, *arrays), gamma, eps, log, kernel, algo)
     B = len(arrays)
     out = np.empty(B, dtype=np.float64)
     if B == 0:
@@ -193,13 +215,42 @@ def KDE_JS_divergence_pairs(sets, pairs, gamma=1.0, eps=1e-12, log=False, *,
     pr = np.asarray(list(pairs), dtype=np.int32).reshape(-1, 2)
     ia = np.ascontiguousarray(pr[:, 0])
     ib = np.ascontiguousarray(pr[:, 1])
-    common = _common(resolution, bandwidth, gamma, eps, log, kernel, algo)
+    common = _common(resolution, _bandwidth(bandwidth, *arrays), gamma, eps, log, kernel, algo)
     out = np.empty(len(pr), dtype=np.float64)
     ptrs, counts = nat.pointer_array(arrays)
     dev = default_device() if device is None else int(device)
     nat.check(nat.lib().kdejs_discrepancy_pairs(dev, ptrs, counts, len(arrays), nat.ptr(ia), nat.ptr(ib),
                                                 len(pr), *common, nat.ptr(out)))
     return out
+
+
+def summary_batch(obs, sims, sims_freqs, observed, gamma, core_threshold, rare_threshold, *, eps=0.0, log=False,
+                  resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BANDWIDTH, algo=None, device=None):
+    """The simulator's summary vectors for B simulations against one target, and the two ELFI nodes on top of them,
+    in one device pass (kdejs_summary_batch): returns (summary (B,4) = [JS, freq_core, freq_intermediate, freq_rare],
+    d (B,), log_d (B,)) -- process_result, poppunk_mod.py:351-382 with calculate_gene_freqs :285-291, then
+    Distance("euclidean") against `observed` = [0, fc, fi, fr] (:494, :571) and Operation(np.log) (:572)."""
+    o = nat.as_points(obs, "obs")
+    arrays = [nat.as_points(s, f"sims[{i}]") for i, s in enumerate(sims)]
+    freqs = [np.ascontiguousarray(np.asarray(f, dtype=np.float64).reshape(-1)) for f in sims_freqs]
+    if len(freqs) != len(arrays):
+        raise ValueError("one gene-frequency vector per simulation is required")
+    obs4 = np.ascontiguousarray(np.asarray(observed, dtype=np.float64).reshape(-1))
+    if obs4.shape != (4,):
+        raise ValueError("observed must be the 4-vector [0, freq_core, freq_intermediate, freq_rare]")
+    common = _common(resolution, _bandwidth(bandwidth, o, *arrays), gamma, eps, log, "epanechnikov", algo)
+    B = len(arrays)
+    summary, d, logd = np.empty((B, 4)), np.empty(B), np.empty(B)
+    if B == 0:
+        return summary, d, logd
+    ptrs, counts = nat.pointer_array(arrays)
+    fptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in freqs])
+    fcnt = (ctypes.c_int64 * B)(*[f.shape[0] for f in freqs])
+    dev = default_device() if device is None else int(device)
+    nat.check(nat.lib().kdejs_summary_batch(dev, nat.ptr(o), o.shape[0], ptrs, counts, fptrs, fcnt, B,
+                                            float(core_threshold), float(rare_threshold), nat.ptr(obs4), *common,
+                                            nat.ptr(summary), nat.ptr(d), nat.ptr(logd)))
+    return summary, d, logd
 
 
 def kde_density(df_scaled, resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BANDWIDTH,
@@ -210,7 +261,7 @@ def kde_density(df_scaled, resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BA
     X = nat.as_points(df_scaled, "df_scaled")
     if not np.isfinite(X).all():
         raise ValueError("Input X contains NaN or infinity.")
-    R, h, _, _, _, k, al = _common(resolution, bandwidth, 1.0, 0.0, False, kernel, algo)
+    R, h, _, _, _, k, al = _common(resolution, _bandwidth(bandwidth, X), 1.0, 0.0, False, kernel, algo)
     out = np.empty(R * R, dtype=np.float64)
     dev = default_device() if device is None else int(device)
     nat.check(nat.lib().kdejs_kde_density(dev, nat.ptr(X), X.shape[0], float(minimum), float(maximum), R, h, k,

@@ -39,6 +39,9 @@ _SIGNATURES = {
                                          ctypes.c_int64] + _COMMON + [_c_dp] + [ctypes.c_void_p] * 4),
     "kdejs_discrepancy_batch": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p,
                                                ctypes.c_int] + _COMMON + [ctypes.c_void_p]),
+    "kdejs_summary_batch": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p, _c_dpp, _c_i64p,
+                                           ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p] + _COMMON +
+                            [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "kdejs_discrepancy_pairs": (ctypes.c_int, [ctypes.c_int, _c_dpp, _c_i64p, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_int64] + _COMMON + [ctypes.c_void_p]),
     "kdejs_discrepancy_batch_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p,
@@ -55,6 +58,25 @@ _SIGNATURES = {
                                                    ctypes.c_int64, ctypes.c_int] + _COMMON +
                                     [ctypes.c_int, ctypes.c_int, _c_dp, ctypes.POINTER(ctypes.c_int)]),
     "kdejs_shard_phase2": (ctypes.c_int, [ctypes.c_int, _c_dp, _c_dp]),
+    "kdejs_band_geometry": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "kdejs_band_minmax_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                             ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
+    "kdejs_band_sort_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                           ctypes.c_int64] + _COMMON + [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                                        ctypes.c_void_p, ctypes.c_void_p]),
+    "kdejs_band_plan": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + _COMMON +
+                        [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    "kdejs_band_cuts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "kdejs_band_cell_rows": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_int)]),
+    "kdejs_band_phase1_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                             ctypes.c_int, ctypes.c_void_p] + _COMMON +
+                              [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                               ctypes.c_void_p]),
+    "kdejs_band_phase2_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     "kdejs_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "kdejs_host_free": (None, [ctypes.c_void_p]),
     "kdejs_tsv_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -67,6 +89,8 @@ _SIGNATURES = {
     "kdejs_launch_count": (ctypes.c_int, [ctypes.c_int, _c_i64p, ctypes.c_int]),
     "kdejs_work_counters": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int]),
     "kdejs_peak_flops": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_dp, _c_dp]),
+    "kdejs_fp32_stats": (ctypes.c_int, [ctypes.c_int, _c_dp, ctypes.c_int]),
+    "kdejs_loop_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_dp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -122,10 +122,13 @@ struct Ctx {
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> free_events;
     int64_t launches = 0;
-    unsigned long long *d_work = nullptr;
+    unsigned long long *d_work = nullptr, *d_stats32 = nullptr;
     // row-sharded evaluation state (phase 1 -> phase 2)
     bool shard_valid = false;
     WaveDesc shard_wd; GridGeom shard_geom; int shard_kb = 0, shard_ke = 0;
+    // band mode state (kdejs_band_phase1_dev -> kdejs_band_phase2_dev)
+    bool band_valid = false;
+    GridGeom band_geom; int band_ty0 = 0, band_ty1 = 0;
 };
 
 constexpr int kMaxDevices = 64;
@@ -140,6 +143,8 @@ int init_ctx(Ctx &c) {
     CU(cudaMemset(c.slot.tickets.p, 0, c.slot.tickets.cap));
     CU(cudaMalloc(&c.d_work, sizeof(unsigned long long)));
     CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
+    CU(cudaMalloc(&c.d_stats32, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(c.d_stats32, 0, 8 * sizeof(unsigned long long)));
     CU(cudaFuncSetAttribute(k_scale_count, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             kSortWarps * kMaxCells * (int)sizeof(uint16_t)));
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned<false>, kDensThreads, 0));
@@ -167,6 +172,7 @@ void destroy_ctx(Ctx &c) {
     for (auto e : c.free_events) cudaEventDestroy(e);
     c.free_events.clear();
     if (c.d_work) { cudaFree(c.d_work); c.d_work = nullptr; }
+    if (c.d_stats32) { cudaFree(c.d_stats32); c.d_stats32 = nullptr; }
     if (c.scratch_busy) { cudaEventDestroy(c.scratch_busy); c.scratch_busy = nullptr; }
     if (c.s_compute) { cudaStreamDestroy(c.s_compute); c.s_compute = nullptr; }
     if (c.s_copy) { cudaStreamDestroy(c.s_copy); c.s_copy = nullptr; }
@@ -301,6 +307,8 @@ GridGeom make_geom(const Params &p) {
     g.gamma_mode = (p.gamma == 1.0) ? 1 : (p.gamma == 0.5) ? 2 : (p.gamma == 0.25) ? 3 : 0;
     g.tile_row_begin = 0;
     g.tile_row_end = g.NT;
+    g.tile_col_begin = 0;
+    g.tile_col_end = g.NT;
     g.sets_per_group = kMaxWaveSets;      // one group until run_wave() knows the wave
     g.pad3 = 0;
     g.heavy_log2 = 13;
@@ -345,6 +353,12 @@ struct WaveIO {
     bool shard = false;              // row-sharded: no k_js, caller runs the phases
     int balance_rank = -1, balance_world = 0;   // row-sharded with work-balanced bands chosen here
     int *out_tile_rows = nullptr;               // [2]: the tile rows this rank ended up with
+    // band mode (one evaluation over several GPUs, kdejs_band_*)
+    bool rstat_ready = false;        // slot.rstat already holds the (global) extrema: no k_minmax
+    bool sort_only = false;          // stop after k_place (the caller ships the sorted points)
+    bool presorted = false;          // slot.sorted / sorted_q / cellstart were assembled by k_band_merge: no sort
+    int force_moments = -1;          // -1: decide from this wave's point count; 0 / 1: decided by the caller (all ranks alike)
+    const int64_t *n_global = nullptr;   // [n_sets]: sizes of the WHOLE sets (the 1/N of the density) when this wave holds a part
 };
 
 int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
@@ -370,7 +384,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     for (int s = 0; s < n_sets; ++s) {
         wd.set[s].off = P;
         P += wd.set[s].n;
-        wd.set[s].knorm_over_n = g.knorm / (double)wd.set[s].n;
+        wd.set[s].knorm_over_n = g.knorm / (double)(io.n_global ? io.n_global[s] : (int64_t)wd.set[s].n);
     }
     int chw, nb_max;
     sort_shape(wd, c.sm_count, chw, nb_max);
@@ -383,12 +397,14 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     const bool fast32 = binned && g.q_shift > 0 && (force32 >= 0 ? force32 != 0 : p.algo == KDEJS_ALGO_BINNED32);
     // a moment cell costs a tile as much as one point plus some per-row bookkeeping: it pays once cells hold
     // hundreds of points (measured: -40 % density time at 1200 points per cell, +48 % at 49)
-    if (g.use_moments == 1 && P < (int64_t)128 * n_sets * ncells) g.use_moments = 0;
+    if (io.force_moments >= 0 && g_in.use_moments == 1) g.use_moments = io.force_moments ? 1 : 0;
+    else if (g.use_moments == 1 && P < (int64_t)128 * n_sets * ncells) g.use_moments = 0;
     // Plain discrepancies (no grids requested, one launch for the whole grid): tiles without candidates are only
     // flagged and the divergence kernel reads the flag instead of 16 node values -- ~70 % of the grid is never
     // written or read.
     const bool lazy_empty = binned && !io.want_z && !io.density_only && !io.shard && io.balance_world == 0 &&
-                            g.tile_row_begin == 0 && g.tile_row_end == g.NT;
+                            g.tile_row_begin == 0 && g.tile_row_end == g.NT && g.tile_col_begin == 0 &&
+                            g.tile_col_end == g.NT;
     if (lazy_empty) OKR(sl.tileflag.ensure((size_t)n_sets * g.NT * g.NT));
     const int nparts = binned ? g.NT * g.NT : (int)((G + 255) / 256);
 
@@ -433,7 +449,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     unsigned *tk_js = sl.tickets.as<unsigned>() + kMaxWaveSets;
     unsigned *tk_scan = sl.tickets.as<unsigned>() + 2 * kMaxWaveSets;
 
-    if (!io.identity_scaler) {
+    if (!io.identity_scaler && !io.rstat_ready) {
         KTimer t(c, 0, st);
         k_minmax<<<dim3(mm_blocks, wd.n_raw), kMinmaxThreads, 0, st>>>(
             wd, p.log_flag, p.eps, sl.rpart.as<RawStat>(), tk_minmax, sl.rstat.as<RawStat>());
@@ -443,7 +459,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         // one block per set scans <= 4096 cells over a few sort blocks fastest; otherwise one thread per cell
         static const int force_wide = getenv("KDEJS_SCAN_WIDE") ? atoi(getenv("KDEJS_SCAN_WIDE")) : -1;
         const bool wide_scan = force_wide >= 0 ? force_wide != 0 : (ncells > 4096 || nb_max > 32);
-        {
+        if (!io.presorted) {
             KTimer t(c, 1, st);
             k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
@@ -451,7 +467,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 nullptr, sl.cellid.as<uint16_t>(), sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(),
                 sl.blockhist.as<uint32_t>());
         }
-        {
+        if (!io.presorted) {
             KTimer t(c, 2, st);
             if (wide_scan)
                 k_scan_wide<<<dim3((ncells + 1023) / 1024, n_sets), 1024, 0, st>>>(
@@ -461,7 +477,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 k_scan_narrow<<<n_sets, 1024, 0, st>>>(wd, ncells, nb_max, sl.blockhist.as<uint32_t>(),
                                                        sl.cellstart.as<uint32_t>(), sl.counters.as<unsigned>());
         }
-        {
+        if (!io.presorted) {
             KTimer t(c, 3, st);
             int nmax = 0;
             for (int s = 0; s < n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
@@ -472,6 +488,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>(),
                 fast32 ? sl.sorted_q.as<uint2>() : nullptr, g);
         }
+        if (io.sort_only) { CU(cudaGetLastError()); return KDEJS_OK; }
+        if (io.presorted) CU(cudaMemsetAsync(sl.counters.p, 0, kAllCounters * sizeof(unsigned), st));   // k_scan's job otherwise
         if (g.use_moments) {
             KTimer t(c, 7, st);
             k_cell_moments<<<dim3((ncells + 3) / 4, n_sets), 128, 0, st>>>(
@@ -502,7 +520,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             g.tile_row_end = cut[io.balance_rank + 1];
         }
         if (io.out_tile_rows) { io.out_tile_rows[0] = g.tile_row_begin; io.out_tile_rows[1] = g.tile_row_end; }
-        const int tiles = (g.tile_row_end - g.tile_row_begin) * g.NT;
+        const int tiles = (g.tile_row_end - g.tile_row_begin) * (g.tile_col_end - g.tile_col_begin);
         const unsigned capacity = (unsigned)tiles * (unsigned)g.sets_per_group;      // entries per (group, class) list
         if (tiles > 0) {
             KTimer t(c, 6, st);
@@ -512,6 +530,9 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 c.prof_on ? c.d_work : nullptr, lazy_empty ? sl.tileflag.as<uint8_t>() : nullptr);
         }
         if (tiles > 0 && fast32) {
+            // nodes whose fp32 sum stays below this are not trusted to fp32 (relative error ~1.5e-7 / sum): their
+            // tile is walked a second time and, unless every such node is certified exactly zero, redone in fp64
+            static const float fp32_min_thr = getenv("KDEJS_FP32_THR") ? (float)atof(getenv("KDEJS_FP32_THR")) : 0.0f;
             {
                 KTimer t(c, 4, st);
                 const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * c.dens32_blocks_per_sm);
@@ -519,12 +540,14 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                     k_density_binned32<true><<<blocks, kDensThreads, 0, st>>>(
                         wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
                         sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
-                        sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>());
+                        sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>(),
+                        fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr);
                 else
                     k_density_binned32<false><<<blocks, kDensThreads, 0, st>>>(
                         wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), nullptr,
                         sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
-                        sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>());
+                        sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>(),
+                        fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr);
             }
             // tiles with a node the fp32 arithmetic could not certify (a nearest candidate within ~1e-6 of the
             // support's edge): the fp64 kernel on the redo list -- usually empty, a few tiles per evaluation at most
@@ -832,13 +855,20 @@ int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, 
     return finish_status(c->h_status, 1);
 }
 
-int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const double *const *sims,
-                            const int64_t *n_sims, int B, int resolution, double bandwidth, double gamma,
-                            double eps, int log_flag, int kernel, int algo, double *out_js) {
+namespace {
+struct SummaryArgs {          // kdejs_summary_batch: what is fused behind the discrepancies of the batch
+    const double *const *freqs; const int64_t *n_freqs; double core_thr, rare_thr; const double *observed;
+    double *out_summary, *out_d, *out_log_d;
+};
+}  // namespace
+
+static int batch_impl(int device, const double *obs, int64_t n_obs, const double *const *sims,
+                      const int64_t *n_sims, int B, int resolution, double bandwidth, double gamma,
+                      double eps, int log_flag, int kernel, int algo, double *out_js, const SummaryArgs *sum) {
     Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
     OKR(check_params(p));
     OKR(check_set(obs, n_obs, "obs"));
-    if (B < 0 || (B > 0 && (!sims || !n_sims || !out_js))) return fail(KDEJS_ERR_ARG, "batch arrays missing");
+    if (B < 0 || (B > 0 && (!sims || !n_sims))) return fail(KDEJS_ERR_ARG, "batch arrays missing");
     for (int i = 0; i < B; ++i) OKR(check_set(sims[i], n_sims[i], "sim"));
     if (B == 0) return KDEJS_OK;
     Ctx *c;
@@ -938,6 +968,34 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
         cudaEventRecord(ed, c->s_compute);
         i0 += items;
     }
+    std::vector<double> h_freqs, h_sum;
+    std::vector<int64_t> h_offs;
+    if (rc == KDEJS_OK && sum) {
+        // gene frequencies of all simulations as one upload, the summary kernel behind the last wave, one read-back
+        h_offs.assign(B + 1, 0);
+        for (int i = 0; i < B; ++i) h_offs[i + 1] = h_offs[i] + sum->n_freqs[i];
+        h_freqs.resize((size_t)std::max<int64_t>(h_offs[B], 1));
+        for (int i = 0; i < B; ++i) memcpy(h_freqs.data() + h_offs[i], sum->freqs[i], sizeof(double) * (size_t)sum->n_freqs[i]);
+        const size_t off_bytes = ((size_t)(B + 1) * 8 + 255) / 256 * 256, fr_bytes = (h_freqs.size() * 8 + 255) / 256 * 256;
+        if ((rc = c->summary.ensure(off_bytes + fr_bytes + (size_t)B * 48)) == KDEJS_OK) {
+            char *base = c->summary.as<char>();
+            h_sum.resize((size_t)B * 6);
+            if (cudaMemcpyAsync(base, h_offs.data(), (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess ||
+                cudaMemcpyAsync(base + off_bytes, h_freqs.data(), h_freqs.size() * 8, cudaMemcpyHostToDevice, c->s_compute) != cudaSuccess)
+                rc = fail(KDEJS_ERR_CUDA, "H2D copy of the gene frequencies failed");
+            else {
+                {
+                    KTimer t(*c, 9, c->s_compute);
+                    k_summary<<<B, 256, 0, c->s_compute>>>(
+                        reinterpret_cast<const double *>(base + off_bytes), reinterpret_cast<const int64_t *>(base),
+                        sum->core_thr, sum->rare_thr, c->js_out.as<double>(), sum->observed[0], sum->observed[1],
+                        sum->observed[2], sum->observed[3], reinterpret_cast<double *>(base + off_bytes + fr_bytes));
+                }
+                if (cudaMemcpyAsync(h_sum.data(), base + off_bytes + fr_bytes, (size_t)B * 48, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess)
+                    rc = fail(KDEJS_ERR_CUDA, "D2H copy of the summary vectors failed");
+            }
+        }
+    }
     if (rc == KDEJS_OK) {
         if (cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
             cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess)
@@ -951,8 +1009,37 @@ int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const 
     for (auto e : ev_done) c->free_plain_events.push_back(e);
     if (rc != KDEJS_OK) return rc;
     if (se != cudaSuccess) return fail(KDEJS_ERR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(se));
-    memcpy(out_js, c->h_js, sizeof(double) * (size_t)B);
+    if (out_js) memcpy(out_js, c->h_js, sizeof(double) * (size_t)B);
+    if (sum)
+        for (int i = 0; i < B; ++i) {
+            memcpy(sum->out_summary + 4 * (size_t)i, h_sum.data() + 6 * (size_t)i, 32);
+            if (sum->out_d) sum->out_d[i] = h_sum[6 * (size_t)i + 4];
+            if (sum->out_log_d) sum->out_log_d[i] = h_sum[6 * (size_t)i + 5];
+        }
     return finish_status(c->h_status, B);
+}
+
+int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const double *const *sims,
+                            const int64_t *n_sims, int B, int resolution, double bandwidth, double gamma,
+                            double eps, int log_flag, int kernel, int algo, double *out_js) {
+    if (B > 0 && !out_js) return fail(KDEJS_ERR_ARG, "batch arrays missing");
+    return batch_impl(device, obs, n_obs, sims, n_sims, B, resolution, bandwidth, gamma, eps, log_flag, kernel, algo,
+                      out_js, nullptr);
+}
+
+int kdejs_summary_batch(int device, const double *obs, int64_t n_obs, const double *const *sims,
+                        const int64_t *n_sims, const double *const *freqs, const int64_t *n_freqs, int B,
+                        double core_threshold, double rare_threshold, const double observed[4], int resolution,
+                        double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                        double *out_summary, double *out_d, double *out_log_d) {
+    if (B < 0) return fail(KDEJS_ERR_ARG, "negative batch size");
+    if (B == 0) return KDEJS_OK;
+    if (!freqs || !n_freqs || !observed || !out_summary) return fail(KDEJS_ERR_ARG, "summary arrays missing");
+    for (int i = 0; i < B; ++i)
+        if (n_freqs[i] < 0 || (n_freqs[i] > 0 && !freqs[i])) return fail(KDEJS_ERR_ARG, "bad gene-frequency vector");
+    SummaryArgs sa{freqs, n_freqs, core_threshold, rare_threshold, observed, out_summary, out_d, out_log_d};
+    return batch_impl(device, obs, n_obs, sims, n_sims, B, resolution, bandwidth, gamma, eps, log_flag, kernel, algo,
+                      nullptr, &sa);
 }
 
 int kdejs_discrepancy_batch_dev(int device, const double *obs_dev, int64_t n_obs, const double *const *sims_dev,
@@ -1166,6 +1253,278 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
     return KDEJS_OK;
 }
 
+
+// ============================================================================================
+// Band mode: one huge evaluation over several GPUs with the POINTS sharded too.
+// Layout of a rank's count block (u32): cellstart[2][C*C + 1] of its locally sorted slices, then
+// rowstart[2][C + 1] (= cellstart at the first cell of every cell row).
+namespace {
+struct BandDims { int C, NT, ncells; size_t block_u32; };
+BandDims band_dims(const GridGeom &g) {
+    BandDims d;
+    d.C = g.C; d.NT = g.NT; d.ncells = g.C * g.C;
+    d.block_u32 = 2 * (size_t)(d.ncells + 1) + 2 * (size_t)(g.C + 1);
+    return d;
+}
+int band_params(int resolution, double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo, Params &p) {
+    p = Params{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(check_params(p));
+    if (p.algo != KDEJS_ALGO_BINNED && p.algo != KDEJS_ALGO_BINNED32)
+        return fail(KDEJS_ERR_ARG, "band mode is implemented for the binned algorithms");
+    return KDEJS_OK;
+}
+}  // namespace
+
+int kdejs_band_geometry(int resolution, double bandwidth, int kernel, int out[4]) {
+    if (!out) return fail(KDEJS_ERR_ARG, "out is null");
+    Params p{resolution, bandwidth, 1.0, 0.0, 0, kernel, KDEJS_ALGO_BINNED};
+    OKR(check_params(p));
+    const GridGeom g = make_geom(p);
+    const BandDims d = band_dims(g);
+    out[0] = d.C; out[1] = d.NT; out[2] = (int)d.block_u32; out[3] = g.use_moments;
+    return KDEJS_OK;
+}
+
+int kdejs_band_minmax_dev(int device, const double *a_dev, int64_t na, const double *b_dev, int64_t nb,
+                          int log_flag, double eps, double *out_stats_dev, void *stream) {
+    OKR(check_set(a_dev, na, "df1 slice"));
+    OKR(check_set(b_dev, nb, "df2 slice"));
+    if (!out_stats_dev) return fail(KDEJS_ERR_ARG, "out_stats_dev is null");
+    if ((((uintptr_t)a_dev) | ((uintptr_t)b_dev)) & 15) return fail(KDEJS_ERR_ARG, "device point sets must be 16-byte aligned");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    OKR(acquire_scratch(*c, st));
+    Slot &sl = c->slot;
+    WaveDesc wd;
+    memset(&wd, 0, sizeof wd);
+    wd.raw[0] = RawSet{a_dev, na};
+    wd.raw[1] = RawSet{b_dev, nb};
+    wd.n_raw = 2;
+    const int mm_blocks = std::max(8, std::min(64, 4 * c->sm_count / 2));
+    OKR(sl.rpart.ensure(sizeof(RawStat) * kMaxWaveSets * 64));
+    static_assert(sizeof(RawStat) == 40, "RawStat travels as 5 doubles");
+    {
+        KTimer t(*c, 0, st);
+        k_minmax<<<dim3(mm_blocks, 2), kMinmaxThreads, 0, st>>>(wd, log_flag ? 1 : 0, eps, sl.rpart.as<RawStat>(),
+                                                               sl.tickets.as<unsigned>(),
+                                                               reinterpret_cast<RawStat *>(out_stats_dev));
+    }
+    CU(cudaGetLastError());
+    return release_scratch(*c, st, false);
+}
+
+int kdejs_band_sort_dev(int device, const double *a_dev, int64_t na, const double *b_dev, int64_t nb, int resolution,
+                        double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                        const double *stats_all_dev, int world, double *out_sorted_dev, uint32_t *out_block_dev,
+                        void *stream) {
+    Params p;
+    OKR(band_params(resolution, bandwidth, gamma, eps, log_flag, kernel, algo, p));
+    OKR(check_set(a_dev, na, "df1 slice"));
+    OKR(check_set(b_dev, nb, "df2 slice"));
+    if (!stats_all_dev || !out_sorted_dev || !out_block_dev || world < 1) return fail(KDEJS_ERR_ARG, "null argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    OKR(acquire_scratch(*c, st));
+    Slot &sl = c->slot;
+    GridGeom g = make_geom(p);
+    const BandDims d = band_dims(g);
+    OKR(sl.rstat.ensure(sizeof(RawStat) * kMaxWaveSets));
+    k_band_fold_stats<<<1, 32, 0, st>>>(reinterpret_cast<const RawStat *>(stats_all_dev), world, sl.rstat.as<RawStat>());
+    c->launches++;
+    WaveDesc wd;
+    memset(&wd, 0, sizeof wd);
+    wd.raw[0] = RawSet{a_dev, na};
+    wd.raw[1] = RawSet{b_dev, nb};
+    wd.n_raw = 2; wd.n_sets = 2;
+    wd.set[0].rs_self = 0; wd.set[0].rs_other = 1; wd.set[0].n = (int32_t)na;
+    wd.set[1].rs_self = 1; wd.set[1].rs_other = 0; wd.set[1].n = (int32_t)nb;
+    WaveIO io;
+    io.shard = true; io.rstat_ready = true; io.sort_only = true;
+    Params ps = p;
+    ps.algo = KDEJS_ALGO_BINNED;                 // the sender needs no fixed-point copy
+    OKR(run_wave(*c, sl, st, ps, g, wd, io));
+    CU(cudaMemcpyAsync(out_sorted_dev, sl.sorted.p, (size_t)(na + nb) * 16, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(out_block_dev, sl.cellstart.p, 2 * (size_t)(d.ncells + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    k_band_rowstarts<<<2, 128, 0, st>>>(sl.cellstart.as<uint32_t>(), d.C, out_block_dev + 2 * (size_t)(d.ncells + 1));
+    c->launches++;
+    CU(cudaGetLastError());
+    return release_scratch(*c, st, false);
+}
+
+int kdejs_band_cuts(const double *colwork, int nt, int world, int *cuts) {
+    if (!colwork || !cuts || nt < 1 || world < 1) return fail(KDEJS_ERR_ARG, "bad argument");
+    double total = 0.0;
+    for (int t = 0; t < nt; ++t) total += colwork[t];
+    for (int r = 0; r <= world; ++r) cuts[r] = nt;
+    cuts[0] = 0;
+    double run = 0.0;
+    int r = 1;
+    for (int t = 0; t < nt && r < world; ++t) {
+        run += colwork[t];
+        while (r < world && run >= total * r / world) cuts[r++] = t + 1;
+    }
+    return KDEJS_OK;
+}
+
+int kdejs_band_cell_rows(int resolution, double bandwidth, int ty_begin, int ty_end, int out_cy[2]) {
+    if (!out_cy) return fail(KDEJS_ERR_ARG, "out_cy is null");
+    Params p{resolution, bandwidth, 1.0, 0.0, 0, KDEJS_KERNEL_EPANECHNIKOV, KDEJS_ALGO_BINNED};
+    OKR(check_params(p));
+    const GridGeom g = make_geom(p);
+    if (ty_begin < 0 || ty_end > g.NT || ty_begin > ty_end) return fail(KDEJS_ERR_ARG, "bad tile-column range");
+    if (ty_begin == ty_end) { out_cy[0] = 0; out_cy[1] = -1; return KDEJS_OK; }      // empty band: no rows
+    // the arithmetic of tile_cells() for the band's first and last tile column (cell_of is monotone)
+    auto cell_of_h = [&](double x) {
+        const double v = std::floor((x - g.cell_x0) * g.cell_invw);
+        return (int)std::min<double>(std::max<double>(v, 0.0), (double)(g.C - 1));
+    };
+    const double y_lo = (double)(ty_begin * kTile) * g.step + g.gmin;
+    const double y_hi = (double)std::min(ty_end * kTile - 1, g.R - 1) * g.step + g.gmin;
+    out_cy[0] = cell_of_h(y_lo - g.h - g.margin);
+    out_cy[1] = cell_of_h(y_hi + g.h + g.margin);
+    return KDEJS_OK;
+}
+
+int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int resolution, double bandwidth,
+                    double gamma, double eps, int log_flag, int kernel, int algo, double *out_colwork,
+                    uint32_t *out_rowstart, int *out_use_moments, void *stream) {
+    Params p;
+    OKR(band_params(resolution, bandwidth, gamma, eps, log_flag, kernel, algo, p));
+    if (!blocks_all_dev || !out_colwork || !out_rowstart || !out_use_moments || world < 1)
+        return fail(KDEJS_ERR_ARG, "null argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    OKR(acquire_scratch(*c, st));
+    Slot &sl = c->slot;
+    GridGeom g = make_geom(p);
+    const BandDims d = band_dims(g);
+    // every rank's row starts: world x 2 x (C + 1) u32, a strided device -> host copy
+    const size_t rs_elems = 2 * (size_t)(d.C + 1);
+    CU(cudaMemcpy2DAsync(out_rowstart, rs_elems * 4, blocks_all_dev + 2 * (size_t)(d.ncells + 1), d.block_u32 * 4,
+                         rs_elems * 4, (size_t)world, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int64_t ntot[2] = {0, 0};
+    for (int r = 0; r < world; ++r)
+        for (int s = 0; s < 2; ++s) ntot[s] += out_rowstart[(size_t)r * rs_elems + (size_t)s * (d.C + 1) + d.C];
+    // moment cells: the single-GPU rule applied to the WHOLE evaluation, so every rank (and the one-GPU run) agrees
+    if (g.use_moments == 1 && ntot[0] + ntot[1] < (int64_t)128 * 2 * d.ncells) g.use_moments = 0;
+    *out_use_moments = g.use_moments ? 1 : 0;
+    OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
+    OKR(c->misc.ensure(64 + sizeof(double) * (size_t)g.NT));
+    k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, 0, d.ncells, sl.cellstart.as<uint32_t>());
+    WaveDesc wd;
+    memset(&wd, 0, sizeof wd);
+    wd.n_sets = 2;
+    double *d_cw = c->misc.as<double>() + 8;
+    k_tile_colwork<<<g.NT, 128, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_cw);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out_colwork, d_cw, sizeof(double) * (size_t)g.NT, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return release_scratch(*c, st, true);
+}
+
+int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, const double *stage_b_dev, int64_t nb,
+                          int64_t na_total, int64_t nb_total, const uint32_t *blocks_all_dev, int world,
+                          const double *stats_all_dev, int resolution, double bandwidth, double gamma, double eps,
+                          int log_flag, int kernel, int algo, int ty_begin, int ty_end, int cy_lo, int cy_hi,
+                          int use_moments, double *out_norm_dev, void *stream) {
+    Params p;
+    OKR(band_params(resolution, bandwidth, gamma, eps, log_flag, kernel, algo, p));
+    if (!blocks_all_dev || !stats_all_dev || !out_norm_dev || world < 1) return fail(KDEJS_ERR_ARG, "null argument");
+    if (na < 0 || nb < 0 || na_total < 1 || nb_total < 1 || (na > 0 && !stage_a_dev) || (nb > 0 && !stage_b_dev))
+        return fail(KDEJS_ERR_ARG, "bad staging buffers");
+    if (na + nb > 0x7fffffffLL / 4) return fail(KDEJS_ERR_ARG, "too many points for one band");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    OKR(acquire_scratch(*c, st));
+    c->band_valid = false;
+    Slot &sl = c->slot;
+    GridGeom g = make_geom(p);
+    const BandDims d = band_dims(g);
+    if (ty_begin < 0 || ty_end > g.NT || ty_begin > ty_end) return fail(KDEJS_ERR_ARG, "bad tile-column range");
+    if (ty_begin < ty_end && (cy_lo < 0 || cy_hi >= d.C || cy_lo > cy_hi)) return fail(KDEJS_ERR_ARG, "bad cell-row range");
+    g.tile_col_begin = ty_begin;
+    g.tile_col_end = ty_end;
+    OKR(sl.rstat.ensure(sizeof(RawStat) * kMaxWaveSets));
+    OKR(sl.tilesum.ensure(2 * (size_t)g.NT * g.NT * sizeof(double)));
+    OKR(c->misc.ensure(64));
+    k_band_fold_stats<<<1, 32, 0, st>>>(reinterpret_cast<const RawStat *>(stats_all_dev), world, sl.rstat.as<RawStat>());
+    c->launches++;
+    if (ty_begin == ty_end) {                       // this rank owns no tile column: zero partial normalisers
+        CU(cudaMemsetAsync(out_norm_dev, 0, 16, st));
+        c->band_geom = g; c->band_ty0 = ty_begin; c->band_ty1 = ty_end; c->band_valid = true;
+        return release_scratch(*c, st, false);
+    }
+    const bool fast32 = (p.algo == KDEJS_ALGO_BINNED32) && g.q_shift > 0;
+    const int64_t P = na + nb;
+    OKR(sl.sorted.ensure((size_t)std::max<int64_t>(P, 1) * sizeof(double2)));
+    if (fast32) OKR(sl.sorted_q.ensure((size_t)std::max<int64_t>(P, 1) * sizeof(uint2)));
+    OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
+    const int c_lo = cy_lo * d.C, c_hi = (cy_hi + 1) * d.C;
+    k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, c_lo, c_hi, sl.cellstart.as<uint32_t>());
+    k_band_merge<<<dim3((c_hi - c_lo + 3) / 4, 2), 128, 0, st>>>(
+        reinterpret_cast<const double2 *>(stage_a_dev), reinterpret_cast<const double2 *>(stage_b_dev), blocks_all_dev,
+        world, d.block_u32, g, cy_lo, cy_hi, sl.cellstart.as<uint32_t>(), na, sl.sorted.as<double2>(),
+        fast32 ? sl.sorted_q.as<uint2>() : nullptr);
+    c->launches += 2;
+    WaveDesc wd;
+    memset(&wd, 0, sizeof wd);
+    wd.n_raw = 2; wd.n_sets = 2;
+    wd.set[0].rs_self = 0; wd.set[0].rs_other = 1; wd.set[0].n = (int32_t)na;
+    wd.set[1].rs_self = 1; wd.set[1].rs_other = 0; wd.set[1].n = (int32_t)nb;
+    WaveIO io;
+    io.shard = true; io.rstat_ready = true; io.presorted = true; io.identity_scaler = true;
+    io.force_moments = use_moments ? 1 : 0;
+    const int64_t ng[2] = {na_total, nb_total};
+    io.n_global = ng;
+    OKR(run_wave(*c, sl, st, p, g, wd, io));
+    {
+        KTimer t(*c, 5, st);
+        k_band_norm_totals<<<1, kJsThreads, 0, st>>>(sl.tilesum.as<double>(), g.NT, ty_begin, ty_end, out_norm_dev);
+    }
+    CU(cudaGetLastError());
+    c->band_geom = g; c->band_ty0 = ty_begin; c->band_ty1 = ty_end; c->band_valid = true;
+    return release_scratch(*c, st, false);
+}
+
+int kdejs_band_phase2_dev(int device, const double *norms_all_dev, int world, double *out_lr_dev, void *stream) {
+    if (!norms_all_dev || !out_lr_dev || world < 1) return fail(KDEJS_ERR_ARG, "null argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->band_valid) return fail(KDEJS_ERR_ARG, "kdejs_band_phase2_dev called without a successful phase 1");
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
+    OKR(acquire_scratch(*c, st));
+    Slot &sl = c->slot;
+    const GridGeom &g = c->band_geom;
+    double *d_tot = c->misc.as<double>();
+    k_band_fold_norms<<<1, 32, 0, st>>>(norms_all_dev, world, d_tot);
+    c->launches++;
+    if (c->band_ty0 == c->band_ty1) {
+        // no tiles: zero partial sums, but the infinity flag of the inputs still has to travel
+        CU(cudaMemsetAsync(out_lr_dev, 0, 24, st));
+        return release_scratch(*c, st, false);
+    }
+    OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)g.NT));
+    {
+        KTimer t(*c, 5, st);
+        k_band_js<<<g.NT, kJsThreads, 0, st>>>(g, c->band_ty0, c->band_ty1, sl.pz.as<double>(), d_tot,
+                                              sl.rstat.as<RawStat>(), sl.jspart.as<double>(),
+                                              sl.tickets.as<unsigned>() + kMaxWaveSets, out_lr_dev);
+    }
+    CU(cudaGetLastError());
+    return release_scratch(*c, st, false);
+}
+
 int kdejs_profile_enable(int device, int on) {
     Ctx *c;
     OKR(get_ctx(device, &c));
@@ -1214,6 +1573,61 @@ int kdejs_work_counters(int device, double *pair_tests, int reset) {
     CU(cudaMemcpy(&v, c->d_work, sizeof v, cudaMemcpyDeviceToHost));
     if (pair_tests) *pair_tests = (double)v;
     if (reset) CU(cudaMemset(c->d_work, 0, sizeof v));
+    return KDEJS_OK;
+}
+
+int kdejs_fp32_stats(int device, double out[5], int reset) {
+    if (!out) return fail(KDEJS_ERR_ARG, "out is null");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaDeviceSynchronize());
+    unsigned long long v[8];
+    CU(cudaMemcpy(v, c->d_stats32, sizeof v, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; ++i) out[i] = (double)v[i];
+    if (reset) CU(cudaMemset(c->d_stats32, 0, sizeof v));
+    return KDEJS_OK;
+}
+
+int kdejs_loop_peak(int device, int which, double *pair_tests_per_s) {
+    if (which < 0 || which > 2 || !pair_tests_per_s) return fail(KDEJS_ERR_ARG, "bad argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    OKR(acquire_scratch(*c, c->s_compute));
+    OKR(c->misc.ensure(64 + 1024 * 16 + 1024 * 8));
+    double *sink = c->misc.as<double>();
+    double2 *pts = reinterpret_cast<double2 *>(c->misc.as<char>() + 64);
+    uint2 *ptsq = reinterpret_cast<uint2 *>(c->misc.as<char>() + 64 + 1024 * 16);
+    std::vector<double2> hp(1024);
+    std::vector<uint2> hq(1024);
+    for (int i = 0; i < 1024; ++i) {
+        const double x = 0.2 + 0.1 * ((i * 37) % 1024) / 1024.0, y = 0.2 + 0.1 * ((i * 101) % 1024) / 1024.0;
+        hp[i] = make_double2(x, y);
+        hq[i] = make_uint2(0x10000000u + (uint32_t)((x - 0.25) * 33.0 * 536870912.0), 0x10000000u + (uint32_t)((y - 0.25) * 33.0 * 536870912.0));
+    }
+    CU(cudaMemcpyAsync(pts, hp.data(), 1024 * 16, cudaMemcpyHostToDevice, c->s_compute));
+    CU(cudaMemcpyAsync(ptsq, hq.data(), 1024 * 8, cudaMemcpyHostToDevice, c->s_compute));
+    const int blocks = c->sm_count * 5, trips = 1 << 13;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, c->s_compute));
+        if (which == 0) k_loop_peak<0><<<blocks, kDensThreads, 0, c->s_compute>>>(trips, pts, ptsq, sink);
+        else if (which == 1) k_loop_peak<1><<<blocks, kDensThreads, 0, c->s_compute>>>(trips, pts, ptsq, sink);
+        else k_loop_peak<2><<<blocks, kDensThreads, 0, c->s_compute>>>(trips, pts, ptsq, sink);
+        CU(cudaEventRecord(e1, c->s_compute));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    release_scratch(*c, c->s_compute, true);
+    *pair_tests_per_s = (double)blocks * kDensThreads * (double)trips * 16.0 / (best * 1e-3);
     return KDEJS_OK;
 }
 

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <thread>
 #include <vector>
@@ -20,10 +21,23 @@
 namespace {
 thread_local std::string g_io_err;
 
+// pandas' default NA tokens (pd.read_csv, the reader scripts/pairwise_2D_distance.py:38-45 and
+// poppunk_mod.py:266-267 use): a field spelled like one of these is a missing distance and becomes NaN, which the
+// path maps to scaled 0 like the reference (KDE_distance.py:53).  An EMPTY field is missing, too.
+bool is_na_token(const char *b, const char *e) {
+    static const char *const kNa[] = {"NA", "N/A", "NaN", "nan", "-NaN", "-nan", "NULL", "null", "n/a", "#N/A",
+                                      "#NA", "<NA>", "#N/A N/A", "-1.#IND", "1.#IND", "-1.#QNAN", "1.#QNAN", "None"};
+    const size_t n = (size_t)(e - b);
+    for (const char *tok : kNa)
+        if (std::strlen(tok) == n && std::memcmp(tok, b, n) == 0) return true;
+    return false;
+}
+
 bool parse_double(const char *b, const char *e, double &v) {
     while (b < e && (*b == ' ' || *b == '\r')) ++b;
     while (e > b && (e[-1] == ' ' || e[-1] == '\r')) --e;
-    if (b < e && *b == '+') ++b;                       // from_chars rejects a leading '+'
+    if (b >= e || is_na_token(b, e)) { v = std::numeric_limits<double>::quiet_NaN(); return true; }
+    if (*b == '+') ++b;                                // from_chars rejects a leading '+'
     if (b >= e) return false;
     auto r = std::from_chars(b, e, v);
     return r.ec == std::errc() && r.ptr == e;
@@ -77,6 +91,7 @@ int kdejs_tsv_load(const char *path, int skip_rows, int pinned, int threads, dou
         if (!lines.empty()) {
             const char *nl = (const char *)std::memchr(lines[0], '\n', (size_t)(end - lines[0]) + 1);
             double x, y;
+            // a header is a first line whose last two fields are neither numbers nor missing-value tokens
             if (!last_two(lines[0], nl, x, y)) first = 1;
         }
     } else first = std::min((size_t)skip_rows, lines.size());

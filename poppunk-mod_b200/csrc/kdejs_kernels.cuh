@@ -74,6 +74,8 @@ struct GridGeom {
     double cell_w;                       // nominal cell side = extent / C
     double knorm, gamma, eps;
     int32_t tile_row_begin, tile_row_end;   // tile rows (index of column 0) this launch covers
+    int32_t tile_col_begin, tile_col_end;   // ... and tile columns (index of column 1): band mode shards along these,
+                                            // because cell ROWS (the sort's major order) run along column 1
     int32_t sets_per_group, pad3;           // work-list locality: sets [k*spg, (k+1)*spg) form group k (see kMaxGroups)
     int32_t heavy_log2, use_moments;        // tiles with >= 2^heavy_log2 candidates are processed per block;
                                             // use_moments: cells wholly inside a tile's support go in as moments
@@ -457,7 +459,9 @@ k_scan_wide(const __grid_constant__ WaveDesc wd, int ncells, int nb_max,
 // grid's extent: they cannot be within h of any node) are clamped so that differences to in-reach nodes never wrap.
 __device__ __forceinline__ uint32_t quantise(double x, const GridGeom &g) {
     const double c = fmin(fmax(x, g.q_lo), g.q_hi);
-    return (uint32_t)(long long)__double2ll_rn((c - g.gmin) * g.q_scale);
+    // rint(v) mod 2^32 without a 64-bit conversion: adding 1.5 * 2^52 leaves round-to-nearest(v) in the low
+    // mantissa bits (|v| < 2^51 here: at most (extent/h + 4) * 2^29)
+    return (uint32_t)__double2loint((c - g.gmin) * g.q_scale + 6755399441055744.0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -584,12 +588,13 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 double *__restrict__ pz, double *__restrict__ tilesum, uint32_t *__restrict__ worklist,
                 unsigned *__restrict__ counters, unsigned capacity,
                 unsigned long long *__restrict__ work_counter, uint8_t *__restrict__ tileflag) {
-    const int ntl = (g.tile_row_end - g.tile_row_begin) * g.NT;
+    const int nty = g.tile_col_end - g.tile_col_begin;
+    const int ntl = (g.tile_row_end - g.tile_row_begin) * nty;
     const int tl = blockIdx.x * (blockDim.x / kClassifyLanes) + threadIdx.x / kClassifyLanes;
     const int sub = threadIdx.x % kClassifyLanes;
     const int set = blockIdx.y;
     const bool live = tl < ntl;
-    const int tx = g.tile_row_begin + (live ? tl / g.NT : 0), ty = live ? tl % g.NT : 0;
+    const int tx = g.tile_row_begin + (live ? tl / nty : 0), ty = g.tile_col_begin + (live ? tl % nty : 0);
     const int ix0 = tx * kTile, iy0 = ty * kTile;
     uint32_t total = 0u;
     if (live) {
@@ -1031,9 +1036,16 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
 // FFMA/FMUL for the node offsets in units of h, four FFMA for a_i = 1 - ux_i^2, then per node
 //     t = sat(a_i - uy_j^2)        FFMA.SAT: multiply, add and an exact ReLU in one instruction (t <= 1 always)
 //     acc_ij += t                  FADD2 (packed f32x2: one issue slot for two nodes)
-// i.e. 44 FMA-pipe cycles and ~48 issue slots where the fp64 kernel spends 92 fp64-pipe cycles.  fp32 partial sums
-// are folded into per-lane fp64 sums every kFlushTrips candidates, so the accumulation error does not grow with
-// the tile's weight; the cross-lane reduction is fp64 and fixed-shape (bit-reproducible like the fp64 path).
+// i.e. 44 FMA-pipe cycles and ~50 issue slots where the fp64 loop takes 135 cycles (measured, kdejs_loop_peak).
+//
+// The loop is half as long as the fp64 one, so it can no longer hide an L2 round trip behind ONE trip of its own
+// arithmetic: a tile's candidate runs are therefore flattened into one stream of 32-candidate trips that a small
+// register queue fetches kPrefetch trips ahead (the bookkeeping of run boundaries lives on the fetch side, is
+// warp-uniform and costs a few instructions per trip; the arithmetic side just consumes the queue).
+//
+// Accumulation: fp32 partial sums are folded every kFoldTrips trips into a second fp32 level (and, for the heavy
+// tiles a whole block works on, every kFoldTrips^2 trips into a third), so no fp32 sum ever runs over more than
+// 16 terms of its own level; the cross-lane reduction is fp64 and fixed-shape (bit-reproducible like the fp64 path).
 //
 // Exact zeros stay exact zeros.  The error of a computed t is below kBias32/2 (coordinates: 2^-29 h quantisation,
 // one I2FP rounding of |u| <= 2.5, fp32 node offsets), so
@@ -1043,7 +1055,8 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
 //   * a node that is neither (0 < true |t| of its nearest candidate < ~1e-6: a handful per evaluation) sends its
 //     tile to the redo list, which k_density_binned (fp64) processes right after this kernel.
 // Phase A (heavy tiles, block per tile) skips the biased walk and re-queues directly; it practically never happens.
-constexpr int kFlushTrips = 16;
+constexpr int kFoldTrips = 16;
+constexpr int kPrefetch = 3;                          // trips in flight per warp
 constexpr float kBias32 = 9.5367431640625e-07f;       // 2^-20
 constexpr uint32_t kFarQ = 0x40000000u;               // a padding candidate 2^30 units (>= 2 h, q_shift <= 29) LEFT of the
                                                       // tile's first node: out of every node's support, adds exactly 0
@@ -1068,6 +1081,17 @@ __device__ __forceinline__ void accumulate_point32(const uint2 q, const uint32_t
             acc[i][j + 1] = r.y;
         }
 }
+// hi += lo; lo = 0   (packed adds)
+__device__ __forceinline__ void fold32(float (&lo)[kTile][kTile], float (&hi)[kTile][kTile]) {
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; j += 2) {
+            const float2 r = __fadd2_rn(make_float2(hi[i][j], hi[i][j + 1]), make_float2(lo[i][j], lo[i][j + 1]));
+            hi[i][j] = r.x; hi[i][j + 1] = r.y;
+            lo[i][j] = 0.f; lo[i][j + 1] = 0.f;
+        }
+}
 __device__ __forceinline__ void flush32(float (&a32)[kTile][kTile], double (&a64)[kTile][kTile]) {
 #pragma unroll
     for (int i = 0; i < kTile; ++i)
@@ -1075,18 +1099,70 @@ __device__ __forceinline__ void flush32(float (&a32)[kTile][kTile], double (&a64
         for (int j = 0; j < kTile; ++j) { a64[i][j] += (double)a32[i][j]; a32[i][j] = 0.f; }
 }
 
+// One walk of a warp over the flattened runs of its tile (phase B).  wstart / wlen: the tile's non-empty runs in
+// processing order (per-warp shared memory); returns the lane's 16 partial sums in `tot` (fp64).
+__device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const uint32_t *wstart, const uint32_t *wlen,
+                                            const int nruns, const uint32_t total_trips, const int lane,
+                                            const uint32_t gxq, const uint32_t gyq, const float unit, const float f1,
+                                            const float f2, const float f3, const float one,
+                                            double (&tot)[kTile][kTile]) {
+    float lo[kTile][kTile], hi[kTile][kTile];
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) { lo[i][j] = 0.f; hi[i][j] = 0.f; }
+    const uint2 far = make_uint2(gxq - kFarQ, gyq);
+    // fetch side: (run, trip within run) of the next trip to load
+    int r_pf = 0;
+    uint32_t t_pf = 0u, cur_len = 0u, cur_trips = 0u;
+    const uint2 *cur_ptr = pts;
+    if (nruns > 0) { cur_len = wlen[0]; cur_ptr = pts + wstart[0]; cur_trips = (cur_len + 31u) >> 5; }
+    auto fetch = [&]() -> uint2 {
+        uint2 v = far;
+        if (r_pf < nruns) {                                   // warp-uniform
+            const uint32_t j = t_pf * 32u + (uint32_t)lane;
+            if (j < cur_len) v = cur_ptr[j];
+            if (++t_pf == cur_trips) {
+                ++r_pf;
+                t_pf = 0u;
+                if (r_pf < nruns) { cur_len = wlen[r_pf]; cur_ptr = pts + wstart[r_pf]; cur_trips = (cur_len + 31u) >> 5; }
+            }
+        }
+        return v;
+    };
+    uint2 q0 = fetch(), q1 = fetch(), q2 = fetch();
+    static_assert(kPrefetch == 3, "the register queue below holds three trips");
+    int budget = kFoldTrips;
+    for (uint32_t t = 0; t < total_trips; ++t) {
+        const uint2 p = q0;
+        q0 = q1; q1 = q2;
+        q2 = fetch();
+        accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, one, lo);
+        if (--budget == 0) { fold32(lo, hi); budget = kFoldTrips; }
+    }
+    fold32(lo, hi);
+#pragma unroll
+    for (int i = 0; i < kTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) tot[i][j] = (double)hi[i][j];
+}
+
 template <bool MOMENTS>
-__global__ void __launch_bounds__(kDensThreads, 5)
+__global__ void __launch_bounds__(kDensThreads, 6)
 k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
                    const uint2 *__restrict__ sorted_q, const uint32_t *__restrict__ cellstart,
                    const double *__restrict__ moments,
                    double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
                    const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
-                   unsigned capacity, uint32_t *__restrict__ redo_list) {
-    __shared__ uint32_t s_rs[2 * kMaxRows];
+                   unsigned capacity, uint32_t *__restrict__ redo_list, const float min_thr,
+                   unsigned long long *__restrict__ stats) {
+    // stats (profiling only): [0] tiles, [1] tiles walked a second time, [2] warp trips of first walks,
+    // [3] warp trips of second walks, [4] tiles re-queued for fp64
+    __shared__ uint32_t s_rs[2 * kMaxRows];          // phase A: the tile's runs; phase B: per-warp compacted runs
     __shared__ uint32_t s_len[2 * kMaxRows];
+    __shared__ uint32_t s_cpre[2 * kMaxRows + 1];    // phase A: 32-candidate chunks before each run
+    __shared__ uint32_t s_wstart[kDensThreads / 32][2 * kMaxRows], s_wlen[kDensThreads / 32][2 * kMaxRows];
     __shared__ int s_mlo[kMaxRows], s_mcnt[kMaxRows], s_rows, s_cy0;
-    __shared__ uint8_t s_base[2 * kMaxRows];
     __shared__ double s_red[kRedDoubles];
     __shared__ unsigned s_item;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1154,43 +1230,56 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 uint32_t t = __shfl_up_sync(0xffffffffu, cinc, o);
                 if (lane >= o) cinc += t;
             }
-            s_base[2 * lane] = (uint8_t)((cinc - c1n - c2n) & 3u);
-            s_base[2 * lane + 1] = (uint8_t)((cinc - c2n) & 3u);
+            s_cpre[2 * lane] = cinc - c1n - c2n;
+            s_cpre[2 * lane + 1] = cinc - c2n;
+            if (lane == 31) s_cpre[2 * kMaxRows] = cinc;
             s_mlo[lane] = rr.mlo;
             s_mcnt[lane] = rr.mcnt;
             if (lane == 0) { s_rows = rows; s_cy0 = tc.cy_lo; }
         }
         __syncthreads();
-        float acc[kTile][kTile];
+        float lo[kTile][kTile], hi[kTile][kTile], top[kTile][kTile];
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) { lo[i][j] = 0.f; hi[i][j] = 0.f; top[i][j] = 0.f; }
+        const uint2 *__restrict__ pts = sorted_q + sd.off;
+        const uint32_t gtot = s_cpre[2 * kMaxRows];         // 32-candidate chunks of the tile, dealt round-robin to the warps
+        const uint32_t my_trips = (uint32_t)warp < gtot ? (gtot - (uint32_t)warp + 3u) >> 2 : 0u;
+        const uint2 far = make_uint2(gxq - kFarQ, gyq);
+        uint32_t g_pf = (uint32_t)warp;
+        int e_pf = 0;
+        auto fetch = [&]() -> uint2 {
+            uint2 v = far;
+            if (g_pf < gtot) {                                // warp-uniform
+                while (g_pf >= s_cpre[e_pf + 1]) ++e_pf;
+                const uint32_t j = (g_pf - s_cpre[e_pf]) * 32u + (uint32_t)lane;
+                if (j < s_len[e_pf]) v = pts[s_rs[e_pf] + j];
+                g_pf += kDensThreads / 32;
+            }
+            return v;
+        };
+        uint2 q0 = fetch(), q1 = fetch(), q2 = fetch();
+        int budget = kFoldTrips, budget2 = kFoldTrips;
+        for (uint32_t t = 0; t < my_trips; ++t) {
+            const uint2 p = q0;
+            q0 = q1; q1 = q2;
+            q2 = fetch();
+            accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, 1.0f, lo);
+            if (--budget == 0) {
+                fold32(lo, hi);
+                budget = kFoldTrips;
+                if (--budget2 == 0) { fold32(hi, top); budget2 = kFoldTrips; }
+            }
+        }
+        fold32(lo, hi);
+        fold32(hi, top);
         double acc64[kTile][kTile];
 #pragma unroll
         for (int i = 0; i < kTile; ++i)
 #pragma unroll
-            for (int j = 0; j < kTile; ++j) { acc[i][j] = 0.f; acc64[i][j] = 0.0; }
-        const uint2 *__restrict__ pts = sorted_q + sd.off;
-        const int nruns = (MOMENTS ? 2 : 1) * s_rows;
-        int budget = kFlushTrips;
-        uint32_t ncand = 0u;
-        for (int k = 0; k < nruns; ++k) {
-            const int e = MOMENTS ? k : 2 * k;
-            const uint32_t len = s_len[e];
-            ncand += len;
-            const uint2 *__restrict__ rp = pts + s_rs[e];
-            const uint32_t nch = (len + 31u) >> 5, first = ((uint32_t)warp - s_base[e]) & 3u;
-            const uint32_t trips = first < nch ? (nch - first + 3u) >> 2 : 0u;      // warp-uniform
-            uint32_t j = first * 32u + lane;
-            uint2 pn = make_uint2(gxq - kFarQ, gyq);
-            if (j < len) pn = rp[j];
-            for (uint32_t t = 0; t < trips; ++t) {
-                const uint2 p = pn;
-                j += kDensThreads;
-                pn = make_uint2(gxq - kFarQ, gyq);
-                if (j < len) pn = rp[j];
-                accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, 1.0f, acc);
-                if (--budget == 0) { flush32(acc, acc64); budget = kFlushTrips; }
-            }
-        }
-        flush32(acc, acc64);
+            for (int j = 0; j < kTile; ++j) acc64[i][j] = (double)top[i][j];
+        uint32_t ncand = gtot * 32u;                          // upper bound of the candidates (last chunks are ragged)
         if (MOMENTS) {
             const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
             const int rows = s_rows, cy0 = s_cy0;
@@ -1218,10 +1307,12 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         S += __shfl_xor_sync(0xffffffffu, S, 4);
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         const bool valid = ix < g.R && iy < g.R;
-        const double thr = (double)kBias32 * (double)max(ncand, 1024u);
+        const double thr = fmax((double)kBias32 * (double)max(ncand, 1024u), (double)min_thr);
         const int low = __syncthreads_or(valid && S < thr);      // also: everyone is done reading s_red
+        if (stats && threadIdx.x == 0) { atomicAdd(&stats[0], 1ull); atomicAdd(&stats[2], (unsigned long long)gtot); }
         if (low) {                                               // cannot certify a node here: fp64 does this tile
             if (threadIdx.x == 0) {
+                if (stats) atomicAdd(&stats[4], 1ull);
                 const unsigned slot = atomicAdd(&redo_counters[list], 1u);
                 redo_list[(size_t)list * capacity + slot] = entry;
             }
@@ -1245,6 +1336,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 
     // ---------------- phase B: warp per tile ----------------
     double *__restrict__ wred = s_red + warp * (kTile * kTile * kWarpRedStride);
+    uint32_t *wstart = s_wstart[warp], *wlen = s_wlen[warp];
     __syncthreads();
     for (;;) {
         unsigned item = 0u;
@@ -1266,10 +1358,23 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int rows = tc.cy_hi - tc.cy_lo + 1;
         RowRuns rr = {0u, 0u, 0u, 0u, 0, 0};
         if (lane < rows) rr = tile_row_runs(g, tc, cs, tc.cy_lo + lane, MOMENTS);
+        // compact the non-empty runs, in (row, part) order, into this warp's shared arrays
+        const unsigned m1 = __ballot_sync(0xffffffffu, rr.l1 > 0u);
+        const unsigned m2 = MOMENTS ? __ballot_sync(0xffffffffu, rr.l2 > 0u) : 0u;
+        const unsigned lt = (1u << lane) - 1u;
+        __syncwarp();
+        if (rr.l1 > 0u) { const int k = __popc(m1 & lt) + __popc(m2 & lt); wstart[k] = rr.s1; wlen[k] = rr.l1; }
+        if (MOMENTS && rr.l2 > 0u) { const int k = __popc(m1 & lt) + __popc(m2 & lt) + (rr.l1 > 0u ? 1 : 0); wstart[k] = rr.s2; wlen[k] = rr.l2; }
+        const int nruns = __popc(m1) + __popc(m2);
+        uint32_t total_trips = ((rr.l1 + 31u) >> 5) + ((rr.l2 + 31u) >> 5);
         uint32_t ncand = rr.l1 + rr.l2 + (uint32_t)rr.mcnt;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
-        const double thr = (double)kBias32 * (double)max(ncand, 1024u);
+        for (int o = 16; o > 0; o >>= 1) {
+            total_trips += __shfl_xor_sync(0xffffffffu, total_trips, o);
+            ncand += __shfl_xor_sync(0xffffffffu, ncand, o);
+        }
+        __syncwarp();
+        const double thr = fmax((double)kBias32 * (double)max(ncand, 1024u), (double)min_thr);
         const int node = lane >> 1, half = lane & 1;
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         const bool valid = ix < g.R && iy < g.R;
@@ -1278,43 +1383,19 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         bool requeue = false;
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
-            float acc[kTile][kTile];
             double acc64[kTile][kTile];
-#pragma unroll
-            for (int i = 0; i < kTile; ++i)
-#pragma unroll
-                for (int j = 0; j < kTile; ++j) { acc[i][j] = 0.f; acc64[i][j] = 0.0; }
-            constexpr int nparts = MOMENTS ? 2 : 1;
-            int budget = kFlushTrips;
-            for (int r = 0; r < rows; ++r) {
-#pragma unroll 1
-                for (int part = 0; part < nparts; ++part) {
-                    const uint32_t len = __shfl_sync(0xffffffffu, part ? rr.l2 : rr.l1, r);
-                    const uint2 *__restrict__ rp = pts + __shfl_sync(0xffffffffu, part ? rr.s2 : rr.s1, r);
-                    const uint32_t trips = (len + 31u) >> 5;
-                    uint32_t j = lane;
-                    uint2 pn = make_uint2(gxq - kFarQ, gyq);
-                    if (j < len) pn = rp[j];
-                    for (uint32_t t = 0; t < trips; ++t) {
-                        const uint2 p = pn;
-                        j += 32;
-                        pn = make_uint2(gxq - kFarQ, gyq);
-                        if (j < len) pn = rp[j];
-                        accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, one, acc);
-                        if (--budget == 0) { flush32(acc, acc64); budget = kFlushTrips; }
-                    }
-                }
-                if (MOMENTS) {
+            walk_tile32(pts, wstart, wlen, nruns, total_trips, lane, gxq, gyq, unit, f1, f2, f3, one, acc64);
+            if (MOMENTS) {
+                const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
+                for (int r = 0; r < rows; ++r) {
                     const int mc = __shfl_sync(0xffffffffu, rr.mcnt, r);
                     const int mlo = __shfl_sync(0xffffffffu, rr.mlo, r);
                     const int cy = tc.cy_lo + r;
-                    const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
                     for (int k = lane; k < mc; k += 32)
                         accumulate_cell(mom + (size_t)(cy * g.C + mlo + k) * kMomentDoubles, cell_centre(g, mlo + k),
                                         cell_centre(g, cy), gx0, gy0, g.inv_h, c1, c2, c3, acc64);
                 }
             }
-            flush32(acc, acc64);
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < kTile; ++i)
@@ -1325,6 +1406,10 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll
             for (int k = 0; k < 16; ++k) S += wred[node * kWarpRedStride + half + 2 * k];
             S += __shfl_xor_sync(0xffffffffu, S, 1);
+            if (stats && lane == 0) {
+                atomicAdd(&stats[pass == 0 ? 0 : 1], 1ull);
+                atomicAdd(&stats[pass == 0 ? 2 : 3], (unsigned long long)total_trips);
+            }
             if (pass == 0) {
                 if (!__any_sync(0xffffffffu, valid && S < thr)) break;      // every node certainly non-zero
                 S1 = S;
@@ -1337,6 +1422,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         }
         if (requeue) {
             if (lane == 0) {
+                if (stats) atomicAdd(&stats[4], 1ull);
                 const unsigned slot = atomicAdd(&redo_counters[list], 1u);
                 redo_list[(size_t)list * capacity + slot] = entry;
             }
@@ -1676,6 +1762,285 @@ k_norm_totals(int count, int stride, const double *__restrict__ tilesum, double 
     if (threadIdx.x == 0) { out_norm[0] = a; out_norm[1] = b; }
 }
 
+
+// ==========================================================================================
+// Band mode: ONE huge evaluation over several GPUs (config C5).  The grid is cut along column 1 (tile columns ty)
+// into one band per rank; cell rows of the sort run along the same axis, so "every point within h of a band" is a
+// contiguous slice of a rank's locally sorted points.  Per rank:
+//   k_minmax (own slices) -> all-gather of the extrema -> k_band_fold_stats (joint scaler, identical on all ranks)
+//   local sort of the own slices (k_scale_count / k_scan / k_place) -> all-gather of the per-cell counts
+//   k_band_cells (global counts: work per tile column -> band cuts; local counts of the rows a band needs)
+//   point exchange (NCCL all-to-all of contiguous slices) -> k_band_merge (per cell: sources in rank order ==
+//   original index order, so the band's sorted array is exactly the single-GPU one restricted to its rows)
+//   moments / classify / density on the band's tiles -> k_band_norm_totals -> all-gather (2 doubles)
+//   k_band_fold_norms -> k_js_tiles over the band -> all-gather (2 doubles) -> sqrt on the host.
+
+// Joint extrema of the two sets from every rank's partial extrema (rank order; min/max are order-independent).
+__global__ void k_band_fold_stats(const RawStat *__restrict__ all, int world, RawStat *__restrict__ out) {
+    const int set = threadIdx.x;
+    if (set >= 2) return;
+    RawStat a = all[set];
+    for (int r = 1; r < world; ++r) {
+        const RawStat b = all[(size_t)r * 2 + set];
+        a.mn[0] = fmin(a.mn[0], b.mn[0]); a.mx[0] = fmax(a.mx[0], b.mx[0]);
+        a.mn[1] = fmin(a.mn[1], b.mn[1]); a.mx[1] = fmax(a.mx[1], b.mx[1]);
+        a.flags |= b.flags;
+    }
+    a.pad = 0;
+    out[set] = a;
+}
+
+// Row starts of a locally sorted set: rowstart[set][cy] = cellstart[set][cy * C], cy = 0..C (appended to the
+// per-rank count block that is all-gathered, so the host can size the exchange from a few KB).
+__global__ void k_band_rowstarts(const uint32_t *__restrict__ cellstart, int C, uint32_t *__restrict__ rowstart) {
+    const int set = blockIdx.x, ncells = C * C;
+    for (int cy = threadIdx.x; cy <= C; cy += blockDim.x)
+        rowstart[(size_t)set * (C + 1) + cy] = cellstart[(size_t)set * (ncells + 1) + (size_t)cy * C];
+}
+
+// cellstart_out[set][c] = exclusive scan over cells of  sum over ranks of count_r(set, c)  restricted to cells
+// [c_lo, c_hi) (all others count 0).  cs_all: per rank a block of `rank_stride` u32 starting with
+// cellstart_r[2][ncells + 1].  grid (2), 1024 threads.  With [0, ncells) this is the GLOBAL cell table (the same
+// numbers the single-GPU sort produces), with a band's rows it is the band's local table.
+__global__ void __launch_bounds__(1024)
+k_band_cells(const uint32_t *__restrict__ cs_all, int world, size_t rank_stride, int ncells, int c_lo, int c_hi,
+             uint32_t *__restrict__ cellstart_out) {
+    const int set = blockIdx.x;
+    constexpr int kCptMax = kMaxCells / 1024;
+    const int cpt = (ncells + 1023) / 1024;
+    const int c0 = threadIdx.x * cpt;
+    uint32_t tot[kCptMax];
+    uint32_t tsum = 0u;
+#pragma unroll
+    for (int k = 0; k < kCptMax; ++k) {
+        uint32_t t = 0u;
+        const int c = c0 + k;
+        if (k < cpt && c < ncells && c >= c_lo && c < c_hi)
+            for (int r = 0; r < world; ++r) {
+                const uint32_t *cs = cs_all + (size_t)r * rank_stride + (size_t)set * (ncells + 1);
+                t += cs[c + 1] - cs[c];
+            }
+        tot[k] = t;
+        tsum += t;
+    }
+    __shared__ uint32_t s_w[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t v = s_w[lane], iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_w[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = s_w[w] + inc - tsum;
+    uint32_t *out = cellstart_out + (size_t)set * (ncells + 1);
+#pragma unroll
+    for (int k = 0; k < kCptMax; ++k) {
+        if (k < cpt && c0 + k < ncells) out[c0 + k] = run;
+        run += tot[k];
+    }
+    if (threadIdx.x == 1023) out[ncells] = run;
+}
+
+// k_band_merge: grid (ceil(cells in the band's rows / 4), 2 sets), 128 threads, one warp per cell.  The staging
+// buffer of a set holds, source rank after source rank, that rank's sorted points of cell rows [cy_lo, cy_hi]
+// (row-major cells).  The cell's points are copied source by source to their final place -- rank order is original
+// index order, so the result equals the single-GPU stable sort restricted to these rows.  Also writes the
+// fixed-point copy for the fp32 kernel.
+__global__ void __launch_bounds__(128)
+k_band_merge(const double2 *__restrict__ stage_a, const double2 *__restrict__ stage_b,
+             const uint32_t *__restrict__ cs_all, int world, size_t rank_stride, const GridGeom g, int cy_lo, int cy_hi,
+             const uint32_t *__restrict__ cellstart_local, int64_t off_b,
+             double2 *__restrict__ sorted, uint2 *__restrict__ sorted_q) {
+    const int set = blockIdx.y, lane = threadIdx.x & 31;
+    const int ncells = g.C * g.C;
+    const int c_lo = cy_lo * g.C, c_hi = (cy_hi + 1) * g.C;
+    const int cell = c_lo + blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (cell >= c_hi) return;
+    const double2 *__restrict__ stage = set ? stage_b : stage_a;
+    uint32_t dst = cellstart_local[(size_t)set * (ncells + 1) + cell];
+    const int64_t base = set ? off_b : 0;
+    uint32_t src_base = 0u;                       // first point of source r in the staging buffer
+    for (int r = 0; r < world; ++r) {
+        const uint32_t *cs = cs_all + (size_t)r * rank_stride + (size_t)set * (ncells + 1);
+        const uint32_t r_lo = cs[c_lo], r_hi = cs[c_hi];
+        const uint32_t b = cs[cell], e = cs[cell + 1];
+        const double2 *__restrict__ sp = stage + src_base + (b - r_lo);
+        for (uint32_t k = lane; k < e - b; k += 32) {
+            const double2 p = sp[k];
+            sorted[base + dst + k] = p;
+            if (sorted_q) sorted_q[base + dst + k] = make_uint2(quantise(p.x, g), quantise(p.y, g));
+        }
+        dst += e - b;
+        src_base += r_hi - r_lo;
+    }
+}
+
+// Estimated density work of one tile COLUMN (all tile rows, both sets): the band cuts are derived from these.
+__global__ void __launch_bounds__(128)
+k_tile_colwork(const __grid_constant__ WaveDesc wd, const GridGeom g,
+               const uint32_t *__restrict__ cellstart, double *__restrict__ colwork) {
+    __shared__ double s_w[32];
+    const int ty = blockIdx.x;
+    double work = 0.0;
+    for (int idx = threadIdx.x; idx < wd.n_sets * g.NT; idx += blockDim.x) {
+        const int set = idx / g.NT, tx = idx % g.NT;
+        const TileCells tc = tile_cells(g, tx * kTile, ty * kTile);
+        const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
+        uint32_t total = 0u;
+        for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy) {
+            const RowRuns rr = tile_row_runs(g, tc, cs, cy, g.use_moments != 0);
+            total += rr.l1 + rr.l2 + (uint32_t)rr.mcnt;
+        }
+        work += (double)total + (total ? 64.0 : 2.0);
+    }
+    work = block_sum(work, s_w);
+    if (threadIdx.x == 0) colwork[ty] = work;
+}
+
+// Partial normalisers of a band: per-tile partials of tile columns [ty_b, ty_e), all tile rows, summed in a fixed
+// order (thread-strided over the band's tiles in (tx, ty) order, then the block tree).  1 block.
+__global__ void __launch_bounds__(kJsThreads)
+k_band_norm_totals(const double *__restrict__ tilesum, int NT, int ty_b, int ty_e, double *__restrict__ out_norm) {
+    __shared__ double s_w[32];
+    const int nty = ty_e - ty_b, count = NT * nty;
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < count; k += kJsThreads) {
+        const int tile = (k / nty) * NT + ty_b + k % nty;
+        a += tilesum[tile];
+        b += tilesum[(size_t)NT * NT + tile];
+    }
+    a = block_sum(a, s_w);
+    b = block_sum(b, s_w);
+    if (threadIdx.x == 0) { out_norm[0] = a; out_norm[1] = b; }
+}
+
+// Normalisers of the whole grid = the ranks' partials added in rank order (every rank gets the same bits).
+__global__ void k_band_fold_norms(const double *__restrict__ norms_all, int world, double *__restrict__ totals) {
+    if (threadIdx.x >= 2) return;
+    double t = 0.0;
+    for (int r = 0; r < world; ++r) t += norms_all[2 * r + threadIdx.x];
+    totals[threadIdx.x] = t;
+}
+
+// Divergence partial of a band: k_js_tiles' arithmetic over tile columns [ty_b, ty_e) of one item, every node
+// value read from pz (band mode writes empty tiles too).  grid (NT tile rows), 256 threads; the last block folds
+// the block partials in block order into out_lr[0] ([1] = 0, [2] = 1 if an input held an infinity).
+__global__ void __launch_bounds__(kJsThreads)
+k_band_js(const GridGeom g, int ty_b, int ty_e, const double *__restrict__ pz, const double *__restrict__ totals,
+          const RawStat *__restrict__ rstat, double *__restrict__ jspart, unsigned *__restrict__ ticket,
+          double *__restrict__ out_lr) {
+    __shared__ double s_w[32];
+    __shared__ bool s_last;
+    const double tp = totals[0], tq = totals[1];
+    const bool normal = (tp > 0.0) && (tq > 0.0);
+    const size_t G = (size_t)g.R * g.R;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x, ix = tx * kTile + ((lane & 15) >> 2), jj = lane & 3;
+    double left = 0.0;
+    if (ix < g.R) {
+        for (int ty = ty_b + warp * 2 + (lane >> 4); ty < ty_e; ty += 2 * (kJsThreads / 32)) {
+            const int iy = ty * kTile + jj;
+            if (iy >= g.R) continue;
+            const size_t k = (size_t)ix * g.R + iy;
+            const double a = pz[k], b = pz[G + k];
+            if (normal && a == 0.0 && b == 0.0) continue;
+            const double p = a / tp, q = b / tq;
+            const double m = (p + q) / 2.0;
+            double node = 0.0;
+            if (p > 0.0) node = p * log_ratio(p, m);
+            if (q > 0.0) node += q * log_ratio(q, m);
+            left += node;
+            if (p != p) left = p;
+            if (q != q) left = q;
+        }
+    }
+    left = block_sum(left, s_w);
+    if (threadIdx.x == 0) {
+        jspart[blockIdx.x] = left;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        const volatile double *vp = jspart;
+        double L = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) L += vp[i];
+        L = warp_sum(L);
+        if (threadIdx.x == 0) {
+            out_lr[0] = L;
+            out_lr[1] = 0.0;
+            out_lr[2] = (double)((rstat[0].flags | rstat[1].flags) & 1);
+            *ticket = 0u;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// k_summary: process_result's summary vector and the two ELFI nodes built on it, fused behind the JS reduction
+// (poppunk_mod.py:285-291 calculate_gene_freqs, :379 [divergence, freq_core, freq_intermediate, freq_rare],
+// :571-572 Distance("euclidean") against the observed vector and log).  grid (B), 256 threads; block b counts its
+// simulation's gene frequencies X in exact integers and thread 0 writes out[b] = {JS, fc, fi, fr, d, log d}.
+// Divisions are int / int in fp64 exactly as numpy's; the squared differences are summed in index order with
+// separately rounded multiplies and adds (scipy's euclidean loop; no FMA contraction).
+__global__ void __launch_bounds__(256)
+k_summary(const double *__restrict__ freqs, const int64_t *__restrict__ offs, double core_thr, double rare_thr,
+          const double *__restrict__ js, double o0, double o1, double o2, double o3, double *__restrict__ out) {
+    __shared__ unsigned long long s_cnt[4];
+    const int b = blockIdx.x;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned n_pos = 0u, n_core = 0u, n_rare = 0u, n_mid = 0u;
+    for (int64_t k = offs[b] + threadIdx.x; k < offs[b + 1]; k += blockDim.x) {
+        const double X = freqs[k];
+        n_pos += (X > 0.0);
+        n_core += (X >= core_thr);
+        n_rare += (0.0 < X) && (X < rare_thr);
+        n_mid += (rare_thr <= X) && (X < core_thr);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+        n_core += __shfl_xor_sync(0xffffffffu, n_core, o);
+        n_rare += __shfl_xor_sync(0xffffffffu, n_rare, o);
+        n_mid += __shfl_xor_sync(0xffffffffu, n_mid, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[0], (unsigned long long)n_pos);
+        atomicAdd(&s_cnt[1], (unsigned long long)n_core);
+        atomicAdd(&s_cnt[2], (unsigned long long)n_rare);
+        atomicAdd(&s_cnt[3], (unsigned long long)n_mid);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double genes = (double)s_cnt[0];
+        const double fc = (double)s_cnt[1] / genes, fr = (double)s_cnt[2] / genes, fi = (double)s_cnt[3] / genes;
+        const double v[4] = {js[b], fc, fi, fr}, o[4] = {o0, o1, o2, o3};
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double df = __dsub_rn(v[k], o[k]);
+            acc = __dadd_rn(acc, __dmul_rn(df, df));
+        }
+        const double d = sqrt(acc);
+        double *r = out + (size_t)b * 6;
+        r[0] = v[0]; r[1] = fc; r[2] = fi; r[3] = fr; r[4] = d; r[5] = log(d);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Issue-rate microbenchmarks (roofline denominators measured on the box, not quoted).
 template <int WHICH>
@@ -1744,6 +2109,57 @@ __global__ void __launch_bounds__(256) k_peak(int iters, float *sink_f, double *
 #pragma unroll
         for (int i = 0; i < 8; ++i) s ^= a[i];
         if (s == 0x12345678ULL) sink_d[0] = (double)s;
+    }
+}
+
+
+// Candidate-loop microbenchmarks: the inner loops of the two culled density kernels over an L1-resident run of
+// candidates, no per-tile work -- what the loops themselves sustain (pair tests / s = lanes * 16 nodes).
+template <int WHICH>
+__global__ void __launch_bounds__(kDensThreads) k_loop_peak(int trips, const double2 *__restrict__ pts,
+                                                            const uint2 *__restrict__ ptsq, double *sink) {
+    const int lane = threadIdx.x & 31;
+    if (WHICH == 0) {
+        double acc[kTile][kTile];
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
+        double2 pn = pts[lane];
+        for (int t = 0; t < trips; ++t) {
+            const double2 p = pn;
+            pn = pts[((t + 1) & 31) * 32 + lane];
+            accumulate_point(p, 0.25, 0.25, 33.0, 0.13, 0.26, 0.39, acc);
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) s += acc[i][j];
+        if (s == 12345.678) sink[0] = s;
+    } else {
+        float acc[kTile][kTile], hi[kTile][kTile];
+        double acc64[kTile][kTile];
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) { acc[i][j] = 0.f; hi[i][j] = 0.f; acc64[i][j] = 0.0; }
+        uint2 pn = ptsq[lane];
+        int budget = kFoldTrips;
+        for (int t = 0; t < trips; ++t) {
+            const uint2 p = pn;
+            pn = ptsq[((t + 1) & 31) * 32 + lane];
+            accumulate_point32(p, 0x10000000u, 0x10000000u, 1.862645149230957e-09f, 0.13f, 0.26f, 0.39f, 1.0f, acc);
+            if (WHICH == 2 && --budget == 0) { fold32(acc, hi); budget = kFoldTrips; }
+        }
+        fold32(acc, hi);
+        flush32(hi, acc64);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < kTile; ++i)
+#pragma unroll
+            for (int j = 0; j < kTile; ++j) s += acc64[i][j];
+        if (s == 12345.678) sink[0] = s;
     }
 }
 

@@ -3,10 +3,14 @@
 * Batches / sweeps (BOLFI batches, Latin-hypercube grids, all-pairs tables): evaluations are
   independent -- each has its own joint scaler (KDE_distance.py:81-86) -- so items are dealt to
   ranks and only the scalar discrepancies are gathered.  No collective touches the data path.
-* One huge evaluation (config C5: 10 M pairs on a 1024^2 grid): node rows are split over ranks;
-  the path has two real exchange steps, the normalisers (2 doubles) and the relative-entropy
-  partials (2 doubles).  They are all-gathered and summed in rank order, so every rank ends with
-  the same bit pattern.
+* One huge evaluation (config C5: 10 M pairs on a 1024^2 grid): the grid is split into bands of tile
+  columns, one per rank, AND the points are sharded: every rank holds a slice of each table, sorts
+  it locally, and receives only the points of the cell rows within h of its band
+  (band_sharded_discrepancy; one all-to-all of contiguous slices over NVLink).  The remaining
+  exchange steps are tiny: the extrema (10 doubles), the per-cell counts, the normalisers (2
+  doubles) and the relative-entropy partials (3 doubles); each is all-gathered and folded in rank
+  order, so every rank ends with the same bit pattern.  (row_sharded_discrepancy with complete
+  tables on every rank is the older replicate-and-sort variant.)
 
 torch.distributed is used for plumbing only (NCCL on GPUs, gloo in the CPU tests).
 """
@@ -121,17 +125,24 @@ def _gather_slices(local, group, device):
 
 
 def row_sharded_discrepancy(df1, df2, gamma=1.0, eps=1e-12, log=False, *, resolution=100, bandwidth=0.03,
-                            group=None, device=None, sliced=False, phase1=None, phase2=None):
+                            group=None, device=None, sliced=False, phase1=None, phase2=None, algo=None,
+                            gather_all=False):
     """KDE_JS_divergence of ONE pair of (large) point sets with the grid's node rows split over
     the ranks of `group`.  Returns the same np.float64 on all ranks.
 
     sliced=False: every rank passes both complete sets (each rank uploads everything).
     sliced=True : every rank passes only ITS contiguous slice of each set (rank order = row order of the
-                  table); slices are exchanged GPU-to-GPU with one all-gather per set."""
+                  table).  On GPUs the points stay sharded (band_sharded_discrepancy: local sort, only the rows a
+                  band needs are exchanged); gather_all=True forces the older variant that all-gathers both
+                  tables to every rank (also the path of the CPU tests, which inject phase1/phase2)."""
     dist = _dist()
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = kd.default_device() if device is None else int(device)
+    if sliced and phase1 is None and (world == 1 or dist.get_backend(group) == "nccl") and not gather_all:
+        # the points stay sharded: local sort, band-wise point exchange (band mode)
+        return band_sharded_discrepancy(df1, df2, gamma, eps, log, resolution=resolution, bandwidth=bandwidth,
+                                        group=group, device=dev, algo=algo)
     common = kd._common(resolution, bandwidth, gamma, eps, log, "epanechnikov", "binned")
     if sliced and dist.is_initialized():
         df1, df2 = _gather_slices(df1, group, dev), _gather_slices(df2, group, dev)
@@ -160,5 +171,172 @@ def row_sharded_discrepancy(df1, df2, gamma=1.0, eps=1e-12, log=False, *, resolu
     parts = _all_gather_f64(lr, group, dev)
     js2 = (parts[:, 0].sum() + parts[:, 1].sum()) / 2.0
     if js2 < 0.0:            # rounding noise around an exact 0; NaN compares false and stays NaN
+        js2 = 0.0
+    return np.float64(np.sqrt(js2))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Band mode: the points are sharded too (C ABI: kdejs_band_*, include/kdejs.h)
+
+class _GpuBandOps:
+    """The device steps of band mode on this rank's GPU, all enqueued on torch's current stream (so they are
+    ordered with the NCCL collectives torch issues in between without any host synchronisation)."""
+
+    def __init__(self, device, common):
+        import torch
+
+        self.torch, self.dev, self.common = torch, int(device), common
+        self.L = nat.lib()
+        geo = (ctypes.c_int * 4)()
+        nat.check(self.L.kdejs_band_geometry(common[0], common[1], common[5], geo))
+        self.C, self.NT, self.block_u32 = geo[0], geo[1], geo[2]
+        self.tdev = torch.device("cuda", self.dev)
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.tdev).cuda_stream
+
+    def to_device(self, x, name):
+        torch = self.torch
+        if hasattr(x, "data_ptr"):
+            if x.dtype != torch.float64 or x.dim() != 2 or x.shape[1] != 2 or not x.is_contiguous() or not x.is_cuda:
+                raise ValueError(f"{name}: device slices must be contiguous (n,2) float64 CUDA tensors")
+            return x
+        return torch.from_numpy(nat.as_points(x, name)).to(self.tdev, non_blocking=True)
+
+    def empty(self, shape, dtype="f8"):
+        t = self.torch
+        return t.empty(shape, dtype={"f8": t.float64, "i4": t.int32}[dtype], device=self.tdev)
+
+    def minmax(self, a, b):
+        out = self.empty(10)
+        nat.check(self.L.kdejs_band_minmax_dev(self.dev, a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0],
+                                               self.common[4], self.common[3], out.data_ptr(), self._stream()))
+        return out
+
+    def sort(self, a, b, stats_all, world):
+        srt = self.empty((a.shape[0] + b.shape[0], 2))
+        block = self.empty(self.block_u32, "i4")
+        nat.check(self.L.kdejs_band_sort_dev(self.dev, a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], *self.common,
+                                             stats_all.data_ptr(), world, srt.data_ptr(), block.data_ptr(),
+                                             self._stream()))
+        return srt, block
+
+    def plan(self, blocks_all, world):
+        colwork = np.empty(self.NT, dtype=np.float64)
+        rowstart = np.empty((world, 2, self.C + 1), dtype=np.uint32)
+        use_m = ctypes.c_int(0)
+        nat.check(self.L.kdejs_band_plan(self.dev, blocks_all.data_ptr(), world, *self.common, colwork.ctypes.data,
+                                         rowstart.ctypes.data, ctypes.byref(use_m), self._stream()))
+        return colwork, rowstart.astype(np.int64), use_m.value
+
+    def phase1(self, stage_a, stage_b, na_tot, nb_tot, blocks_all, stats_all, world, ty, cy, use_m):
+        out = self.empty(2)
+        nat.check(self.L.kdejs_band_phase1_dev(
+            self.dev, stage_a.data_ptr() if stage_a.shape[0] else None, stage_a.shape[0],
+            stage_b.data_ptr() if stage_b.shape[0] else None, stage_b.shape[0], int(na_tot), int(nb_tot),
+            blocks_all.data_ptr(), world, stats_all.data_ptr(), *self.common, ty[0], ty[1], cy[0], cy[1], use_m,
+            out.data_ptr(), self._stream()))
+        return out
+
+    def phase2(self, norms_all, world):
+        out = self.empty(3)
+        nat.check(self.L.kdejs_band_phase2_dev(self.dev, norms_all.data_ptr(), world, out.data_ptr(), self._stream()))
+        return out
+
+    def to_host(self, t):
+        return t.cpu().numpy()
+
+
+def band_cuts(colwork, world):
+    """Equal-work bands of tile columns: cuts[r] .. cuts[r+1] for rank r (kdejs_band_cuts, pure host)."""
+    cw = np.ascontiguousarray(colwork, dtype=np.float64)
+    cuts = (ctypes.c_int * (world + 1))()
+    nat.check(nat.lib().kdejs_band_cuts(cw.ctypes.data, len(cw), world, cuts))
+    return list(cuts)
+
+
+def band_cell_rows(resolution, bandwidth, ty_begin, ty_end):
+    """Cell rows [lo, hi] whose points can reach tile columns [ty_begin, ty_end) (hi < lo: empty band)."""
+    cy = (ctypes.c_int * 2)()
+    nat.check(nat.lib().kdejs_band_cell_rows(int(resolution), float(bandwidth), int(ty_begin), int(ty_end), cy))
+    return cy[0], cy[1]
+
+
+def _gather_cat(t, group, world):
+    """Rank-ordered concatenation of equally sized 1-D/2-D tensors from all ranks (no host round trip)."""
+    dist = _dist()
+    if world == 1:
+        return t
+    import torch
+
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+def _exchange(send, recv, group, rank, world):
+    """send[d] -> rank d, recv[s] <- rank s.  Slices of `send` may overlap (halo rows go to two neighbours)."""
+    dist = _dist()
+    if world == 1:
+        recv[0].copy_(send[0])
+        return
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, [t.contiguous() for t in send], group=group)
+        return
+    recv[rank].copy_(send[rank])                      # gloo (CPU tests): point-to-point
+    ops = []
+    for k in range(1, world):
+        d, s_ = (rank + k) % world, (rank - k) % world
+        ops.append(dist.P2POp(dist.isend, send[d].contiguous(), dist.get_global_rank(group, d) if group else d, group))
+        ops.append(dist.P2POp(dist.irecv, recv[s_], dist.get_global_rank(group, s_) if group else s_, group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+
+
+def band_sharded_discrepancy(a_slice, b_slice, gamma=1.0, eps=1e-12, log=False, *, resolution=100, bandwidth=0.03,
+                             algo=None, group=None, device=None, ops=None, info=None):
+    """KDE_JS_divergence of ONE pair of (large) tables whose rows are sharded over the ranks of `group`: every rank
+    passes ITS contiguous slice of each table (rank order = row order; numpy, pinned numpy or a CUDA tensor).
+    Returns the same np.float64 on all ranks; raises ValueError on infinity like the single-GPU call.
+    `info` (a dict) receives the band this rank owned and the sizes of the exchange."""
+    dist = _dist()
+    inited = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if inited else 1
+    rank = dist.get_rank(group) if inited else 0
+    dev = kd.default_device() if device is None else int(device)
+    common = kd._common(resolution, bandwidth, gamma, eps, log, "epanechnikov", algo)
+    if ops is None:
+        ops = _GpuBandOps(dev, common)
+    a, b = ops.to_device(a_slice, "df1 slice"), ops.to_device(b_slice, "df2 slice")
+    na = a.shape[0]
+    stats_all = _gather_cat(ops.minmax(a, b), group, world)                    # joint scaler: 10 doubles per rank
+    srt, block = ops.sort(a, b, stats_all, world)
+    blocks_all = _gather_cat(block, group, world)                              # per-cell counts of every rank
+    colwork, rs, use_m = ops.plan(blocks_all, world)                           # the one host synchronisation
+    cuts = band_cuts(colwork, world)
+    rows = [band_cell_rows(resolution, bandwidth, cuts[d], cuts[d + 1]) for d in range(world)]
+    lo_me, hi_me = rows[rank]
+    stages = []
+    for st in (0, 1):
+        base = 0 if st == 0 else na
+        send = [srt[base + rs[rank, st, lo]: base + rs[rank, st, hi + 1]] if hi >= lo else srt[0:0] for lo, hi in rows]
+        counts = [int(rs[s_, st, hi_me + 1] - rs[s_, st, lo_me]) if hi_me >= lo_me else 0 for s_ in range(world)]
+        stage = ops.empty((sum(counts), 2))
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        recv = [stage[offs[s_]:offs[s_ + 1]] for s_ in range(world)]
+        _exchange(send, recv, group, rank, world)
+        stages.append(stage)
+    n_tot = rs[:, :, -1].sum(axis=0)
+    norm = ops.phase1(stages[0], stages[1], n_tot[0], n_tot[1], blocks_all, stats_all, world,
+                      (cuts[rank], cuts[rank + 1]), (lo_me, hi_me), use_m)
+    lr = ops.phase2(_gather_cat(norm, group, world), world)
+    parts = ops.to_host(_gather_cat(lr, group, world)).reshape(world, 3)        # final synchronisation
+    if info is not None:
+        info.update({"tile_columns": (cuts[rank], cuts[rank + 1]), "cell_rows": (lo_me, hi_me),
+                     "points_received": (int(stages[0].shape[0]), int(stages[1].shape[0])), "moment_cells": bool(use_m)})
+    if parts[:, 2].any():
+        raise ValueError("Input X contains infinity or a value too large for dtype('float64').")
+    js2 = (parts[:, 0].sum() + parts[:, 1].sum()) / 2.0
+    if js2 < 0.0:
         js2 = 0.0
     return np.float64(np.sqrt(js2))

@@ -65,6 +65,28 @@ def test_reader_errors(nat, tmp_path):
         nat.TsvTable(str(empty), pinned=False)
 
 
+def test_missing_values_become_nan_like_pandas(nat, tmp_path):
+    """pd.read_csv (scripts/pairwise_2D_distance.py:38-45, poppunk_mod.py:266-267) turns NA tokens and empty fields
+    into NaN, and the path maps NaN to scaled 0 (KDE_distance.py:53): tables with missing distances must load."""
+    import pandas as pd
+
+    f = tmp_path / "missing.tsv"
+    f.write_text("a\tb\t0.001\t0.2\n"
+                 "a\tc\tNA\t0.3\n"
+                 "a\td\t0.002\t\n"
+                 "b\tc\tnan\tN/A\n"
+                 "b\td\t#N/A\tnull\n"
+                 "c\td\t0.004\t0.5\n")
+    got = nat.TsvTable(str(f), skip_rows=0, pinned=False).array
+    want = pd.read_csv(str(f), header=None, sep="\t").iloc[:, -2:].to_numpy(dtype=np.float64)
+    np.testing.assert_array_equal(got, want)                   # NaN positions and values alike
+    assert np.isnan(got).sum() == 6
+    junk = tmp_path / "junk.tsv"
+    junk.write_text("0.1\t0.2\n0.3\tabc\n")
+    with pytest.raises(ValueError, match="row 2"):
+        nat.TsvTable(str(junk), pinned=False)
+
+
 @pytest.mark.skipif(not os.path.exists("/root/reference/distances/2_column/Escherichia_coli.txt"),
                     reason="reference fixtures not present")
 def test_reference_fixture_files(nat):
@@ -72,12 +94,9 @@ def test_reference_fixture_files(nat):
     np.testing.assert_array_equal(nat.TsvTable(f, pinned=False).array, np.loadtxt(f, delimiter="\t"))
 
 
-def test_gene_frequency_classes_and_log_discrepancy():
+def test_log_discrepancy_of_host_summaries():
     from poppunk_mod_b200 import simulator as sim
 
-    X = np.array([0.0, 0.0, 0.01, 0.04, 0.5, 0.95, 0.99, 1.0])
-    fc, fi, fr = sim.calculate_gene_freqs(X, core_threshold=0.95, rare_threshold=0.05)
-    assert (fc, fi, fr) == (3 / 6, 1 / 6, 2 / 6)                # poppunk_mod.py:285-291 on the 6 present genes
     s = np.array([[0.3, 0.5, 0.2, 0.3], [0.0, 0.4, 0.3, 0.3]])
     o = np.array([0.0, 0.4, 0.3, 0.3])
     with np.errstate(divide="ignore"):

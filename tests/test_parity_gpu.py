@@ -476,6 +476,59 @@ def test_sweep_drivers_and_simulator_summary(pk, ko, tmp_path):
     assert batch.shape == (2, 4) and batch[0, 0] == vec[0]
 
 
+def test_summary_vector_and_elfi_nodes_on_device(pk, ko):
+    """kdejs_summary_batch against a numpy restatement of poppunk_mod.py:285-291 (gene-frequency classes), :379
+    (summary vector), :494 / :571-572 (euclidean distance to the observed vector, log)."""
+    from oracle import workloads as wl
+    from poppunk_mod_b200 import simulator
+
+    rng = np.random.default_rng(12)
+    obs = wl.synthetic_target(9000)
+    sims = [wl.sim_batch_member(s, n=4000 + 500 * s) for s in range(5)]
+    freqs = [np.round(rng.beta(0.3, 0.3, 3000 + 101 * s), 3) * (rng.random(3000 + 101 * s) > 0.2) for s in range(5)]
+    freqs[3][:5] = [0.05, 0.95, 0.0, np.nan, 1.0]                       # values exactly on the thresholds, a NaN
+    core, rare = 0.95, 0.05
+    observed = np.array([0.0, 0.31, 0.22, 0.47])
+    summary, d, log_d = pk.KDE_distance.summary_batch(obs, sims, freqs, observed, 0.25, core, rare)
+    js = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0)
+    for i, X in enumerate(freqs):
+        with np.errstate(invalid="ignore"):
+            genes = (X > 0).sum()
+            want = np.array([js[i], (X >= core).sum() / genes, np.count_nonzero((rare <= X) & (X < core)) / genes,
+                             np.count_nonzero((0 < X) & (X < rare)) / genes])
+        np.testing.assert_array_equal(summary[i], want)                 # integer counts, IEEE divisions: exact
+        dd = np.sqrt(((want - observed) ** 2).sum())
+        assert d[i] == pytest.approx(dd, rel=1e-15) and log_d[i] == pytest.approx(np.log(dd), rel=1e-14)
+    s2, d2, l2 = simulator.process_results_batch(sims, freqs, obs, 0.25, core, rare, observed=observed)
+    np.testing.assert_array_equal(s2, summary)
+    np.testing.assert_array_equal(l2, log_d)
+    np.testing.assert_allclose(simulator.log_euclidean_discrepancy(summary, observed), log_d, rtol=1e-14)
+    one = simulator.process_result(sims[2], freqs[2], obs, 0.25, core, rare)
+    np.testing.assert_array_equal(one, summary[2])
+
+
+def test_rule_of_thumb_bandwidths_against_sklearn(pk):
+    """bandwidth="scott" | "silverman" (sklearn:neighbors/_kde.py:223-229) on the Gaussian kernel."""
+    from sklearn.neighbors import KernelDensity
+
+    rng = np.random.default_rng(3)
+    X = rng.random((700, 2))
+    R = 40
+    _, _, xy = pk.get_grid(0, 1, R)
+    for rule in ("scott", "silverman"):
+        want = np.exp(KernelDensity(bandwidth=rule, kernel="gaussian").fit(X).score_samples(xy)).reshape(R, R)
+        got = pk.kde_density(X, resolution=R, bandwidth=rule, kernel="gaussian")
+        np.testing.assert_allclose(got, want, rtol=1e-9)
+        assert pk.KDE_distance.rule_bandwidth(rule, 700) == pytest.approx(KernelDensity(bandwidth=rule).fit(X).bandwidth_)
+    Y = rng.random((700, 2)) * 0.8
+    a = pk.KDE_JS_divergence(X, Y, bandwidth="scott")                    # equal sizes: one bandwidth for both sets
+    assert a == pk.KDE_JS_divergence(X, Y, bandwidth=700 ** (-1 / 6))
+    with pytest.raises(ValueError, match="equal size"):
+        pk.KDE_JS_divergence(X, Y[:500], bandwidth="silverman")
+    with pytest.raises(ValueError):
+        pk.kde_density(X, bandwidth="botev")
+
+
 def test_large_evaluation_against_oracle(pk, ko):
     """1 M + 0.7 M pairs on a 512^2 grid (one wave of one, large sort chunks, many heavy tiles) and the
     chunk-size switch of the sort (kMaxChw) at 3 M points."""
