@@ -201,7 +201,10 @@ def KDE_JS_divergence_batch(obs, sims, gamma=1.0, eps=1e-12, log=False, *,
     if first_err:
         rc, err = first_err
         if rc in (nat.KDEJS_ERR_ARG, nat.KDEJS_ERR_INF):
-            raise ValueError(err)
+            e = ValueError(err)
+            if rc == nat.KDEJS_ERR_INF:
+                e.partial_results = out      # the other evaluations finished; the offending ones are NaN
+            raise e
         raise RuntimeError(f"kdejs: {err}")
     return out
 

@@ -11,6 +11,8 @@
 #include "kdejs_kernels.cuh"
 #include "kdejs_stager.h"
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX 3: ranges cost nothing unless a profiler is attached
+
 #include <algorithm>
 #include <atomic>
 #include <cctype>
@@ -66,6 +68,11 @@ int h2d_ranges(int device, const std::vector<Stager::Range> &ranges, cudaStream_
     return KDEJS_OK;
 }
 
+struct NvtxRange {     // RAII range on the calling thread (Nsight Systems / ncu --nvtx timelines: entry points and waves)
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -88,7 +95,7 @@ struct DevBuf {
 
 struct Slot {
     DevBuf scaled, sorted, sorted_q, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
-    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, redo, counters, totals, rank16, warpprefix, tileflag;
+    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, redo, counters, totals, rank16, warpprefix, tileflag, misc;
 };
 
 struct Params {
@@ -104,13 +111,20 @@ struct Ctx {
     int sm_count = 0;
     int dens_blocks_per_sm = 1, dens32_blocks_per_sm = 1;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    Slot slot;
-    // Cross-stream ordering of the scratch (slot, tickets, counters, rstat): an entry point that returns with work
-    // still enqueued on `scratch_stream` records `scratch_busy` there; the next user on a DIFFERENT stream waits for it.
-    cudaEvent_t scratch_busy = nullptr;
-    cudaStream_t scratch_stream = nullptr;
-    bool scratch_pending = false;
-    DevBuf pool_raw, js_out, status_out, misc, sim_ring, summary;
+    // Two sets of scratch buffers (slot, tickets, counters, rstat).  Work on ONE stream always reuses the slot it
+    // used last (stream order protects it); a second stream gets the other slot, so two callers' waves can overlap
+    // on the GPU (the sort of one beside the density kernel of the other).  An entry point that returns with work
+    // still enqueued records busy_ev[slot] on its stream; a user on a DIFFERENT stream that needs that slot waits
+    // for it.  `cur` is the slot of the call in progress (callers hold `mu`).
+    static constexpr int kSlots = 2;
+    Slot slots[kSlots];
+    int cur = 0;
+    Slot &S() { return slots[cur]; }
+    cudaEvent_t busy_ev[kSlots] = {nullptr, nullptr};
+    cudaStream_t busy_stream[kSlots] = {nullptr, nullptr};
+    bool busy_pending[kSlots] = {false, false};
+    uint64_t last_use[kSlots] = {0, 0}, use_tick = 0;
+    DevBuf pool_raw, js_out, status_out, sim_ring, summary;
     std::vector<cudaEvent_t> free_plain_events;
     double *h_js = nullptr; int32_t *h_status = nullptr; size_t h_cap = 0;   // pinned results
     std::mutex mu;
@@ -125,10 +139,10 @@ struct Ctx {
     unsigned long long *d_work = nullptr, *d_stats32 = nullptr;
     // row-sharded evaluation state (phase 1 -> phase 2)
     bool shard_valid = false;
-    WaveDesc shard_wd; GridGeom shard_geom; int shard_kb = 0, shard_ke = 0;
+    WaveDesc shard_wd; GridGeom shard_geom; int shard_kb = 0, shard_ke = 0, shard_slot = 0;
     // band mode state (kdejs_band_phase1_dev -> kdejs_band_phase2_dev)
     bool band_valid = false;
-    GridGeom band_geom; int band_ty0 = 0, band_ty1 = 0;
+    GridGeom band_geom; int band_ty0 = 0, band_ty1 = 0, band_slot = 0;
 };
 
 constexpr int kMaxDevices = 64;
@@ -138,9 +152,11 @@ std::mutex g_init_mu;
 int init_ctx(Ctx &c) {
     CU(cudaStreamCreateWithFlags(&c.s_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c.s_copy, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c.scratch_busy, cudaEventDisableTiming));
-    OKR(c.slot.tickets.ensure(sizeof(unsigned) * 3 * kMaxWaveSets));   // self-resetting tickets
-    CU(cudaMemset(c.slot.tickets.p, 0, c.slot.tickets.cap));
+    for (int i = 0; i < Ctx::kSlots; ++i) {
+        CU(cudaEventCreateWithFlags(&c.busy_ev[i], cudaEventDisableTiming));
+        OKR(c.slots[i].tickets.ensure(sizeof(unsigned) * 3 * kMaxWaveSets));   // self-resetting tickets
+        CU(cudaMemset(c.slots[i].tickets.p, 0, c.slots[i].tickets.cap));
+    }
     CU(cudaMalloc(&c.d_work, sizeof(unsigned long long)));
     CU(cudaMemset(c.d_work, 0, sizeof(unsigned long long)));
     CU(cudaMalloc(&c.d_stats32, 8 * sizeof(unsigned long long)));
@@ -151,16 +167,24 @@ int init_ctx(Ctx &c) {
     c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens32_blocks_per_sm, k_density_binned32<false>, kDensThreads, 0));
     c.dens32_blocks_per_sm = std::max(1, c.dens32_blocks_per_sm);
+    // fewer resident density blocks leave registers for another stream's sort kernels (two-stream callers)
+    if (const char *e = getenv("KDEJS_DENS_BLOCKS")) {
+        const int v = atoi(e);
+        if (v > 0) { c.dens_blocks_per_sm = std::min(c.dens_blocks_per_sm, v); c.dens32_blocks_per_sm = std::min(c.dens32_blocks_per_sm, v); }
+    }
     return KDEJS_OK;
 }
 
 // Release everything a context owns (shutdown, or a failed init).  The caller holds g_init_mu.
 void destroy_ctx(Ctx &c) {
-    Slot &s = c.slot;
-    for (DevBuf *b : {&s.scaled, &s.sorted, &s.sorted_q, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
-                      &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart, &s.dense_partial,
-                      &s.worklist, &s.redo, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag,
-                      &c.pool_raw, &c.js_out, &c.status_out, &c.misc, &c.sim_ring, &c.summary}) {
+    for (Slot &s : c.slots)
+        for (DevBuf *b : {&s.scaled, &s.sorted, &s.sorted_q, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
+                          &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart, &s.dense_partial,
+                          &s.worklist, &s.redo, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag, &s.misc}) {
+            if (b->p) cudaFree(b->p);
+            b->p = nullptr; b->cap = 0;
+        }
+    for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.sim_ring, &c.summary}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr; b->cap = 0;
     }
@@ -173,29 +197,50 @@ void destroy_ctx(Ctx &c) {
     c.free_events.clear();
     if (c.d_work) { cudaFree(c.d_work); c.d_work = nullptr; }
     if (c.d_stats32) { cudaFree(c.d_stats32); c.d_stats32 = nullptr; }
-    if (c.scratch_busy) { cudaEventDestroy(c.scratch_busy); c.scratch_busy = nullptr; }
+    for (int i = 0; i < Ctx::kSlots; ++i) {
+        if (c.busy_ev[i]) { cudaEventDestroy(c.busy_ev[i]); c.busy_ev[i] = nullptr; }
+        c.busy_pending[i] = false;
+        c.busy_stream[i] = nullptr;
+    }
     if (c.s_compute) { cudaStreamDestroy(c.s_compute); c.s_compute = nullptr; }
     if (c.s_copy) { cudaStreamDestroy(c.s_copy); c.s_copy = nullptr; }
-    c.scratch_pending = false;
-    c.scratch_stream = nullptr;
     c.shard_valid = false;
+    c.band_valid = false;
 }
 
-// Every user of the scratch calls this first with the stream it is about to enqueue on.
-int acquire_scratch(Ctx &c, cudaStream_t st) {
-    if (c.scratch_pending && c.scratch_stream != st) CU(cudaStreamWaitEvent(st, c.scratch_busy, 0));
+// Every user of the scratch calls this first with the stream it is about to enqueue on: picks the slot (c.cur).
+// want >= 0: the caller continues work whose state lives in that slot (phase 2 after phase 1).
+int acquire_scratch(Ctx &c, cudaStream_t st, int want = -1) {
+    for (int i = 0; i < Ctx::kSlots; ++i)
+        if (c.busy_pending[i] && cudaEventQuery(c.busy_ev[i]) == cudaSuccess) c.busy_pending[i] = false;
+    int pick = want;
+    if (pick < 0)
+        for (int i = 0; i < Ctx::kSlots; ++i)
+            if (c.busy_stream[i] == st && (c.busy_pending[i] || c.last_use[i])) { pick = i; break; }   // this stream's slot
+    if (pick < 0)
+        for (int i = 0; i < Ctx::kSlots; ++i)
+            if (!c.busy_pending[i] && !c.last_use[i]) { pick = i; break; }                            // never used
+    if (pick < 0) {                                                                                   // least recently used
+        pick = 0;
+        for (int i = 1; i < Ctx::kSlots; ++i)
+            if (c.last_use[i] < c.last_use[pick]) pick = i;
+    }
+    if (c.busy_pending[pick] && c.busy_stream[pick] != st) CU(cudaStreamWaitEvent(st, c.busy_ev[pick], 0));
+    c.cur = pick;
+    c.last_use[pick] = ++c.use_tick;
+    c.busy_stream[pick] = st;
     return KDEJS_OK;
 }
 // ... and this last: `synced` = the entry point synchronised `st` before returning (nothing is left in flight).
 int release_scratch(Ctx &c, cudaStream_t st, bool synced) {
     if (synced) {
-        // a wait on scratch_busy was enqueued before our work, so whatever recorded it has finished too
-        c.scratch_pending = false;
+        // a wait on busy_ev was enqueued before our work, so whatever recorded it has finished too
+        c.busy_pending[c.cur] = false;
         return KDEJS_OK;
     }
-    CU(cudaEventRecord(c.scratch_busy, st));
-    c.scratch_pending = true;
-    c.scratch_stream = st;
+    CU(cudaEventRecord(c.busy_ev[c.cur], st));
+    c.busy_pending[c.cur] = true;
+    c.busy_stream[c.cur] = st;
     return KDEJS_OK;
 }
 
@@ -377,6 +422,7 @@ int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
 // Enqueue the launches of one wave on `st`.  wd.set[].nb is filled here.
 int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom &g_in, WaveDesc &wd,
              const WaveIO &io) {
+    NvtxRange nvtx_wave(io.sort_only ? "kdejs wave: sort only" : io.presorted ? "kdejs wave: band density" : "kdejs wave");
     GridGeom g = g_in;
     const int n_sets = wd.n_sets, n_items = n_sets / 2;
     const size_t G = (size_t)p.R * p.R;
@@ -394,7 +440,12 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     const bool binned = (p.algo == KDEJS_ALGO_BINNED || p.algo == KDEJS_ALGO_BINNED32);
     // the fp32 kernel needs a geometry its fixed-point format covers; otherwise the fp64 kernel does the work
     static const int force32 = getenv("KDEJS_FP32") ? atoi(getenv("KDEJS_FP32")) : -1;
-    const bool fast32 = binned && g.q_shift > 0 && (force32 >= 0 ? force32 != 0 : p.algo == KDEJS_ALGO_BINNED32);
+    // ... and sets large enough for the absolute part of its error bound (1e-7 of the LARGEST node sum) to mean
+    // something: with a handful of points no node sum exceeds ~1 and fp32 terms are themselves 1e-7 off
+    int64_t min_n = INT64_MAX;
+    for (int s = 0; s < wd.n_sets; ++s) min_n = std::min<int64_t>(min_n, io.n_global ? io.n_global[s] : (int64_t)wd.set[s].n);
+    const bool fast32 = binned && g.q_shift > 0 && min_n >= 64 &&
+                        (force32 >= 0 ? force32 != 0 : p.algo == KDEJS_ALGO_BINNED32);
     // a moment cell costs a tile as much as one point plus some per-row bookkeeping: it pays once cells hold
     // hundreds of points (measured: -40 % density time at 1200 points per cell, +48 % at 49)
     if (io.force_moments >= 0 && g_in.use_moments == 1) g.use_moments = io.force_moments ? 1 : 0;
@@ -497,8 +548,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         }
         if (io.balance_world > 0) {
             // cut the tile rows into bands of equal estimated work; all ranks derive the same cuts
-            OKR(c.misc.ensure(64 + sizeof(double) * (size_t)g.NT));
-            double *d_rw = c.misc.as<double>() + 8;
+            OKR(c.S().misc.ensure(64 + sizeof(double) * (size_t)g.NT));
+            double *d_rw = c.S().misc.as<double>() + 8;
             {
                 KTimer t(c, 6, st);
                 k_tile_rowwork<<<g.NT, 128, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_rw);
@@ -552,7 +603,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             // tiles with a node the fp32 arithmetic could not certify (a nearest candidate within ~1e-6 of the
             // support's edge): the fp64 kernel on the redo list -- usually empty, a few tiles per evaluation at most
             KTimer t(c, 8, st);
-            const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * 2);
+            // a handful of tiles: one block per SM is plenty (and the launch costs less when the list is empty)
+            const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count);
             if (g.use_moments)
                 k_density_binned<true><<<blocks, kDensThreads, 0, st>>>(
                     wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
@@ -593,6 +645,11 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             int nmax = 0;
             for (int s = 0; s < n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
             nslices = (nmax + kD32Slice - 1) / kD32Slice;
+            // one fp64 partial grid per 1024-point slice and set: the brute-force kernel is a small-problem tool
+            if (nslices > 65535 || (double)nslices * n_sets * (double)G * 8.0 > 16.0e9)
+                return fail(KDEJS_ERR_ARG, "algo=dense: point sets too large for the brute-force kernel (its slice "
+                                           "partials would need " + std::to_string((size_t)((double)nslices * n_sets * G * 8.0 / 1e9)) +
+                                           " GB); use the binned algorithm");
             OKR(sl.dense_partial.ensure((size_t)nslices * n_sets * G * sizeof(double)));
             KTimer t(c, 4, st);
             const int nbx = (p.R + kD32NodesX - 1) / kD32NodesX, nby = (p.R + kD32NodesY - 1) / kD32NodesY;
@@ -697,7 +754,7 @@ int run_pairs_dev(Ctx &c, cudaStream_t st, const Params &p, const std::vector<Ra
         wd.n_sets = 2 * items;
         WaveIO io;
         io.out_js = out_js_dev; io.out_status = status_dev; io.item_base = (int)(out_base + i); io.want_z = want_z;
-        OKR(run_wave(c, c.slot, st, p, g, wd, io));
+        OKR(run_wave(c, c.S(), st, p, g, wd, io));
         i += items;
     }
     return KDEJS_OK;
@@ -844,7 +901,7 @@ int kdejs_discrepancy(int device, const double *a, int64_t na, const double *b, 
     CU(cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     const size_t G = (size_t)resolution * resolution;
-    Slot &sl = c->slot;
+    Slot &sl = c->S();
     if (out_z1) CU(cudaMemcpyAsync(out_z1, sl.zout.as<double>(), G * 8, cudaMemcpyDeviceToHost, st));
     if (out_z2) CU(cudaMemcpyAsync(out_z2, sl.zout.as<double>() + G, G * 8, cudaMemcpyDeviceToHost, st));
     if (out_d1) CU(cudaMemcpyAsync(out_d1, sl.dens.as<double>(), G * 8, cudaMemcpyDeviceToHost, st));
@@ -865,6 +922,7 @@ struct SummaryArgs {          // kdejs_summary_batch: what is fused behind the d
 static int batch_impl(int device, const double *obs, int64_t n_obs, const double *const *sims,
                       const int64_t *n_sims, int B, int resolution, double bandwidth, double gamma,
                       double eps, int log_flag, int kernel, int algo, double *out_js, const SummaryArgs *sum) {
+    NvtxRange nvtx_call(sum ? "kdejs_summary_batch" : "kdejs_discrepancy_batch");
     Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
     OKR(check_params(p));
     OKR(check_set(obs, n_obs, "obs"));
@@ -1094,8 +1152,8 @@ int kdejs_kde_density(int device, const double *pts, int64_t n, double gmin, dou
     wd.set[0].rs_self = 0; wd.set[0].rs_other = 0; wd.set[0].n = (int32_t)n;
     WaveIO io;
     io.density_only = true; io.identity_scaler = true;
-    OKR(run_wave(*c, c->slot, st, p, g, wd, io));
-    CU(cudaMemcpyAsync(out_dens, c->slot.dens.p, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost, st));
+    OKR(run_wave(*c, c->S(), st, p, g, wd, io));
+    CU(cudaMemcpyAsync(out_dens, c->S().dens.p, (size_t)resolution * resolution * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     release_scratch(*c, st, true);
     return KDEJS_OK;
@@ -1122,22 +1180,22 @@ static int shard_phase1_core(Ctx *c, const Params &p, RawSet ra, RawSet rb, int 
     int tile_rows[2] = {g.tile_row_begin, g.tile_row_end};
     io.out_tile_rows = tile_rows;
     if (balance_world > 0) { io.balance_rank = balance_rank; io.balance_world = balance_world; }
-    Slot &sl = c->slot;
+    Slot &sl = c->S();
     OKR(run_wave(*c, sl, st, p, g, wd, io));
     g.tile_row_begin = tile_rows[0];
     g.tile_row_end = tile_rows[1];
     row_begin = std::min(p.R, g.tile_row_begin * kTile);
     row_end = std::min(p.R, g.tile_row_end * kTile);
     if (out_rows) { out_rows[0] = row_begin; out_rows[1] = row_end; }
-    OKR(c->misc.ensure(64));
+    OKR(c->S().misc.ensure(64));
     const int nparts = g.NT * g.NT;
     const int lo = g.tile_row_begin * g.NT, cnt = (g.tile_row_end - g.tile_row_begin) * g.NT;
     {   // local normaliser partials: tiles [lo, lo+cnt) of each set (set 1 sits nparts after set 0)
         KTimer t(*c, 5, st);
-        k_norm_totals<<<1, kJsThreads, 0, st>>>(cnt, nparts, sl.tilesum.as<double>() + lo, c->misc.as<double>());
+        k_norm_totals<<<1, kJsThreads, 0, st>>>(cnt, nparts, sl.tilesum.as<double>() + lo, c->S().misc.as<double>());
     }
     OKR(ensure_host_results(*c, 4));
-    CU(cudaMemcpyAsync(c->h_js, c->misc.p, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_js, c->S().misc.p, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_status, &sl.rstat.as<RawStat>()[0].flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_status + 1, &sl.rstat.as<RawStat>()[1].flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1150,6 +1208,7 @@ static int shard_phase1_core(Ctx *c, const Params &p, RawSet ra, RawSet rb, int 
     c->shard_kb = row_begin * p.R;
     c->shard_ke = row_end * p.R;
     c->shard_valid = true;
+    c->shard_slot = c->cur;
     return KDEJS_OK;
 }
 
@@ -1226,11 +1285,11 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->shard_valid) return fail(KDEJS_ERR_ARG, "kdejs_shard_phase2 called without a successful phase 1");
     cudaStream_t st = c->s_compute;
-    OKR(acquire_scratch(*c, st));
-    Slot &sl = c->slot;
+    OKR(acquire_scratch(*c, st, c->shard_slot));
+    Slot &sl = c->S();
     const GridGeom &g = c->shard_geom;
     const int G = g.R * g.R;
-    double *d = c->misc.as<double>();      // [0,1] totals in, [2,3] (left,right) out
+    double *d = c->S().misc.as<double>();      // [0,1] totals in, [2,3] (left,right) out
     CU(cudaMemcpyAsync(d, total_norm, 16, cudaMemcpyHostToDevice, st));
     const int n = c->shard_ke - c->shard_kb;
     if (n <= 0) { out_lr[0] = 0.0; out_lr[1] = 0.0; return KDEJS_OK; }     // this rank owns no rows
@@ -1296,7 +1355,7 @@ int kdejs_band_minmax_dev(int device, const double *a_dev, int64_t na, const dou
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     OKR(acquire_scratch(*c, st));
-    Slot &sl = c->slot;
+    Slot &sl = c->S();
     WaveDesc wd;
     memset(&wd, 0, sizeof wd);
     wd.raw[0] = RawSet{a_dev, na};
@@ -1329,7 +1388,7 @@ int kdejs_band_sort_dev(int device, const double *a_dev, int64_t na, const doubl
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     OKR(acquire_scratch(*c, st));
-    Slot &sl = c->slot;
+    Slot &sl = c->S();
     GridGeom g = make_geom(p);
     const BandDims d = band_dims(g);
     OKR(sl.rstat.ensure(sizeof(RawStat) * kMaxWaveSets));
@@ -1401,7 +1460,7 @@ int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int r
     std::lock_guard<std::mutex> lk(c->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     OKR(acquire_scratch(*c, st));
-    Slot &sl = c->slot;
+    Slot &sl = c->S();
     GridGeom g = make_geom(p);
     const BandDims d = band_dims(g);
     // every rank's row starts: world x 2 x (C + 1) u32, a strided device -> host copy
@@ -1416,12 +1475,12 @@ int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int r
     if (g.use_moments == 1 && ntot[0] + ntot[1] < (int64_t)128 * 2 * d.ncells) g.use_moments = 0;
     *out_use_moments = g.use_moments ? 1 : 0;
     OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
-    OKR(c->misc.ensure(64 + sizeof(double) * (size_t)g.NT));
+    OKR(c->S().misc.ensure(64 + sizeof(double) * (size_t)g.NT));
     k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, 0, d.ncells, sl.cellstart.as<uint32_t>());
     WaveDesc wd;
     memset(&wd, 0, sizeof wd);
     wd.n_sets = 2;
-    double *d_cw = c->misc.as<double>() + 8;
+    double *d_cw = c->S().misc.as<double>() + 8;
     k_tile_colwork<<<g.NT, 128, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_cw);
     c->launches += 2;
     CU(cudaGetLastError());
@@ -1447,7 +1506,7 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     OKR(acquire_scratch(*c, st));
     c->band_valid = false;
-    Slot &sl = c->slot;
+    Slot &sl = c->S();
     GridGeom g = make_geom(p);
     const BandDims d = band_dims(g);
     if (ty_begin < 0 || ty_end > g.NT || ty_begin > ty_end) return fail(KDEJS_ERR_ARG, "bad tile-column range");
@@ -1456,12 +1515,12 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
     g.tile_col_end = ty_end;
     OKR(sl.rstat.ensure(sizeof(RawStat) * kMaxWaveSets));
     OKR(sl.tilesum.ensure(2 * (size_t)g.NT * g.NT * sizeof(double)));
-    OKR(c->misc.ensure(64));
+    OKR(c->S().misc.ensure(64));
     k_band_fold_stats<<<1, 32, 0, st>>>(reinterpret_cast<const RawStat *>(stats_all_dev), world, sl.rstat.as<RawStat>());
     c->launches++;
     if (ty_begin == ty_end) {                       // this rank owns no tile column: zero partial normalisers
         CU(cudaMemsetAsync(out_norm_dev, 0, 16, st));
-        c->band_geom = g; c->band_ty0 = ty_begin; c->band_ty1 = ty_end; c->band_valid = true;
+        c->band_geom = g; c->band_ty0 = ty_begin; c->band_ty1 = ty_end; c->band_slot = c->cur; c->band_valid = true;
         return release_scratch(*c, st, false);
     }
     const bool fast32 = (p.algo == KDEJS_ALGO_BINNED32) && g.q_shift > 0;
@@ -1492,7 +1551,7 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
         k_band_norm_totals<<<1, kJsThreads, 0, st>>>(sl.tilesum.as<double>(), g.NT, ty_begin, ty_end, out_norm_dev);
     }
     CU(cudaGetLastError());
-    c->band_geom = g; c->band_ty0 = ty_begin; c->band_ty1 = ty_end; c->band_valid = true;
+    c->band_geom = g; c->band_ty0 = ty_begin; c->band_ty1 = ty_end; c->band_slot = c->cur; c->band_valid = true;
     return release_scratch(*c, st, false);
 }
 
@@ -1503,10 +1562,10 @@ int kdejs_band_phase2_dev(int device, const double *norms_all_dev, int world, do
     std::lock_guard<std::mutex> lk(c->mu);
     if (!c->band_valid) return fail(KDEJS_ERR_ARG, "kdejs_band_phase2_dev called without a successful phase 1");
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
-    OKR(acquire_scratch(*c, st));
-    Slot &sl = c->slot;
+    OKR(acquire_scratch(*c, st, c->band_slot));
+    Slot &sl = c->S();
     const GridGeom &g = c->band_geom;
-    double *d_tot = c->misc.as<double>();
+    double *d_tot = c->S().misc.as<double>();
     k_band_fold_norms<<<1, 32, 0, st>>>(norms_all_dev, world, d_tot);
     c->launches++;
     if (c->band_ty0 == c->band_ty1) {
@@ -1595,10 +1654,10 @@ int kdejs_loop_peak(int device, int which, double *pair_tests_per_s) {
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     OKR(acquire_scratch(*c, c->s_compute));
-    OKR(c->misc.ensure(64 + 1024 * 16 + 1024 * 8));
-    double *sink = c->misc.as<double>();
-    double2 *pts = reinterpret_cast<double2 *>(c->misc.as<char>() + 64);
-    uint2 *ptsq = reinterpret_cast<uint2 *>(c->misc.as<char>() + 64 + 1024 * 16);
+    OKR(c->S().misc.ensure(64 + 1024 * 16 + 1024 * 8));
+    double *sink = c->S().misc.as<double>();
+    double2 *pts = reinterpret_cast<double2 *>(c->S().misc.as<char>() + 64);
+    uint2 *ptsq = reinterpret_cast<uint2 *>(c->S().misc.as<char>() + 64 + 1024 * 16);
     std::vector<double2> hp(1024);
     std::vector<uint2> hq(1024);
     for (int i = 0; i < 1024; ++i) {
@@ -1636,7 +1695,7 @@ int kdejs_peak_flops(int device, int which, double *tflops, double *sm_clock_mhz
     Ctx *c;
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
-    OKR(c->misc.ensure(64));
+    OKR(c->S().misc.ensure(64));
     const int blocks = c->sm_count * 8, iters = 1 << 15;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -1644,11 +1703,11 @@ int kdejs_peak_flops(int device, int which, double *tflops, double *sm_clock_mhz
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         CU(cudaEventRecord(e0, c->s_compute));
-        if (which == 0) k_peak<0><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
-        else if (which == 1) k_peak<1><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
-        else if (which == 2) k_peak<2><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
-        else if (which == 3) k_peak<3><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
-        else k_peak<4><<<blocks, 256, 0, c->s_compute>>>(iters, c->misc.as<float>(), c->misc.as<double>());
+        if (which == 0) k_peak<0><<<blocks, 256, 0, c->s_compute>>>(iters, c->S().misc.as<float>(), c->S().misc.as<double>());
+        else if (which == 1) k_peak<1><<<blocks, 256, 0, c->s_compute>>>(iters, c->S().misc.as<float>(), c->S().misc.as<double>());
+        else if (which == 2) k_peak<2><<<blocks, 256, 0, c->s_compute>>>(iters, c->S().misc.as<float>(), c->S().misc.as<double>());
+        else if (which == 3) k_peak<3><<<blocks, 256, 0, c->s_compute>>>(iters, c->S().misc.as<float>(), c->S().misc.as<double>());
+        else k_peak<4><<<blocks, 256, 0, c->s_compute>>>(iters, c->S().misc.as<float>(), c->S().misc.as<double>());
         CU(cudaEventRecord(e1, c->s_compute));
         CU(cudaEventSynchronize(e1));
         float ms = 0.f;

@@ -1099,52 +1099,73 @@ __device__ __forceinline__ void flush32(float (&a32)[kTile][kTile], double (&a64
         for (int j = 0; j < kTile; ++j) { a64[i][j] += (double)a32[i][j]; a32[i][j] = 0.f; }
 }
 
-// One walk of a warp over the flattened runs of its tile (phase B).  wstart / wlen: the tile's non-empty runs in
-// processing order (per-warp shared memory); returns the lane's 16 partial sums in `tot` (fp64).
+// One walk of a warp over its flattened runs of a tile.  wstart / wlen: the warp's non-empty runs in processing
+// order (per-warp shared memory): first candidate of the warp's first 32-candidate chunk in the run, and how many
+// candidates the run holds from there on; the warp takes every (STRIDE/32)-th chunk (phase B: all of them, phase
+// A: the four warps of the block interleave).  Returns the lane's 16 partial sums in `tot` (fp64).
+template <int STRIDE, bool THREE_LEVEL>
 __device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const uint32_t *wstart, const uint32_t *wlen,
                                             const int nruns, const uint32_t total_trips, const int lane,
                                             const uint32_t gxq, const uint32_t gyq, const float unit, const float f1,
                                             const float f2, const float f3, const float one,
                                             double (&tot)[kTile][kTile]) {
-    float lo[kTile][kTile], hi[kTile][kTile];
+    float lo[kTile][kTile], hi[kTile][kTile], top[kTile][kTile];
 #pragma unroll
     for (int i = 0; i < kTile; ++i)
 #pragma unroll
-        for (int j = 0; j < kTile; ++j) { lo[i][j] = 0.f; hi[i][j] = 0.f; }
+        for (int j = 0; j < kTile; ++j) { lo[i][j] = 0.f; hi[i][j] = 0.f; top[i][j] = 0.f; }
     const uint2 far = make_uint2(gxq - kFarQ, gyq);
-    // fetch side: (run, trip within run) of the next trip to load
+    // fetch side: a running pointer into the current run, the lane's remaining candidates in it and the run's
+    // remaining trips; run boundaries cost a few warp-uniform instructions, a trip five
     int r_pf = 0;
-    uint32_t t_pf = 0u, cur_len = 0u, cur_trips = 0u;
-    const uint2 *cur_ptr = pts;
-    if (nruns > 0) { cur_len = wlen[0]; cur_ptr = pts + wstart[0]; cur_trips = (cur_len + 31u) >> 5; }
+    int rem = 0;                                  // candidates of the current run at or after this lane's next one
+    uint32_t trips_left = 0u;
+    const uint2 *nxt = pts;
+    if (nruns > 0) { rem = (int)wlen[0] - lane; nxt = pts + wstart[0] + lane; trips_left = (wlen[0] + STRIDE - 1u) / STRIDE; }
     auto fetch = [&]() -> uint2 {
         uint2 v = far;
         if (r_pf < nruns) {                                   // warp-uniform
-            const uint32_t j = t_pf * 32u + (uint32_t)lane;
-            if (j < cur_len) v = cur_ptr[j];
-            if (++t_pf == cur_trips) {
+            if (rem > 0) v = *nxt;
+            nxt += STRIDE;
+            rem -= STRIDE;
+            if (--trips_left == 0u) {
                 ++r_pf;
-                t_pf = 0u;
-                if (r_pf < nruns) { cur_len = wlen[r_pf]; cur_ptr = pts + wstart[r_pf]; cur_trips = (cur_len + 31u) >> 5; }
+                if (r_pf < nruns) {
+                    const uint32_t len = wlen[r_pf];
+                    rem = (int)len - lane;
+                    nxt = pts + wstart[r_pf] + lane;
+                    trips_left = (len + STRIDE - 1u) / STRIDE;
+                }
             }
         }
         return v;
     };
-    uint2 q0 = fetch(), q1 = fetch(), q2 = fetch();
+    // three trips in flight; the loop is unrolled by three so the queue is renamed, not moved
     static_assert(kPrefetch == 3, "the register queue below holds three trips");
-    int budget = kFoldTrips;
-    for (uint32_t t = 0; t < total_trips; ++t) {
-        const uint2 p = q0;
-        q0 = q1; q1 = q2;
-        q2 = fetch();
+    uint2 q0 = fetch(), q1 = fetch(), q2 = fetch();
+    int budget = kFoldTrips, budget2 = kFoldTrips;
+    auto use = [&](const uint2 p) {
         accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, one, lo);
-        if (--budget == 0) { fold32(lo, hi); budget = kFoldTrips; }
+        if (--budget == 0) {
+            fold32(lo, hi);
+            budget = kFoldTrips;
+            if (THREE_LEVEL && --budget2 == 0) { fold32(hi, top); budget2 = kFoldTrips; }
+        }
+    };
+    uint32_t t = 0;
+    for (; t + 3 <= total_trips; t += 3) {
+        use(q0); q0 = fetch();
+        use(q1); q1 = fetch();
+        use(q2); q2 = fetch();
     }
+    if (t < total_trips) use(q0);
+    if (t + 1 < total_trips) use(q1);
     fold32(lo, hi);
+    if (THREE_LEVEL) fold32(hi, top);
 #pragma unroll
     for (int i = 0; i < kTile; ++i)
 #pragma unroll
-        for (int j = 0; j < kTile; ++j) tot[i][j] = (double)hi[i][j];
+        for (int j = 0; j < kTile; ++j) tot[i][j] = (double)(THREE_LEVEL ? top[i][j] : hi[i][j]);
 }
 
 template <bool MOMENTS>
@@ -1238,47 +1259,37 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
             if (lane == 0) { s_rows = rows; s_cy0 = tc.cy_lo; }
         }
         __syncthreads();
-        float lo[kTile][kTile], hi[kTile][kTile], top[kTile][kTile];
-#pragma unroll
-        for (int i = 0; i < kTile; ++i)
-#pragma unroll
-            for (int j = 0; j < kTile; ++j) { lo[i][j] = 0.f; hi[i][j] = 0.f; top[i][j] = 0.f; }
         const uint2 *__restrict__ pts = sorted_q + sd.off;
         const uint32_t gtot = s_cpre[2 * kMaxRows];         // 32-candidate chunks of the tile, dealt round-robin to the warps
-        const uint32_t my_trips = (uint32_t)warp < gtot ? (gtot - (uint32_t)warp + 3u) >> 2 : 0u;
-        const uint2 far = make_uint2(gxq - kFarQ, gyq);
-        uint32_t g_pf = (uint32_t)warp;
-        int e_pf = 0;
-        auto fetch = [&]() -> uint2 {
-            uint2 v = far;
-            if (g_pf < gtot) {                                // warp-uniform
-                while (g_pf >= s_cpre[e_pf + 1]) ++e_pf;
-                const uint32_t j = (g_pf - s_cpre[e_pf]) * 32u + (uint32_t)lane;
-                if (j < s_len[e_pf]) v = pts[s_rs[e_pf] + j];
-                g_pf += kDensThreads / 32;
+        // this warp's share of every run: chunks first, first + 4, ... with first = (warp - chunks before the run) mod 4;
+        // compacted into the warp's own run list (two run slots per lane: left / right of the moment cells)
+        uint32_t my_trips = 0u;
+        int my_runs = 0;
+        {
+            uint32_t *ws = s_wstart[warp], *wl = s_wlen[warp];
+            uint32_t st2[2], ln2[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int e = 2 * lane + k;
+                const uint32_t len = s_len[e], nch = (len + 31u) >> 5;
+                const uint32_t first = ((uint32_t)warp - s_cpre[e]) & 3u;
+                st2[k] = s_rs[e] + first * 32u;
+                ln2[k] = first < nch ? len - first * 32u : 0u;
+                my_trips += (ln2[k] + kDensThreads - 1u) / kDensThreads;
             }
-            return v;
-        };
-        uint2 q0 = fetch(), q1 = fetch(), q2 = fetch();
-        int budget = kFoldTrips, budget2 = kFoldTrips;
-        for (uint32_t t = 0; t < my_trips; ++t) {
-            const uint2 p = q0;
-            q0 = q1; q1 = q2;
-            q2 = fetch();
-            accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, 1.0f, lo);
-            if (--budget == 0) {
-                fold32(lo, hi);
-                budget = kFoldTrips;
-                if (--budget2 == 0) { fold32(hi, top); budget2 = kFoldTrips; }
-            }
+            const unsigned m0 = __ballot_sync(0xffffffffu, ln2[0] > 0u), m1 = __ballot_sync(0xffffffffu, ln2[1] > 0u);
+            const unsigned lt = (1u << lane) - 1u;
+            const int k0 = __popc(m0 & lt) + __popc(m1 & lt);
+            if (ln2[0] > 0u) { ws[k0] = st2[0]; wl[k0] = ln2[0]; }
+            if (ln2[1] > 0u) { const int k1 = k0 + (ln2[0] > 0u ? 1 : 0); ws[k1] = st2[1]; wl[k1] = ln2[1]; }
+            my_runs = __popc(m0) + __popc(m1);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) my_trips += __shfl_xor_sync(0xffffffffu, my_trips, o);
+            __syncwarp();
         }
-        fold32(lo, hi);
-        fold32(hi, top);
         double acc64[kTile][kTile];
-#pragma unroll
-        for (int i = 0; i < kTile; ++i)
-#pragma unroll
-            for (int j = 0; j < kTile; ++j) acc64[i][j] = (double)top[i][j];
+        walk_tile32<kDensThreads, true>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, gxq, gyq, unit,
+                                        f1, f2, f3, 1.0f, acc64);
         uint32_t ncand = gtot * 32u;                          // upper bound of the candidates (last chunks are ragged)
         if (MOMENTS) {
             const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
@@ -1384,7 +1395,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
             double acc64[kTile][kTile];
-            walk_tile32(pts, wstart, wlen, nruns, total_trips, lane, gxq, gyq, unit, f1, f2, f3, one, acc64);
+            walk_tile32<32, false>(pts, wstart, wlen, nruns, total_trips, lane, gxq, gyq, unit, f1, f2, f3, one, acc64);
             if (MOMENTS) {
                 const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
                 for (int r = 0; r < rows; ++r) {

@@ -179,8 +179,10 @@ def row_sharded_discrepancy(df1, df2, gamma=1.0, eps=1e-12, log=False, *, resolu
 # Band mode: the points are sharded too (C ABI: kdejs_band_*, include/kdejs.h)
 
 class _GpuBandOps:
-    """The device steps of band mode on this rank's GPU, all enqueued on torch's current stream (so they are
-    ordered with the NCCL collectives torch issues in between without any host synchronisation)."""
+    """The device steps of band mode on this rank's GPU.  Everything -- the library's kernels, torch's own copies and
+    the NCCL collectives torch issues in between -- runs on ONE dedicated torch stream (`run()` makes it current), so
+    the steps are ordered without any host synchronisation.  It must be a real stream: torch's default stream has
+    the NULL handle, which the C ABI reads as "the library's own stream", and that one is not ordered with torch."""
 
     def __init__(self, device, common):
         import torch
@@ -191,9 +193,16 @@ class _GpuBandOps:
         nat.check(self.L.kdejs_band_geometry(common[0], common[1], common[5], geo))
         self.C, self.NT, self.block_u32 = geo[0], geo[1], geo[2]
         self.tdev = torch.device("cuda", self.dev)
+        self.stream = _band_stream(torch, self.tdev)
+
+    def run(self):
+        """Context manager: inputs produced on the caller's current stream are waited for, then the band stream is
+        made current for everything inside."""
+        self.stream.wait_stream(self.torch.cuda.current_stream(self.tdev))
+        return self.torch.cuda.stream(self.stream)
 
     def _stream(self):
-        return self.torch.cuda.current_stream(self.tdev).cuda_stream
+        return self.stream.cuda_stream
 
     def to_device(self, x, name):
         torch = self.torch
@@ -245,6 +254,17 @@ class _GpuBandOps:
 
     def to_host(self, t):
         return t.cpu().numpy()
+
+
+_BAND_STREAMS = {}
+
+
+def _band_stream(torch, tdev):
+    """One long-lived non-default stream per device for band mode (creating a stream per call costs ~10 us)."""
+    key = (tdev.type, tdev.index)
+    if key not in _BAND_STREAMS:
+        _BAND_STREAMS[key] = torch.cuda.Stream(tdev)
+    return _BAND_STREAMS[key]
 
 
 def band_cuts(colwork, world):
@@ -307,6 +327,11 @@ def band_sharded_discrepancy(a_slice, b_slice, gamma=1.0, eps=1e-12, log=False, 
     common = kd._common(resolution, bandwidth, gamma, eps, log, "epanechnikov", algo)
     if ops is None:
         ops = _GpuBandOps(dev, common)
+    with ops.run():
+        return _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world, info)
+
+
+def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world, info):
     a, b = ops.to_device(a_slice, "df1 slice"), ops.to_device(b_slice, "df2 slice")
     na = a.shape[0]
     stats_all = _gather_cat(ops.minmax(a, b), group, world)                    # joint scaler: 10 doubles per rank

@@ -24,6 +24,11 @@ def virtual_band(pk, a, b, world, gamma, eps, log=False, resolution=100, bandwid
 
     common = pk.KDE_distance._common(resolution, bandwidth, gamma, eps, log, "epanechnikov", algo)
     ops = D._GpuBandOps(0, common)
+    with ops.run():
+        return _virtual_band(torch, D, ops, a, b, world, resolution, bandwidth, cuts)
+
+
+def _virtual_band(torch, D, ops, a, b, world, resolution, bandwidth, cuts):
     sl = lambda x, r: x[len(x) * r // world: len(x) * (r + 1) // world]
     A = [ops.to_device(np.ascontiguousarray(sl(a, r)), "a") for r in range(world)]
     B = [ops.to_device(np.ascontiguousarray(sl(b, r)), "b") for r in range(world)]
@@ -75,11 +80,12 @@ def test_band_mode_equals_single_gpu(pk, world, algo):
     assert abs(js - want) <= (1e-10 if algo == "binned" else 2e-7) * want
 
 
-def test_band_mode_fine_grid_with_moment_cells_and_empty_bands(pk):
+def test_band_mode_fine_grid_with_moment_cells_and_empty_bands(pk, monkeypatch):
     """R = 1024 (128 x 128 cells, moment cells), eight bands of a concentrated cloud: some bands are thin, the
     explicit cuts below also leave two ranks without any tile column."""
     from oracle import workloads as wl
 
+    monkeypatch.setenv("KDEJS_MOMENTS", "1")       # 400 k points are below the points-per-cell rule: force the path
     a, b = wl.c5_inputs(400_000, seed=3)
     full = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=1024)
     js, cuts, rows, use_m = virtual_band(pk, a, b, 8, 0.25, 0.0, resolution=1024)

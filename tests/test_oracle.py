@@ -149,3 +149,40 @@ def test_cell_moment_identity_used_by_the_fine_grid_path():
         u, v = (gx - cx) / h, (gy - cy) / h
         via_moments = ((n - sxx) + u * (2 * sx - n * u)) - (syy - v * (2 * sy - n * v))
         assert abs(via_moments - direct) <= 1e-12 * direct
+
+
+def test_raw_reference_gap_where_the_callers_use_it():
+    """tests/golden/raw_gap_study.json (oracle/raw_gap_study.py): 200 synthetic simulations against the example
+    target at the reference's own grid and its two production call sites, scored by the UNMODIFIED reference and by
+    the exact oracle.  Pins what the ball-tree residue does to the decisions downstream."""
+    import json
+    import os
+
+    from conftest import GOLDEN_DIR
+    from oracle import kde_oracle as ko, workloads as wl
+
+    with open(os.path.join(GOLDEN_DIR, "raw_gap_study.json")) as f:
+        doc = json.load(f)
+    s = doc["summary"]
+    bolfi, grid = s["bolfi_g025"], s["gridsearch_g1e-12_log"]
+    # gamma = 0.25 (poppunk_mod.py:373, pairwise_2D_distance.py:54): a near-constant shift, decisions unchanged
+    assert bolfi["n"] == 200 and bolfi["argmin_agrees"] and bolfi["top10_overlap"] == 10
+    assert bolfi["spearman_rho"] > 0.99999 and bolfi["pairwise_order_flips"] <= 4
+    assert 9e-5 < bolfi["rel_gap_min"] and bolfi["rel_gap_max"] < 7.5e-4
+    assert abs(bolfi["log_d_shift_mean"] + 4.08e-4) < 1e-5 and bolfi["log_d_shift_std"] < 2e-4
+    # gamma = 1e-12, log=True (distance_to_gridsearch.py:50): the reference's value is residue-dominated; the
+    # ranking and the arg-min it keeps are NOT those of its own exact arithmetic
+    assert not grid["argmin_agrees"] and grid["top10_overlap"] == 3
+    assert 0.11 < grid["rel_gap_max"] < 0.12 and 0.98 < grid["spearman_rho"] < 0.99
+    assert grid["pairwise_order_flips"] == 1010 and grid["pairs"] == 19900
+    T = wl.example_target()
+    rows = {r["seed"]: r for r in doc["rows"]}
+    for seed in (0, 79, 184):
+        S = wl.sim_batch_member(seed)
+        assert ko.discrepancy(T, S, 0.25, 0.0, False) == pytest.approx(rows[seed]["bolfi_g025"]["exact"], rel=1e-12)
+        assert ko.discrepancy(T, S, 1e-12, 1e-12, True) == pytest.approx(
+            rows[seed]["gridsearch_g1e-12_log"]["exact"], rel=1e-12)
+    if ref_shim.available():
+        S = wl.sim_batch_member(119)
+        assert float(ref_shim.js(T.copy(), S.copy(), 1e-12, 1e-12, True)) == pytest.approx(
+            rows[119]["gridsearch_g1e-12_log"]["ref_raw"], rel=1e-12)

@@ -1,49 +1,83 @@
-"""torchrun --nproc-per-node N tools/mgpu_check.py : NCCL-backed checks of distributed.py on real GPUs."""
-import os
-import sys
-import time
-
+"""Multi-GPU check over NCCL (one process per GPU):
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/mgpu_check.py
+MGPU_SMALL=1 keeps it to the small parity cases (tests/test_nccl_gpu.py); otherwise config C5 is timed too."""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 import torch.distributed as dist
 
-rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 import poppunk_mod_b200 as pk
-from oracle import workloads as wl
+from oracle import kde_oracle as ko, workloads as wl
 from poppunk_mod_b200 import distributed as D
 
+cut = lambda x: x[len(x) * rank // world: len(x) * (rank + 1) // world]
+
+# batches: items dealt to ranks, scalars gathered
 obs = wl.synthetic_target(50_000)
 sims = [wl.sim_batch_member(s, n=40_000) for s in range(13)]
 got = D.batch_discrepancy_sharded(obs, sims, 0.25, 0.0, False, resolution=128)
 want = pk.KDE_JS_divergence_batch(obs, sims, 0.25, 0.0, False, resolution=128)
 assert np.array_equal(got, want), (got, want)
 
-# config C5 shape at reduced and full scale: one evaluation, node rows split over the ranks
-for n, R in ((1_000_000, 512), (int(os.environ.get("C5_N", 10_000_000)), 1024)):
-    pool = pk._native.PinnedPool()                      # page-locked inputs: H2D at PCIe speed
-    a = pool.empty((n, 2)); a[:] = wl.synthetic_target(n, seed=11)
-    b = pool.empty((n, 2)); b[:] = wl.sim_S(5, 1800, 0.36, n=n)
-    D.row_sharded_discrepancy(a, b, 0.25, 0.0, resolution=R)          # warm-up (scratch allocation)
+# one evaluation, points sharded (band mode) against the single GPU and the oracle; both culled kernels
+a, b = wl.synthetic_target(200_000, seed=3), wl.sim_S(8, 2100, 0.31, n=150_000)
+for algo in ("binned", "binned32"):
+    for R in (100, 256):
+        info = {}
+        js = D.band_sharded_discrepancy(cut(a), cut(b), 0.25, 0.0, resolution=R, algo=algo, info=info)
+        full = pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R, algo=algo)
+        assert abs(js - full) <= 1e-12 * full, (algo, R, js, full)
+        if rank == 0:
+            o = ko.discrepancy(a, b, 0.25, 0.0, resolution=R)
+            assert abs(js - o) <= (1e-10 if algo == "binned" else 2e-7) * o, (algo, R, js, o)
+            print(f"band mode {algo} R={R}: {js!r} single {full!r} oracle {o!r} band {info}", flush=True)
+# the older replicate-and-sort variant still agrees
+js_old = D.row_sharded_discrepancy(cut(a), cut(b), 0.25, 0.0, resolution=256, sliced=True, gather_all=True)
+assert abs(js_old - pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=256)) <= 1e-12 * js_old
+# infinity in one rank's slice raises on every rank
+bad = cut(b).copy()
+if rank == world - 1:
+    bad[3, 1] = np.inf
+try:
+    D.band_sharded_discrepancy(cut(a), bad, 0.25, 0.0, resolution=100)
+    raise SystemExit("infinity was not reported")
+except ValueError:
+    pass
+
+if os.environ.get("MGPU_SMALL", "0") != "1":
+    n = int(os.environ.get("C5_N", 10_000_000))
+    A, B = wl.c5_inputs(n, seed=5)
+    pool = pk._native.PinnedPool()
+    ha = pool.empty(cut(A).shape); ha[:] = cut(A)
+    hb = pool.empty(cut(B).shape); hb[:] = cut(B)
+    da, db = torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
+    for name, x, y in (("host slices", ha, hb), ("device slices", da, db)):
+        for algo in ("binned", "binned32"):
+            ts = []
+            for it in range(4):
+                torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+                js = D.band_sharded_discrepancy(x, y, 0.25, 0.0, resolution=1024, algo=algo)
+                torch.cuda.synchronize(); dist.barrier(); ts.append(time.perf_counter() - t0)
+            if rank == 0:
+                print(f"C5 n={n} R=1024 over {world} ranks, {name}, {algo}: {js!r} in {1e3*min(ts[1:]):.2f} ms", flush=True)
+    t0 = time.perf_counter()
+    js_g = D.row_sharded_discrepancy(ha, hb, 0.25, 0.0, resolution=1024, sliced=True, gather_all=True)
+    js_g = D.row_sharded_discrepancy(ha, hb, 0.25, 0.0, resolution=1024, sliced=True, gather_all=True)
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-    js = D.row_sharded_discrepancy(a, b, 0.25, 0.0, resolution=R)
+    js_g = D.row_sharded_discrepancy(ha, hb, 0.25, 0.0, resolution=1024, sliced=True, gather_all=True)
     torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
-    # the same evaluation with the TABLE sharded too: each rank uploads 1/world of the rows, NCCL all-gather
-    ca = [len(a) * r // world for r in range(world + 1)]; cb = [len(b) * r // world for r in range(world + 1)]
-    sa, sb = a[ca[rank]:ca[rank + 1]], b[cb[rank]:cb[rank + 1]]
-    D.row_sharded_discrepancy(sa, sb, 0.25, 0.0, resolution=R, sliced=True)
-    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-    js2 = D.row_sharded_discrepancy(sa, sb, 0.25, 0.0, resolution=R, sliced=True)
-    torch.cuda.synchronize(); dist.barrier(); dt2 = time.perf_counter() - t0
-    assert js2 == js, (js2, js)
     if rank == 0:
-        print(f"   sliced inputs + NCCL all-gather: {dt2*1e3:.1f} ms", flush=True)
-        pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R)
-        t0 = time.perf_counter(); full = pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R); d1 = time.perf_counter() - t0
-        print(f"C5-like n={n} R={R}: sharded over {world} = {js!r} in {dt*1e3:.1f} ms ; single GPU = {full!r} in {d1*1e3:.1f} ms ; rel {abs(js-full)/full:.2e}", flush=True)
-        assert abs(js - full) <= 1e-12 * full
+        print(f"   older variant (all-gather everything, every rank sorts everything): {js_g!r} in {1e3*dt:.2f} ms", flush=True)
+        pa = pool.empty(A.shape); pa[:] = A
+        pb = pool.empty(B.shape); pb[:] = B
+        pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=1024)
+        t0 = time.perf_counter(); full = pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=1024); d1 = time.perf_counter() - t0
+        print(f"   single GPU from pinned host memory: {full!r} in {1e3*d1:.2f} ms ; rel gap {abs(js_g-full)/full:.2e}", flush=True)
 if rank == 0:
     print("mgpu_check ok", flush=True)
+dist.barrier()
 dist.destroy_process_group()
