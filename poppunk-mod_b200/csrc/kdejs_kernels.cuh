@@ -1140,26 +1140,30 @@ __device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const
         }
         return v;
     };
-    // three trips in flight; the loop is unrolled by three so the queue is renamed, not moved
-    static_assert(kPrefetch == 3, "the register queue below holds three trips");
+    // three trips in flight; the loop is unrolled by three so the queue is renamed, not moved; fp32 partial sums are
+    // folded every 15 trips (a level never sums more than 16 terms of its own): no per-trip counter in the hot loop
+    static_assert(kPrefetch == 3 && kFoldTrips == 16, "queue of three, folds every 15 (< 16) trips");
     uint2 q0 = fetch(), q1 = fetch(), q2 = fetch();
-    int budget = kFoldTrips, budget2 = kFoldTrips;
-    auto use = [&](const uint2 p) {
-        accumulate_point32(p, gxq, gyq, unit, f1, f2, f3, one, lo);
-        if (--budget == 0) {
-            fold32(lo, hi);
-            budget = kFoldTrips;
-            if (THREE_LEVEL && --budget2 == 0) { fold32(hi, top); budget2 = kFoldTrips; }
-        }
-    };
     uint32_t t = 0;
-    for (; t + 3 <= total_trips; t += 3) {
-        use(q0); q0 = fetch();
-        use(q1); q1 = fetch();
-        use(q2); q2 = fetch();
+    int folds = kFoldTrips;
+    while (t + 15u <= total_trips) {
+#pragma unroll 1
+        for (int k = 0; k < 5; ++k) {
+            accumulate_point32(q0, gxq, gyq, unit, f1, f2, f3, one, lo); q0 = fetch();
+            accumulate_point32(q1, gxq, gyq, unit, f1, f2, f3, one, lo); q1 = fetch();
+            accumulate_point32(q2, gxq, gyq, unit, f1, f2, f3, one, lo); q2 = fetch();
+        }
+        t += 15u;
+        fold32(lo, hi);
+        if (THREE_LEVEL && --folds == 0) { fold32(hi, top); folds = kFoldTrips; }
     }
-    if (t < total_trips) use(q0);
-    if (t + 1 < total_trips) use(q1);
+    for (; t + 3u <= total_trips; t += 3u) {                   // fewer than 15 trips left
+        accumulate_point32(q0, gxq, gyq, unit, f1, f2, f3, one, lo); q0 = fetch();
+        accumulate_point32(q1, gxq, gyq, unit, f1, f2, f3, one, lo); q1 = fetch();
+        accumulate_point32(q2, gxq, gyq, unit, f1, f2, f3, one, lo); q2 = fetch();
+    }
+    if (t < total_trips) accumulate_point32(q0, gxq, gyq, unit, f1, f2, f3, one, lo);
+    if (t + 1u < total_trips) accumulate_point32(q1, gxq, gyq, unit, f1, f2, f3, one, lo);
     fold32(lo, hi);
     if (THREE_LEVEL) fold32(hi, top);
 #pragma unroll
