@@ -413,8 +413,10 @@ int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
     int nmax = 0;
     int64_t total = 0;
     for (int s = 0; s < wd.n_sets; ++s) { nmax = std::max(nmax, wd.set[s].n); total += wd.set[s].n; }
+    // ... rounded up to a power of two (k_place turns a point's index into its chunk with a shift)
     int64_t per_warp = total / ((int64_t)4 * sm_count * kSortWarps);
-    chw = (int)std::min<int64_t>(std::max<int64_t>((per_warp + 31) / 32 * 32, 512), kMaxChw);
+    chw = 512;
+    while (chw < per_warp && chw < kMaxChw) chw <<= 1;
     nb_max = std::max(1, (int)(((int64_t)nmax + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)));
     return KDEJS_OK;
 }
@@ -534,7 +536,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             for (int s = 0; s < n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
             k_place<<<dim3((nmax + 255) / 256, n_sets), 256, 0, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
-                io.identity_scaler ? 1 : 0, ncells, chw, nb_max, sl.cellid.as<uint16_t>(),
+                io.identity_scaler ? 1 : 0, ncells, 31 - __builtin_clz((unsigned)chw), nb_max, sl.cellid.as<uint16_t>(),
                 sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
                 wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>(),
                 fast32 ? sl.sorted_q.as<uint2>() : nullptr, g);
@@ -543,7 +545,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         if (io.presorted) CU(cudaMemsetAsync(sl.counters.p, 0, kAllCounters * sizeof(unsigned), st));   // k_scan's job otherwise
         if (g.use_moments) {
             KTimer t(c, 7, st);
-            k_cell_moments<<<dim3((ncells + 3) / 4, n_sets), 128, 0, st>>>(
+            k_cell_moments<<<dim3(ncells, n_sets), kMomentThreads, 0, st>>>(
                 wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>());
         }
         if (io.balance_world > 0) {
@@ -1530,7 +1532,7 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
     OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
     const int c_lo = cy_lo * d.C, c_hi = (cy_hi + 1) * d.C;
     k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, c_lo, c_hi, sl.cellstart.as<uint32_t>());
-    k_band_merge<<<dim3((c_hi - c_lo + 3) / 4, 2), 128, 0, st>>>(
+    k_band_merge<<<dim3(c_hi - c_lo, 2, kMergeSplit), 256, 0, st>>>(
         reinterpret_cast<const double2 *>(stage_a_dev), reinterpret_cast<const double2 *>(stage_b_dev), blocks_all_dev,
         world, d.block_u32, g, cy_lo, cy_hi, sl.cellstart.as<uint32_t>(), na, sl.sorted.as<double2>(),
         fast32 ? sl.sorted_q.as<uint2>() : nullptr);

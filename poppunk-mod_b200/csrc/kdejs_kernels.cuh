@@ -237,7 +237,11 @@ __device__ __forceinline__ void zero_u16(uint16_t *p, int n) {
 }
 
 constexpr int kSortUnroll = 4;        // independent 32-point groups a warp keeps in flight
-constexpr int kMaxChw = 16352;        // points per warp sub-chunk: 4 warps * kMaxChw < 65536 (u16 counters)
+#ifndef KDEJS_MATCH_BALLOTS
+#define KDEJS_MATCH_BALLOTS 0
+#endif
+constexpr bool kMatchByBallots = KDEJS_MATCH_BALLOTS != 0;
+constexpr int kMaxChw = 8192;         // points per warp sub-chunk, a power of two: 4 warps * kMaxChw < 65536 (u16 counters)
 
 // k_scale_count: grid (nb_max, n_sets), kSortThreads threads, dyn smem kSortWarps*ncells u16 (a warp's
 // sub-chunk holds at most kMaxChw points, so 16-bit counters cannot overflow).
@@ -258,6 +262,7 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
     const SetDesc sd = wd.set[blockIdx.y];
     if ((int)blockIdx.x >= sd.nb) return;
     const int ncells = C * C;
+    const int cell_bits = 32 - __clz(max(ncells - 1, 1));
     zero_u16(s_hist, kSortWarps * ncells);
     __syncthreads();
     const Scaler sc = make_scaler(rstat, sd, identity_scaler);
@@ -288,8 +293,21 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
             uint32_t before = 0u;
             int leader = lane;
             unsigned m = 0u;
+            if (kMatchByBallots) {
+                // lanes of this group that fall into the same cell: one ballot per bit of the cell id instead of
+                // one MATCH.ANY.  Measured twice (rounds 1 and 2): slower (k_scale_count 2.06 -> 2.92 us per
+                // evaluation) although a third of the kernel's stall samples sit right behind the MATCH -- kept
+                // only as a compile-time experiment (-DKDEJS_MATCH_BALLOTS=1)
+                m = act;
+                for (int bit = 0; bit < cell_bits; ++bit) {
+                    const unsigned v = __ballot_sync(0xffffffffu, (cell >> bit) & 1);
+                    m &= ((cell >> bit) & 1) ? v : ~v;
+                }
+                if (!valid) m = 0u;
+            } else if (valid) {
+                m = __match_any_sync(act, cell);
+            }
             if (valid) {
-                m = __match_any_sync(act, cell);      // one MATCH beats twelve ballots here: the kernel is ALU-bound
                 leader = __ffs(m) - 1;
                 if (lane == leader) { before = hw[cell]; hw[cell] = (uint16_t)(before + __popc(m)); }
             }
@@ -471,24 +489,26 @@ __device__ __forceinline__ uint32_t quantise(double x, const GridGeom &g) {
 // arithmetic as k_scale_count and written straight to that slot.  No shared memory, no ranking.
 __global__ void __launch_bounds__(256)
 k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, int log_flag, double eps,
-        int identity_scaler, int ncells, int chw, int nb_max, const uint16_t *__restrict__ cellid,
+        int identity_scaler, int ncells, int chw_log2, int nb_max, const uint16_t *__restrict__ cellid,
         const uint16_t *__restrict__ rank16, const uint16_t *__restrict__ warpprefix,
         const uint32_t *__restrict__ blockbase, const uint32_t *__restrict__ cellstart,
         double2 *__restrict__ sorted, uint2 *__restrict__ sorted_q, const GridGeom g) {
+    __shared__ Scaler s_sc;                 // two fp64 divisions: once per block, not once per point
     const SetDesc sd = wd.set[blockIdx.y];
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= sd.n) return;
+    if (threadIdx.x == 0) s_sc = make_scaler(rstat, sd, identity_scaler);
+    __syncthreads();
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;          // a set holds < 2^29 points (check_set)
+    if (j >= (uint32_t)sd.n) return;
     const double2 v = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p)[j];
     const int cell = cellid[sd.off + j];
     const uint32_t rank = rank16[sd.off + j];
-    const int64_t wchunk = j / chw;                       // global warp sub-chunk index of the point
+    const uint32_t wchunk = j >> chw_log2;                // global warp sub-chunk index of the point (chw is a power of two)
     const size_t row = (size_t)blockIdx.y * nb_max + (size_t)(wchunk / kSortWarps);
     // cellstart is null when k_scan_narrow left absolute positions in blockbase
     const uint32_t pos = (cellstart ? cellstart[(size_t)blockIdx.y * (ncells + 1) + cell] : 0u) +
                          blockbase[row * ncells + cell] +
                          warpprefix[(row * kSortWarps + (size_t)(wchunk % kSortWarps)) * ncells + cell] + rank;
-    const Scaler sc = make_scaler(rstat, sd, identity_scaler);
-    const double2 X = scale_point(v, sc, log_flag, eps, identity_scaler);
+    const double2 X = scale_point(v, s_sc, log_flag, eps, identity_scaler);
     sorted[sd.off + pos] = X;
     if (sorted_q) sorted_q[sd.off + pos] = make_uint2(quantise(X.x, g), quantise(X.y, g));
 }
@@ -734,30 +754,43 @@ __device__ __forceinline__ double cell_centre(const GridGeom &g, int c) {
     return g.cell_x0 + ((double)c + 0.5) * g.cell_w;
 }
 
-// k_cell_moments: grid (ceil(ncells/4), n_sets), 128 threads, one warp per cell: the five moments
-// accumulate_cell() needs, summed lane-strided and folded with a fixed butterfly (bit-reproducible).
-__global__ void __launch_bounds__(128)
+// k_cell_moments: grid (ncells, n_sets), 256 threads, one block per cell: the five moments accumulate_cell()
+// needs, summed thread-strided, folded with a fixed butterfly per warp and then warp after warp
+// (bit-reproducible).  A block and not a warp per cell: real clouds put ~1 % of a 10 M-point set into its fullest
+// cell, and one warp walking 100 k points alone was 0.6 ms -- a fixed cost that did not shrink when the
+// evaluation was spread over more GPUs.
+constexpr int kMomentThreads = 256;
+__global__ void __launch_bounds__(kMomentThreads)
 k_cell_moments(const __grid_constant__ WaveDesc wd, const GridGeom g, const double2 *__restrict__ sorted,
                const uint32_t *__restrict__ cellstart, double *__restrict__ moments) {
-    const int set = blockIdx.y, lane = threadIdx.x & 31;
+    __shared__ double s_part[kMomentThreads / 32][4];
+    const int set = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncells = g.C * g.C;
-    const int cell = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (cell >= ncells) return;
+    const int cell = blockIdx.x;
     const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
     const uint32_t b = cs[cell], e = cs[cell + 1];
+    double *m = moments + ((size_t)set * ncells + cell) * kMomentDoubles;
+    if (e == b) {                                          // block-uniform
+        if (threadIdx.x < kMomentDoubles) m[threadIdx.x] = 0.0;
+        return;
+    }
     const double cx = cell_centre(g, cell % g.C), cy = cell_centre(g, cell / g.C);
     const double2 *__restrict__ pts = sorted + wd.set[set].off;
     double sx = 0.0, sy = 0.0, sxx = 0.0, syy = 0.0;
-    for (uint32_t k = b + lane; k < e; k += 32) {
+    for (uint32_t k = b + threadIdx.x; k < e; k += kMomentThreads) {
         const double2 p = pts[k];
         const double dx = (p.x - cx) * g.inv_h, dy = (p.y - cy) * g.inv_h;
         sx += dx; sy += dy;
         sxx = fma(dx, dx, sxx); syy = fma(dy, dy, syy);
     }
     sx = warp_sum(sx); sy = warp_sum(sy); sxx = warp_sum(sxx); syy = warp_sum(syy);
-    if (lane == 0) {
-        double *m = moments + ((size_t)set * ncells + cell) * kMomentDoubles;
-        m[0] = (double)(e - b); m[1] = sx; m[2] = sy; m[3] = sxx; m[4] = syy;
+    if (lane == 0) { s_part[warp][0] = sx; s_part[warp][1] = sy; s_part[warp][2] = sxx; s_part[warp][3] = syy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int w = 0; w < kMomentThreads / 32; ++w)
+            for (int q = 0; q < 4; ++q) t[q] += s_part[w][q];
+        m[0] = (double)(e - b); m[1] = t[0]; m[2] = t[1]; m[3] = t[2]; m[4] = t[3];
     }
 }
 
@@ -1118,24 +1151,25 @@ __device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const
     // fetch side: a running pointer into the current run, the lane's remaining candidates in it and the run's
     // remaining trips; run boundaries cost a few warp-uniform instructions, a trip five
     int r_pf = 0;
-    int rem = 0;                                  // candidates of the current run at or after this lane's next one
-    uint32_t trips_left = 0u;
+    int rem = -0x40000000;                        // candidates of the current run at or after this lane's next one
+    uint32_t trips_left = 0xffffffffu;            // (past the last run: nothing left to load, never switches again)
     const uint2 *nxt = pts;
     if (nruns > 0) { rem = (int)wlen[0] - lane; nxt = pts + wstart[0] + lane; trips_left = (wlen[0] + STRIDE - 1u) / STRIDE; }
     auto fetch = [&]() -> uint2 {
         uint2 v = far;
-        if (r_pf < nruns) {                                   // warp-uniform
-            if (rem > 0) v = *nxt;
-            nxt += STRIDE;
-            rem -= STRIDE;
-            if (--trips_left == 0u) {
-                ++r_pf;
-                if (r_pf < nruns) {
-                    const uint32_t len = wlen[r_pf];
-                    rem = (int)len - lane;
-                    nxt = pts + wstart[r_pf] + lane;
-                    trips_left = (len + STRIDE - 1u) / STRIDE;
-                }
+        if (rem > 0) v = *nxt;
+        nxt += STRIDE;
+        rem -= STRIDE;
+        if (--trips_left == 0u) {                             // warp-uniform, once per run
+            ++r_pf;
+            if (r_pf < nruns) {
+                const uint32_t len = wlen[r_pf];
+                rem = (int)len - lane;
+                nxt = pts + wstart[r_pf] + lane;
+                trips_left = (len + STRIDE - 1u) / STRIDE;
+            } else {
+                rem = -0x40000000;
+                trips_left = 0xffffffffu;
             }
         }
         return v;
@@ -1868,23 +1902,26 @@ k_band_cells(const uint32_t *__restrict__ cs_all, int world, size_t rank_stride,
     if (threadIdx.x == 1023) out[ncells] = run;
 }
 
-// k_band_merge: grid (ceil(cells in the band's rows / 4), 2 sets), 128 threads, one warp per cell.  The staging
-// buffer of a set holds, source rank after source rank, that rank's sorted points of cell rows [cy_lo, cy_hi]
-// (row-major cells).  The cell's points are copied source by source to their final place -- rank order is original
-// index order, so the result equals the single-GPU stable sort restricted to these rows.  Also writes the
-// fixed-point copy for the fp32 kernel.
-__global__ void __launch_bounds__(128)
+// k_band_merge: grid (cells in the band's rows, 2 sets, kMergeSplit), 256 threads.  The staging buffer of a set
+// holds, source rank after source rank, that rank's sorted points of cell rows [cy_lo, cy_hi] (row-major cells).
+// A cell's points are copied source by source to their final place -- rank order is original index order, so the
+// result equals the single-GPU stable sort restricted to these rows.  Real distance clouds are concentrated (a few
+// cells hold most of the points), so the kMergeSplit blocks of a cell interleave over 256-point chunks of every
+// source's piece.  Also writes the fixed-point copy for the fp32 kernel.
+constexpr int kMergeSplit = 8;
+__global__ void __launch_bounds__(256)
 k_band_merge(const double2 *__restrict__ stage_a, const double2 *__restrict__ stage_b,
              const uint32_t *__restrict__ cs_all, int world, size_t rank_stride, const GridGeom g, int cy_lo, int cy_hi,
              const uint32_t *__restrict__ cellstart_local, int64_t off_b,
              double2 *__restrict__ sorted, uint2 *__restrict__ sorted_q) {
-    const int set = blockIdx.y, lane = threadIdx.x & 31;
+    const int set = blockIdx.y;
     const int ncells = g.C * g.C;
     const int c_lo = cy_lo * g.C, c_hi = (cy_hi + 1) * g.C;
-    const int cell = c_lo + blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int cell = c_lo + blockIdx.x;
     if (cell >= c_hi) return;
     const double2 *__restrict__ stage = set ? stage_b : stage_a;
     uint32_t dst = cellstart_local[(size_t)set * (ncells + 1) + cell];
+    if (cellstart_local[(size_t)set * (ncells + 1) + cell + 1] == dst) return;      // empty cell
     const int64_t base = set ? off_b : 0;
     uint32_t src_base = 0u;                       // first point of source r in the staging buffer
     for (int r = 0; r < world; ++r) {
@@ -1892,7 +1929,7 @@ k_band_merge(const double2 *__restrict__ stage_a, const double2 *__restrict__ st
         const uint32_t r_lo = cs[c_lo], r_hi = cs[c_hi];
         const uint32_t b = cs[cell], e = cs[cell + 1];
         const double2 *__restrict__ sp = stage + src_base + (b - r_lo);
-        for (uint32_t k = lane; k < e - b; k += 32) {
+        for (uint32_t k = blockIdx.z * 256u + threadIdx.x; k < e - b; k += kMergeSplit * 256u) {
             const double2 p = sp[k];
             sorted[base + dst + k] = p;
             if (sorted_q) sorted_q[base + dst + k] = make_uint2(quantise(p.x, g), quantise(p.y, g));

@@ -332,12 +332,28 @@ def band_sharded_discrepancy(a_slice, b_slice, gamma=1.0, eps=1e-12, log=False, 
 
 
 def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world, info):
+    import time
+
+    timing = info is not None and info.get("timing")           # per-step wall clock with a device sync after each step
+    marks = []
+
+    def mark(name):
+        if timing:
+            ops.torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     a, b = ops.to_device(a_slice, "df1 slice"), ops.to_device(b_slice, "df2 slice")
     na = a.shape[0]
+    mark("upload")
     stats_all = _gather_cat(ops.minmax(a, b), group, world)                    # joint scaler: 10 doubles per rank
+    mark("minmax+gather")
     srt, block = ops.sort(a, b, stats_all, world)
+    mark("local sort")
     blocks_all = _gather_cat(block, group, world)                              # per-cell counts of every rank
+    mark("gather counts")
     colwork, rs, use_m = ops.plan(blocks_all, world)                           # the one host synchronisation
+    mark("plan")
     cuts = band_cuts(colwork, world)
     rows = [band_cell_rows(resolution, bandwidth, cuts[d], cuts[d + 1]) for d in range(world)]
     lo_me, hi_me = rows[rank]
@@ -351,11 +367,16 @@ def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world
         recv = [stage[offs[s_]:offs[s_ + 1]] for s_ in range(world)]
         _exchange(send, recv, group, rank, world)
         stages.append(stage)
+    mark("exchange")
     n_tot = rs[:, :, -1].sum(axis=0)
     norm = ops.phase1(stages[0], stages[1], n_tot[0], n_tot[1], blocks_all, stats_all, world,
                       (cuts[rank], cuts[rank + 1]), (lo_me, hi_me), use_m)
+    mark("merge+density")
     lr = ops.phase2(_gather_cat(norm, group, world), world)
     parts = ops.to_host(_gather_cat(lr, group, world)).reshape(world, 3)        # final synchronisation
+    mark("divergence+gathers")
+    if timing:
+        info["timing_ms"] = {n: 1e3 * (t - marks[i][1]) for i, (n, t) in enumerate(marks[1:])}
     if info is not None:
         info.update({"tile_columns": (cuts[rank], cuts[rank + 1]), "cell_rows": (lo_me, hi_me),
                      "points_received": (int(stages[0].shape[0]), int(stages[1].shape[0])), "moment_cells": bool(use_m)})

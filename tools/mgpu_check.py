@@ -64,6 +64,45 @@ if os.environ.get("MGPU_SMALL", "0") != "1":
                 torch.cuda.synchronize(); dist.barrier(); ts.append(time.perf_counter() - t0)
             if rank == 0:
                 print(f"C5 n={n} R=1024 over {world} ranks, {name}, {algo}: {js!r} in {1e3*min(ts[1:]):.2f} ms", flush=True)
+    for algo in ("binned", "binned32"):
+        info = {"timing": True}
+        D.band_sharded_discrepancy(da, db, 0.25, 0.0, resolution=1024, algo=algo, info=info)
+        allinfo = [None] * world
+        dist.all_gather_object(allinfo, {"rank": rank, "ms": {k: round(v, 3) for k, v in info["timing_ms"].items()},
+                                         "cols": info["tile_columns"], "recv": info["points_received"]})
+        if rank == 0:
+            for x in allinfo:
+                print("   steps (synchronised after each)", algo, x, flush=True)
+    import ctypes
+    nat = pk._native; L = nat.lib()
+    def kernel_ms():
+        out = {}
+        pm, pn = ctypes.c_double(), ctypes.c_int64()
+        for k, nm in enumerate(nat.KERNEL_NAMES):
+            nat.check(L.kdejs_profile_read(local, k, ctypes.byref(pm), ctypes.byref(pn)))
+            if pn.value: out[nm] = round(pm.value, 3)
+        return out
+    for algo in ("binned", "binned32"):
+        nat.check(L.kdejs_profile_reset(local)); nat.check(L.kdejs_profile_enable(local, 1))
+        D.band_sharded_discrepancy(da, db, 0.25, 0.0, resolution=1024, algo=algo)
+        km = kernel_ms(); nat.check(L.kdejs_profile_enable(local, 0))
+        allk = [None] * world
+        dist.all_gather_object(allk, km)
+        if rank == 0:
+            for r_, x in enumerate(allk):
+                print(f"   kernel ms (CUDA events) {algo} rank {r_}: {x}", flush=True)
+            ta, tb = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+            o = torch.zeros(1, dtype=torch.float64, device="cuda")
+            ptr = (ctypes.c_void_p * 1)(tb.data_ptr()); cnt = (ctypes.c_int64 * 1)(len(B))
+            st = torch.cuda.Stream()
+            call = lambda: nat.check(L.kdejs_discrepancy_batch_dev(local, ta.data_ptr(), len(A), ptr, cnt, 1, 1024, 0.03, 0.25, 0.0, 0, 0, nat.ALGOS[algo], o.data_ptr(), None, st.cuda_stream))
+            call(); torch.cuda.synchronize()
+            nat.check(L.kdejs_profile_reset(local)); nat.check(L.kdejs_profile_enable(local, 1))
+            t0 = time.perf_counter(); call(); torch.cuda.synchronize(); d1 = time.perf_counter() - t0
+            print(f"   single GPU device-resident {algo}: {1e3*d1:.2f} ms; kernel ms {kernel_ms()}", flush=True)
+            nat.check(L.kdejs_profile_enable(local, 0))
+            del ta, tb
+        dist.barrier()
     t0 = time.perf_counter()
     js_g = D.row_sharded_discrepancy(ha, hb, 0.25, 0.0, resolution=1024, sliced=True, gather_all=True)
     js_g = D.row_sharded_discrepancy(ha, hb, 0.25, 0.0, resolution=1024, sliced=True, gather_all=True)

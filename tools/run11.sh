@@ -1,0 +1,2 @@
+python -m pytest tests -m gpu -x -q > gpurun_out/t11.log 2>&1; tail -6 gpurun_out/t11.log
+PROBE_LOOPS=0 python tools/fp32_probe.py 2>&1 | grep -E "us/eval|rel gap"
