@@ -96,6 +96,7 @@ struct DevBuf {
 struct Slot {
     DevBuf scaled, sorted, sorted_q, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
     DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, redo, counters, totals, rank16, warpprefix, tileflag, misc;
+    DevBuf partinfo, redo_partinfo, split_partial, split_ticket;     // very heavy tiles processed in parts (SplitBufs)
 };
 
 struct Params {
@@ -180,7 +181,8 @@ void destroy_ctx(Ctx &c) {
     for (Slot &s : c.slots)
         for (DevBuf *b : {&s.scaled, &s.sorted, &s.sorted_q, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
                           &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart, &s.dense_partial,
-                          &s.worklist, &s.redo, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag, &s.misc}) {
+                          &s.worklist, &s.redo, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag, &s.misc,
+                          &s.partinfo, &s.redo_partinfo, &s.split_partial, &s.split_ticket}) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr; b->cap = 0;
         }
@@ -413,10 +415,11 @@ int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
     int nmax = 0;
     int64_t total = 0;
     for (int s = 0; s < wd.n_sets; ++s) { nmax = std::max(nmax, wd.set[s].n); total += wd.set[s].n; }
-    // ... rounded up to a power of two (k_place turns a point's index into its chunk with a shift)
+    // ... rounded DOWN to a power of two (k_place turns a point's index into its chunk with a shift; rounding up
+    // left 3.5 blocks per SM with a nearly empty last block per set: k_scale_count 2.06 -> 2.84 us per evaluation)
     int64_t per_warp = total / ((int64_t)4 * sm_count * kSortWarps);
     chw = 512;
-    while (chw < per_warp && chw < kMaxChw) chw <<= 1;
+    while (2 * chw <= per_warp && chw < kMaxChw) chw <<= 1;
     nb_max = std::max(1, (int)(((int64_t)nmax + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)));
     return KDEJS_OK;
 }
@@ -490,12 +493,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             if (const char *e = getenv("KDEJS_GROUPS")) n_groups = std::max(1, std::min(std::min(atoi(e), kMaxGroups), n_sets));
             g.sets_per_group = (n_sets + n_groups - 1) / n_groups;
         }
-        OKR(sl.worklist.ensure((size_t)kNumLists * g.sets_per_group * g.NT * g.NT * sizeof(uint32_t)));
         OKR(sl.counters.ensure(kAllCounters * sizeof(unsigned)));
-        if (fast32) {
-            OKR(sl.sorted_q.ensure((size_t)P * sizeof(uint2)));
-            OKR(sl.redo.ensure((size_t)kNumLists * g.sets_per_group * g.NT * g.NT * sizeof(uint32_t)));
-        }
+        if (fast32) OKR(sl.sorted_q.ensure((size_t)P * sizeof(uint2)));
     }
 
     unsigned *tk_minmax = sl.tickets.as<unsigned>();
@@ -574,13 +573,34 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         }
         if (io.out_tile_rows) { io.out_tile_rows[0] = g.tile_row_begin; io.out_tile_rows[1] = g.tile_row_end; }
         const int tiles = (g.tile_row_end - g.tile_row_begin) * (g.tile_col_end - g.tile_col_begin);
-        const unsigned capacity = (unsigned)tiles * (unsigned)g.sets_per_group;      // entries per (group, class) list
+        // Part slots for very heavy tiles (SplitBufs).  A tile is split into <= kMaxParts parts of ~2^kPartLog2
+        // candidates; the sum of all tiles' candidates is at most (points) x (tiles one point can reach).
+        const double reach = std::min((double)g.NT, (2.0 * p.h + g.cell_w) / (kTile * g.step > 0.0 ? kTile * g.step : 1.0) + 2.0);
+        const double parts_bound = std::min((double)kMaxParts * tiles * n_sets,
+                                            1.5 * (double)P * reach * reach / (double)(1 << kPartLog2) + 64.0);
+        const unsigned parts_cap = (unsigned)std::min(parts_bound, 8.0e6);
+        const unsigned capacity = (unsigned)tiles * (unsigned)g.sets_per_group +      // entries per (group, class) list
+                                  std::min(parts_cap, (unsigned)(kMaxParts - 1) * (unsigned)tiles * (unsigned)g.sets_per_group);
+        OKR(sl.worklist.ensure((size_t)kNumLists * capacity * sizeof(uint32_t)));
+        OKR(sl.partinfo.ensure((size_t)kMaxGroups * capacity * sizeof(uint2)));
+        OKR(sl.split_partial.ensure((size_t)parts_cap * 16 * sizeof(double)));
+        if ((size_t)parts_cap * sizeof(unsigned) > sl.split_ticket.cap) {
+            OKR(sl.split_ticket.ensure((size_t)parts_cap * sizeof(unsigned)));
+            CU(cudaMemsetAsync(sl.split_ticket.p, 0, sl.split_ticket.cap, st));     // self-resetting afterwards
+        }
+        const SplitBufs sb{sl.partinfo.as<uint2>(), sl.split_partial.as<double>(), sl.split_ticket.as<unsigned>(), parts_cap};
+        if (fast32) {
+            OKR(sl.redo.ensure((size_t)kNumLists * capacity * sizeof(uint32_t)));
+            OKR(sl.redo_partinfo.ensure((size_t)kMaxGroups * capacity * sizeof(uint2)));
+        }
+        // the redo list of the fp32 path holds whole tiles: its class-0 entries are single parts
+        const SplitBufs sb_redo{sl.redo_partinfo.as<uint2>(), sl.split_partial.as<double>(), sl.split_ticket.as<unsigned>(), 0u};
         if (tiles > 0) {
             KTimer t(c, 6, st);
             k_tile_classify<<<dim3((tiles + 31) / 32, n_sets), 256, 0, st>>>(
                 wd, g, sl.cellstart.as<uint32_t>(), sl.dens.as<double>(), sl.pz.as<double>(),
                 sl.tilesum.as<double>(), sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity,
-                c.prof_on ? c.d_work : nullptr, lazy_empty ? sl.tileflag.as<uint8_t>() : nullptr);
+                c.prof_on ? c.d_work : nullptr, lazy_empty ? sl.tileflag.as<uint8_t>() : nullptr, sb);
         }
         if (tiles > 0 && fast32) {
             // nodes whose fp32 sum stays below this are not trusted to fp32 (relative error ~1.5e-7 / sum): their
@@ -594,13 +614,13 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                         wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
                         sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
                         sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>(),
-                        fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr);
+                        fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr, sb, sl.redo_partinfo.as<uint2>());
                 else
                     k_density_binned32<false><<<blocks, kDensThreads, 0, st>>>(
                         wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), nullptr,
                         sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
                         sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>(),
-                        fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr);
+                        fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr, sb, sl.redo_partinfo.as<uint2>());
             }
             // tiles with a node the fp32 arithmetic could not certify (a nearest candidate within ~1e-6 of the
             // support's edge): the fp64 kernel on the redo list -- usually empty, a few tiles per evaluation at most
@@ -611,12 +631,12 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 k_density_binned<true><<<blocks, kDensThreads, 0, st>>>(
                     wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
                     sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
-                    sl.redo.as<uint32_t>(), sl.counters.as<unsigned>() + kRedoBase, capacity);
+                    sl.redo.as<uint32_t>(), sl.counters.as<unsigned>() + kRedoBase, capacity, sb_redo);
             else
                 k_density_binned<false><<<blocks, kDensThreads, 0, st>>>(
                     wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), nullptr,
                     sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
-                    sl.redo.as<uint32_t>(), sl.counters.as<unsigned>() + kRedoBase, capacity);
+                    sl.redo.as<uint32_t>(), sl.counters.as<unsigned>() + kRedoBase, capacity, sb_redo);
         } else if (tiles > 0) {
             KTimer t(c, 4, st);
             const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * c.dens_blocks_per_sm);
@@ -624,12 +644,12 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 k_density_binned<true><<<blocks, kDensThreads, 0, st>>>(
                     wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
                     sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
-                    sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity);
+                    sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sb);
             else
                 k_density_binned<false><<<blocks, kDensThreads, 0, st>>>(
                     wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), nullptr,
                     sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
-                    sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity);
+                    sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sb);
         }
     } else {
         // dense fp64: scale only (C = 1: every point lands in cell 0, the histogram is unused)

@@ -42,12 +42,28 @@ constexpr int kMaxGroups = 4;      // measured: 4 groups bring the kernel's DRAM
                                    // evaluations (algorithmic 339 MB incl. writes); 8 cost 1 % in the list lookup
 constexpr int kNumLists = kMaxGroups * kNumClasses;
 constexpr int kTicketA = kNumLists, kTicketB = kNumLists + 1;
-constexpr int kNumCounters = kNumLists + 2;
+constexpr int kSplitParts = kNumLists + 2;        // part slots handed out to split tiles (see SplitBufs)
+constexpr int kNumCounters = kNumLists + 3;
 constexpr int kRedoBase = kNumCounters;           // counters[kRedoBase ...]: the same layout again for the redo list
 constexpr int kAllCounters = 2 * kNumCounters;
 constexpr int kJsThreads = 256;
 constexpr int kJsNodesPerBlock = 2048;
 constexpr int kMinmaxThreads = 256;
+
+// Very heavy tiles are split.  A block-per-tile item (class 0) with >= 2^kSplitLog2 candidates is entered K times
+// into its list, K = ceil(candidates / 2^kPartLog2) <= kMaxParts; part k walks chunks [gtot k / K, gtot (k+1) / K)
+// of the tile's flattened sequence of 32-candidate chunks and leaves its 16 partial node sums in `partial`; the
+// part that finishes last (ticket) adds the K partials in part order and runs the tile's epilogue.  The split is
+// a function of the tile's candidate runs alone, so results stay bit-reproducible and identical between one GPU
+// and a band of a sharded evaluation.  Why: on config C5 the heaviest tiles hold 1.7 M candidates -- 0.9 ms on
+// one block, more than a rank's whole share of the density work once the grid is spread over eight GPUs.
+constexpr int kSplitLog2 = 17, kPartLog2 = 16, kMaxParts = 32;
+struct SplitBufs {
+    uint2 *partinfo;       // per class-0 list entry [group][capacity]: {part | parts << 8, first part slot}
+    double *partial;       // [part slot][16]
+    unsigned *ticket;      // [part slot] (the tile's first slot is used), zero between waves (self-resetting)
+    unsigned parts_cap;    // part slots available; a tile that would not fit is not split
+};
 
 struct RawSet {            // a point set as the caller gave it: (n,2) interleaved fp64, device memory
     const double *p;
@@ -607,7 +623,7 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 const uint32_t *__restrict__ cellstart, double *__restrict__ dens,
                 double *__restrict__ pz, double *__restrict__ tilesum, uint32_t *__restrict__ worklist,
                 unsigned *__restrict__ counters, unsigned capacity,
-                unsigned long long *__restrict__ work_counter, uint8_t *__restrict__ tileflag) {
+                unsigned long long *__restrict__ work_counter, uint8_t *__restrict__ tileflag, const SplitBufs sb) {
     const int nty = g.tile_col_end - g.tile_col_begin;
     const int ntl = (g.tile_row_end - g.tile_row_begin) * nty;
     const int tl = blockIdx.x * (blockDim.x / kClassifyLanes) + threadIdx.x / kClassifyLanes;
@@ -648,9 +664,20 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
             }
         } else if (sub == 0) {
             const int cls = tile_class(total, g.heavy_log2);
-            const int list = (set / g.sets_per_group) * kNumClasses + cls;
-            const unsigned slot = atomicAdd(&counters[list], 1u);
-            worklist[(size_t)list * capacity + slot] = ((uint32_t)set << 24) | (uint32_t)tile;
+            const int grp = set / g.sets_per_group;
+            const int list = grp * kNumClasses + cls;
+            const uint32_t entry = ((uint32_t)set << 24) | (uint32_t)tile;
+            uint32_t K = 1u, pbase = 0u;
+            if (cls == 0 && total >= (1u << kSplitLog2)) {
+                K = min((uint32_t)kMaxParts, (total + (1u << kPartLog2) - 1u) >> kPartLog2);
+                pbase = atomicAdd(&counters[kSplitParts], K);
+                if (pbase + K > sb.parts_cap) K = 1u;                  // out of part slots: process it whole
+            }
+            const unsigned slot = atomicAdd(&counters[list], K);
+            for (uint32_t k = 0; k < K; ++k) {
+                worklist[(size_t)list * capacity + slot + k] = entry;
+                if (cls == 0) sb.partinfo[(size_t)grp * capacity + slot + k] = make_uint2(k | (K << 8), pbase);
+            }
         }
     }
     if (work_counter) {
@@ -812,14 +839,57 @@ __device__ __forceinline__ uint32_t list_entry(const uint32_t *__restrict__ work
 // redo set when it cannot certify a node).
 __device__ __forceinline__ uint32_t list_entry_ex(const uint32_t *__restrict__ worklist, unsigned capacity,
                                                   unsigned item, const unsigned *s_pre, const uint8_t *s_list,
-                                                  int n_lists, int &list) {
+                                                  int n_lists, int &list, unsigned &index) {
     int lo = 0, hi = n_lists - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (s_pre[mid] <= item) lo = mid; else hi = mid - 1;
     }
     list = s_list[lo];
-    return worklist[(size_t)s_list[lo] * capacity + (item - s_pre[lo])];
+    index = item - s_pre[lo];
+    return worklist[(size_t)s_list[lo] * capacity + index];
+}
+
+// The share of one warp (of the four of a block) in cell-row run e of a tile, for the part that covers chunks
+// [c0, c1) of the tile's flattened chunk sequence: the run holds chunks [cpre_e, cpre_e1); inside the part the
+// chunks are dealt to the warps round-robin, (chunk - c0) mod 4 == warp.  Returns the first candidate of the warp's
+// first chunk and how many candidates follow it up to the end of the run or of the part (0: nothing).
+__device__ __forceinline__ void part_run(uint32_t cpre_e, uint32_t cpre_e1, uint32_t rs_e, uint32_t len_e,
+                                         uint32_t c0, uint32_t c1, int warp, uint32_t &start, uint32_t &rem) {
+    const uint32_t lo = max(cpre_e, c0), hi = min(cpre_e1, c1);
+    start = 0u;
+    rem = 0u;
+    if (lo < hi) {
+        const uint32_t g0 = lo + (((uint32_t)warp - (lo - c0)) & 3u);
+        if (g0 < hi) {
+            const uint32_t off = (g0 - cpre_e) * 32u;
+            const uint32_t end = (hi == cpre_e1) ? len_e : (hi - cpre_e) * 32u;     // a run's last chunk is ragged
+            start = rs_e + off;
+            rem = end - off;
+        }
+    }
+}
+// After a part's block-level reduction: `S` is valid in the owner thread of each node (owner == true for 16
+// threads of the block).  K == 1: nothing to do.  Otherwise the partial goes to memory and the call returns true
+// only in the block that finished the tile's last part, with S replaced by the sum of all parts in part order.
+__device__ __forceinline__ bool combine_parts(const SplitBufs &sb, uint32_t k, uint32_t K, uint32_t pbase, bool owner,
+                                              int node, double &S, unsigned *s_ticket) {
+    if (K == 1u) return true;
+    if (owner) sb.partial[(size_t)(pbase + k) * 16 + node] = S;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(&sb.ticket[pbase], 1u);
+    __syncthreads();
+    if (*s_ticket != K - 1u) return false;
+    __threadfence();
+    if (owner) {
+        const volatile double *vp = sb.partial + (size_t)pbase * 16 + node;
+        double t = 0.0;
+        for (uint32_t q = 0; q < K; ++q) t += vp[(size_t)q * 16];
+        S = t;
+    }
+    if (threadIdx.x == 0) sb.ticket[pbase] = 0u;              // self-resetting
+    return true;
 }
 
 // k_density_binned: persistent, (#SM x resident) blocks of 128 threads pulling 4x4-node tiles from
@@ -842,13 +912,13 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
                  const double *__restrict__ moments,
                  double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
                  const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
-                 unsigned capacity) {
+                 unsigned capacity, const SplitBufs sb) {
     __shared__ uint32_t s_rs[2 * kMaxRows];          // two point runs per cell row (left / right of the moment cells)
     __shared__ uint32_t s_len[2 * kMaxRows];         // their lengths
     __shared__ int s_mlo[kMaxRows], s_mcnt[kMaxRows], s_rows, s_cy0;
-    __shared__ uint8_t s_base[2 * kMaxRows];
+    __shared__ uint32_t s_cpre[2 * kMaxRows + 1];    // 32-candidate chunks before each run
     __shared__ double s_red[kRedDoubles];
-    __shared__ unsigned s_item;
+    __shared__ unsigned s_item, s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncells = g.C * g.C;
     // processing order: phase A = class 0 of every group; phase B = for each group, classes 1..9
@@ -887,7 +957,11 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         __syncthreads();
         const unsigned item = s_item;
         if (item >= n0) break;
-        const uint32_t entry = list_entry(worklist, capacity, item, s_preA, s_listA, kMaxGroups);
+        int list;
+        unsigned index;
+        const uint32_t entry = list_entry_ex(worklist, capacity, item, s_preA, s_listA, kMaxGroups, list, index);
+        const uint2 pinfo = sb.partinfo[(size_t)(list / kNumClasses) * capacity + index];
+        const uint32_t part_k = pinfo.x & 0xffu, part_K = pinfo.x >> 8, pbase = pinfo.y;
         const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
         const SetDesc sd = wd.set[set];
         const int tx = tile / g.NT, ty = tile % g.NT;
@@ -903,7 +977,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
             s_rs[2 * lane + 1] = rr.s2;
             s_len[2 * lane] = rr.l1;
             s_len[2 * lane + 1] = rr.l2;
-            // 32-candidate chunks are dealt to the four warps round-robin ACROSS runs: s_base = chunks before a run
+            // 32-candidate chunks are dealt to the four warps round-robin ACROSS runs: s_cpre = chunks before a run
             const uint32_t c1n = (rr.l1 + 31u) >> 5, c2n = (rr.l2 + 31u) >> 5;
             uint32_t cinc = c1n + c2n;
 #pragma unroll
@@ -911,8 +985,9 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 uint32_t t = __shfl_up_sync(0xffffffffu, cinc, o);
                 if (lane >= o) cinc += t;
             }
-            s_base[2 * lane] = (uint8_t)((cinc - c1n - c2n) & 3u);
-            s_base[2 * lane + 1] = (uint8_t)((cinc - c2n) & 3u);
+            s_cpre[2 * lane] = cinc - c1n - c2n;
+            s_cpre[2 * lane + 1] = cinc - c2n;
+            if (lane == 31) s_cpre[2 * kMaxRows] = cinc;
             s_mlo[lane] = rr.mlo;
             s_mcnt[lane] = rr.mcnt;
             if (lane == 0) { s_rows = rows; s_cy0 = tc.cy_lo; }
@@ -924,14 +999,18 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll
             for (int j = 0; j < kTile; ++j) acc[i][j] = 0.0;
         const double2 *__restrict__ pts = sorted + sd.off;
+        // this part's chunks of the tile's flattened chunk sequence (a tile that is not split is one part)
+        const uint32_t gtot = s_cpre[2 * kMaxRows];
+        const uint32_t pc0 = (uint32_t)((uint64_t)gtot * part_k / part_K), pc1 = (uint32_t)((uint64_t)gtot * (part_k + 1u) / part_K);
         // run by run, each warp strides through every fourth 32-candidate chunk: the same loop as phase B (no
         // per-candidate run lookup), and only the last chunk of a run is ragged
         const int nruns = (MOMENTS ? 2 : 1) * s_rows;
         for (int k = 0; k < nruns; ++k) {
             const int e = MOMENTS ? k : 2 * k;               // without moment cells only the even entries are used
-            const uint32_t len = s_len[e];
-            const double2 *__restrict__ rp = pts + s_rs[e];
-            uint32_t j = (((uint32_t)warp - s_base[e]) & 3u) * 32u + lane;
+            uint32_t start, len;
+            part_run(s_cpre[e], s_cpre[e + 1], s_rs[e], s_len[e], pc0, pc1, warp, start, len);
+            const double2 *__restrict__ rp = pts + start;
+            uint32_t j = lane;
             double2 pn = make_double2(0.0, 0.0);
             if (j < len) pn = rp[j];
             while (j < len) {
@@ -941,7 +1020,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 accumulate_point(p, gx0, gy0, g.inv_h, c1, c2, c3, acc);
             }
         }
-        if (MOMENTS) {
+        if (MOMENTS && part_k == 0u) {                       // the moment cells go with the first part
             const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
             const int rows = s_rows, cy0 = s_cy0;
             for (int rr = 0; rr < rows; ++rr) {
@@ -966,6 +1045,7 @@ k_density_binned(const __grid_constant__ WaveDesc wd, const GridGeom g,
         S += __shfl_xor_sync(0xffffffffu, S, 1);
         S += __shfl_xor_sync(0xffffffffu, S, 2);
         S += __shfl_xor_sync(0xffffffffu, S, 4);
+        if (!combine_parts(sb, part_k, part_K, pbase, part == 0, node, S, &s_ticket)) continue;   // not the last part
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         double P = 0.0;
         if (part == 0 && ix < g.R && iy < g.R) {
@@ -1214,7 +1294,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
                    double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
                    const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
                    unsigned capacity, uint32_t *__restrict__ redo_list, const float min_thr,
-                   unsigned long long *__restrict__ stats) {
+                   unsigned long long *__restrict__ stats, const SplitBufs sb, uint2 *__restrict__ redo_partinfo) {
     // stats (profiling only): [0] tiles, [1] tiles walked a second time, [2] warp trips of first walks,
     // [3] warp trips of second walks, [4] tiles re-queued for fp64
     __shared__ uint32_t s_rs[2 * kMaxRows];          // phase A: the tile's runs; phase B: per-warp compacted runs
@@ -1223,7 +1303,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
     __shared__ uint32_t s_wstart[kDensThreads / 32][2 * kMaxRows], s_wlen[kDensThreads / 32][2 * kMaxRows];
     __shared__ int s_mlo[kMaxRows], s_mcnt[kMaxRows], s_rows, s_cy0;
     __shared__ double s_red[kRedDoubles];
-    __shared__ unsigned s_item;
+    __shared__ unsigned s_item, s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ncells = g.C * g.C;
     __shared__ unsigned s_preA[kMaxGroups + 1], s_preB[kMaxGroups * (kNumClasses - 1) + 1];
@@ -1265,7 +1345,10 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const unsigned item = s_item;
         if (item >= n0) break;
         int list;
-        const uint32_t entry = list_entry_ex(worklist, capacity, item, s_preA, s_listA, kMaxGroups, list);
+        unsigned index;
+        const uint32_t entry = list_entry_ex(worklist, capacity, item, s_preA, s_listA, kMaxGroups, list, index);
+        const uint2 pinfo = sb.partinfo[(size_t)(list / kNumClasses) * capacity + index];
+        const uint32_t part_k = pinfo.x & 0xffu, part_K = pinfo.x >> 8, pbase = pinfo.y;
         const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
         const SetDesc sd = wd.set[set];
         const int tx = tile / g.NT, ty = tile % g.NT;
@@ -1299,8 +1382,10 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         __syncthreads();
         const uint2 *__restrict__ pts = sorted_q + sd.off;
         const uint32_t gtot = s_cpre[2 * kMaxRows];         // 32-candidate chunks of the tile, dealt round-robin to the warps
-        // this warp's share of every run: chunks first, first + 4, ... with first = (warp - chunks before the run) mod 4;
-        // compacted into the warp's own run list (two run slots per lane: left / right of the moment cells)
+        // this part's chunks of the flattened sequence (a tile that is not split is one part), and in them this
+        // warp's share of every run, compacted into the warp's own run list (two run slots per lane: left / right
+        // of the moment cells)
+        const uint32_t pc0 = (uint32_t)((uint64_t)gtot * part_k / part_K), pc1 = (uint32_t)((uint64_t)gtot * (part_k + 1u) / part_K);
         uint32_t my_trips = 0u;
         int my_runs = 0;
         {
@@ -1309,10 +1394,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int e = 2 * lane + k;
-                const uint32_t len = s_len[e], nch = (len + 31u) >> 5;
-                const uint32_t first = ((uint32_t)warp - s_cpre[e]) & 3u;
-                st2[k] = s_rs[e] + first * 32u;
-                ln2[k] = first < nch ? len - first * 32u : 0u;
+                part_run(s_cpre[e], s_cpre[e + 1], s_rs[e], s_len[e], pc0, pc1, warp, st2[k], ln2[k]);
                 my_trips += (ln2[k] + kDensThreads - 1u) / kDensThreads;
             }
             const unsigned m0 = __ballot_sync(0xffffffffu, ln2[0] > 0u), m1 = __ballot_sync(0xffffffffu, ln2[1] > 0u);
@@ -1329,7 +1411,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         walk_tile32<kDensThreads, true>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, gxq, gyq, unit,
                                         f1, f2, f3, 1.0f, acc64);
         uint32_t ncand = gtot * 32u;                          // upper bound of the candidates (last chunks are ragged)
-        if (MOMENTS) {
+        if (MOMENTS && part_k == 0u) {                        // the moment cells go with the first part
             const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
             const int rows = s_rows, cy0 = s_cy0;
             for (int rr = 0; rr < rows; ++rr) {
@@ -1354,16 +1436,20 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         S += __shfl_xor_sync(0xffffffffu, S, 1);
         S += __shfl_xor_sync(0xffffffffu, S, 2);
         S += __shfl_xor_sync(0xffffffffu, S, 4);
+        if (stats && threadIdx.x == 0) { atomicAdd(&stats[0], part_k == 0u ? 1ull : 0ull); atomicAdd(&stats[2], (unsigned long long)(pc1 - pc0)); }
+        if (!combine_parts(sb, part_k, part_K, pbase, part == 0, node, S, &s_ticket)) continue;   // not the last part
         const int ix = ix0 + node / kTile, iy = iy0 + node % kTile;
         const bool valid = ix < g.R && iy < g.R;
+        if (MOMENTS && part_k != 0u)                              // thr counts the whole tile's candidates
+            for (int rr = 0; rr < s_rows; ++rr) ncand += (uint32_t)s_mcnt[rr];
         const double thr = fmax((double)kBias32 * (double)max(ncand, 1024u), (double)min_thr);
         const int low = __syncthreads_or(valid && S < thr);      // also: everyone is done reading s_red
-        if (stats && threadIdx.x == 0) { atomicAdd(&stats[0], 1ull); atomicAdd(&stats[2], (unsigned long long)gtot); }
         if (low) {                                               // cannot certify a node here: fp64 does this tile
             if (threadIdx.x == 0) {
                 if (stats) atomicAdd(&stats[4], 1ull);
                 const unsigned slot = atomicAdd(&redo_counters[list], 1u);
                 redo_list[(size_t)list * capacity + slot] = entry;
+                redo_partinfo[(size_t)(list / kNumClasses) * capacity + slot] = make_uint2(1u << 8, 0u);   // whole, one part
             }
             continue;
         }
@@ -1393,8 +1479,9 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= nB) break;
         int list;
+        unsigned index;
         const uint32_t entry = list_entry_ex(worklist, capacity, item, s_preB, s_listB,
-                                             kMaxGroups * (kNumClasses - 1), list);
+                                             kMaxGroups * (kNumClasses - 1), list, index);
         const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
         const double knorm_over_n = wd.set[set].knorm_over_n;
         const uint2 *__restrict__ pts = sorted_q + wd.set[set].off;

@@ -742,3 +742,26 @@ def test_dev_entry_interleaved_with_host_calls_without_sync(pk):
         np.testing.assert_array_equal(out2.cpu().numpy(), want_dev)
         np.testing.assert_array_equal(got_host, want_host)
         assert single == want_dev[3]
+
+
+@pytest.mark.parametrize("algo", ["binned", "binned32"])
+def test_very_heavy_tiles_are_processed_in_parts(pk, ko, algo):
+    """Tiles with >= 2^17 candidates are split into parts that separate blocks walk; the part that finishes last
+    adds the partial sums in part order.  Concentrated clouds on a coarse grid put several hundred thousand
+    candidates into the central tiles."""
+    rng = np.random.default_rng(17)
+    a = np.vstack([rng.normal([0.5, 0.5], 0.05, (300_000, 2)), [[0.0, 0.0], [1.0, 1.0]]])
+    b = np.vstack([rng.normal([0.55, 0.5], 0.07, (250_000, 2)), [[0.0, 0.0], [1.0, 1.0]]])
+    for R in (20, 100):
+        got = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=R, algo=algo)
+        want = ko.discrepancy(a, b, 0.25, 0.0, resolution=R)
+        assert rel(got, want) < (JS_RTOL_EXPECT if algo == "binned" else 2e-7)
+        again = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=R, algo=algo)
+        assert again == got                                           # whichever block finishes last: same bits
+    js, z1, z2, d1, d2 = pk.KDE_distance._discrepancy(a, b, 0.25, 0.0, False, 20, 0.03, "epanechnikov", algo, None,
+                                                      want_z=True, want_density=True)
+    _, _, _, od1, od2 = ko.discrepancy(a, b, 0.25, 0.0, resolution=20, return_grids=True)
+    tol = 1e-12 if algo == "binned" else 1e-7
+    for got_d, want_d in ((d1, od1), (d2, od2)):
+        assert np.all(np.abs(got_d - want_d) <= 1e-6 * want_d + tol * want_d.max())
+        assert np.array_equal(got_d == 0, want_d == 0)
