@@ -47,9 +47,14 @@ __all__ = ["get_grid", "scale_KDE", "KDE_JS_divergence", "KDE_KL_divergence", "K
 
 _DEFAULT_RESOLUTION = 100      # KDE_distance.py:89
 _DEFAULT_BANDWIDTH = 0.03      # KDE_distance.py:50
-# Density algorithm used when a caller does not name one (Epanechnikov kernel): "binned" = fp64 culled sum,
-# "binned32" = the same sum with fp32 terms on the FP32 pipe (exact zeros kept, ~1e-8 on the JS value).
-DEFAULT_ALGO = os.environ.get("KDEJS_DEFAULT_ALGO", "binned")
+# Density algorithm used when a caller does not name one (Epanechnikov kernel):
+#   "binned32"  the culled sum with fp32 terms on the FP32 pipe: exact zeros stay exact (nodes the fp32 arithmetic
+#               cannot certify are redone in fp64), non-zero node densities within ~1e-7 relative, JS within ~1e-8
+#               of the exact sum (bar: 1e-5); geometries its fixed-point format does not cover, sets of fewer than
+#               64 points and fine grids with dense cells (moment cells) run the fp64 kernel anyway;
+#   "binned"    the same sum entirely in fp64 (the reference's exact arithmetic to ~1e-16), ~20 % slower.
+# KDEJS_DEFAULT_ALGO overrides the choice for a whole process.
+DEFAULT_ALGO = os.environ.get("KDEJS_DEFAULT_ALGO", "binned32")
 
 
 def default_device() -> int:

@@ -444,17 +444,22 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     const int ncells = g.C * g.C;
     const bool binned = (p.algo == KDEJS_ALGO_BINNED || p.algo == KDEJS_ALGO_BINNED32);
     // the fp32 kernel needs a geometry its fixed-point format covers; otherwise the fp64 kernel does the work
-    static const int force32 = getenv("KDEJS_FP32") ? atoi(getenv("KDEJS_FP32")) : -1;
+    const int force32 = getenv("KDEJS_FP32") ? atoi(getenv("KDEJS_FP32")) : -1;     // 0 / 1: override the algorithm's choice
     // ... and sets large enough for the absolute part of its error bound (1e-7 of the LARGEST node sum) to mean
     // something: with a handful of points no node sum exceeds ~1 and fp32 terms are themselves 1e-7 off
     int64_t min_n = INT64_MAX;
     for (int s = 0; s < wd.n_sets; ++s) min_n = std::min<int64_t>(min_n, io.n_global ? io.n_global[s] : (int64_t)wd.set[s].n);
-    const bool fast32 = binned && g.q_shift > 0 && min_n >= 64 &&
-                        (force32 >= 0 ? force32 != 0 : p.algo == KDEJS_ALGO_BINNED32);
+    bool fast32 = binned && g.q_shift > 0 && min_n >= 64 &&
+                  (force32 >= 0 ? force32 != 0 : p.algo == KDEJS_ALGO_BINNED32);
     // a moment cell costs a tile as much as one point plus some per-row bookkeeping: it pays once cells hold
     // hundreds of points (measured: -40 % density time at 1200 points per cell, +48 % at 49)
     if (io.force_moments >= 0 && g_in.use_moments == 1) g.use_moments = io.force_moments ? 1 : 0;
     else if (g.use_moments == 1 && P < (int64_t)128 * n_sets * ncells) g.use_moments = 0;
+    // Fine grids with dense cells (config C5) stay on the fp64 kernel unless fp32 is forced: most of their sum
+    // comes from moment cells (fp64 either way), and their very heavy edge tiles hold nodes whose sum stays below
+    // the fp32 certification threshold (bias x candidates), so a third of the work was redone in fp64 anyway
+    // (measured, 10 M + 10 M points: 7.2 ms + 4.2 ms redo against 12.8 ms fp64, and a band-to-band imbalance).
+    if (g.use_moments && force32 <= 0) fast32 = false;
     // Plain discrepancies (no grids requested, one launch for the whole grid): tiles without candidates are only
     // flagged and the divergence kernel reads the flag instead of 16 node values -- ~70 % of the grid is never
     // written or read.
@@ -494,7 +499,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             g.sets_per_group = (n_sets + n_groups - 1) / n_groups;
         }
         OKR(sl.counters.ensure(kAllCounters * sizeof(unsigned)));
-        if (fast32) OKR(sl.sorted_q.ensure((size_t)P * sizeof(uint2)));
+        if (fast32 && !kFp32FromDoubles) OKR(sl.sorted_q.ensure((size_t)P * sizeof(uint2)));
     }
 
     unsigned *tk_minmax = sl.tickets.as<unsigned>();
@@ -538,7 +543,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 io.identity_scaler ? 1 : 0, ncells, 31 - __builtin_clz((unsigned)chw), nb_max, sl.cellid.as<uint16_t>(),
                 sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
                 wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>(),
-                fast32 ? sl.sorted_q.as<uint2>() : nullptr, g);
+                fast32 && !kFp32FromDoubles ? sl.sorted_q.as<uint2>() : nullptr, g);
         }
         if (io.sort_only) { CU(cudaGetLastError()); return KDEJS_OK; }
         if (io.presorted) CU(cudaMemsetAsync(sl.counters.p, 0, kAllCounters * sizeof(unsigned), st));   // k_scan's job otherwise
@@ -593,8 +598,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             OKR(sl.redo.ensure((size_t)kNumLists * capacity * sizeof(uint32_t)));
             OKR(sl.redo_partinfo.ensure((size_t)kMaxGroups * capacity * sizeof(uint2)));
         }
-        // the redo list of the fp32 path holds whole tiles: its class-0 entries are single parts
-        const SplitBufs sb_redo{sl.redo_partinfo.as<uint2>(), sl.split_partial.as<double>(), sl.split_ticket.as<unsigned>(), 0u};
+        // the redo list of the fp32 path: a split tile comes back in the same parts, with the same part slots
+        const SplitBufs sb_redo{sl.redo_partinfo.as<uint2>(), sl.split_partial.as<double>(), sl.split_ticket.as<unsigned>(), parts_cap};
         if (tiles > 0) {
             KTimer t(c, 6, st);
             k_tile_classify<<<dim3((tiles + 31) / 32, n_sets), 256, 0, st>>>(
@@ -611,13 +616,13 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
                 const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * c.dens32_blocks_per_sm);
                 if (g.use_moments)
                     k_density_binned32<true><<<blocks, kDensThreads, 0, st>>>(
-                        wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
+                        wd, g, kFp32FromDoubles ? sl.sorted.as<Cand32>() : sl.sorted_q.as<Cand32>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
                         sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
                         sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>(),
                         fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr, sb, sl.redo_partinfo.as<uint2>());
                 else
                     k_density_binned32<false><<<blocks, kDensThreads, 0, st>>>(
-                        wd, g, sl.sorted_q.as<uint2>(), sl.cellstart.as<uint32_t>(), nullptr,
+                        wd, g, kFp32FromDoubles ? sl.sorted.as<Cand32>() : sl.sorted_q.as<Cand32>(), sl.cellstart.as<uint32_t>(), nullptr,
                         sl.dens.as<double>(), sl.pz.as<double>(), sl.tilesum.as<double>(),
                         sl.worklist.as<uint32_t>(), sl.counters.as<unsigned>(), capacity, sl.redo.as<uint32_t>(),
                         fp32_min_thr, c.prof_on ? c.d_stats32 : nullptr, sb, sl.redo_partinfo.as<uint2>());
@@ -625,8 +630,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             // tiles with a node the fp32 arithmetic could not certify (a nearest candidate within ~1e-6 of the
             // support's edge): the fp64 kernel on the redo list -- usually empty, a few tiles per evaluation at most
             KTimer t(c, 8, st);
-            // a handful of tiles: one block per SM is plenty (and the launch costs less when the list is empty)
-            const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count);
+            const int blocks = (int)std::min<int64_t>((int64_t)tiles * n_sets, (int64_t)c.sm_count * c.dens_blocks_per_sm);
             if (g.use_moments)
                 k_density_binned<true><<<blocks, kDensThreads, 0, st>>>(
                     wd, g, sl.sorted.as<double2>(), sl.cellstart.as<uint32_t>(), sl.moments.as<double>(),
@@ -1485,29 +1489,27 @@ int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int r
     Slot &sl = c->S();
     GridGeom g = make_geom(p);
     const BandDims d = band_dims(g);
-    // every rank's row starts: world x 2 x (C + 1) u32, a strided device -> host copy
-    const size_t rs_elems = 2 * (size_t)(d.C + 1);
-    CU(cudaMemcpy2DAsync(out_rowstart, rs_elems * 4, blocks_all_dev + 2 * (size_t)(d.ncells + 1), d.block_u32 * 4,
-                         rs_elems * 4, (size_t)world, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    int64_t ntot[2] = {0, 0};
-    for (int r = 0; r < world; ++r)
-        for (int s = 0; s < 2; ++s) ntot[s] += out_rowstart[(size_t)r * rs_elems + (size_t)s * (d.C + 1) + d.C];
-    // moment cells: the single-GPU rule applied to the WHOLE evaluation, so every rank (and the one-GPU run) agrees
-    if (g.use_moments == 1 && ntot[0] + ntot[1] < (int64_t)128 * 2 * d.ncells) g.use_moments = 0;
-    *out_use_moments = g.use_moments ? 1 : 0;
+    // the global cell table (the numbers a single-GPU sort produces), the work per tile column from it, and every
+    // rank's row starts (world x 2 x (C + 1) u32, a strided copy): one synchronisation for all of it
     OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
-    OKR(c->S().misc.ensure(64 + sizeof(double) * (size_t)g.NT));
+    OKR(sl.misc.ensure(64 + sizeof(double) * (size_t)(g.NT + 1)));
     k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, 0, d.ncells, sl.cellstart.as<uint32_t>());
     WaveDesc wd;
     memset(&wd, 0, sizeof wd);
     wd.n_sets = 2;
-    double *d_cw = c->S().misc.as<double>() + 8;
-    k_tile_colwork<<<g.NT, 128, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_cw);
+    double *d_cw = sl.misc.as<double>() + 8;
+    // moment cells: the single-GPU rule applied to the WHOLE evaluation, so every rank (and the one-GPU run) agrees
+    k_tile_colwork<<<g.NT, 128, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_cw, (long long)128 * 2 * d.ncells);
     c->launches += 2;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out_colwork, d_cw, sizeof(double) * (size_t)g.NT, cudaMemcpyDeviceToHost, st));
+    const size_t rs_elems = 2 * (size_t)(d.C + 1);
+    std::vector<double> cw((size_t)g.NT + 1);
+    CU(cudaMemcpy2DAsync(out_rowstart, rs_elems * 4, blocks_all_dev + 2 * (size_t)(d.ncells + 1), d.block_u32 * 4,
+                         rs_elems * 4, (size_t)world, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(cw.data(), d_cw, sizeof(double) * cw.size(), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    memcpy(out_colwork, cw.data(), sizeof(double) * (size_t)g.NT);
+    *out_use_moments = cw[(size_t)g.NT] != 0.0 ? 1 : 0;
     return release_scratch(*c, st, true);
 }
 
@@ -1548,14 +1550,14 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
     const bool fast32 = (p.algo == KDEJS_ALGO_BINNED32) && g.q_shift > 0;
     const int64_t P = na + nb;
     OKR(sl.sorted.ensure((size_t)std::max<int64_t>(P, 1) * sizeof(double2)));
-    if (fast32) OKR(sl.sorted_q.ensure((size_t)std::max<int64_t>(P, 1) * sizeof(uint2)));
+    if (fast32 && !kFp32FromDoubles) OKR(sl.sorted_q.ensure((size_t)std::max<int64_t>(P, 1) * sizeof(uint2)));
     OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
     const int c_lo = cy_lo * d.C, c_hi = (cy_hi + 1) * d.C;
     k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, c_lo, c_hi, sl.cellstart.as<uint32_t>());
     k_band_merge<<<dim3(c_hi - c_lo, 2, kMergeSplit), 256, 0, st>>>(
         reinterpret_cast<const double2 *>(stage_a_dev), reinterpret_cast<const double2 *>(stage_b_dev), blocks_all_dev,
         world, d.block_u32, g, cy_lo, cy_hi, sl.cellstart.as<uint32_t>(), na, sl.sorted.as<double2>(),
-        fast32 ? sl.sorted_q.as<uint2>() : nullptr);
+        fast32 && !kFp32FromDoubles ? sl.sorted_q.as<uint2>() : nullptr);
     c->launches += 2;
     WaveDesc wd;
     memset(&wd, 0, sizeof wd);

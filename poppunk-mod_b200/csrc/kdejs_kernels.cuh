@@ -1174,13 +1174,47 @@ constexpr float kBias32 = 9.5367431640625e-07f;       // 2^-20
 constexpr uint32_t kFarQ = 0x40000000u;               // a padding candidate 2^30 units (>= 2 h, q_shift <= 29) LEFT of the
                                                       // tile's first node: out of every node's support, adds exactly 0
 
-__device__ __forceinline__ void accumulate_point32(const uint2 q, const uint32_t gxq, const uint32_t gyq,
-                                                   const float unit, const float c1, const float c2, const float c3,
+// Where the fp32 kernel takes its candidates from.  0 (default): a 32-bit fixed-point copy of the sorted points
+// written by k_place (8 bytes per candidate to load; k_place scatters 24 instead of 16 bytes per point: 1.9 -> 2.8 us
+// per evaluation).  1: the fp64 sorted points themselves, re-centred on the tile's first node in fp64 (2 DADD + 2
+// DMUL on the otherwise idle fp64 pipe) and rounded to fp32 (2 F2F) -- no second copy, but measured slower overall:
+// k_place -0.9 us, density +1.9 us per evaluation (16-byte candidates, a wider register queue, spills).
+#ifndef KDEJS_FP32_FROM_DOUBLES
+#define KDEJS_FP32_FROM_DOUBLES 0
+#endif
+constexpr bool kFp32FromDoubles = KDEJS_FP32_FROM_DOUBLES != 0;
+struct TileOrigin32 {                // per tile: its first node in the candidates' representation
+    uint32_t gxq, gyq;               // fixed point
+    double gx0, gy0, inv_h;          // fp64
+    float unit;                      // 2^-q_shift
+};
+#if KDEJS_FP32_FROM_DOUBLES
+using Cand32 = double2;
+__device__ __forceinline__ Cand32 far_candidate(const TileOrigin32 &o, const GridGeom &g) {
+    return make_double2(o.gx0 - 2.0 * g.h, o.gy0);         // 2 h left of the first node: adds exactly 0 to every node
+}
+__device__ __forceinline__ void candidate_offsets(const Cand32 q, const TileOrigin32 &o, float &u0, float &v0) {
+    u0 = (float)((q.x - o.gx0) * o.inv_h);                 // offsets from the tile's first node, units of h
+    v0 = (float)((q.y - o.gy0) * o.inv_h);
+}
+#else
+using Cand32 = uint2;
+__device__ __forceinline__ Cand32 far_candidate(const TileOrigin32 &o, const GridGeom &) {
+    return make_uint2(o.gxq - kFarQ, o.gyq);
+}
+__device__ __forceinline__ void candidate_offsets(const Cand32 q, const TileOrigin32 &o, float &u0, float &v0) {
+    u0 = (float)(int)(q.x - o.gxq) * o.unit;
+    v0 = (float)(int)(q.y - o.gyq) * o.unit;
+}
+#endif
+
+__device__ __forceinline__ void accumulate_point32(const Cand32 q, const TileOrigin32 &o,
+                                                   const float c1, const float c2, const float c3,
                                                    const float one, float (&acc)[kTile][kTile]) {
-    const float fx = (float)(int)(q.x - gxq), fy = (float)(int)(q.y - gyq);
-    const float u0 = fx * unit, v0 = fy * unit;                       // offsets from the tile's first node, units of h
-    const float u1 = fmaf(fx, unit, -c1), u2 = fmaf(fx, unit, -c2), u3 = fmaf(fx, unit, -c3);
-    const float v1 = fmaf(fy, unit, -c1), v2 = fmaf(fy, unit, -c2), v3 = fmaf(fy, unit, -c3);
+    float u0, v0;
+    candidate_offsets(q, o, u0, v0);
+    const float u1 = u0 - c1, u2 = u0 - c2, u3 = u0 - c3;
+    const float v1 = v0 - c1, v2 = v0 - c2, v3 = v0 - c3;
     const float a[kTile] = {fmaf(-u0, u0, one), fmaf(-u1, u1, one), fmaf(-u2, u2, one), fmaf(-u3, u3, one)};
     const float v[kTile] = {v0, v1, v2, v3};
 #pragma unroll
@@ -1217,9 +1251,9 @@ __device__ __forceinline__ void flush32(float (&a32)[kTile][kTile], double (&a64
 // candidates the run holds from there on; the warp takes every (STRIDE/32)-th chunk (phase B: all of them, phase
 // A: the four warps of the block interleave).  Returns the lane's 16 partial sums in `tot` (fp64).
 template <int STRIDE, bool THREE_LEVEL>
-__device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const uint32_t *wstart, const uint32_t *wlen,
+__device__ __forceinline__ void walk_tile32(const Cand32 *__restrict__ pts, const uint32_t *wstart, const uint32_t *wlen,
                                             const int nruns, const uint32_t total_trips, const int lane,
-                                            const uint32_t gxq, const uint32_t gyq, const float unit, const float f1,
+                                            const TileOrigin32 &o, const Cand32 far, const float f1,
                                             const float f2, const float f3, const float one,
                                             double (&tot)[kTile][kTile]) {
     float lo[kTile][kTile], hi[kTile][kTile], top[kTile][kTile];
@@ -1227,16 +1261,15 @@ __device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const
     for (int i = 0; i < kTile; ++i)
 #pragma unroll
         for (int j = 0; j < kTile; ++j) { lo[i][j] = 0.f; hi[i][j] = 0.f; top[i][j] = 0.f; }
-    const uint2 far = make_uint2(gxq - kFarQ, gyq);
     // fetch side: a running pointer into the current run, the lane's remaining candidates in it and the run's
     // remaining trips; run boundaries cost a few warp-uniform instructions, a trip five
     int r_pf = 0;
     int rem = -0x40000000;                        // candidates of the current run at or after this lane's next one
     uint32_t trips_left = 0xffffffffu;            // (past the last run: nothing left to load, never switches again)
-    const uint2 *nxt = pts;
+    const Cand32 *nxt = pts;
     if (nruns > 0) { rem = (int)wlen[0] - lane; nxt = pts + wstart[0] + lane; trips_left = (wlen[0] + STRIDE - 1u) / STRIDE; }
-    auto fetch = [&]() -> uint2 {
-        uint2 v = far;
+    auto fetch = [&]() -> Cand32 {
+        Cand32 v = far;
         if (rem > 0) v = *nxt;
         nxt += STRIDE;
         rem -= STRIDE;
@@ -1257,27 +1290,27 @@ __device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const
     // three trips in flight; the loop is unrolled by three so the queue is renamed, not moved; fp32 partial sums are
     // folded every 15 trips (a level never sums more than 16 terms of its own): no per-trip counter in the hot loop
     static_assert(kPrefetch == 3 && kFoldTrips == 16, "queue of three, folds every 15 (< 16) trips");
-    uint2 q0 = fetch(), q1 = fetch(), q2 = fetch();
+    Cand32 q0 = fetch(), q1 = fetch(), q2 = fetch();
     uint32_t t = 0;
     int folds = kFoldTrips;
     while (t + 15u <= total_trips) {
 #pragma unroll 1
         for (int k = 0; k < 5; ++k) {
-            accumulate_point32(q0, gxq, gyq, unit, f1, f2, f3, one, lo); q0 = fetch();
-            accumulate_point32(q1, gxq, gyq, unit, f1, f2, f3, one, lo); q1 = fetch();
-            accumulate_point32(q2, gxq, gyq, unit, f1, f2, f3, one, lo); q2 = fetch();
+            accumulate_point32(q0, o, f1, f2, f3, one, lo); q0 = fetch();
+            accumulate_point32(q1, o, f1, f2, f3, one, lo); q1 = fetch();
+            accumulate_point32(q2, o, f1, f2, f3, one, lo); q2 = fetch();
         }
         t += 15u;
         fold32(lo, hi);
         if (THREE_LEVEL && --folds == 0) { fold32(hi, top); folds = kFoldTrips; }
     }
     for (; t + 3u <= total_trips; t += 3u) {                   // fewer than 15 trips left
-        accumulate_point32(q0, gxq, gyq, unit, f1, f2, f3, one, lo); q0 = fetch();
-        accumulate_point32(q1, gxq, gyq, unit, f1, f2, f3, one, lo); q1 = fetch();
-        accumulate_point32(q2, gxq, gyq, unit, f1, f2, f3, one, lo); q2 = fetch();
+        accumulate_point32(q0, o, f1, f2, f3, one, lo); q0 = fetch();
+        accumulate_point32(q1, o, f1, f2, f3, one, lo); q1 = fetch();
+        accumulate_point32(q2, o, f1, f2, f3, one, lo); q2 = fetch();
     }
-    if (t < total_trips) accumulate_point32(q0, gxq, gyq, unit, f1, f2, f3, one, lo);
-    if (t + 1u < total_trips) accumulate_point32(q1, gxq, gyq, unit, f1, f2, f3, one, lo);
+    if (t < total_trips) accumulate_point32(q0, o, f1, f2, f3, one, lo);
+    if (t + 1u < total_trips) accumulate_point32(q1, o, f1, f2, f3, one, lo);
     fold32(lo, hi);
     if (THREE_LEVEL) fold32(hi, top);
 #pragma unroll
@@ -1289,7 +1322,7 @@ __device__ __forceinline__ void walk_tile32(const uint2 *__restrict__ pts, const
 template <bool MOMENTS>
 __global__ void __launch_bounds__(kDensThreads, 6)
 k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
-                   const uint2 *__restrict__ sorted_q, const uint32_t *__restrict__ cellstart,
+                   const Cand32 *__restrict__ sorted_q, const uint32_t *__restrict__ cellstart,
                    const double *__restrict__ moments,
                    double *__restrict__ dens, double *__restrict__ pz, double *__restrict__ tilesum,
                    const uint32_t *__restrict__ worklist, unsigned *__restrict__ counters,
@@ -1354,7 +1387,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         const int tx = tile / g.NT, ty = tile % g.NT;
         const int ix0 = tx * kTile, iy0 = ty * kTile;
         const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
-        const uint32_t gxq = quantise(gx0, g), gyq = quantise(gy0, g);
+        const TileOrigin32 org{kFp32FromDoubles ? 0u : quantise(gx0, g), kFp32FromDoubles ? 0u : quantise(gy0, g), gx0, gy0, g.inv_h, unit};
         if (warp == 0) {
             const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
             const TileCells tc = tile_cells(g, ix0, iy0);
@@ -1380,7 +1413,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
             if (lane == 0) { s_rows = rows; s_cy0 = tc.cy_lo; }
         }
         __syncthreads();
-        const uint2 *__restrict__ pts = sorted_q + sd.off;
+        const Cand32 *__restrict__ pts = sorted_q + sd.off;
         const uint32_t gtot = s_cpre[2 * kMaxRows];         // 32-candidate chunks of the tile, dealt round-robin to the warps
         // this part's chunks of the flattened sequence (a tile that is not split is one part), and in them this
         // warp's share of every run, compacted into the warp's own run list (two run slots per lane: left / right
@@ -1408,8 +1441,8 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
             __syncwarp();
         }
         double acc64[kTile][kTile];
-        walk_tile32<kDensThreads, true>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, gxq, gyq, unit,
-                                        f1, f2, f3, 1.0f, acc64);
+        walk_tile32<kDensThreads, true>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, org,
+                                        far_candidate(org, g), f1, f2, f3, 1.0f, acc64);
         uint32_t ncand = gtot * 32u;                          // upper bound of the candidates (last chunks are ragged)
         if (MOMENTS && part_k == 0u) {                        // the moment cells go with the first part
             const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
@@ -1447,9 +1480,12 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         if (low) {                                               // cannot certify a node here: fp64 does this tile
             if (threadIdx.x == 0) {
                 if (stats) atomicAdd(&stats[4], 1ull);
-                const unsigned slot = atomicAdd(&redo_counters[list], 1u);
-                redo_list[(size_t)list * capacity + slot] = entry;
-                redo_partinfo[(size_t)(list / kNumClasses) * capacity + slot] = make_uint2(1u << 8, 0u);   // whole, one part
+                // the fp64 kernel walks it in the same parts (the part slots are free again: the ticket was reset)
+                const unsigned slot = atomicAdd(&redo_counters[list], part_K);
+                for (uint32_t q = 0; q < part_K; ++q) {
+                    redo_list[(size_t)list * capacity + slot + q] = entry;
+                    redo_partinfo[(size_t)(list / kNumClasses) * capacity + slot + q] = make_uint2(q | (part_K << 8), pbase);
+                }
             }
             continue;
         }
@@ -1484,11 +1520,11 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
                                              kMaxGroups * (kNumClasses - 1), list, index);
         const int set = (int)(entry >> 24), tile = (int)(entry & 0xffffffu);
         const double knorm_over_n = wd.set[set].knorm_over_n;
-        const uint2 *__restrict__ pts = sorted_q + wd.set[set].off;
+        const Cand32 *__restrict__ pts = sorted_q + wd.set[set].off;
         const int tx = tile / g.NT, ty = tile % g.NT;
         const int ix0 = tx * kTile, iy0 = ty * kTile;
         const double gx0 = (double)ix0 * g.step + g.gmin, gy0 = (double)iy0 * g.step + g.gmin;
-        const uint32_t gxq = quantise(gx0, g), gyq = quantise(gy0, g);
+        const TileOrigin32 org{kFp32FromDoubles ? 0u : quantise(gx0, g), kFp32FromDoubles ? 0u : quantise(gy0, g), gx0, gy0, g.inv_h, unit};
         const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
         const TileCells tc = tile_cells(g, ix0, iy0);
         const int rows = tc.cy_hi - tc.cy_lo + 1;
@@ -1520,7 +1556,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
             double acc64[kTile][kTile];
-            walk_tile32<32, false>(pts, wstart, wlen, nruns, total_trips, lane, gxq, gyq, unit, f1, f2, f3, one, acc64);
+            walk_tile32<32, false>(pts, wstart, wlen, nruns, total_trips, lane, org, far_candidate(org, g), f1, f2, f3, one, acc64);
             if (MOMENTS) {
                 const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
                 for (int r = 0; r < rows; ++r) {
@@ -2027,16 +2063,26 @@ k_band_merge(const double2 *__restrict__ stage_a, const double2 *__restrict__ st
 }
 
 // Estimated density work of one tile COLUMN (all tile rows, both sets): the band cuts are derived from these.
+// moments_min_points >= 0: the moment-cell rule of the single-GPU path is applied here to the WHOLE evaluation
+// (eligible geometry and at least that many points in total, read from the global cell table), and the decision is
+// left in colwork[NT] so that the host learns it with the same copy.
 __global__ void __launch_bounds__(128)
-k_tile_colwork(const __grid_constant__ WaveDesc wd, const GridGeom g,
-               const uint32_t *__restrict__ cellstart, double *__restrict__ colwork) {
+k_tile_colwork(const __grid_constant__ WaveDesc wd, const GridGeom g_in,
+               const uint32_t *__restrict__ cellstart, double *__restrict__ colwork, long long moments_min_points) {
     __shared__ double s_w[32];
+    GridGeom g = g_in;
+    const int ncells = g.C * g.C;
+    if (moments_min_points >= 0 && g.use_moments == 1) {
+        long long total = 0;
+        for (int s = 0; s < wd.n_sets; ++s) total += cellstart[(size_t)s * (ncells + 1) + ncells];
+        if (total < moments_min_points) g.use_moments = 0;
+    }
     const int ty = blockIdx.x;
     double work = 0.0;
     for (int idx = threadIdx.x; idx < wd.n_sets * g.NT; idx += blockDim.x) {
         const int set = idx / g.NT, tx = idx % g.NT;
         const TileCells tc = tile_cells(g, tx * kTile, ty * kTile);
-        const uint32_t *__restrict__ cs = cellstart + (size_t)set * (g.C * g.C + 1);
+        const uint32_t *__restrict__ cs = cellstart + (size_t)set * (ncells + 1);
         uint32_t total = 0u;
         for (int cy = tc.cy_lo; cy <= tc.cy_hi; ++cy) {
             const RowRuns rr = tile_row_runs(g, tc, cs, cy, g.use_moments != 0);
@@ -2045,7 +2091,10 @@ k_tile_colwork(const __grid_constant__ WaveDesc wd, const GridGeom g,
         work += (double)total + (total ? 64.0 : 2.0);
     }
     work = block_sum(work, s_w);
-    if (threadIdx.x == 0) colwork[ty] = work;
+    if (threadIdx.x == 0) {
+        colwork[ty] = work;
+        if (ty == 0) colwork[g.NT] = g.use_moments ? 1.0 : 0.0;
+    }
 }
 
 // Partial normalisers of a band: per-tile partials of tile columns [ty_b, ty_e), all tile rows, summed in a fixed
@@ -2283,12 +2332,18 @@ __global__ void __launch_bounds__(kDensThreads) k_loop_peak(int trips, const dou
         for (int i = 0; i < kTile; ++i)
 #pragma unroll
             for (int j = 0; j < kTile; ++j) { acc[i][j] = 0.f; hi[i][j] = 0.f; acc64[i][j] = 0.0; }
-        uint2 pn = ptsq[lane];
+        const TileOrigin32 org{0x10000000u, 0x10000000u, 0.25, 0.25, 33.0, 1.862645149230957e-09f};
+#if KDEJS_FP32_FROM_DOUBLES
+        const double2 *src = pts;
+#else
+        const uint2 *src = ptsq;
+#endif
+        Cand32 pn = src[lane];
         int budget = kFoldTrips;
         for (int t = 0; t < trips; ++t) {
-            const uint2 p = pn;
-            pn = ptsq[((t + 1) & 31) * 32 + lane];
-            accumulate_point32(p, 0x10000000u, 0x10000000u, 1.862645149230957e-09f, 0.13f, 0.26f, 0.39f, 1.0f, acc);
+            const Cand32 p = pn;
+            pn = src[((t + 1) & 31) * 32 + lane];
+            accumulate_point32(p, org, 0.13f, 0.26f, 0.39f, 1.0f, acc);
             if (WHICH == 2 && --budget == 0) { fold32(acc, hi); budget = kFoldTrips; }
         }
         fold32(acc, hi);

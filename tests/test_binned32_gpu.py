@@ -170,9 +170,13 @@ def test_fine_grid_moments_fp32(pk, ko, monkeypatch):
 
     a, b = wl.synthetic_target(300_000, seed=11), wl.sim_S(5, 1800, 0.36, n=300_000)
     monkeypatch.setenv("KDEJS_MOMENTS", "1")
-    got = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=1024, algo="binned32")
     exact = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=1024, algo="binned")
-    assert rel(got, exact) < JS_RTOL_EXPECT
+    # by default moment geometries stay on the fp64 kernel whatever the algorithm says ...
+    assert pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=1024, algo="binned32") == exact
+    # ... KDEJS_FP32=1 forces the fp32 kernel (moment cells in fp64, point runs in fp32)
+    monkeypatch.setenv("KDEJS_FP32", "1")
+    got = pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=1024, algo="binned32")
+    assert got != exact and rel(got, exact) < JS_RTOL_EXPECT
 
 
 def test_device_entry_and_profile_slots_fp32(pk):

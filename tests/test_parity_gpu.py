@@ -16,10 +16,16 @@ JS_RTOL_EXPECT = 1e-10  # what the fp64 path actually has to deliver
 
 @pytest.fixture(scope="module")
 def pk():
+    """This module pins the EXACT fp64 culled sum (algo="binned") wherever a test does not name an algorithm: its
+    bars are 1e-10 and bitwise equalities.  The package default (the fp32 culled kernel) is covered, with fp32
+    bars, by tests/test_binned32_gpu.py."""
     import poppunk_mod_b200 as pkg
 
     assert pkg._native.device_count() > 0, "no CUDA device: the product has no CPU fallback"
-    return pkg
+    old = pkg.KDE_distance.DEFAULT_ALGO
+    pkg.KDE_distance.DEFAULT_ALGO = "binned"
+    yield pkg
+    pkg.KDE_distance.DEFAULT_ALGO = old
 
 
 @pytest.fixture(scope="module")
@@ -428,7 +434,7 @@ def test_fork_after_import_before_first_use(golden):
     assert out.returncode == 0, out.stderr[-2000:]
     v0, v1 = (float(x) for x in out.stdout.split()[-2:])
     want = golden["cases"]["G1_g025"]["oracle"]
-    assert v0 == v1 and abs(v0 - want) <= 1e-10 * want
+    assert v0 == v1 and abs(v0 - want) <= 1e-7 * want       # the child runs the package default (fp32 culled kernel)
 
 
 def test_sweep_drivers_and_simulator_summary(pk, ko, tmp_path):
