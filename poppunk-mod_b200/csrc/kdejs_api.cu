@@ -408,7 +408,7 @@ struct WaveIO {
     const int64_t *n_global = nullptr;   // [n_sets]: sizes of the WHOLE sets (the 1/N of the density) when this wave holds a part
 };
 
-int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
+int sort_shape(const WaveDesc &wd, int sm_count, int ncells, int &chw, int &nb_max) {
     // Points per warp sub-chunk.  Every sort block pays a fixed cost for its C*C counters (zeroing, prefix,
     // histogram write-out), so chunks grow with the wave until the launch still has ~4 blocks per SM
     // (8 per SM was measured: k_scale_count -4 %, k_scan +75 %).
@@ -417,7 +417,11 @@ int sort_shape(const WaveDesc &wd, int sm_count, int &chw, int &nb_max) {
     for (int s = 0; s < wd.n_sets; ++s) { nmax = std::max(nmax, wd.set[s].n); total += wd.set[s].n; }
     // ... rounded DOWN to a power of two (k_place turns a point's index into its chunk with a shift; rounding up
     // left 3.5 blocks per SM with a nearly empty last block per set: k_scale_count 2.06 -> 2.84 us per evaluation)
-    int64_t per_warp = total / ((int64_t)4 * sm_count * kSortWarps);
+    // With the 128 x 128 cell geometry a block's counters fill half an SM's shared memory (one block per SM is
+    // resident anyway) and every block costs k_scan another pass over 16 384 cells: aim for one block per SM there
+    // (a band of config C5 on eight GPUs: k_scan 0.11 -> 0.03 ms, 4x less histogram traffic).
+    const int blocks_per_sm = ncells > 4096 ? 1 : 4;
+    int64_t per_warp = total / ((int64_t)blocks_per_sm * sm_count * kSortWarps);
     chw = 512;
     while (2 * chw <= per_warp && chw < kMaxChw) chw <<= 1;
     nb_max = std::max(1, (int)(((int64_t)nmax + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)));
@@ -438,7 +442,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         wd.set[s].knorm_over_n = g.knorm / (double)(io.n_global ? io.n_global[s] : (int64_t)wd.set[s].n);
     }
     int chw, nb_max;
-    sort_shape(wd, c.sm_count, chw, nb_max);
+    sort_shape(wd, c.sm_count, g.C * g.C, chw, nb_max);
     for (int s = 0; s < n_sets; ++s)
         wd.set[s].nb = (int)(((int64_t)wd.set[s].n + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps));
     const int ncells = g.C * g.C;

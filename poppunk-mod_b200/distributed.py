@@ -294,23 +294,29 @@ def _gather_cat(t, group, world):
     return out
 
 
-def _exchange(send, recv, group, rank, world):
-    """send[d] -> rank d, recv[s] <- rank s.  Slices of `send` may overlap (halo rows go to two neighbours)."""
+def _exchange(pairs, group, rank, world):
+    """pairs: [(send, recv), ...] with send[d] -> rank d and recv[s] <- rank s for every pair (one pair per point
+    set).  All transfers of all pairs go out as ONE group of point-to-point operations (one NCCL group launch, not
+    one collective per set); slices of a `send` may overlap (halo rows go to two neighbours); empty slices are
+    skipped on both sides (both know the count from the gathered row starts)."""
     dist = _dist()
+    for send, recv in pairs:
+        if recv[rank].shape[0]:
+            recv[rank].copy_(send[rank])
     if world == 1:
-        recv[0].copy_(send[0])
         return
-    if dist.get_backend(group) == "nccl":
-        dist.all_to_all(recv, [t.contiguous() for t in send], group=group)
-        return
-    recv[rank].copy_(send[rank])                      # gloo (CPU tests): point-to-point
+    peer = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     ops = []
     for k in range(1, world):
         d, s_ = (rank + k) % world, (rank - k) % world
-        ops.append(dist.P2POp(dist.isend, send[d].contiguous(), dist.get_global_rank(group, d) if group else d, group))
-        ops.append(dist.P2POp(dist.irecv, recv[s_], dist.get_global_rank(group, s_) if group else s_, group))
-    for w in dist.batch_isend_irecv(ops):
-        w.wait()
+        for send, recv in pairs:
+            if send[d].shape[0]:
+                ops.append(dist.P2POp(dist.isend, send[d].contiguous(), peer(d), group))
+            if recv[s_].shape[0]:
+                ops.append(dist.P2POp(dist.irecv, recv[s_], peer(s_), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
 
 
 def band_sharded_discrepancy(a_slice, b_slice, gamma=1.0, eps=1e-12, log=False, *, resolution=100, bandwidth=0.03,
@@ -357,16 +363,16 @@ def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world
     cuts = band_cuts(colwork, world)
     rows = [band_cell_rows(resolution, bandwidth, cuts[d], cuts[d + 1]) for d in range(world)]
     lo_me, hi_me = rows[rank]
-    stages = []
+    stages, pairs = [], []
     for st in (0, 1):
         base = 0 if st == 0 else na
         send = [srt[base + rs[rank, st, lo]: base + rs[rank, st, hi + 1]] if hi >= lo else srt[0:0] for lo, hi in rows]
         counts = [int(rs[s_, st, hi_me + 1] - rs[s_, st, lo_me]) if hi_me >= lo_me else 0 for s_ in range(world)]
         stage = ops.empty((sum(counts), 2))
         offs = np.concatenate([[0], np.cumsum(counts)])
-        recv = [stage[offs[s_]:offs[s_ + 1]] for s_ in range(world)]
-        _exchange(send, recv, group, rank, world)
+        pairs.append((send, [stage[offs[s_]:offs[s_ + 1]] for s_ in range(world)]))
         stages.append(stage)
+    _exchange(pairs, group, rank, world)
     mark("exchange")
     n_tot = rs[:, :, -1].sum(axis=0)
     norm = ops.phase1(stages[0], stages[1], n_tot[0], n_tot[1], blocks_all, stats_all, world,

@@ -37,7 +37,7 @@ for algo in ("binned", "binned32"):
             print(f"band mode {algo} R={R}: {js!r} single {full!r} oracle {o!r} band {info}", flush=True)
 # the older replicate-and-sort variant still agrees
 js_old = D.row_sharded_discrepancy(cut(a), cut(b), 0.25, 0.0, resolution=256, sliced=True, gather_all=True)
-assert abs(js_old - pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=256)) <= 1e-12 * js_old
+assert abs(js_old - pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=256, algo="binned")) <= 1e-12 * js_old
 # infinity in one rank's slice raises on every rank
 bad = cut(b).copy()
 if rank == world - 1:
@@ -113,8 +113,8 @@ if os.environ.get("MGPU_SMALL", "0") != "1":
         print(f"   older variant (all-gather everything, every rank sorts everything): {js_g!r} in {1e3*dt:.2f} ms", flush=True)
         pa = pool.empty(A.shape); pa[:] = A
         pb = pool.empty(B.shape); pb[:] = B
-        pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=1024)
-        t0 = time.perf_counter(); full = pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=1024); d1 = time.perf_counter() - t0
+        pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=1024, algo="binned")
+        t0 = time.perf_counter(); full = pk.KDE_JS_divergence(pa, pb, 0.25, 0.0, resolution=1024, algo="binned"); d1 = time.perf_counter() - t0
         print(f"   single GPU from pinned host memory: {full!r} in {1e3*d1:.2f} ms ; rel gap {abs(js_g-full)/full:.2e}", flush=True)
 if rank == 0:
     print("mgpu_check ok", flush=True)
