@@ -1247,15 +1247,20 @@ __device__ __forceinline__ void flush32(float (&a32)[kTile][kTile], double (&a64
 }
 
 // One walk of a warp over its flattened runs of a tile.  wstart / wlen: the warp's non-empty runs in processing
-// order (per-warp shared memory): first candidate of the warp's first 32-candidate chunk in the run, and how many
-// candidates the run holds from there on; the warp takes every (STRIDE/32)-th chunk (phase B: all of them, phase
-// A: the four warps of the block interleave).  Returns the lane's 16 partial sums in `tot` (fp64).
-template <int STRIDE, bool THREE_LEVEL>
+// order (per-warp shared memory): first candidate of the warp's first chunk in the run, and how many candidates the
+// run holds from there on.  PAIR = false (phase A): a trip is 32 candidates, one per lane, and the warp takes every
+// (STRIDE/32)-th chunk (the four warps of a block interleave).  PAIR = true (phase B, STRIDE 64): a trip is 64
+// candidates, TWO consecutive ones per lane -- the fetch bookkeeping and the loop overhead are paid once per 64
+// candidates (about a third of the instructions of a 32-candidate trip were not arithmetic).
+// Returns the lane's 16 partial sums in `tot` (fp64).
+struct CandPair { Cand32 a, b; };
+template <int STRIDE, bool THREE_LEVEL, bool PAIR>
 __device__ __forceinline__ void walk_tile32(const Cand32 *__restrict__ pts, const uint32_t *wstart, const uint32_t *wlen,
                                             const int nruns, const uint32_t total_trips, const int lane,
                                             const TileOrigin32 &o, const Cand32 far, const float f1,
                                             const float f2, const float f3, const float one,
                                             double (&tot)[kTile][kTile]) {
+    constexpr int kPer = PAIR ? 2 : 1;            // candidates per lane and trip
     float lo[kTile][kTile], hi[kTile][kTile], top[kTile][kTile];
 #pragma unroll
     for (int i = 0; i < kTile; ++i)
@@ -1267,18 +1272,19 @@ __device__ __forceinline__ void walk_tile32(const Cand32 *__restrict__ pts, cons
     int rem = -0x40000000;                        // candidates of the current run at or after this lane's next one
     uint32_t trips_left = 0xffffffffu;            // (past the last run: nothing left to load, never switches again)
     const Cand32 *nxt = pts;
-    if (nruns > 0) { rem = (int)wlen[0] - lane; nxt = pts + wstart[0] + lane; trips_left = (wlen[0] + STRIDE - 1u) / STRIDE; }
-    auto fetch = [&]() -> Cand32 {
-        Cand32 v = far;
-        if (rem > 0) v = *nxt;
+    if (nruns > 0) { rem = (int)wlen[0] - kPer * lane; nxt = pts + wstart[0] + kPer * lane; trips_left = (wlen[0] + STRIDE - 1u) / STRIDE; }
+    auto fetch = [&]() -> CandPair {
+        CandPair v{far, far};
+        if (rem > 0) v.a = nxt[0];
+        if (PAIR && rem > 1) v.b = nxt[1];
         nxt += STRIDE;
         rem -= STRIDE;
         if (--trips_left == 0u) {                             // warp-uniform, once per run
             ++r_pf;
             if (r_pf < nruns) {
                 const uint32_t len = wlen[r_pf];
-                rem = (int)len - lane;
-                nxt = pts + wstart[r_pf] + lane;
+                rem = (int)len - kPer * lane;
+                nxt = pts + wstart[r_pf] + kPer * lane;
                 trips_left = (len + STRIDE - 1u) / STRIDE;
             } else {
                 rem = -0x40000000;
@@ -1287,30 +1293,37 @@ __device__ __forceinline__ void walk_tile32(const Cand32 *__restrict__ pts, cons
         }
         return v;
     };
-    // three trips in flight; the loop is unrolled by three so the queue is renamed, not moved; fp32 partial sums are
-    // folded every 15 trips (a level never sums more than 16 terms of its own): no per-trip counter in the hot loop
-    static_assert(kPrefetch == 3 && kFoldTrips == 16, "queue of three, folds every 15 (< 16) trips");
-    Cand32 q0 = fetch(), q1 = fetch(), q2 = fetch();
+    auto use = [&](const CandPair &c) {
+        accumulate_point32(c.a, o, f1, f2, f3, one, lo);
+        if (PAIR) accumulate_point32(c.b, o, f1, f2, f3, one, lo);
+    };
+    // kQ trips in flight (96 / 128 candidates per warp); the loop is unrolled by kQ so the queue is renamed, not
+    // moved; fp32 partial sums are folded every kBlock trips (a level never sums more than 16 terms of its own): no
+    // per-trip counter in the hot loop
+    constexpr int kQ = PAIR ? 2 : 3, kBlock = PAIR ? 8 : 15;
+    static_assert(kFoldTrips == 16 && kBlock * kPer <= kFoldTrips && kBlock % kQ == 0, "fold blocks");
+    CandPair q[kQ];
+#pragma unroll
+    for (int i = 0; i < kQ; ++i) q[i] = fetch();
     uint32_t t = 0;
     int folds = kFoldTrips;
-    while (t + 15u <= total_trips) {
+    while (t + kBlock <= total_trips) {
 #pragma unroll 1
-        for (int k = 0; k < 5; ++k) {
-            accumulate_point32(q0, o, f1, f2, f3, one, lo); q0 = fetch();
-            accumulate_point32(q1, o, f1, f2, f3, one, lo); q1 = fetch();
-            accumulate_point32(q2, o, f1, f2, f3, one, lo); q2 = fetch();
+        for (int k = 0; k < kBlock / kQ; ++k) {
+#pragma unroll
+            for (int i = 0; i < kQ; ++i) { use(q[i]); q[i] = fetch(); }
         }
-        t += 15u;
+        t += kBlock;
         fold32(lo, hi);
         if (THREE_LEVEL && --folds == 0) { fold32(hi, top); folds = kFoldTrips; }
     }
-    for (; t + 3u <= total_trips; t += 3u) {                   // fewer than 15 trips left
-        accumulate_point32(q0, o, f1, f2, f3, one, lo); q0 = fetch();
-        accumulate_point32(q1, o, f1, f2, f3, one, lo); q1 = fetch();
-        accumulate_point32(q2, o, f1, f2, f3, one, lo); q2 = fetch();
+    for (; t + kQ <= total_trips; t += kQ) {                   // fewer than kBlock trips left
+#pragma unroll
+        for (int i = 0; i < kQ; ++i) { use(q[i]); q[i] = fetch(); }
     }
-    if (t < total_trips) accumulate_point32(q0, o, f1, f2, f3, one, lo);
-    if (t + 1u < total_trips) accumulate_point32(q1, o, f1, f2, f3, one, lo);
+#pragma unroll
+    for (int i = 0; i < kQ - 1; ++i)
+        if (t + i < total_trips) use(q[i]);
     fold32(lo, hi);
     if (THREE_LEVEL) fold32(hi, top);
 #pragma unroll
@@ -1441,7 +1454,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
             __syncwarp();
         }
         double acc64[kTile][kTile];
-        walk_tile32<kDensThreads, true>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, org,
+        walk_tile32<kDensThreads, true, false>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, org,
                                         far_candidate(org, g), f1, f2, f3, 1.0f, acc64);
         uint32_t ncand = gtot * 32u;                          // upper bound of the candidates (last chunks are ragged)
         if (MOMENTS && part_k == 0u) {                        // the moment cells go with the first part
@@ -1538,7 +1551,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         if (rr.l1 > 0u) { const int k = __popc(m1 & lt) + __popc(m2 & lt); wstart[k] = rr.s1; wlen[k] = rr.l1; }
         if (MOMENTS && rr.l2 > 0u) { const int k = __popc(m1 & lt) + __popc(m2 & lt) + (rr.l1 > 0u ? 1 : 0); wstart[k] = rr.s2; wlen[k] = rr.l2; }
         const int nruns = __popc(m1) + __popc(m2);
-        uint32_t total_trips = ((rr.l1 + 31u) >> 5) + ((rr.l2 + 31u) >> 5);
+        uint32_t total_trips = ((rr.l1 + 63u) >> 6) + ((rr.l2 + 63u) >> 6);      // 64 candidates per trip here
         uint32_t ncand = rr.l1 + rr.l2 + (uint32_t)rr.mcnt;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -1556,7 +1569,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll 1
         for (int pass = 0;; ++pass) {
             double acc64[kTile][kTile];
-            walk_tile32<32, false>(pts, wstart, wlen, nruns, total_trips, lane, org, far_candidate(org, g), f1, f2, f3, one, acc64);
+            walk_tile32<64, false, true>(pts, wstart, wlen, nruns, total_trips, lane, org, far_candidate(org, g), f1, f2, f3, one, acc64);
             if (MOMENTS) {
                 const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
                 for (int r = 0; r < rows; ++r) {

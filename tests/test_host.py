@@ -150,3 +150,20 @@ def test_cpulist_parser_and_numa_bind_opt_out(monkeypatch):
     if not nat.device_count():
         assert nat.bind_host_to_device(0) == -1
         assert os.sched_getaffinity(0) == before
+
+
+def test_default_algorithm_and_its_override():
+    """The package default is the fp32 culled kernel; KDEJS_DEFAULT_ALGO selects another one for a whole process."""
+    import subprocess
+    import sys
+
+    code = "import sys; sys.path.insert(0, %r); import poppunk_mod_b200 as pk; print(pk.KDE_distance.DEFAULT_ALGO)" % ROOT
+    env = {k: v for k, v in os.environ.items() if k != "KDEJS_DEFAULT_ALGO"}
+    assert subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env).stdout.strip() == "binned32"
+    env["KDEJS_DEFAULT_ALGO"] = "binned"
+    assert subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env).stdout.strip() == "binned"
+    import poppunk_mod_b200 as pk
+
+    assert set(pk._native.ALGOS) == {"binned", "binned32", "dense", "dense64"}
+    with pytest.raises(ValueError):
+        pk.KDE_distance._common(100, 0.03, 1.0, 0.0, False, "epanechnikov", "fastest")

@@ -1,20 +1,19 @@
 #!/bin/bash
 # Run ON the GPU box (through gpurun): bench lines + ncu launch list + ncu full captures -> gpurun_out/.
-# usage: tools/capture_profiles.sh <tag>
+# usage: tools/capture_profiles.sh <tag>          (every ncu pass runs only after the same command exited 0 without ncu)
 set -u
 TAG="${1:-rX}"
 OUT=gpurun_out
 python bench.py > $OUT/bench_${TAG}_n1.json 2> $OUT/bench_${TAG}_n1.err || exit 1
+python bench.py --algo binned --steps 200 --no-cpu-baseline > $OUT/bench_${TAG}_n1_binned.json 2> $OUT/bench_${TAG}_n1_binned.err || exit 1
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_${TAG}_reference.json 2> $OUT/bench_${TAG}_reference.err
-CMD="python bench.py --steps 10 --warmup 3 --no-cpu-baseline"
+python tools/fp32_probe.py > $OUT/fp32_probe_${TAG}.log 2>&1
+CMD="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras"
 $CMD > $OUT/plain_${TAG}.log 2>&1 || exit 2
-ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_density_binned -s 10 -c 2 -o $OUT/prof_binned_${TAG} $CMD > $OUT/ncu_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_density_dense32 -c 1 -o $OUT/prof_dense32_${TAG} $CMD > $OUT/ncu_d.log 2>&1
-ncu --set full --clock-control none -k regex:"k_minmax|k_scale_count|k_scan|k_place|k_tile_classify|k_set_totals|k_js" -s 21 -c 7 -o $OUT/prof_small_${TAG} $CMD > $OUT/ncu_s.log 2>&1
-for f in ncu_b ncu_d ncu_s; do tail -n 1 $OUT/$f.log; done
-# fine-grid path (128x128 cells, cell moments): config C5 at 3 M + 3 M points, R = 1024
-C5CMD="python tools/c5_probe.py"
-C5_N=3000000 $C5CMD > $OUT/plain_c5_${TAG}.log 2>&1 || exit 3
-C5_N=3000000 ncu --set full --clock-control none --import-source on -k regex:"k_density_binned|k_cell_moments|k_scan_wide" -c 3 -o $OUT/prof_c5_${TAG} $C5CMD > $OUT/ncu_c5.log 2>&1
-tail -n 1 $OUT/ncu_c5.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_l.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_density_binned32 -s 10 -c 2 -o $OUT/prof_binned32_${TAG} $CMD > $OUT/ncu_b32.log 2>&1
+ncu --set full --clock-control none -k regex:'k_minmax|k_scale_count|k_scan|k_place|k_tile_classify|k_set_totals|k_js|^k_density_binned$' -s 27 -c 9 -o $OUT/prof_small_${TAG} $CMD > $OUT/ncu_s.log 2>&1
+CMD64="python bench.py --algo binned --steps 10 --warmup 3 --no-cpu-baseline --no-extras"
+$CMD64 > $OUT/plain64_${TAG}.log 2>&1 || exit 3
+ncu --set full --clock-control none --import-source on -k 'regex:^k_density_binned$' -s 10 -c 2 -o $OUT/prof_binned_${TAG} $CMD64 > $OUT/ncu_b64.log 2>&1
+for f in ncu_b32 ncu_s ncu_b64; do tail -n 1 $OUT/$f.log; done
