@@ -178,7 +178,20 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
  *                           density of the band's tiles, partial normalisers       -> all-gather (2 doubles)
  *   kdejs_band_phase2_dev   normalisers folded in rank order, rel_entr partials of the band -> all-gather (3 doubles);
  *                           JS = sqrt(max(0, sum of out_lr[0] + out_lr[1]) / 2); out_lr[2] != 0: an input held infinity.
- * A rank's count block (u32): cellstart[2][C*C + 1] of its sorted slices, then rowstart[2][C + 1]. */
+ * A rank's count block (u32): cellstart[2][C*C + 1] of its sorted slices, then rowstart[2][C + 1], then 16 words
+ * for the CUDA IPC handle of the buffer the rank's sorted points live in (zero: none).  kdejs_band_plan returns, per
+ * rank, the row starts AND those 16 words (out_rowstart: world x (2 (C + 1) + 16) u32).
+ *
+ * Exchange over peer memory (ranks of ONE node with NVLink/P2P access; replaces the all-to-all AND the staging copy):
+ *   kdejs_band_peer_buffer    this rank's exchange buffer (grown on demand) and its IPC handle: pass the pointer to
+ *                             kdejs_band_sort_dev as out_sorted_dev, put the handle words at the end of the count block
+ *   kdejs_band_peer_open      after kdejs_band_plan: map every peer's buffer from the gathered handles (cached; only
+ *                             a handle that changed is opened again)
+ *   kdejs_band_phase1_peer_dev  as kdejs_band_phase1_dev, but the merge kernel reads each source rank's points
+ *                             straight from that rank's buffer over NVLink -- the copy is the exchange.
+ * Ordering (the caller keeps everything on one stream per rank): a peer's sort precedes its contribution to the
+ * all-gather of the count blocks, which precedes this rank's merge; this rank's merge precedes its contribution to
+ * the all-gather of the normalisers, which precedes any peer's next sort. */
 int kdejs_band_geometry(int resolution, double bandwidth, int kernel, int out[4]);   /* C, NT, block_u32, moments eligible */
 int kdejs_band_minmax_dev(int device, const double *a_dev, int64_t na, const double *b_dev, int64_t nb,
                           int log_flag, double eps, double *out_stats_dev, void *stream);
@@ -197,6 +210,13 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
                           int log_flag, int kernel, int algo, int ty_begin, int ty_end, int cy_lo, int cy_hi,
                           int use_moments, double *out_norm_dev, void *stream);
 int kdejs_band_phase2_dev(int device, const double *norms_all_dev, int world, double *out_lr_dev, void *stream);
+int kdejs_band_peer_buffer(int device, int64_t points, void **out_ptr, uint32_t *out_handle_words /* [16] */);
+int kdejs_band_peer_open(int device, const uint32_t *handle_words /* [world][16], host */, int world, int rank);
+int kdejs_band_phase1_peer_dev(int device, int64_t na, int64_t nb, int64_t na_total, int64_t nb_total,
+                               const uint32_t *blocks_all_dev, int world, const double *stats_all_dev, int resolution,
+                               double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                               int ty_begin, int ty_end, int cy_lo, int cy_hi, int use_moments, double *out_norm_dev,
+                               void *stream);
 
 /* ---- host memory --------------------------------------------------------------------- */
 void *kdejs_host_alloc(size_t bytes);   /* pinned (page-locked) host memory, NULL on failure */

@@ -77,6 +77,13 @@ _SIGNATURES = {
                                ctypes.c_void_p]),
     "kdejs_band_phase2_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                              ctypes.c_void_p]),
+    "kdejs_band_peer_buffer": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_void_p),
+                                              ctypes.c_void_p]),
+    "kdejs_band_peer_open": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "kdejs_band_phase1_peer_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p] +
+                                   _COMMON + [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p]),
     "kdejs_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "kdejs_host_free": (None, [ctypes.c_void_p]),
     "kdejs_tsv_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -97,6 +97,7 @@ struct Slot {
     DevBuf scaled, sorted, sorted_q, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
     DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, redo, counters, totals, rank16, warpprefix, tileflag, misc;
     DevBuf partinfo, redo_partinfo, split_partial, split_ticket;     // very heavy tiles processed in parts (SplitBufs)
+    DevBuf bandtot;                                                   // band mode: per-cell totals over ranks
 };
 
 struct Params {
@@ -144,6 +145,15 @@ struct Ctx {
     // band mode state (kdejs_band_phase1_dev -> kdejs_band_phase2_dev)
     bool band_valid = false;
     GridGeom band_geom; int band_ty0 = 0, band_ty1 = 0, band_slot = 0;
+    // band mode over peer memory (kdejs_band_peer_*): this rank's locally sorted points live in peer_buf, exported
+    // through a CUDA IPC handle; peer_map[r] is rank r's buffer mapped into this process
+    DevBuf peer_buf;
+    unsigned char peer_handle[64] = {0};
+    bool peer_handle_valid = false;
+    struct PeerMap { unsigned char handle[64]; void *ptr; bool open; };
+    PeerMap peer_map[kMaxPeers] = {};
+    int peer_world = 0, peer_rank = -1;
+    std::vector<void *> peer_retired;
 };
 
 constexpr int kMaxDevices = 64;
@@ -182,11 +192,18 @@ void destroy_ctx(Ctx &c) {
         for (DevBuf *b : {&s.scaled, &s.sorted, &s.sorted_q, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
                           &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart, &s.dense_partial,
                           &s.worklist, &s.redo, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag, &s.misc,
-                          &s.partinfo, &s.redo_partinfo, &s.split_partial, &s.split_ticket}) {
+                          &s.partinfo, &s.redo_partinfo, &s.split_partial, &s.split_ticket, &s.bandtot}) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr; b->cap = 0;
         }
-    for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.sim_ring, &c.summary}) {
+    for (auto &m : c.peer_map) {
+        if (m.open) cudaIpcCloseMemHandle(m.ptr);
+        m.open = false; m.ptr = nullptr;
+    }
+    c.peer_world = 0; c.peer_rank = -1; c.peer_handle_valid = false;
+    for (void *q : c.peer_retired) cudaFree(q);
+    c.peer_retired.clear();
+    for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.sim_ring, &c.summary, &c.peer_buf}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr; b->cap = 0;
     }
@@ -415,15 +432,24 @@ int sort_shape(const WaveDesc &wd, int sm_count, int ncells, int &chw, int &nb_m
     int nmax = 0;
     int64_t total = 0;
     for (int s = 0; s < wd.n_sets; ++s) { nmax = std::max(nmax, wd.set[s].n); total += wd.set[s].n; }
-    // ... rounded DOWN to a power of two (k_place turns a point's index into its chunk with a shift; rounding up
-    // left 3.5 blocks per SM with a nearly empty last block per set: k_scale_count 2.06 -> 2.84 us per evaluation)
+    // ... rounded DOWN to a power of two for the 64 x 64 cell geometry (rounding up left 3.5 blocks per SM with a
+    // nearly empty last block per set: k_scale_count 2.06 -> 2.84 us per evaluation).
     // With the 128 x 128 cell geometry a block's counters fill half an SM's shared memory (one block per SM is
-    // resident anyway) and every block costs k_scan another pass over 16 384 cells: aim for one block per SM there
-    // (a band of config C5 on eight GPUs: k_scan 0.11 -> 0.03 ms, 4x less histogram traffic).
-    const int blocks_per_sm = ncells > 4096 ? 1 : 4;
-    int64_t per_warp = total / ((int64_t)blocks_per_sm * sm_count * kSortWarps);
-    chw = 512;
-    while (2 * chw <= per_warp && chw < kMaxChw) chw <<= 1;
+    // resident anyway) and every block costs k_scan another pass over 16 384 cells: exactly one block per SM there,
+    // chunks cut to measure (a band of config C5 on eight GPUs: 2 x 77 power-of-two blocks were 1.04 waves of the
+    // 148 SMs and took twice the time of 2 x 74).
+    if (ncells > 4096) {
+        const int blocks_per_set = std::max(1, sm_count / std::max(1, (int)wd.n_sets));
+        chw = 512;
+        for (int s = 0; s < wd.n_sets; ++s) {
+            const int64_t per_warp = ((int64_t)wd.set[s].n + (int64_t)blocks_per_set * kSortWarps - 1) / ((int64_t)blocks_per_set * kSortWarps);
+            chw = (int)std::max<int64_t>(chw, std::min<int64_t>((per_warp + 31) / 32 * 32, kMaxChw));
+        }
+    } else {
+        int64_t per_warp = total / ((int64_t)4 * sm_count * kSortWarps);
+        chw = 512;
+        while (2 * chw <= per_warp && chw < kMaxChw) chw <<= 1;
+    }
     nb_max = std::max(1, (int)(((int64_t)nmax + (int64_t)chw * kSortWarps - 1) / ((int64_t)chw * kSortWarps)));
     return KDEJS_OK;
 }
@@ -544,7 +570,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             for (int s = 0; s < n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
             k_place<<<dim3((nmax + 255) / 256, n_sets), 256, 0, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
-                io.identity_scaler ? 1 : 0, ncells, 31 - __builtin_clz((unsigned)chw), nb_max, sl.cellid.as<uint16_t>(),
+                io.identity_scaler ? 1 : 0, ncells, chw, nb_max, sl.cellid.as<uint16_t>(),
                 sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
                 wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>(),
                 fast32 && !kFp32FromDoubles ? sl.sorted_q.as<uint2>() : nullptr, g);
@@ -1346,13 +1372,17 @@ int kdejs_shard_phase2(int device, const double total_norm[2], double out_lr[2])
 // ============================================================================================
 // Band mode: one huge evaluation over several GPUs with the POINTS sharded too.
 // Layout of a rank's count block (u32): cellstart[2][C*C + 1] of its locally sorted slices, then
-// rowstart[2][C + 1] (= cellstart at the first cell of every cell row).
+// rowstart[2][C + 1] (= cellstart at the first cell of every cell row), then kBandHandleWords words the caller may
+// fill with the CUDA IPC handle of the buffer its sorted points live in (all zero: none) -- the handle travels with
+// the counts, so a reallocated buffer needs no collective of its own.
 namespace {
+constexpr int kBandHandleWords = 16;
+static_assert(sizeof(cudaIpcMemHandle_t) == 4 * kBandHandleWords, "a CUDA IPC handle is 64 bytes");
 struct BandDims { int C, NT, ncells; size_t block_u32; };
 BandDims band_dims(const GridGeom &g) {
     BandDims d;
     d.C = g.C; d.NT = g.NT; d.ncells = g.C * g.C;
-    d.block_u32 = 2 * (size_t)(d.ncells + 1) + 2 * (size_t)(g.C + 1);
+    d.block_u32 = 2 * (size_t)(d.ncells + 1) + 2 * (size_t)(g.C + 1) + kBandHandleWords;
     return d;
 }
 int band_params(int resolution, double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo, Params &p) {
@@ -1497,16 +1527,21 @@ int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int r
     // rank's row starts (world x 2 x (C + 1) u32, a strided copy): one synchronisation for all of it
     OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
     OKR(sl.misc.ensure(64 + sizeof(double) * (size_t)(g.NT + 1)));
-    k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, 0, d.ncells, sl.cellstart.as<uint32_t>());
+    OKR(sl.bandtot.ensure(2 * (size_t)d.ncells * sizeof(uint32_t)));
+    k_band_cell_totals<<<dim3((d.ncells + 255) / 256, 2), 256, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, 0,
+                                                                        d.ncells, sl.bandtot.as<uint32_t>());
+    k_band_cells<<<2, 1024, 0, st>>>(sl.bandtot.as<uint32_t>(), d.ncells, sl.cellstart.as<uint32_t>());
+    c->launches++;
     WaveDesc wd;
     memset(&wd, 0, sizeof wd);
     wd.n_sets = 2;
     double *d_cw = sl.misc.as<double>() + 8;
     // moment cells: the single-GPU rule applied to the WHOLE evaluation, so every rank (and the one-GPU run) agrees
-    k_tile_colwork<<<g.NT, 128, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_cw, (long long)128 * 2 * d.ncells);
+    // one (set, tile) per thread: the work numbers are integers, so the block's sum does not depend on its shape
+    k_tile_colwork<<<g.NT, 512, 0, st>>>(wd, g, sl.cellstart.as<uint32_t>(), d_cw, (long long)128 * 2 * d.ncells);
     c->launches += 2;
     CU(cudaGetLastError());
-    const size_t rs_elems = 2 * (size_t)(d.C + 1);
+    const size_t rs_elems = 2 * (size_t)(d.C + 1) + kBandHandleWords;     // row starts and the handle words behind them
     std::vector<double> cw((size_t)g.NT + 1);
     CU(cudaMemcpy2DAsync(out_rowstart, rs_elems * 4, blocks_all_dev + 2 * (size_t)(d.ncells + 1), d.block_u32 * 4,
                          rs_elems * 4, (size_t)world, cudaMemcpyDeviceToHost, st));
@@ -1517,20 +1552,32 @@ int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int r
     return release_scratch(*c, st, true);
 }
 
-int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, const double *stage_b_dev, int64_t nb,
-                          int64_t na_total, int64_t nb_total, const uint32_t *blocks_all_dev, int world,
-                          const double *stats_all_dev, int resolution, double bandwidth, double gamma, double eps,
-                          int log_flag, int kernel, int algo, int ty_begin, int ty_end, int cy_lo, int cy_hi,
-                          int use_moments, double *out_norm_dev, void *stream) {
+}  // extern "C"
+namespace {
+// peer = true: the sources are the ranks' own sorted arrays (Ctx::peer_map), stage_* unused
+int band_phase1_core(int device, bool peer, const double *stage_a_dev, int64_t na, const double *stage_b_dev, int64_t nb,
+                     int64_t na_total, int64_t nb_total, const uint32_t *blocks_all_dev, int world,
+                     const double *stats_all_dev, int resolution, double bandwidth, double gamma, double eps,
+                     int log_flag, int kernel, int algo, int ty_begin, int ty_end, int cy_lo, int cy_hi,
+                     int use_moments, double *out_norm_dev, void *stream) {
     Params p;
     OKR(band_params(resolution, bandwidth, gamma, eps, log_flag, kernel, algo, p));
     if (!blocks_all_dev || !stats_all_dev || !out_norm_dev || world < 1) return fail(KDEJS_ERR_ARG, "null argument");
-    if (na < 0 || nb < 0 || na_total < 1 || nb_total < 1 || (na > 0 && !stage_a_dev) || (nb > 0 && !stage_b_dev))
+    if (na < 0 || nb < 0 || na_total < 1 || nb_total < 1 || (!peer && ((na > 0 && !stage_a_dev) || (nb > 0 && !stage_b_dev))))
         return fail(KDEJS_ERR_ARG, "bad staging buffers");
     if (na + nb > 0x7fffffffLL / 4) return fail(KDEJS_ERR_ARG, "too many points for one band");
     Ctx *c;
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
+    PeerPtrs peers;
+    memset(&peers, 0, sizeof peers);
+    if (peer) {
+        if (c->peer_world != world) return fail(KDEJS_ERR_ARG, "kdejs_band_peer_open was not called for this world size");
+        for (int r = 0; r < world; ++r) {
+            peers.p[r] = reinterpret_cast<const double2 *>(r == c->peer_rank ? c->peer_buf.p : c->peer_map[r].ptr);
+            if (!peers.p[r]) return fail(KDEJS_ERR_ARG, "a peer's sorted points are not mapped");
+        }
+    }
     cudaStream_t st = stream ? (cudaStream_t)stream : c->s_compute;
     OKR(acquire_scratch(*c, st));
     c->band_valid = false;
@@ -1557,11 +1604,22 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
     if (fast32 && !kFp32FromDoubles) OKR(sl.sorted_q.ensure((size_t)std::max<int64_t>(P, 1) * sizeof(uint2)));
     OKR(sl.cellstart.ensure(2 * (size_t)(d.ncells + 1) * sizeof(uint32_t)));
     const int c_lo = cy_lo * d.C, c_hi = (cy_hi + 1) * d.C;
-    k_band_cells<<<2, 1024, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, c_lo, c_hi, sl.cellstart.as<uint32_t>());
-    k_band_merge<<<dim3(c_hi - c_lo, 2, kMergeSplit), 256, 0, st>>>(
-        reinterpret_cast<const double2 *>(stage_a_dev), reinterpret_cast<const double2 *>(stage_b_dev), blocks_all_dev,
-        world, d.block_u32, g, cy_lo, cy_hi, sl.cellstart.as<uint32_t>(), na, sl.sorted.as<double2>(),
-        fast32 && !kFp32FromDoubles ? sl.sorted_q.as<uint2>() : nullptr);
+    OKR(sl.bandtot.ensure(2 * (size_t)d.ncells * sizeof(uint32_t)));
+    k_band_cell_totals<<<dim3((d.ncells + 255) / 256, 2), 256, 0, st>>>(blocks_all_dev, world, d.block_u32, d.ncells, c_lo,
+                                                                        c_hi, sl.bandtot.as<uint32_t>());
+    k_band_cells<<<2, 1024, 0, st>>>(sl.bandtot.as<uint32_t>(), d.ncells, sl.cellstart.as<uint32_t>());
+    c->launches++;
+    const dim3 merge_grid((unsigned)((std::max<int64_t>(std::max(na, nb), 1) + 256 * kMergePer - 1) / (256 * kMergePer)), 2);
+    if (peer)
+        k_band_merge<true><<<merge_grid, 256, 0, st>>>(
+            nullptr, nullptr, peers, blocks_all_dev,
+            world, d.block_u32, g, cy_lo, cy_hi, sl.cellstart.as<uint32_t>(), na, sl.sorted.as<double2>(),
+            fast32 && !kFp32FromDoubles ? sl.sorted_q.as<uint2>() : nullptr);
+    else
+        k_band_merge<false><<<merge_grid, 256, 0, st>>>(
+            reinterpret_cast<const double2 *>(stage_a_dev), reinterpret_cast<const double2 *>(stage_b_dev), peers, blocks_all_dev,
+            world, d.block_u32, g, cy_lo, cy_hi, sl.cellstart.as<uint32_t>(), na, sl.sorted.as<double2>(),
+            fast32 && !kFp32FromDoubles ? sl.sorted_q.as<uint2>() : nullptr);
     c->launches += 2;
     WaveDesc wd;
     memset(&wd, 0, sizeof wd);
@@ -1581,6 +1639,93 @@ int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, con
     CU(cudaGetLastError());
     c->band_geom = g; c->band_ty0 = ty_begin; c->band_ty1 = ty_end; c->band_slot = c->cur; c->band_valid = true;
     return release_scratch(*c, st, false);
+}
+}  // namespace
+extern "C" {
+
+int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, const double *stage_b_dev, int64_t nb,
+                          int64_t na_total, int64_t nb_total, const uint32_t *blocks_all_dev, int world,
+                          const double *stats_all_dev, int resolution, double bandwidth, double gamma, double eps,
+                          int log_flag, int kernel, int algo, int ty_begin, int ty_end, int cy_lo, int cy_hi,
+                          int use_moments, double *out_norm_dev, void *stream) {
+    return band_phase1_core(device, false, stage_a_dev, na, stage_b_dev, nb, na_total, nb_total, blocks_all_dev, world,
+                            stats_all_dev, resolution, bandwidth, gamma, eps, log_flag, kernel, algo, ty_begin, ty_end,
+                            cy_lo, cy_hi, use_moments, out_norm_dev, stream);
+}
+
+int kdejs_band_phase1_peer_dev(int device, int64_t na, int64_t nb, int64_t na_total, int64_t nb_total,
+                               const uint32_t *blocks_all_dev, int world, const double *stats_all_dev, int resolution,
+                               double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
+                               int ty_begin, int ty_end, int cy_lo, int cy_hi, int use_moments, double *out_norm_dev,
+                               void *stream) {
+    return band_phase1_core(device, true, nullptr, na, nullptr, nb, na_total, nb_total, blocks_all_dev, world,
+                            stats_all_dev, resolution, bandwidth, gamma, eps, log_flag, kernel, algo, ty_begin, ty_end,
+                            cy_lo, cy_hi, use_moments, out_norm_dev, stream);
+}
+
+int kdejs_band_peer_buffer(int device, int64_t points, void **out_ptr, uint32_t *out_handle_words) {
+    if (points < 0 || !out_ptr || !out_handle_words) return fail(KDEJS_ERR_ARG, "bad argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const size_t need = (size_t)std::max<int64_t>(points, 1) * sizeof(double2);
+    if (need > c->peer_buf.cap) {
+        // Grow with headroom: every reallocation makes all peers map the buffer again.  An exported allocation
+        // must not be freed while another process has it mapped, and peers drop their mapping only when they see
+        // the new handle: the old buffer is parked until the context goes away.
+        if (c->peer_buf.p) c->peer_retired.push_back(c->peer_buf.p);
+        c->peer_buf.p = nullptr; c->peer_buf.cap = 0;
+        c->peer_handle_valid = false;
+        OKR(c->peer_buf.ensure(need + need / 4));
+    }
+    if (!c->peer_handle_valid) {
+        cudaIpcMemHandle_t h;
+        CU(cudaIpcGetMemHandle(&h, c->peer_buf.p));
+        memcpy(c->peer_handle, &h, 64);
+        c->peer_handle_valid = true;
+    }
+    *out_ptr = c->peer_buf.p;
+    memcpy(out_handle_words, c->peer_handle, 64);
+    return KDEJS_OK;
+}
+
+int kdejs_band_peer_open(int device, const uint32_t *handle_words, int world, int rank) {
+    if (!handle_words || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(KDEJS_ERR_ARG, "bad argument (at most 16 ranks share points over peer memory)");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    static const unsigned char zero[64] = {0};
+    for (int r = 0; r < world; ++r) {
+        const unsigned char *h = reinterpret_cast<const unsigned char *>(handle_words) + (size_t)r * 64;
+        if (memcmp(h, zero, 64) == 0) return fail(KDEJS_ERR_ARG, "a rank exported no peer buffer");
+        Ctx::PeerMap &m = c->peer_map[r];
+        if (r == rank) {
+            if (!c->peer_handle_valid || memcmp(h, c->peer_handle, 64) != 0)
+                return fail(KDEJS_ERR_ARG, "this rank's handle is not the one kdejs_band_peer_buffer returned");
+            continue;
+        }
+        if (m.open && memcmp(m.handle, h, 64) == 0) continue;           // still the mapping of the last evaluation
+        if (m.open) {
+            CU(cudaDeviceSynchronize());                                 // nothing of ours may still be reading it
+            CU(cudaIpcCloseMemHandle(m.ptr));
+            m.open = false; m.ptr = nullptr;
+        }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, h, 64);
+        void *ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+        memcpy(m.handle, h, 64);
+        m.ptr = ptr;
+        m.open = true;
+    }
+    for (int r = world; r < kMaxPeers; ++r) {
+        Ctx::PeerMap &m = c->peer_map[r];
+        if (m.open) { CU(cudaDeviceSynchronize()); cudaIpcCloseMemHandle(m.ptr); m.open = false; m.ptr = nullptr; }
+    }
+    c->peer_world = world;
+    c->peer_rank = rank;
+    return KDEJS_OK;
 }
 
 int kdejs_band_phase2_dev(int device, const double *norms_all_dev, int world, double *out_lr_dev, void *stream) {

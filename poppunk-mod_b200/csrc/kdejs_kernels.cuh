@@ -257,7 +257,7 @@ constexpr int kSortUnroll = 4;        // independent 32-point groups a warp keep
 #define KDEJS_MATCH_BALLOTS 0
 #endif
 constexpr bool kMatchByBallots = KDEJS_MATCH_BALLOTS != 0;
-constexpr int kMaxChw = 8192;         // points per warp sub-chunk, a power of two: 4 warps * kMaxChw < 65536 (u16 counters)
+constexpr int kMaxChw = 8192;         // points per warp sub-chunk: 4 warps * kMaxChw < 65536 (u16 counters)
 
 // k_scale_count: grid (nb_max, n_sets), kSortThreads threads, dyn smem kSortWarps*ncells u16 (a warp's
 // sub-chunk holds at most kMaxChw points, so 16-bit counters cannot overflow).
@@ -505,7 +505,7 @@ __device__ __forceinline__ uint32_t quantise(double x, const GridGeom &g) {
 // arithmetic as k_scale_count and written straight to that slot.  No shared memory, no ranking.
 __global__ void __launch_bounds__(256)
 k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, int log_flag, double eps,
-        int identity_scaler, int ncells, int chw_log2, int nb_max, const uint16_t *__restrict__ cellid,
+        int identity_scaler, int ncells, int chw, int nb_max, const uint16_t *__restrict__ cellid,
         const uint16_t *__restrict__ rank16, const uint16_t *__restrict__ warpprefix,
         const uint32_t *__restrict__ blockbase, const uint32_t *__restrict__ cellstart,
         double2 *__restrict__ sorted, uint2 *__restrict__ sorted_q, const GridGeom g) {
@@ -518,7 +518,7 @@ k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, 
     const double2 v = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p)[j];
     const int cell = cellid[sd.off + j];
     const uint32_t rank = rank16[sd.off + j];
-    const uint32_t wchunk = j >> chw_log2;                // global warp sub-chunk index of the point (chw is a power of two)
+    const uint32_t wchunk = j / (uint32_t)chw;            // global warp sub-chunk index of the point
     const size_t row = (size_t)blockIdx.y * nb_max + (size_t)(wchunk / kSortWarps);
     // cellstart is null when k_scan_narrow left absolute positions in blockbase
     const uint32_t pos = (cellstart ? cellstart[(size_t)blockIdx.y * (ncells + 1) + cell] : 0u) +
@@ -1983,13 +1983,28 @@ __global__ void k_band_rowstarts(const uint32_t *__restrict__ cellstart, int C, 
         rowstart[(size_t)set * (C + 1) + cy] = cellstart[(size_t)set * (ncells + 1) + (size_t)cy * C];
 }
 
-// cellstart_out[set][c] = exclusive scan over cells of  sum over ranks of count_r(set, c)  restricted to cells
-// [c_lo, c_hi) (all others count 0).  cs_all: per rank a block of `rank_stride` u32 starting with
-// cellstart_r[2][ncells + 1].  grid (2), 1024 threads.  With [0, ncells) this is the GLOBAL cell table (the same
-// numbers the single-GPU sort produces), with a band's rows it is the band's local table.
+// k_band_cell_totals: grid (ceil(ncells / 256), 2), 256 threads.  totals[set][c] = sum over ranks of count_r(set, c)
+// for cells in [c_lo, c_hi), 0 for all others.  cs_all: per rank a block of `rank_stride` u32 starting with
+// cellstart_r[2][ncells + 1].
+__global__ void __launch_bounds__(256)
+k_band_cell_totals(const uint32_t *__restrict__ cs_all, int world, size_t rank_stride, int ncells, int c_lo, int c_hi,
+                   uint32_t *__restrict__ totals) {
+    const int set = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= ncells) return;
+    uint32_t t = 0u;
+    if (c >= c_lo && c < c_hi)
+        for (int r = 0; r < world; ++r) {
+            const uint32_t *cs = cs_all + (size_t)r * rank_stride + (size_t)set * (ncells + 1);
+            t += cs[c + 1] - cs[c];
+        }
+    totals[(size_t)set * ncells + c] = t;
+}
+
+// k_band_cells: grid (2), 1024 threads.  cellstart_out[set][0..ncells] = exclusive scan of totals[set][].  With
+// [0, ncells) in k_band_cell_totals this is the GLOBAL cell table (the same numbers the single-GPU sort produces),
+// with a band's rows it is the band's local table.
 __global__ void __launch_bounds__(1024)
-k_band_cells(const uint32_t *__restrict__ cs_all, int world, size_t rank_stride, int ncells, int c_lo, int c_hi,
-             uint32_t *__restrict__ cellstart_out) {
+k_band_cells(const uint32_t *__restrict__ totals, int ncells, uint32_t *__restrict__ cellstart_out) {
     const int set = blockIdx.x;
     constexpr int kCptMax = kMaxCells / 1024;
     const int cpt = (ncells + 1023) / 1024;
@@ -1998,15 +2013,9 @@ k_band_cells(const uint32_t *__restrict__ cs_all, int world, size_t rank_stride,
     uint32_t tsum = 0u;
 #pragma unroll
     for (int k = 0; k < kCptMax; ++k) {
-        uint32_t t = 0u;
         const int c = c0 + k;
-        if (k < cpt && c < ncells && c >= c_lo && c < c_hi)
-            for (int r = 0; r < world; ++r) {
-                const uint32_t *cs = cs_all + (size_t)r * rank_stride + (size_t)set * (ncells + 1);
-                t += cs[c + 1] - cs[c];
-            }
-        tot[k] = t;
-        tsum += t;
+        tot[k] = (k < cpt && c < ncells) ? totals[(size_t)set * ncells + c] : 0u;
+        tsum += tot[k];
     }
     __shared__ uint32_t s_w[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -2038,40 +2047,78 @@ k_band_cells(const uint32_t *__restrict__ cs_all, int world, size_t rank_stride,
     if (threadIdx.x == 1023) out[ncells] = run;
 }
 
-// k_band_merge: grid (cells in the band's rows, 2 sets, kMergeSplit), 256 threads.  The staging buffer of a set
-// holds, source rank after source rank, that rank's sorted points of cell rows [cy_lo, cy_hi] (row-major cells).
-// A cell's points are copied source by source to their final place -- rank order is original index order, so the
-// result equals the single-GPU stable sort restricted to these rows.  Real distance clouds are concentrated (a few
-// cells hold most of the points), so the kMergeSplit blocks of a cell interleave over 256-point chunks of every
-// source's piece.  Also writes the fixed-point copy for the fp32 kernel.
-constexpr int kMergeSplit = 8;
+// k_band_merge: grid (ceil(points of the larger set / (256 * kMergePer)), 2 sets), 256 threads: one thread per point
+// of the band's sorted array.  Destination slot i of a set belongs to the cell c with cellstart_local[c] <= i <
+// cellstart_local[c + 1] (binary search; neighbouring threads share the answer) and, inside the cell, to the first
+// source rank whose piece reaches that far -- rank order is original index order, so the result equals the
+// single-GPU stable sort restricted to these rows.  Real distance clouds are concentrated (a few cells hold most of
+// the points): dealing out destination slots, not cells, keeps every thread busy, and kMergePer independent loads
+// per thread keep enough bytes in flight for NVLink latency.  Also writes the fixed-point copy for the fp32 kernel.
+// Where a source's points come from:
+//   PEER = false  a staging buffer per set that holds, source after source, that rank's sorted points of cell rows
+//                 [cy_lo, cy_hi] (filled by the NCCL point-to-point exchange)
+//   PEER = true   the source rank's OWN locally sorted array (set A, then set B), mapped into this process over
+//                 NVLink (kdejs_band_peer_*): the copy IS the exchange -- no staging buffer, no second pass
+constexpr int kMergePer = 4;
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { const double2 *p[kMaxPeers]; };
+template <bool PEER>
 __global__ void __launch_bounds__(256)
-k_band_merge(const double2 *__restrict__ stage_a, const double2 *__restrict__ stage_b,
+k_band_merge(const double2 *__restrict__ stage_a, const double2 *__restrict__ stage_b, const PeerPtrs peers,
              const uint32_t *__restrict__ cs_all, int world, size_t rank_stride, const GridGeom g, int cy_lo, int cy_hi,
              const uint32_t *__restrict__ cellstart_local, int64_t off_b,
              double2 *__restrict__ sorted, uint2 *__restrict__ sorted_q) {
+    __shared__ uint32_t s_srcbase[kMaxPeers];     // PEER: first point of the set in rank r's array; else in the staging buffer
     const int set = blockIdx.y;
     const int ncells = g.C * g.C;
     const int c_lo = cy_lo * g.C, c_hi = (cy_hi + 1) * g.C;
-    const int cell = c_lo + blockIdx.x;
-    if (cell >= c_hi) return;
-    const double2 *__restrict__ stage = set ? stage_b : stage_a;
-    uint32_t dst = cellstart_local[(size_t)set * (ncells + 1) + cell];
-    if (cellstart_local[(size_t)set * (ncells + 1) + cell + 1] == dst) return;      // empty cell
-    const int64_t base = set ? off_b : 0;
-    uint32_t src_base = 0u;                       // first point of source r in the staging buffer
-    for (int r = 0; r < world; ++r) {
-        const uint32_t *cs = cs_all + (size_t)r * rank_stride + (size_t)set * (ncells + 1);
-        const uint32_t r_lo = cs[c_lo], r_hi = cs[c_hi];
-        const uint32_t b = cs[cell], e = cs[cell + 1];
-        const double2 *__restrict__ sp = stage + src_base + (b - r_lo);
-        for (uint32_t k = blockIdx.z * 256u + threadIdx.x; k < e - b; k += kMergeSplit * 256u) {
-            const double2 p = sp[k];
-            sorted[base + dst + k] = p;
-            if (sorted_q) sorted_q[base + dst + k] = make_uint2(quantise(p.x, g), quantise(p.y, g));
+    const uint32_t *__restrict__ csl = cellstart_local + (size_t)set * (ncells + 1);
+    const uint32_t n_set = csl[c_hi];
+    if ((uint32_t)blockIdx.x * (256u * kMergePer) >= n_set) return;
+    if (threadIdx.x == 0) {
+        uint32_t run = 0u;
+        for (int r = 0; r < world; ++r) {
+            const uint32_t *cs = cs_all + (size_t)r * rank_stride + (size_t)set * (ncells + 1);
+            if (PEER) s_srcbase[r] = set ? cs_all[(size_t)r * rank_stride + ncells] : 0u;
+            else { s_srcbase[r] = run - cs[c_lo]; run += cs[c_hi] - cs[c_lo]; }      // (mod 2^32: cs[cell] is added back below)
         }
-        dst += e - b;
-        src_base += r_hi - r_lo;
+    }
+    __syncthreads();
+    const double2 *__restrict__ stage = set ? stage_b : stage_a;
+    const int64_t base = set ? off_b : 0;
+    const double2 *src[kMergePer];
+#pragma unroll
+    for (int u = 0; u < kMergePer; ++u) {
+        const uint32_t i = ((uint32_t)blockIdx.x * kMergePer + u) * 256u + threadIdx.x;
+        src[u] = nullptr;
+        if (i >= n_set) continue;
+        int lo = c_lo, hi = c_hi;                 // csl[lo] <= i < csl[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (csl[mid] <= i) lo = mid; else hi = mid;
+        }
+        uint32_t o = i - csl[lo];
+        int r = 0;
+        uint32_t b = 0u;
+        for (; r < world; ++r) {
+            const uint32_t *cs = cs_all + (size_t)r * rank_stride + (size_t)set * (ncells + 1);
+            b = cs[lo];
+            const uint32_t cnt = cs[lo + 1] - b;
+            if (o < cnt) break;
+            o -= cnt;
+        }
+        src[u] = (PEER ? peers.p[r] : stage) + (uint32_t)(s_srcbase[r] + b + o);
+    }
+    double2 p[kMergePer];
+#pragma unroll
+    for (int u = 0; u < kMergePer; ++u)          // a peer rewrites its array between evaluations: no stale lines
+        if (src[u]) p[u] = PEER ? __ldcv(src[u]) : *src[u];
+#pragma unroll
+    for (int u = 0; u < kMergePer; ++u) {
+        const uint32_t i = ((uint32_t)blockIdx.x * kMergePer + u) * 256u + threadIdx.x;
+        if (!src[u]) continue;
+        sorted[base + i] = p[u];
+        if (sorted_q) sorted_q[base + i] = make_uint2(quantise(p[u].x, g), quantise(p[u].y, g));
     }
 }
 
@@ -2079,7 +2126,7 @@ k_band_merge(const double2 *__restrict__ stage_a, const double2 *__restrict__ st
 // moments_min_points >= 0: the moment-cell rule of the single-GPU path is applied here to the WHOLE evaluation
 // (eligible geometry and at least that many points in total, read from the global cell table), and the decision is
 // left in colwork[NT] so that the host learns it with the same copy.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_tile_colwork(const __grid_constant__ WaveDesc wd, const GridGeom g_in,
                const uint32_t *__restrict__ cellstart, double *__restrict__ colwork, long long moments_min_points) {
     __shared__ double s_w[32];

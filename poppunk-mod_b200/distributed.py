@@ -6,7 +6,9 @@
 * One huge evaluation (config C5: 10 M pairs on a 1024^2 grid): the grid is split into bands of tile
   columns, one per rank, AND the points are sharded: every rank holds a slice of each table, sorts
   it locally, and receives only the points of the cell rows within h of its band
-  (band_sharded_discrepancy; one all-to-all of contiguous slices over NVLink).  The remaining
+  (band_sharded_discrepancy).  On the GPUs of one node the band's merge kernel reads those rows straight
+  out of the peers' sorted arrays over NVLink (CUDA IPC mappings, kdejs_band_peer_*): the copy that puts
+  them in order IS the exchange.  Otherwise one grouped NCCL all-to-all of contiguous slices.  The remaining
   exchange steps are tiny: the extrema (10 doubles), the per-cell counts, the normalisers (2
   doubles) and the relative-entropy partials (3 doubles); each is all-gathered and folded in rank
   order, so every rank ends with the same bit pattern.  (row_sharded_discrepancy with complete
@@ -17,6 +19,7 @@ torch.distributed is used for plumbing only (NCCL on GPUs, gloo in the CPU tests
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -194,6 +197,8 @@ class _GpuBandOps:
         self.C, self.NT, self.block_u32 = geo[0], geo[1], geo[2]
         self.tdev = torch.device("cuda", self.dev)
         self.stream = _band_stream(torch, self.tdev)
+        self.peer = os.environ.get("KDEJS_BAND_PEER", "1") != "0"      # exchange over peer memory when all ranks can
+        self.handles = np.zeros((1, HANDLE_WORDS), dtype=np.uint32)
 
     def run(self):
         """Context manager: inputs produced on the caller's current stream are waited for, then the band stream is
@@ -222,9 +227,29 @@ class _GpuBandOps:
                                                self.common[4], self.common[3], out.data_ptr(), self._stream()))
         return out
 
+    def _peer_buffer(self, points):
+        """This rank's exchange buffer as a tensor view, and the device copy of its IPC handle words."""
+        torch = self.torch
+        ptr, words = ctypes.c_void_p(), np.zeros(HANDLE_WORDS, dtype=np.uint32)
+        nat.check(self.L.kdejs_band_peer_buffer(self.dev, int(points), ctypes.byref(ptr), words.ctypes.data))
+        key = words.tobytes()
+        cached = _HANDLE_DEV.get(self.dev)
+        if cached is None or cached[0] != key:                      # uploaded once per (re)allocation of the buffer
+            cached = _HANDLE_DEV[self.dev] = (key, torch.from_numpy(words.view(np.int32)).to(self.tdev))
+        view = torch.as_tensor(_DevView(ptr.value, (max(int(points), 1), 2)), device=self.tdev)
+        return view[:int(points)], cached[1]
+
     def sort(self, a, b, stats_all, world):
-        srt = self.empty((a.shape[0] + b.shape[0], 2))
         block = self.empty(self.block_u32, "i4")
+        if self.peer and world > 1:
+            try:
+                srt, handle = self._peer_buffer(a.shape[0] + b.shape[0])
+                block[-HANDLE_WORDS:] = handle
+            except RuntimeError:                 # no IPC export here: the zero handle makes every rank use NCCL
+                self.peer = False
+        if not (self.peer and world > 1):
+            srt = self.empty((a.shape[0] + b.shape[0], 2))
+            block[-HANDLE_WORDS:] = 0
         nat.check(self.L.kdejs_band_sort_dev(self.dev, a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], *self.common,
                                              stats_all.data_ptr(), world, srt.data_ptr(), block.data_ptr(),
                                              self._stream()))
@@ -232,11 +257,28 @@ class _GpuBandOps:
 
     def plan(self, blocks_all, world):
         colwork = np.empty(self.NT, dtype=np.float64)
-        rowstart = np.empty((world, 2, self.C + 1), dtype=np.uint32)
+        out = np.empty((world, 2 * (self.C + 1) + HANDLE_WORDS), dtype=np.uint32)
         use_m = ctypes.c_int(0)
         nat.check(self.L.kdejs_band_plan(self.dev, blocks_all.data_ptr(), world, *self.common, colwork.ctypes.data,
-                                         rowstart.ctypes.data, ctypes.byref(use_m), self._stream()))
+                                         out.ctypes.data, ctypes.byref(use_m), self._stream()))
+        self.handles = np.ascontiguousarray(out[:, -HANDLE_WORDS:])             # every rank's IPC handle words
+        rowstart = out[:, :-HANDLE_WORDS].reshape(world, 2, self.C + 1)
         return colwork, rowstart.astype(np.int64), use_m.value
+
+    def peer_ready(self, rank, world):
+        """True when every rank exported its sorted points (all ranks see the same handles, so all agree) and this
+        rank could map them.  A rank that cannot map a peer raises: the others would wait for it otherwise."""
+        if world == 1 or not self.handles.any(axis=1).all():
+            return False
+        nat.check(self.L.kdejs_band_peer_open(self.dev, self.handles.ctypes.data, world, rank))
+        return True
+
+    def phase1_peer(self, na, nb, na_tot, nb_tot, blocks_all, stats_all, world, ty, cy, use_m):
+        out = self.empty(2)
+        nat.check(self.L.kdejs_band_phase1_peer_dev(
+            self.dev, int(na), int(nb), int(na_tot), int(nb_tot), blocks_all.data_ptr(), world, stats_all.data_ptr(),
+            *self.common, ty[0], ty[1], cy[0], cy[1], use_m, out.data_ptr(), self._stream()))
+        return out
 
     def phase1(self, stage_a, stage_b, na_tot, nb_tot, blocks_all, stats_all, world, ty, cy, use_m):
         out = self.empty(2)
@@ -256,7 +298,19 @@ class _GpuBandOps:
         return t.cpu().numpy()
 
 
+HANDLE_WORDS = 16      # a CUDA IPC handle, as u32 words at the end of a rank's count block (include/kdejs.h)
+
+
+class _DevView:
+    """A device allocation of the library as something torch.as_tensor can wrap without a copy."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
 _BAND_STREAMS = {}
+_HANDLE_DEV = {}
 
 
 def _band_stream(torch, tdev):
@@ -363,20 +417,28 @@ def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world
     cuts = band_cuts(colwork, world)
     rows = [band_cell_rows(resolution, bandwidth, cuts[d], cuts[d + 1]) for d in range(world)]
     lo_me, hi_me = rows[rank]
-    stages, pairs = [], []
-    for st in (0, 1):
-        base = 0 if st == 0 else na
-        send = [srt[base + rs[rank, st, lo]: base + rs[rank, st, hi + 1]] if hi >= lo else srt[0:0] for lo, hi in rows]
-        counts = [int(rs[s_, st, hi_me + 1] - rs[s_, st, lo_me]) if hi_me >= lo_me else 0 for s_ in range(world)]
-        stage = ops.empty((sum(counts), 2))
-        offs = np.concatenate([[0], np.cumsum(counts)])
-        pairs.append((send, [stage[offs[s_]:offs[s_ + 1]] for s_ in range(world)]))
-        stages.append(stage)
-    _exchange(pairs, group, rank, world)
-    mark("exchange")
     n_tot = rs[:, :, -1].sum(axis=0)
-    norm = ops.phase1(stages[0], stages[1], n_tot[0], n_tot[1], blocks_all, stats_all, world,
-                      (cuts[rank], cuts[rank + 1]), (lo_me, hi_me), use_m)
+    recv = [[int(rs[s_, st, hi_me + 1] - rs[s_, st, lo_me]) if hi_me >= lo_me else 0 for s_ in range(world)]
+            for st in (0, 1)]
+    over_peer_memory = bool(getattr(ops, "peer_ready", None)) and ops.peer_ready(rank, world)
+    if over_peer_memory:
+        # the merge kernel pulls the rows it needs out of every rank's sorted array over NVLink
+        mark("exchange")
+        norm = ops.phase1_peer(sum(recv[0]), sum(recv[1]), n_tot[0], n_tot[1], blocks_all, stats_all, world,
+                               (cuts[rank], cuts[rank + 1]), (lo_me, hi_me), use_m)
+    else:
+        stages, pairs = [], []
+        for st in (0, 1):
+            base = 0 if st == 0 else na
+            send = [srt[base + rs[rank, st, lo]: base + rs[rank, st, hi + 1]] if hi >= lo else srt[0:0] for lo, hi in rows]
+            stage = ops.empty((sum(recv[st]), 2))
+            offs = np.concatenate([[0], np.cumsum(recv[st])])
+            pairs.append((send, [stage[offs[s_]:offs[s_ + 1]] for s_ in range(world)]))
+            stages.append(stage)
+        _exchange(pairs, group, rank, world)
+        mark("exchange")
+        norm = ops.phase1(stages[0], stages[1], n_tot[0], n_tot[1], blocks_all, stats_all, world,
+                          (cuts[rank], cuts[rank + 1]), (lo_me, hi_me), use_m)
     mark("merge+density")
     lr = ops.phase2(_gather_cat(norm, group, world), world)
     parts = ops.to_host(_gather_cat(lr, group, world)).reshape(world, 3)        # final synchronisation
@@ -385,7 +447,8 @@ def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world
         info["timing_ms"] = {n: 1e3 * (t - marks[i][1]) for i, (n, t) in enumerate(marks[1:])}
     if info is not None:
         info.update({"tile_columns": (cuts[rank], cuts[rank + 1]), "cell_rows": (lo_me, hi_me),
-                     "points_received": (int(stages[0].shape[0]), int(stages[1].shape[0])), "moment_cells": bool(use_m)})
+                     "points_received": (sum(recv[0]), sum(recv[1])), "moment_cells": bool(use_m),
+                     "exchange": "peer memory" if over_peer_memory else "nccl"})
     if parts[:, 2].any():
         raise ValueError("Input X contains infinity or a value too large for dtype('float64').")
     js2 = (parts[:, 0].sum() + parts[:, 1].sum()) / 2.0

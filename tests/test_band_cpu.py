@@ -72,14 +72,14 @@ class NumpyBandOps:
             start = np.concatenate([[0], np.cumsum(np.bincount(cell, minlength=nc))])
             cs.append(start)
             rs.append(start[::C][:C + 1])
-        block = np.concatenate(cs + rs).astype(np.int32)
+        block = np.concatenate(cs + rs + [np.zeros(16)]).astype(np.int32)    # 16 words: no peer-memory handle
         assert len(block) == self.block_u32
         return self.torch.from_numpy(np.vstack(srt)), self.torch.from_numpy(block)
 
     def plan(self, blocks_all, world):
         C, nc = self.C, self.C * self.C
         blk = blocks_all.numpy().reshape(world, -1)
-        rowstart = blk[:, 2 * (nc + 1):].reshape(world, 2, C + 1).astype(np.int64)
+        rowstart = blk[:, 2 * (nc + 1):-16].reshape(world, 2, C + 1).astype(np.int64)
         per_row = np.diff(rowstart, axis=2).sum(axis=(0, 1)).astype(np.float64)           # points per cell row
         colwork = 1.0 + np.interp(np.linspace(0, C - 1, self.NT), np.arange(C), per_row)  # any positive proxy will do
         return colwork, rowstart, 0
@@ -177,7 +177,7 @@ def test_band_host_helpers():
 
     geo = (ctypes.c_int * 4)()
     pk._native.check(pk._native.lib().kdejs_band_geometry(1024, 0.03, 0, geo))
-    assert list(geo)[:3] == [128, 256, 2 * (128 * 128 + 1) + 2 * 129]
+    assert list(geo)[:3] == [128, 256, 2 * (128 * 128 + 1) + 2 * 129 + 16]      # + the peer-memory handle words
     cw = np.ones(256)
     cw[100:130] = 50.0
     for world in (1, 2, 5, 8):

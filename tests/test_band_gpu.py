@@ -24,6 +24,7 @@ def virtual_band(pk, a, b, world, gamma, eps, log=False, resolution=100, bandwid
 
     common = pk.KDE_distance._common(resolution, bandwidth, gamma, eps, log, "epanechnikov", algo)
     ops = D._GpuBandOps(0, common)
+    ops.peer = False          # the virtual ranks share one device, hence one exchange buffer: keep the staged path
     with ops.run():
         return _virtual_band(torch, D, ops, a, b, world, resolution, bandwidth, cuts)
 
@@ -129,3 +130,45 @@ def test_band_sharded_discrepancy_world_one(pk):
     bad[7, 0] = np.inf
     with pytest.raises(ValueError, match="infinity"):
         D.band_sharded_discrepancy(a, bad, 0.25, 0.0, resolution=256)
+
+
+@pytest.mark.parametrize("algo", ["binned", "binned32"])
+def test_merge_from_the_exchange_buffer_world_one(pk, algo):
+    """kdejs_band_peer_*: the merge kernel reads the sorted points out of the rank's exported exchange buffer (with
+    one rank: its own).  Same answer as the evaluation on one GPU; the buffer grows and is exported again on demand."""
+    import ctypes
+
+    import torch
+
+    from oracle import workloads as wl
+    from poppunk_mod_b200 import distributed as D
+
+    nat, L = pk._native, pk._native.lib()
+    for n in (30_000, 90_000):                       # the second size makes the buffer grow: a new handle
+        a, b = wl.synthetic_target(n), wl.sim_S(4, 1700, 0.3, n=n // 2)
+        R = 200
+        common = pk.KDE_distance._common(R, 0.03, 0.25, 0.0, False, "epanechnikov", algo)
+        ops = D._GpuBandOps(0, common)
+        with ops.run():
+            A, B = ops.to_device(a, "a"), ops.to_device(b, "b")
+            stats_all = ops.minmax(A, B)
+            srt, handle = ops._peer_buffer(len(a) + len(b))
+            block = ops.empty(ops.block_u32, "i4")
+            block[-D.HANDLE_WORDS:] = handle
+            nat.check(L.kdejs_band_sort_dev(0, A.data_ptr(), len(a), B.data_ptr(), len(b), *common, stats_all.data_ptr(), 1,
+                                            srt.data_ptr(), block.data_ptr(), ops._stream()))
+            colwork, rs, use_m = ops.plan(block, 1)
+            assert ops.handles.any()
+            nat.check(L.kdejs_band_peer_open(0, ops.handles.ctypes.data, 1, 0))
+            NT = ops.NT
+            rows = D.band_cell_rows(R, 0.03, 0, NT)
+            norm = ops.phase1_peer(len(a), len(b), len(a), len(b), block, stats_all, 1, (0, NT), rows, use_m)
+            lr = ops.to_host(ops.phase2(norm, 1))
+        js = np.sqrt(max((lr[0] + lr[1]) / 2.0, 0.0))
+        assert lr[2] == 0
+        assert js == pk.KDE_JS_divergence(a, b, gamma=0.25, eps=0.0, resolution=R, algo=algo)
+    # a handle that is not this rank's own is refused
+    bad = np.array(ops.handles, copy=True)
+    bad[0, 0] ^= 1
+    with pytest.raises(ValueError):
+        nat.check(L.kdejs_band_peer_open(0, bad.ctypes.data, 1, 0))

@@ -31,6 +31,13 @@ for algo in ("binned", "binned32"):
         js = D.band_sharded_discrepancy(cut(a), cut(b), 0.25, 0.0, resolution=R, algo=algo, info=info)
         full = pk.KDE_JS_divergence(a, b, 0.25, 0.0, resolution=R, algo=algo)
         assert abs(js - full) <= 1e-12 * full, (algo, R, js, full)
+        # the exchange over peer memory and the NCCL all-to-all feed the merge the same points in the same order
+        os.environ["KDEJS_BAND_PEER"] = "0"
+        info_nccl = {}
+        js_nccl = D.band_sharded_discrepancy(cut(a), cut(b), 0.25, 0.0, resolution=R, algo=algo, info=info_nccl)
+        del os.environ["KDEJS_BAND_PEER"]
+        assert js_nccl == js and info_nccl["exchange"] == "nccl", (js, js_nccl, info_nccl)
+        assert world == 1 or os.environ.get("EXPECT_PEER", "1") != "1" or info["exchange"] == "peer memory", info
         if rank == 0:
             o = ko.discrepancy(a, b, 0.25, 0.0, resolution=R)
             assert abs(js - o) <= (1e-10 if algo == "binned" else 2e-7) * o, (algo, R, js, o)
@@ -55,15 +62,19 @@ if os.environ.get("MGPU_SMALL", "0") != "1":
     ha = pool.empty(cut(A).shape); ha[:] = cut(A)
     hb = pool.empty(cut(B).shape); hb[:] = cut(B)
     da, db = torch.from_numpy(ha).cuda(), torch.from_numpy(hb).cuda()
-    for name, x, y in (("host slices", ha, hb), ("device slices", da, db)):
+    for name, x, y, peer in (("host slices", ha, hb, "1"), ("device slices", da, db, "1"), ("device slices", da, db, "0")):
+        os.environ["KDEJS_BAND_PEER"] = peer
         for algo in ("binned", "binned32"):
             ts = []
-            for it in range(4):
+            for it in range(5):
+                info = {}
                 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
-                js = D.band_sharded_discrepancy(x, y, 0.25, 0.0, resolution=1024, algo=algo)
+                js = D.band_sharded_discrepancy(x, y, 0.25, 0.0, resolution=1024, algo=algo, info=info)
                 torch.cuda.synchronize(); dist.barrier(); ts.append(time.perf_counter() - t0)
             if rank == 0:
-                print(f"C5 n={n} R=1024 over {world} ranks, {name}, {algo}: {js!r} in {1e3*min(ts[1:]):.2f} ms", flush=True)
+                print(f"C5 n={n} R=1024 over {world} ranks, {name}, {algo}, exchange over {info['exchange']}: {js!r} in "
+                      f"{1e3*min(ts[1:]):.2f} ms", flush=True)
+    del os.environ["KDEJS_BAND_PEER"]
     for algo in ("binned", "binned32"):
         info = {"timing": True}
         D.band_sharded_discrepancy(da, db, 0.25, 0.0, resolution=1024, algo=algo, info=info)
