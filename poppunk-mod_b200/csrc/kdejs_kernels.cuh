@@ -253,10 +253,23 @@ __device__ __forceinline__ void zero_u16(uint16_t *p, int n) {
 }
 
 constexpr int kSortUnroll = 4;        // independent 32-point groups a warp keeps in flight
-#ifndef KDEJS_MATCH_BALLOTS
-#define KDEJS_MATCH_BALLOTS 0
+// How the lanes of a 32-point group find the same-cell lanes below them (k_scale_count):
+//   0  MATCH.ANY on the cell id.  Its cost grows with the number of DISTINCT values in the warp (tools/ubench/
+//      match_probe.cu on a B200 at this kernel's 24 warps per SM: 2 SM-cycles per warp-level MATCH with one value,
+//      21 with 16, 47 with 32 distinct ones) and unsorted points land in ~30 different cells per group: half of the
+//      kernel's 94 SM-cycles per group.
+//   1  one ballot per bit of the cell id (26 SM-cycles in the probe, but slower in the kernel: 2.06 -> 2.92 us
+//      per evaluation, measured in rounds 1 and 2).
+//   2  a 15-step shuffle network sorts (cell, lane) keys across the warp; same-cell lanes become neighbours in lane
+//      order and a ballot of the segment heads gives every point its rank (17 SM-cycles in the probe) -- and yet
+//      slower in the kernel as well: 2.12 -> 2.50 us per evaluation, 0.078 -> 0.093 ms for a band of config C5
+//      (same results bit for bit).  What the kernel waits for is the MIO queue as a whole -- MATCH, the histogram's
+//      LDS/STS and the shuffles share it -- so trading one MATCH for sixteen shuffles does not pay.
+// 0 is the default; 1 and 2 stay as compile-time experiments (-DKDEJS_RANK_MODE=...).
+#ifndef KDEJS_RANK_MODE
+#define KDEJS_RANK_MODE 0
 #endif
-constexpr bool kMatchByBallots = KDEJS_MATCH_BALLOTS != 0;
+constexpr int kRankMode = KDEJS_RANK_MODE;
 constexpr int kMaxChw = 8192;         // points per warp sub-chunk: 4 warps * kMaxChw < 65536 (u16 counters)
 
 // k_scale_count: grid (nb_max, n_sets), kSortThreads threads, dyn smem kSortWarps*ncells u16 (a warp's
@@ -306,14 +319,38 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
                 cellid[sd.off + j] = (uint16_t)cell;
             }
             const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (kRankMode == 2) {
+                // sort (cell, lane) across the warp; invalid lanes carry the largest key and end up on top
+                uint32_t key = valid ? ((uint32_t)cell << 5) | (uint32_t)lane : 0xffffffffu;
+#pragma unroll
+                for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                        const uint32_t other = __shfl_xor_sync(0xffffffffu, key, stride);
+                        // ascending blocks where bit `size` of the lane is clear (the last merge is ascending everywhere)
+                        const bool take_min = (((lane & stride) == 0) == (((lane & size) == 0) || size == 32));
+                        key = take_min ? min(key, other) : max(key, other);
+                    }
+                }
+                const uint32_t below = __shfl_up_sync(0xffffffffu, key, 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || (below >> 5) != (key >> 5));
+                const unsigned upto = heads & ((2u << lane) - 1u);              // heads at or below this lane (lane 31: all)
+                const int seg = 31 - __clz(upto);                               // first lane of this lane's segment
+                const unsigned above = heads & ~((2u << lane) - 1u);
+                const int seg_end = above ? __ffs(above) - 1 : 32;
+                const bool here = key != 0xffffffffu;                           // this sorted slot holds a real point
+                const int scell = (int)(key >> 5);
+                uint32_t before = 0u;
+                if (here && seg == lane) { before = hw[scell]; hw[scell] = (uint16_t)(before + (uint32_t)(seg_end - lane)); }
+                __syncwarp();
+                before = __shfl_sync(0xffffffffu, before, seg);
+                if (here && rank16) rank16[sd.off + j0 + u * 32 + (int)(key & 31u)] = (uint16_t)(before + (uint32_t)(lane - seg));
+                continue;
+            }
             uint32_t before = 0u;
             int leader = lane;
             unsigned m = 0u;
-            if (kMatchByBallots) {
-                // lanes of this group that fall into the same cell: one ballot per bit of the cell id instead of
-                // one MATCH.ANY.  Measured twice (rounds 1 and 2): slower (k_scale_count 2.06 -> 2.92 us per
-                // evaluation) although a third of the kernel's stall samples sit right behind the MATCH -- kept
-                // only as a compile-time experiment (-DKDEJS_MATCH_BALLOTS=1)
+            if (kRankMode == 1) {
                 m = act;
                 for (int bit = 0; bit < cell_bits; ++bit) {
                     const unsigned v = __ballot_sync(0xffffffffu, (cell >> bit) & 1);

@@ -7,7 +7,10 @@ import torch
 import poppunk_mod_b200 as pk
 from oracle import workloads as wl
 
-nat = pk._native; L = nat.lib(); dev = 0
+nat = pk._native
+if os.environ.get("PROBE_LIB"):                       # A/B against another build of the library
+    nat.LIB_PATH = os.path.abspath(os.environ["PROBE_LIB"])
+L = nat.lib(); dev = 0
 nat.check(L.kdejs_init(dev))
 if os.environ.get("PROBE_LOOPS", "1") == "1":
     for which, name in ((0, "fp64 loop"), (1, "fp32 loop"), (2, "fp32 loop + fp64 fold every 16")):
