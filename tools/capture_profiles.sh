@@ -16,4 +16,9 @@ ncu --set full --clock-control none -k regex:'k_minmax|k_scale_count|k_scan|k_pl
 CMD64="python bench.py --algo binned --steps 10 --warmup 3 --no-cpu-baseline --no-extras"
 $CMD64 > $OUT/plain64_${TAG}.log 2>&1 || exit 3
 ncu --set full --clock-control none --import-source on -k 'regex:^k_density_binned$' -s 10 -c 2 -o $OUT/prof_binned_${TAG} $CMD64 > $OUT/ncu_b64.log 2>&1
-for f in ncu_b32 ncu_s ncu_b64; do tail -n 1 $OUT/$f.log; done
+# fine-grid path (config C5's geometry at 3 M + 3 M points): moment cells, wide scan, heavy tiles in parts
+C5_N=3000000 python tools/c5_probe.py > $OUT/plain_c5_${TAG}.log 2>&1 || exit 4
+C5_N=3000000 ncu --set full --clock-control none --import-source on -k 'regex:^k_density_binned$|k_cell_moments|k_scan_wide|k_scale_count' -s 4 -c 4 -o $OUT/prof_c5_${TAG} python tools/c5_probe.py > $OUT/ncu_c5.log 2>&1
+python tools/band_sort_probe.py 1250000 > $OUT/band_sort_probe_${TAG}.log 2>&1
+tools/ubench/match_probe > $OUT/match_probe_${TAG}.log 2>&1
+for f in ncu_b32 ncu_s ncu_b64 ncu_c5; do tail -n 1 $OUT/$f.log; done

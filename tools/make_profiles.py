@@ -55,11 +55,16 @@ full(f"{G}/prof_binned32_{tag}.ncu-rep", f"profiles/{tag}_density_binned32_full.
      f"# ncu --set full --clock-control none --import-source on -k regex:k_density_binned32 -s 10 -c 2 over {cmd}\n"
      "# dominant kernel of the timed step (default algorithm): a wave of 64 evaluations per launch\n")
 full(f"{G}/prof_binned_{tag}.ncu-rep", f"profiles/{tag}_density_binned_full.txt",
-     f"# ncu --set full --clock-control none --import-source on -k 'regex:k_density_binned<' -s 10 -c 2 over bench.py --algo binned ...\n"
+     f"# ncu --set full --clock-control none --import-source on -k 'regex:^k_density_binned$' -s 10 -c 2 over bench.py --algo binned ...\n"
      "# the fp64 culled kernel (algo=\"binned\"): a wave of 64 evaluations per launch\n")
 full(f"{G}/prof_small_{tag}.ncu-rep", f"profiles/{tag}_other_kernels_full.txt",
      f"# ncu --set full --clock-control none, the other kernels of one wave (incl. the fp64 redo launch), over {cmd}\n")
-for name in (f"bench_{tag}_n1.json", f"bench_{tag}_n1_binned.json", f"bench_{tag}_reference.json", f"fp32_probe_{tag}.log"):
+if os.path.exists(f"{G}/prof_c5_{tag}.ncu-rep"):
+    full(f"{G}/prof_c5_{tag}.ncu-rep", f"profiles/{tag}_c5_fine_grid_full.txt",
+         "# C5_N=3000000 ncu --set full --clock-control none -k 'regex:^k_density_binned$|k_cell_moments|k_scan_wide|k_scale_count' "
+         "-s 4 -c 4 over tools/c5_probe.py\n# fine-grid path: 3 M + 3 M points, R = 1024, 128 x 128 cells, moment cells\n")
+for name in (f"bench_{tag}_n1.json", f"bench_{tag}_n1_binned.json", f"bench_{tag}_reference.json", f"fp32_probe_{tag}.log",
+             f"band_sort_probe_{tag}.log", f"match_probe_{tag}.log", f"h2d_probe_{tag}.jsonl"):
     if os.path.exists(f"{G}/{name}"):
         shutil.copy(f"{G}/{name}", f"profiles/{name}")
 d = json.load(open(f"{G}/bench_{tag}_n1.json"))
