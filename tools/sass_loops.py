@@ -38,13 +38,14 @@ def loops(lines, marker, per_candidate):
         if tgt < A[i] and tgt in A:
             body = lines[A.index(tgt): i + 1]
             n = sum(marker in opcode(b) for b in body)
-            if per_candidate <= n <= 3 * per_candidate:
+            if per_candidate <= n <= 4 * per_candidate:
                 out.append((tgt, A[i], body, n // per_candidate))
     return out
 
 
 print("# Candidate loops of the culled density kernels (sm_100a SASS of the shipped libkdejs.so; tools/sass_loops.py)")
-print("# One trip = 32 candidates (one per lane) against the 16 nodes of a 4x4 tile.\n")
+print("# A lane tests one candidate against the 16 nodes of a 4x4 tile; loops are unrolled over 1-4 candidates per lane")
+print("# (fp32, warp-per-tile phase: two trips of two candidates each).\n")
 for name, lines in sorted(funcs.items()):
     if "k_density_binned32ILb0" in name:
         title, marker, per = "k_density_binned32<false>  (fp32 terms: FFMA.SAT + packed FADD2)", "FFMA.SAT", 16
@@ -60,10 +61,10 @@ for name, lines in sorted(funcs.items()):
         if len(body) > 330:             # outer loops (whole tiles): not candidate loops
             continue
         fam = collections.Counter(opcode(b).split(".")[0] for b in body)
-        print(f"\n### loop 0x{tgt:04x}..0x{end:04x}: {len(body)} instructions for {trips} trip(s) = {len(body) / trips:.1f} per trip "
-              "(static count; run-switch and fold code inside the body executes once per run / per 15 trips)")
+        print(f"\n### loop 0x{tgt:04x}..0x{end:04x}: {len(body)} instructions for {trips} candidate(s) per lane = {len(body) / trips:.1f} per candidate "
+              "(static count; run-switch and fold code inside the body executes once per run / per fold block)")
         print("### by opcode family:", ", ".join(f"{k} {v}" for k, v in fam.most_common()))
-        if len(body) <= (80 if "binned32" not in name else 270) and printed < 2:
+        if len(body) <= (80 if "binned32" not in name else 280) and printed < 3:
             printed += 1
             for b in body:
                 print(b)
