@@ -197,7 +197,10 @@ class _GpuBandOps:
         self.C, self.NT, self.block_u32 = geo[0], geo[1], geo[2]
         self.tdev = torch.device("cuda", self.dev)
         self.stream = _band_stream(torch, self.tdev)
-        self.peer = os.environ.get("KDEJS_BAND_PEER", "1") != "0"      # exchange over peer memory when all ranks can
+        # exchange over peer memory when every rank can: one node (torchrun exports LOCAL_WORLD_SIZE; all ranks read
+        # the same value, so all decide alike), at most MAX_PEERS ranks, not switched off
+        self.peer = os.environ.get("KDEJS_BAND_PEER", "1") != "0" and \
+            os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) == os.environ.get("WORLD_SIZE", "1")
         self.handles = np.zeros((1, HANDLE_WORDS), dtype=np.uint32)
 
     def run(self):
@@ -241,13 +244,14 @@ class _GpuBandOps:
 
     def sort(self, a, b, stats_all, world):
         block = self.empty(self.block_u32, "i4")
-        if self.peer and world > 1:
+        use_peer = self.peer and 1 < world <= MAX_PEERS
+        if use_peer:
             try:
                 srt, handle = self._peer_buffer(a.shape[0] + b.shape[0])
                 block[-HANDLE_WORDS:] = handle
             except RuntimeError:                 # no IPC export here: the zero handle makes every rank use NCCL
-                self.peer = False
-        if not (self.peer and world > 1):
+                self.peer = use_peer = False
+        if not use_peer:
             srt = self.empty((a.shape[0] + b.shape[0], 2))
             block[-HANDLE_WORDS:] = 0
         nat.check(self.L.kdejs_band_sort_dev(self.dev, a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0], *self.common,
@@ -299,6 +303,7 @@ class _GpuBandOps:
 
 
 HANDLE_WORDS = 16      # a CUDA IPC handle, as u32 words at the end of a rank's count block (include/kdejs.h)
+MAX_PEERS = 16         # ranks the merge kernel can pull from (kMaxPeers in csrc/kdejs_kernels.cuh)
 
 
 class _DevView:
