@@ -425,6 +425,8 @@ struct WaveIO {
     const int64_t *n_global = nullptr;   // [n_sets]: sizes of the WHOLE sets (the 1/N of the density) when this wave holds a part
 };
 
+constexpr int64_t kMinPoints32 = 64;     // sets smaller than this are summed in fp64 whatever the algorithm says
+
 int sort_shape(const WaveDesc &wd, int sm_count, int ncells, int &chw, int &nb_max) {
     // Points per warp sub-chunk.  Every sort block pays a fixed cost for its C*C counters (zeroing, prefix,
     // histogram write-out), so chunks grow with the wave until the launch still has ~4 blocks per SM
@@ -479,7 +481,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     // something: with a handful of points no node sum exceeds ~1 and fp32 terms are themselves 1e-7 off
     int64_t min_n = INT64_MAX;
     for (int s = 0; s < wd.n_sets; ++s) min_n = std::min<int64_t>(min_n, io.n_global ? io.n_global[s] : (int64_t)wd.set[s].n);
-    bool fast32 = binned && g.q_shift > 0 && min_n >= 64 &&
+    bool fast32 = binned && g.q_shift > 0 && min_n >= kMinPoints32 &&
                   (force32 >= 0 ? force32 != 0 : p.algo == KDEJS_ALGO_BINNED32);
     // a moment cell costs a tile as much as one point plus some per-row bookkeeping: it pays once cells hold
     // hundreds of points (measured: -40 % density time at 1200 points per cell, +48 % at 49)
@@ -781,6 +783,18 @@ int run_pairs_dev(Ctx &c, cudaStream_t st, const Params &p, const std::vector<Ra
                   const int32_t *ia, const int32_t *ib, int64_t n_items, double *out_js_dev,
                   int32_t *status_dev, int64_t out_base, bool want_z) {
     GridGeom g = make_geom(p);
+    // Two choices of run_wave() depend on the sizes of the sets it is given: moment cells (fine grids: at least 128
+    // points per cell on average) and the fp64 kernel for sets too small for the fp32 error bound (< 64 points).  An
+    // evaluation must get the same arithmetic whatever else travels in its wave -- batch results equal single calls
+    // bit for bit -- so both are decided per EVALUATION here and a wave only holds evaluations of one class.
+    const int64_t ncells_g = (int64_t)g.C * g.C;
+    auto eval_class = [&](int64_t k) {
+        const int64_t na = pool[ia[k]].n, nb = pool[ib[k]].n;
+        int cls = 0;
+        if (std::min(na, nb) < kMinPoints32) cls |= 1;
+        if (g.use_moments == 1 && na + nb >= (int64_t)128 * 2 * ncells_g) cls |= 2;
+        return cls;
+    };
     int64_t i = 0;
     while (i < n_items) {
         WaveDesc wd;
@@ -798,7 +812,8 @@ int run_pairs_dev(Ctx &c, cudaStream_t st, const Params &p, const std::vector<Ra
             maxpts = std::max<int64_t>(maxpts, pool[ia[k]].n + pool[ib[k]].n);
         const int cap = wave_capacity(p, maxpts);
         int items = 0;
-        while (items < cap && i + items < n_items) {
+        const int wave_class = eval_class(i);
+        while (items < cap && i + items < n_items && eval_class(i + items) == wave_class) {
             const int a = ia[i + items], b = ib[i + items];
             const int la = local(a), lb = local(b);
             SetDesc &s0 = wd.set[2 * items], &s1 = wd.set[2 * items + 1];
@@ -810,6 +825,7 @@ int run_pairs_dev(Ctx &c, cudaStream_t st, const Params &p, const std::vector<Ra
         wd.n_sets = 2 * items;
         WaveIO io;
         io.out_js = out_js_dev; io.out_status = status_dev; io.item_base = (int)(out_base + i); io.want_z = want_z;
+        io.force_moments = (wave_class & 2) ? 1 : 0;          // (ignored unless the geometry is merely eligible)
         OKR(run_wave(c, c.S(), st, p, g, wd, io));
         i += items;
     }

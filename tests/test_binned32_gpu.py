@@ -86,6 +86,28 @@ def test_batch_equals_singles_bitwise_fp32(pk, ko):
     np.testing.assert_array_equal(pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0, algo="binned32"), got)
 
 
+@pytest.mark.parametrize("algo", ["binned32", "binned"])
+def test_batch_equals_singles_bitwise_in_mixed_batches(pk, algo):
+    """An evaluation gets the same arithmetic whatever else travels in its wave: sets too small for the fp32
+    kernel (< 64 points: fp64 whatever the algorithm says) and, on a fine grid, sets dense enough for moment cells
+    sit next to ordinary ones in one call (tools/stress.py found the first case with the default algorithm)."""
+    from oracle import workloads as wl
+
+    rng = np.random.default_rng(11)
+    obs = wl.synthetic_target(9000)
+    sims = [wl.sim_batch_member(s, n=int(n)) for s, n in enumerate([4000, 3, 700, 63, 64, 12000, 1, 2500, 40, 5000])]
+    got = pk.KDE_JS_divergence_batch(obs, sims, gamma=0.25, eps=0.0, resolution=100, algo=algo)
+    for i in range(len(sims)):
+        assert got[i] == pk.KDE_JS_divergence(obs, sims[i], gamma=0.25, eps=0.0, resolution=100, algo=algo), i
+    # fine grid (128 x 128 cells): 128 points per cell on average = 2.1 M points per set is where moment cells start;
+    # one evaluation above that bar between two below it
+    big = wl.synthetic_target(2_200_000, seed=5)
+    pair = [wl.sim_batch_member(1, n=30_000), wl.sim_S(7, 1800, 0.36, n=2_150_000), wl.sim_batch_member(2, n=50_000)]
+    got = pk.KDE_JS_divergence_batch(big, pair, gamma=0.25, eps=0.0, resolution=640, algo=algo)
+    for i in range(len(pair)):
+        assert got[i] == pk.KDE_JS_divergence(big, pair[i], gamma=0.25, eps=0.0, resolution=640, algo=algo), i
+
+
 def test_full_size_fp32(pk, ko):
     """BASELINE config 2 size on the reference's example target: oracle, identity, symmetry, disjoint."""
     from oracle import workloads as wl
