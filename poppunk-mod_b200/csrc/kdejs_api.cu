@@ -95,7 +95,7 @@ struct DevBuf {
 
 struct Slot {
     DevBuf scaled, sorted, sorted_q, cellid, blockhist, cellstart, moments, dens, pz, zout, tilesum;
-    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, redo, counters, totals, rank16, warpprefix, tileflag, misc;
+    DevBuf rstat, rpart, tickets, jspart, dense_partial, worklist, redo, counters, totals, warpprefix, tileflag, misc;
     DevBuf partinfo, redo_partinfo, split_partial, split_ticket;     // very heavy tiles processed in parts (SplitBufs)
     DevBuf bandtot;                                                   // band mode: per-cell totals over ranks
 };
@@ -191,7 +191,7 @@ void destroy_ctx(Ctx &c) {
     for (Slot &s : c.slots)
         for (DevBuf *b : {&s.scaled, &s.sorted, &s.sorted_q, &s.moments, &s.cellid, &s.blockhist, &s.cellstart, &s.dens,
                           &s.pz, &s.zout, &s.tilesum, &s.rstat, &s.rpart, &s.tickets, &s.jspart, &s.dense_partial,
-                          &s.worklist, &s.redo, &s.counters, &s.totals, &s.rank16, &s.warpprefix, &s.tileflag, &s.misc,
+                          &s.worklist, &s.redo, &s.counters, &s.totals, &s.warpprefix, &s.tileflag, &s.misc,
                           &s.partinfo, &s.redo_partinfo, &s.split_partial, &s.split_ticket, &s.bandtot}) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr; b->cap = 0;
@@ -516,8 +516,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     if (io.want_z) OKR(sl.zout.ensure((size_t)n_sets * G * sizeof(double)));
     if (binned) {
         OKR(sl.sorted.ensure((size_t)P * sizeof(double2)));
-        OKR(sl.cellid.ensure((size_t)P * sizeof(uint16_t)));
-        OKR(sl.rank16.ensure((size_t)P * sizeof(uint16_t)));
+        OKR(sl.cellid.ensure((size_t)P * sizeof(uint32_t)));        // per point: cell id | rank << 16
         OKR(sl.warpprefix.ensure((size_t)n_sets * nb_max * kSortWarps * ncells * sizeof(uint16_t)));
         OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * ncells * sizeof(uint32_t)));
         OKR(sl.cellstart.ensure((size_t)n_sets * (ncells + 1) * sizeof(uint32_t)));
@@ -553,7 +552,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
                 io.identity_scaler ? 1 : 0, g.C, g.cell_x0, g.cell_invw, chw, nb_max,
-                nullptr, sl.cellid.as<uint16_t>(), sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(),
+                nullptr, sl.cellid.as<uint32_t>(), sl.warpprefix.as<uint16_t>(),
                 sl.blockhist.as<uint32_t>());
         }
         if (!io.presorted) {
@@ -572,8 +571,8 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
             for (int s = 0; s < n_sets; ++s) nmax = std::max(nmax, wd.set[s].n);
             k_place<<<dim3((nmax + 255) / 256, n_sets), 256, 0, st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
-                io.identity_scaler ? 1 : 0, ncells, chw, nb_max, sl.cellid.as<uint16_t>(),
-                sl.rank16.as<uint16_t>(), sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
+                io.identity_scaler ? 1 : 0, ncells, chw, nb_max, sl.cellid.as<uint32_t>(),
+                sl.warpprefix.as<uint16_t>(), sl.blockhist.as<uint32_t>(),
                 wide_scan ? sl.cellstart.as<uint32_t>() : nullptr, sl.sorted.as<double2>(),
                 fast32 && !kFp32FromDoubles ? sl.sorted_q.as<uint2>() : nullptr, g);
         }
@@ -691,12 +690,11 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         // dense fp64: scale only (C = 1: every point lands in cell 0, the histogram is unused)
         {
             KTimer t(c, 1, st);
-            OKR(sl.cellid.ensure((size_t)P * sizeof(uint16_t)));
             OKR(sl.blockhist.ensure((size_t)n_sets * nb_max * sizeof(uint32_t)));
             k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, kSortWarps * sizeof(uint16_t), st>>>(
                 wd, sl.rstat.as<RawStat>(), io.identity_scaler ? 0 : p.log_flag, p.eps,
                 io.identity_scaler ? 1 : 0, 1, g.cell_x0, g.cell_invw, chw, nb_max,
-                sl.scaled.as<double2>(), sl.cellid.as<uint16_t>(), nullptr, nullptr, sl.blockhist.as<uint32_t>());
+                sl.scaled.as<double2>(), nullptr, nullptr, sl.blockhist.as<uint32_t>());
         }
         int nslices;
         if (p.algo == KDEJS_ALGO_DENSE) {

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kSortThreads)
 k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat,
               int log_flag, double eps, int identity_scaler, int C, double cell_x0,
               double cell_invw, int chw, int nb_max, double2 *__restrict__ scaled,
-              uint16_t *__restrict__ cellid, uint16_t *__restrict__ rank16,
+              uint32_t *__restrict__ cellrank,
               uint16_t *__restrict__ warpprefix, uint32_t *__restrict__ blockhist) {
     extern __shared__ uint16_t s_hist[];
     const SetDesc sd = wd.set[blockIdx.y];
@@ -316,7 +316,6 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
                 const double2 X = scale_point(v[u], sc, log_flag, eps, identity_scaler);
                 if (scaled) scaled[sd.off + j] = X;
                 cell = cell_of(X.y, cell_x0, cell_invw, C) * C + cell_of(X.x, cell_x0, cell_invw, C);
-                cellid[sd.off + j] = (uint16_t)cell;
             }
             const unsigned act = __ballot_sync(0xffffffffu, valid);
             if (kRankMode == 2) {
@@ -344,7 +343,8 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
                 if (here && seg == lane) { before = hw[scell]; hw[scell] = (uint16_t)(before + (uint32_t)(seg_end - lane)); }
                 __syncwarp();
                 before = __shfl_sync(0xffffffffu, before, seg);
-                if (here && rank16) rank16[sd.off + j0 + u * 32 + (int)(key & 31u)] = (uint16_t)(before + (uint32_t)(lane - seg));
+                if (here && cellrank)
+                    cellrank[sd.off + j0 + u * 32 + (int)(key & 31u)] = (uint32_t)scell | ((before + (uint32_t)(lane - seg)) << 16);
                 continue;
             }
             uint32_t before = 0u;
@@ -366,7 +366,8 @@ k_scale_count(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ r
             }
             __syncwarp();
             before = __shfl_sync(0xffffffffu, before, leader);
-            if (valid && rank16) rank16[sd.off + j] = (uint16_t)(before + __popc(m & ((1u << lane) - 1u)));
+            // one 32-bit record per point: cell id (low half) and rank (high half; both fit 16 bits)
+            if (valid && cellrank) cellrank[sd.off + j] = (uint32_t)cell | ((before + __popc(m & ((1u << lane) - 1u))) << 16);
         }
     }
     __syncthreads();
@@ -542,8 +543,8 @@ __device__ __forceinline__ uint32_t quantise(double x, const GridGeom &g) {
 // arithmetic as k_scale_count and written straight to that slot.  No shared memory, no ranking.
 __global__ void __launch_bounds__(256)
 k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, int log_flag, double eps,
-        int identity_scaler, int ncells, int chw, int nb_max, const uint16_t *__restrict__ cellid,
-        const uint16_t *__restrict__ rank16, const uint16_t *__restrict__ warpprefix,
+        int identity_scaler, int ncells, int chw, int nb_max, const uint32_t *__restrict__ cellrank,
+        const uint16_t *__restrict__ warpprefix,
         const uint32_t *__restrict__ blockbase, const uint32_t *__restrict__ cellstart,
         double2 *__restrict__ sorted, uint2 *__restrict__ sorted_q, const GridGeom g) {
     __shared__ Scaler s_sc;                 // two fp64 divisions: once per block, not once per point
@@ -553,8 +554,9 @@ k_place(const __grid_constant__ WaveDesc wd, const RawStat *__restrict__ rstat, 
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;          // a set holds < 2^29 points (check_set)
     if (j >= (uint32_t)sd.n) return;
     const double2 v = reinterpret_cast<const double2 *>(wd.raw[sd.rs_self].p)[j];
-    const int cell = cellid[sd.off + j];
-    const uint32_t rank = rank16[sd.off + j];
+    const uint32_t cr = cellrank[sd.off + j];
+    const int cell = (int)(cr & 0xffffu);
+    const uint32_t rank = cr >> 16;
     const uint32_t wchunk = j / (uint32_t)chw;            // global warp sub-chunk index of the point
     const size_t row = (size_t)blockIdx.y * nb_max + (size_t)(wchunk / kSortWarps);
     // cellstart is null when k_scan_narrow left absolute positions in blockbase
