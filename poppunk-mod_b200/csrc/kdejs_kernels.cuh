@@ -893,6 +893,7 @@ __device__ __forceinline__ uint32_t list_entry_ex(const uint32_t *__restrict__ w
 // [c0, c1) of the tile's flattened chunk sequence: the run holds chunks [cpre_e, cpre_e1); inside the part the
 // chunks are dealt to the warps round-robin, (chunk - c0) mod 4 == warp.  Returns the first candidate of the warp's
 // first chunk and how many candidates follow it up to the end of the run or of the part (0: nothing).
+template <int CHUNK_LOG2 = 5>
 __device__ __forceinline__ void part_run(uint32_t cpre_e, uint32_t cpre_e1, uint32_t rs_e, uint32_t len_e,
                                          uint32_t c0, uint32_t c1, int warp, uint32_t &start, uint32_t &rem) {
     const uint32_t lo = max(cpre_e, c0), hi = min(cpre_e1, c1);
@@ -901,8 +902,8 @@ __device__ __forceinline__ void part_run(uint32_t cpre_e, uint32_t cpre_e1, uint
     if (lo < hi) {
         const uint32_t g0 = lo + (((uint32_t)warp - (lo - c0)) & 3u);
         if (g0 < hi) {
-            const uint32_t off = (g0 - cpre_e) * 32u;
-            const uint32_t end = (hi == cpre_e1) ? len_e : (hi - cpre_e) * 32u;     // a run's last chunk is ragged
+            const uint32_t off = (g0 - cpre_e) << CHUNK_LOG2;
+            const uint32_t end = (hi == cpre_e1) ? len_e : (hi - cpre_e) << CHUNK_LOG2;     // a run's last chunk is ragged
             start = rs_e + off;
             rem = end - off;
         }
@@ -1371,6 +1372,15 @@ __device__ __forceinline__ void walk_tile32(const Cand32 *__restrict__ pts, cons
         for (int j = 0; j < kTile; ++j) tot[i][j] = (double)(THREE_LEVEL ? top[i][j] : hi[i][j]);
 }
 
+// Phase A of the fp32 kernel (block per heavy tile): candidates per lane and trip, and with that the chunk the four
+// warps deal out round-robin (KDEJS_PAIR_A=0: one candidate per lane, 32-candidate chunks).
+#ifndef KDEJS_PAIR_A
+#define KDEJS_PAIR_A 1
+#endif
+constexpr bool kPairA = KDEJS_PAIR_A != 0;
+constexpr int kChunkALog2 = kPairA ? 6 : 5;
+constexpr uint32_t kChunkA = 1u << kChunkALog2;
+constexpr int kStrideA = (kDensThreads / 32) * (int)kChunkA;      // candidates between a warp's consecutive chunks
 template <bool MOMENTS>
 __global__ void __launch_bounds__(kDensThreads, 6)
 k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
@@ -1450,7 +1460,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
             s_rs[2 * lane + 1] = rr.s2;
             s_len[2 * lane] = rr.l1;
             s_len[2 * lane + 1] = rr.l2;
-            const uint32_t c1n = (rr.l1 + 31u) >> 5, c2n = (rr.l2 + 31u) >> 5;
+            const uint32_t c1n = (rr.l1 + kChunkA - 1u) >> kChunkALog2, c2n = (rr.l2 + kChunkA - 1u) >> kChunkALog2;
             uint32_t cinc = c1n + c2n;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -1466,7 +1476,7 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
         }
         __syncthreads();
         const Cand32 *__restrict__ pts = sorted_q + sd.off;
-        const uint32_t gtot = s_cpre[2 * kMaxRows];         // 32-candidate chunks of the tile, dealt round-robin to the warps
+        const uint32_t gtot = s_cpre[2 * kMaxRows];         // kChunkA-candidate chunks of the tile, dealt round-robin to the warps
         // this part's chunks of the flattened sequence (a tile that is not split is one part), and in them this
         // warp's share of every run, compacted into the warp's own run list (two run slots per lane: left / right
         // of the moment cells)
@@ -1479,8 +1489,8 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const int e = 2 * lane + k;
-                part_run(s_cpre[e], s_cpre[e + 1], s_rs[e], s_len[e], pc0, pc1, warp, st2[k], ln2[k]);
-                my_trips += (ln2[k] + kDensThreads - 1u) / kDensThreads;
+                part_run<kChunkALog2>(s_cpre[e], s_cpre[e + 1], s_rs[e], s_len[e], pc0, pc1, warp, st2[k], ln2[k]);
+                my_trips += (ln2[k] + kStrideA - 1u) / kStrideA;
             }
             const unsigned m0 = __ballot_sync(0xffffffffu, ln2[0] > 0u), m1 = __ballot_sync(0xffffffffu, ln2[1] > 0u);
             const unsigned lt = (1u << lane) - 1u;
@@ -1493,9 +1503,9 @@ k_density_binned32(const __grid_constant__ WaveDesc wd, const GridGeom g,
             __syncwarp();
         }
         double acc64[kTile][kTile];
-        walk_tile32<kDensThreads, true, false>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, org,
-                                        far_candidate(org, g), f1, f2, f3, 1.0f, acc64);
-        uint32_t ncand = gtot * 32u;                          // upper bound of the candidates (last chunks are ragged)
+        walk_tile32<kStrideA, true, kPairA>(pts, s_wstart[warp], s_wlen[warp], my_runs, my_trips, lane, org,
+                                            far_candidate(org, g), f1, f2, f3, 1.0f, acc64);
+        uint32_t ncand = gtot * kChunkA;                      // upper bound of the candidates (last chunks are ragged)
         if (MOMENTS && part_k == 0u) {                        // the moment cells go with the first part
             const double *__restrict__ mom = moments + (size_t)set * ncells * kMomentDoubles;
             const int rows = s_rows, cy0 = s_cy0;
