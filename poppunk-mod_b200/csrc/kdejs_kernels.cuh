@@ -683,6 +683,16 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
     total += __shfl_xor_sync(0xffffffffu, total, 1);
     total += __shfl_xor_sync(0xffffffffu, total, 2);
     total += __shfl_xor_sync(0xffffffffu, total, 4);
+    // List slots are claimed per BLOCK: the 32 tiles of a block count their entries in shared memory and one thread
+    // per class adds the block's total to the global counter.  One global atomic per tile had every non-empty tile
+    // of a wave (150 000 at the headline size) queue up on the same ten addresses -- that, not the arithmetic, was
+    // the kernel's time.  A block's tiles belong to one set, hence to one group: kNumClasses lists.
+    __shared__ unsigned s_cnt[kNumClasses], s_base[kNumClasses];
+    if (threadIdx.x < kNumClasses) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    const int grp = set / g.sets_per_group;
+    int cls = -1;
+    uint32_t K = 1u, pbase = 0u, local = 0u;
     if (live) {
         const int tile = tx * g.NT + ty;
         if (tileflag && sub == 0) tileflag[(size_t)set * g.NT * g.NT + tile] = (total == 0u) ? 1 : 0;
@@ -702,21 +712,26 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
                 tilesum[(size_t)set * g.NT * g.NT + tile] = P0 * (double)nv;
             }
         } else if (sub == 0) {
-            const int cls = tile_class(total, g.heavy_log2);
-            const int grp = set / g.sets_per_group;
-            const int list = grp * kNumClasses + cls;
-            const uint32_t entry = ((uint32_t)set << 24) | (uint32_t)tile;
-            uint32_t K = 1u, pbase = 0u;
+            cls = tile_class(total, g.heavy_log2);
             if (cls == 0 && total >= (1u << kSplitLog2)) {
                 K = min((uint32_t)kMaxParts, (total + (1u << kPartLog2) - 1u) >> kPartLog2);
                 pbase = atomicAdd(&counters[kSplitParts], K);
                 if (pbase + K > sb.parts_cap) K = 1u;                  // out of part slots: process it whole
             }
-            const unsigned slot = atomicAdd(&counters[list], K);
-            for (uint32_t k = 0; k < K; ++k) {
-                worklist[(size_t)list * capacity + slot + k] = entry;
-                if (cls == 0) sb.partinfo[(size_t)grp * capacity + slot + k] = make_uint2(k | (K << 8), pbase);
-            }
+            local = atomicAdd(&s_cnt[cls], K);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumClasses && s_cnt[threadIdx.x] > 0u)
+        s_base[threadIdx.x] = atomicAdd(&counters[grp * kNumClasses + threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (cls >= 0) {
+        const int list = grp * kNumClasses + cls;
+        const uint32_t entry = ((uint32_t)set << 24) | (uint32_t)(tx * g.NT + ty);
+        const unsigned slot = s_base[cls] + local;
+        for (uint32_t k = 0; k < K; ++k) {
+            worklist[(size_t)list * capacity + slot + k] = entry;
+            if (cls == 0) sb.partinfo[(size_t)grp * capacity + slot + k] = make_uint2(k | (K << 8), pbase);
         }
     }
     if (work_counter) {
