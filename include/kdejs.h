@@ -204,6 +204,9 @@ int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int r
                     uint32_t *out_rowstart, int *out_use_moments, void *stream);
 int kdejs_band_cuts(const double *colwork, int nt, int world, int *cuts);
 int kdejs_band_cell_rows(int resolution, double bandwidth, int ty_begin, int ty_end, int out_cy[2]);
+/* kdejs_band_cuts and every rank's kdejs_band_cell_rows in one call: out_cuts[world + 1], out_rows[world][2] */
+int kdejs_band_layout(const double *colwork, int nt, int world, int resolution, double bandwidth, int *out_cuts,
+                      int *out_rows);
 int kdejs_band_phase1_dev(int device, const double *stage_a_dev, int64_t na, const double *stage_b_dev, int64_t nb,
                           int64_t na_total, int64_t nb_total, const uint32_t *blocks_all_dev, int world,
                           const double *stats_all_dev, int resolution, double bandwidth, double gamma, double eps,

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "kdejs_band_cuts": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "kdejs_band_cell_rows": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                             ctypes.POINTER(ctypes.c_int)]),
+    "kdejs_band_layout": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
     "kdejs_band_phase1_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_int, ctypes.c_void_p] + _COMMON +

@@ -1522,6 +1522,14 @@ int kdejs_band_cell_rows(int resolution, double bandwidth, int ty_begin, int ty_
     return KDEJS_OK;
 }
 
+int kdejs_band_layout(const double *colwork, int nt, int world, int resolution, double bandwidth, int *out_cuts,
+                      int *out_rows) {
+    if (!out_rows) return fail(KDEJS_ERR_ARG, "out_rows is null");
+    OKR(kdejs_band_cuts(colwork, nt, world, out_cuts));
+    for (int r = 0; r < world; ++r) OKR(kdejs_band_cell_rows(resolution, bandwidth, out_cuts[r], out_cuts[r + 1], out_rows + 2 * r));
+    return KDEJS_OK;
+}
+
 int kdejs_band_plan(int device, const uint32_t *blocks_all_dev, int world, int resolution, double bandwidth,
                     double gamma, double eps, int log_flag, int kernel, int algo, double *out_colwork,
                     uint32_t *out_rowstart, int *out_use_moments, void *stream) {

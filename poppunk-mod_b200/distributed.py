@@ -341,6 +341,16 @@ def band_cell_rows(resolution, bandwidth, ty_begin, ty_end):
     return cy[0], cy[1]
 
 
+def band_layout(colwork, world, resolution, bandwidth):
+    """band_cuts and every rank's band_cell_rows in one call: (cuts, rows) as plain lists."""
+    cw = np.ascontiguousarray(colwork, dtype=np.float64)
+    cuts = np.empty(world + 1, dtype=np.int32)
+    rows = np.empty((world, 2), dtype=np.int32)
+    nat.check(nat.lib().kdejs_band_layout(cw.ctypes.data, len(cw), world, int(resolution), float(bandwidth),
+                                          cuts.ctypes.data, rows.ctypes.data))
+    return cuts.tolist(), [tuple(r) for r in rows.tolist()]
+
+
 def _gather_cat(t, group, world):
     """Rank-ordered concatenation of equally sized 1-D/2-D tensors from all ranks (no host round trip)."""
     dist = _dist()
@@ -419,12 +429,11 @@ def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world
     mark("gather counts")
     colwork, rs, use_m = ops.plan(blocks_all, world)                           # the one host synchronisation
     mark("plan")
-    cuts = band_cuts(colwork, world)
-    rows = [band_cell_rows(resolution, bandwidth, cuts[d], cuts[d + 1]) for d in range(world)]
+    # (the GPU idles between the plan's synchronisation and the launches of phase 1: keep this stretch short)
+    cuts, rows = band_layout(colwork, world, resolution, bandwidth)
     lo_me, hi_me = rows[rank]
     n_tot = rs[:, :, -1].sum(axis=0)
-    recv = [[int(rs[s_, st, hi_me + 1] - rs[s_, st, lo_me]) if hi_me >= lo_me else 0 for s_ in range(world)]
-            for st in (0, 1)]
+    recv = (rs[:, :, hi_me + 1] - rs[:, :, lo_me]).T.tolist() if hi_me >= lo_me else [[0] * world, [0] * world]
     over_peer_memory = bool(getattr(ops, "peer_ready", None)) and ops.peer_ready(rank, world)
     if over_peer_memory:
         # the merge kernel pulls the rows it needs out of every rank's sorted array over NVLink
