@@ -4,7 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import poppunk_mod_b200 as pk
 from oracle import workloads as wl
-nat = pk._native; L = nat.lib()
+nat = pk._native
+if os.environ.get("PROBE_LIB"):                       # A/B against another build of the library
+    nat.LIB_PATH = os.path.abspath(os.environ["PROBE_LIB"])
+L = nat.lib()
 n = int(os.environ.get("C5_N", 10_000_000)); R = int(os.environ.get("C5_R", 1024))
 a = wl.synthetic_target(n, seed=11); b = wl.sim_S(5, 1800, 0.36, n=n)
 pool = nat.PinnedPool(); pa = pool.empty((n, 2)); pa[:] = a; pb = pool.empty((n, 2)); pb[:] = b
