@@ -244,7 +244,7 @@ class _GpuBandOps:
 
     def sort(self, a, b, stats_all, world):
         block = self.empty(self.block_u32, "i4")
-        use_peer = self.peer and 1 < world <= MAX_PEERS
+        use_peer = self.peer and 1 < world <= MAX_PEERS and not _PEER_BROKEN.get(self.dev)
         if use_peer:
             try:
                 srt, handle = self._peer_buffer(a.shape[0] + b.shape[0])
@@ -269,12 +269,22 @@ class _GpuBandOps:
         rowstart = out[:, :-HANDLE_WORDS].reshape(world, 2, self.C + 1)
         return colwork, rowstart.astype(np.int64), use_m.value
 
-    def peer_ready(self, rank, world):
-        """True when every rank exported its sorted points (all ranks see the same handles, so all agree) and this
-        rank could map them.  A rank that cannot map a peer raises: the others would wait for it otherwise."""
-        if world == 1 or not self.handles.any(axis=1).all():
+    def peer_ready(self, rank, world, group=None):
+        """True when every rank exported its sorted points and every rank could map them.  All ranks see the same
+        handles, so all take the same branch; when the set of handles is new (first call, or a buffer had to grow)
+        the ranks also agree -- one tiny all-gather -- that every mapping succeeded, and fall back to the NCCL
+        exchange together, for good, if one did not."""
+        if world == 1 or _PEER_BROKEN.get(self.dev) or not self.handles.any(axis=1).all():
             return False
-        nat.check(self.L.kdejs_band_peer_open(self.dev, self.handles.ctypes.data, world, rank))
+        key = (world, rank, self.handles.tobytes())
+        if _PEER_OPEN.get(self.dev) == key:
+            return True
+        rc = self.L.kdejs_band_peer_open(self.dev, self.handles.ctypes.data, world, rank)
+        ok = self.torch.tensor([1 if rc == 0 else 0], dtype=self.torch.int32, device=self.tdev)
+        if not bool(_gather_cat(ok, group, world).cpu().numpy().all()):
+            _PEER_BROKEN[self.dev] = True
+            return False
+        _PEER_OPEN[self.dev] = key
         return True
 
     def phase1_peer(self, na, nb, na_tot, nb_tot, blocks_all, stats_all, world, ty, cy, use_m):
@@ -316,6 +326,8 @@ class _DevView:
 
 _BAND_STREAMS = {}
 _HANDLE_DEV = {}
+_PEER_OPEN = {}        # device -> (world, rank, handles) of the mappings that are open
+_PEER_BROKEN = {}      # device -> True once a rank could not map a peer: NCCL exchange from then on
 
 
 def _band_stream(torch, tdev):
@@ -434,7 +446,7 @@ def _band_steps(ops, a_slice, b_slice, resolution, bandwidth, group, rank, world
     lo_me, hi_me = rows[rank]
     n_tot = rs[:, :, -1].sum(axis=0)
     recv = (rs[:, :, hi_me + 1] - rs[:, :, lo_me]).T.tolist() if hi_me >= lo_me else [[0] * world, [0] * world]
-    over_peer_memory = bool(getattr(ops, "peer_ready", None)) and ops.peer_ready(rank, world)
+    over_peer_memory = bool(getattr(ops, "peer_ready", None)) and ops.peer_ready(rank, world, group)
     if over_peer_memory:
         # the merge kernel pulls the rows it needs out of every rank's sorted array over NVLink
         mark("exchange")
