@@ -111,7 +111,7 @@ struct Ctx {
     int dev = -1;
     std::atomic<bool> ready{false};
     int sm_count = 0;
-    int dens_blocks_per_sm = 1, dens32_blocks_per_sm = 1;
+    int dens_blocks_per_sm = 1, dens32_blocks_per_sm = 1, minmax_blocks_per_sm = 4;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     // Two sets of scratch buffers (slot, tickets, counters, rstat).  Work on ONE stream always reuses the slot it
     // used last (stream order protects it); a second stream gets the other slot, so two callers' waves can overlap
@@ -177,6 +177,8 @@ int init_ctx(Ctx &c) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens_blocks_per_sm, k_density_binned<false>, kDensThreads, 0));
     c.dens_blocks_per_sm = std::max(1, c.dens_blocks_per_sm);
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.dens32_blocks_per_sm, k_density_binned32<false>, kDensThreads, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.minmax_blocks_per_sm, k_minmax, kMinmaxThreads, 0));
+    c.minmax_blocks_per_sm = std::max(1, c.minmax_blocks_per_sm);
     c.dens32_blocks_per_sm = std::max(1, c.dens32_blocks_per_sm);
     // fewer resident density blocks leave registers for another stream's sort kernels (two-stream callers)
     if (const char *e = getenv("KDEJS_DENS_BLOCKS")) {
@@ -506,10 +508,12 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     OKR(sl.pz.ensure((size_t)n_sets * G * sizeof(double)));
     OKR(sl.tilesum.ensure((size_t)n_sets * nparts * sizeof(double)));
     OKR(sl.rstat.ensure(sizeof(RawStat) * kMaxWaveSets));
-    // blocks per raw set of the min/max pass: enough to fill the GPU about eight-fold over the whole wave, few enough
-    // that a block's reduction and ticket do not dominate its few hundred points
+    // blocks per raw set of the min/max pass: ONE wave of resident blocks over the whole launch (18 per set at 65 raw
+    // sets were 1.58 waves of the 740 resident slots: 0.53 -> 0.48 us per evaluation with 11), few enough that a
+    // block's reduction and ticket do not dominate its few hundred points
     static const int mm_env = getenv("KDEJS_MM_BLOCKS") ? atoi(getenv("KDEJS_MM_BLOCKS")) : 0;
-    const int mm_blocks = mm_env > 0 ? std::min(mm_env, 64) : std::max(8, std::min(64, (8 * c.sm_count) / std::max(1, (int)wd.n_raw)));
+    const int mm_blocks = mm_env > 0 ? std::min(mm_env, 64)
+                                     : std::max(8, std::min(64, (c.minmax_blocks_per_sm * c.sm_count) / std::max(1, (int)wd.n_raw)));
     OKR(sl.rpart.ensure(sizeof(RawStat) * kMaxWaveSets * mm_blocks));
     const int js_blocks = (int)((G + kJsNodesPerBlock - 1) / kJsNodesPerBlock);
     OKR(sl.jspart.ensure(sizeof(double) * 2 * (size_t)std::max(1, n_items) * std::max(js_blocks, g.NT)));
