@@ -90,7 +90,9 @@ def _bandwidth(bandwidth, *sets):
     The kernels use one bandwidth per evaluation, so with a rule all sets of the call must have the same size."""
     if not isinstance(bandwidth, str):
         return float(bandwidth)
-    sizes = {int(np.shape(x)[0]) for x in sets}
+    sizes = set()
+    for x in sets:
+        sizes |= x.sizes() if isinstance(x, nat.PointSets) else {int(np.shape(x)[0])}
     if len(sizes) != 1:
         raise ValueError(f"bandwidth={bandwidth!r} needs point sets of equal size in one call (sklearn fits the rule "
                          f"per set; sizes here: {sorted(sizes)}); pass a number instead")
@@ -160,12 +162,13 @@ def KDE_JS_divergence_batch(obs, sims, gamma=1.0, eps=1e-12, log=False, *,
                             kernel="epanechnikov", algo=None, devices=None):
     """[KDE_JS_divergence(obs, s, gamma, eps, log) for s in sims] as one float64 array.
 
+    sims: a sequence of (N_i,2) arrays, or one (B,N,2) array (no per-simulation Python work then).
     devices: None (default device), an int, or a list of device indices; with several devices the
     sims are dealt round-robin, one host thread per device, and only the B scalars come back."""
     o = nat.as_points(obs, "obs")
-    arrays = [nat.as_points(s, f"sims[{i}]") for i, s in enumerate(sims)]
-    common = _common(resolution, _bandwidth(bandwidth, o, *arrays), gamma, eps, log, kernel, algo)
-    B = len(arrays)
+    sets = nat.PointSets(sims, "sims")
+    common = _common(resolution, _bandwidth(bandwidth, o, sets), gamma, eps, log, kernel, algo)
+    B = len(sets)
     out = np.empty(B, dtype=np.float64)
     if B == 0:
         return out
@@ -176,22 +179,21 @@ def KDE_JS_divergence_batch(obs, sims, gamma=1.0, eps=1e-12, log=False, *,
     devices = list(devices)
 
     def run(dev, idx):
-        sub = [arrays[i] for i in idx]
-        ptrs, counts = nat.pointer_array(sub)
-        res = np.empty(len(sub), dtype=np.float64)
-        rc = nat.lib().kdejs_discrepancy_batch(int(dev), nat.ptr(o), o.shape[0], ptrs, counts, len(sub),
+        ptrs, counts, n, keep = sets.pointers(idx)
+        res = np.empty(n, dtype=np.float64)
+        rc = nat.lib().kdejs_discrepancy_batch(int(dev), nat.ptr(o), o.shape[0], ptrs, counts, n,
                                                *common, nat.ptr(res))
         err = (nat.lib().kdejs_last_error() or b"").decode() if rc else ""
         return idx, res, rc, err
 
     if len(devices) == 1:
-        results = [run(devices[0], list(range(B)))]
+        results = [run(devices[0], slice(None))]
     else:
         results = [None] * len(devices)
-        shards = [list(range(k, B, len(devices))) for k in range(len(devices))]
+        shards = [slice(k, B, len(devices)) for k in range(len(devices))]
 
         def worker(k):
-            results[k] = run(devices[k], shards[k]) if shards[k] else ([], np.empty(0), 0, "")
+            results[k] = run(devices[k], shards[k]) if k < B else (slice(0, 0), np.empty(0), 0, "")
 
         threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(devices))]
         for t in threads:
@@ -239,19 +241,19 @@ def summary_batch(obs, sims, sims_freqs, observed, gamma, core_threshold, rare_t
     d (B,), log_d (B,)) -- process_result, poppunk_mod.py:351-382 with calculate_gene_freqs :285-291, then
     Distance("euclidean") against `observed` = [0, fc, fi, fr] (:494, :571) and Operation(np.log) (:572)."""
     o = nat.as_points(obs, "obs")
-    arrays = [nat.as_points(s, f"sims[{i}]") for i, s in enumerate(sims)]
+    sets = nat.PointSets(sims, "sims")
     freqs = [np.ascontiguousarray(np.asarray(f, dtype=np.float64).reshape(-1)) for f in sims_freqs]
-    if len(freqs) != len(arrays):
+    if len(freqs) != len(sets):
         raise ValueError("one gene-frequency vector per simulation is required")
     obs4 = np.ascontiguousarray(np.asarray(observed, dtype=np.float64).reshape(-1))
     if obs4.shape != (4,):
         raise ValueError("observed must be the 4-vector [0, freq_core, freq_intermediate, freq_rare]")
-    common = _common(resolution, _bandwidth(bandwidth, o, *arrays), gamma, eps, log, "epanechnikov", algo)
-    B = len(arrays)
+    common = _common(resolution, _bandwidth(bandwidth, o, sets), gamma, eps, log, "epanechnikov", algo)
+    B = len(sets)
     summary, d, logd = np.empty((B, 4)), np.empty(B), np.empty(B)
     if B == 0:
         return summary, d, logd
-    ptrs, counts = nat.pointer_array(arrays)
+    ptrs, counts, _, _keep = sets.pointers()
     fptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in freqs])
     fcnt = (ctypes.c_int64 * B)(*[f.shape[0] for f in freqs])
     dev = default_device() if device is None else int(device)

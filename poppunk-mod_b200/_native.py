@@ -194,6 +194,54 @@ def pointer_array(arrays):
     return arr, cnt
 
 
+_addressof, _c_char = ctypes.addressof, ctypes.c_char
+_F8, _F8_ROW_STRIDES = np.dtype(np.float64), (16, 8)
+
+
+class PointSets:
+    """A batch of (N_i,2) float64 point sets as the C ABI wants it: `addr` (uint64 host addresses) and `count`
+    (int64 rows), numpy arrays that `pointers()` hands to ctypes without a per-set Python loop.
+
+    `sets` is a sequence of (N_i,2) arrays, or ONE (B,N,2) array (what an ELFI batch of equal-sized simulations
+    is): then nothing is touched per set -- 64 sets cost ~5 us of Python instead of ~100."""
+
+    def __init__(self, sets, name="sims"):
+        if isinstance(sets, np.ndarray) and sets.ndim == 3:
+            a = sets
+            if a.shape[2] != 2:
+                raise ValueError(f"{name} must have exactly 2 columns (core, accessory); got shape {a.shape}")
+            if a.shape[0] and a.shape[1] == 0:
+                raise ValueError(f"Found array with 0 sample(s) (shape={a.shape[1:]}) while a minimum of 1 is required.")
+            if a.dtype != np.float64 or a.strides[2] != 8 or a.strides[1] != 16 or a.strides[0] < 0:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+            self.keep = a
+            self.addr = np.uint64(a.ctypes.data) + np.arange(a.shape[0], dtype=np.uint64) * np.uint64(a.strides[0])
+            self.count = np.full(a.shape[0], a.shape[1], dtype=np.int64)
+        else:
+            nd, ok = np.ndarray, _F8_ROW_STRIDES        # already a C-contiguous (N,2) float64 array: taken as it is
+            arrays = [s if (type(s) is nd and s.dtype is _F8 and s.strides == ok and s.shape[1] == 2 and s.shape[0] > 0)
+                      else as_points(s, f"{name}[{i}]") for i, s in enumerate(sets)]
+            self.keep = arrays
+            try:        # cheapest way to an ndarray's address from Python (0.36 us; .ctypes.data costs 0.9)
+                addr = [_addressof(_c_char.from_buffer(a)) for a in arrays]
+            except (TypeError, ValueError):       # a read-only array in the list
+                addr = [a.ctypes.data for a in arrays]
+            self.addr = np.array(addr, dtype=np.uint64)
+            self.count = np.array([a.shape[0] for a in arrays], dtype=np.int64)
+
+    def __len__(self):
+        return self.addr.shape[0]
+
+    def sizes(self):
+        return set(np.unique(self.count).tolist())
+
+    def pointers(self, index=None):
+        """(void**, int64*, n, keepalive) for all sets or for `index` (a slice)."""
+        addr = self.addr if index is None else np.ascontiguousarray(self.addr[index])
+        count = self.count if index is None else np.ascontiguousarray(self.count[index])
+        return addr.ctypes.data_as(_c_dpp), count.ctypes.data_as(_c_i64p), addr.shape[0], (addr, count)
+
+
 class PinnedPool:
     """numpy views over page-locked host memory from kdejs_host_alloc."""
 

@@ -376,7 +376,12 @@ GridGeom make_geom(const Params &p) {
     g.tile_col_begin = 0;
     g.tile_col_end = g.NT;
     g.sets_per_group = kMaxWaveSets;      // one group until run_wave() knows the wave
-    g.pad3 = 0;
+    {
+        int split_log2 = kSplitLog2, part_log2 = kPartLog2;
+        if (const char *e = getenv("KDEJS_SPLIT_LOG2")) split_log2 = std::max(8, std::min(30, atoi(e)));
+        if (const char *e = getenv("KDEJS_PART_LOG2")) part_log2 = std::max(8, std::min(split_log2, atoi(e)));
+        g.split_cfg = split_log2 | (part_log2 << 8);
+    }
     g.heavy_log2 = 13;
     if (const char *e = getenv("KDEJS_HEAVY_LOG2")) g.heavy_log2 = std::max(6, std::min(30, atoi(e)));
     // Cells that lie wholly inside the support of every node of a tile enter through their moments.  A cell
@@ -617,7 +622,7 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
         // candidates; the sum of all tiles' candidates is at most (points) x (tiles one point can reach).
         const double reach = std::min((double)g.NT, (2.0 * p.h + g.cell_w) / (kTile * g.step > 0.0 ? kTile * g.step : 1.0) + 2.0);
         const double parts_bound = std::min((double)kMaxParts * tiles * n_sets,
-                                            1.5 * (double)P * reach * reach / (double)(1 << kPartLog2) + 64.0);
+                                            1.5 * (double)P * reach * reach / (double)(1 << (g.split_cfg >> 8)) + 64.0);
         const unsigned parts_cap = (unsigned)std::min(parts_bound, 8.0e6);
         const unsigned capacity = (unsigned)tiles * (unsigned)g.sets_per_group +      // entries per (group, class) list
                                   std::min(parts_cap, (unsigned)(kMaxParts - 1) * (unsigned)tiles * (unsigned)g.sets_per_group);
@@ -1030,12 +1035,17 @@ static int batch_impl(int device, const double *obs, int64_t n_obs, const double
         std::vector<Stager::Range> plan;
         size_t pageable_bytes = 0;
         if (Stager::pageable(obs)) { staged[B] = 1; pageable_bytes += (size_t)n_obs * 16; plan.push_back(Stager::Range{c->pool_raw.p, obs, (size_t)n_obs * 16}); }
-        for (int i = 0; i < B; ++i)
+        for (int i = 0; i < B; ++i) {
+            // a sim that starts where its page-locked predecessor ends (one arena) is not asked about again: a wrong
+            // guess would only cost speed (cudaMemcpyAsync accepts pageable sources), and 64 queries are ~30 us of
+            // the critical path before the first copy
+            if (i > 0 && !staged[i - 1] && (const char *)sims[i] == (const char *)sims[i - 1] + (size_t)n_sims[i - 1] * 16) continue;
             if (Stager::pageable(sims[i])) {
                 staged[i] = 1;
                 pageable_bytes += (size_t)n_sims[i] * 16;
                 plan.push_back(Stager::Range{(char *)c->sim_ring.p + sim_stride * (size_t)(i % ring_items), sims[i], (size_t)n_sims[i] * 16});
             }
+        }
         if (pageable_bytes >= kStageMinBytes) sg = Stager::get(device);
         if (sg) sg->plan(plan);
     }
@@ -1043,6 +1053,12 @@ static int batch_impl(int device, const double *obs, int64_t n_obs, const double
     else CU(cudaMemcpyAsync(c->pool_raw.p, obs, (size_t)n_obs * 16, cudaMemcpyHostToDevice, c->s_compute));
     int wave_size = std::min(cap, 16);
     if (const char *e = getenv("KDEJS_HOST_WAVE")) wave_size = std::max(1, std::min(cap, atoi(e)));
+    int first_wave = 4, tail_wave = 0;
+    if (const char *e = getenv("KDEJS_FIRST_WAVE")) first_wave = std::max(1, atoi(e));
+    if (const char *e = getenv("KDEJS_TAIL_WAVE")) tail_wave = std::max(0, std::min(cap, atoi(e)));
+    std::vector<int> wave_plan;                       // experiments: explicit wave sizes, the last one repeats
+    if (const char *e = getenv("KDEJS_WAVE_PLAN"))
+        for (const char *q = e; *q;) { wave_plan.push_back(std::max(1, std::min(cap, atoi(q)))); while (*q && *q != ',') ++q; if (*q) ++q; }
     static const bool merge_copies = !(getenv("KDEJS_MERGE_COPIES") && atoi(getenv("KDEJS_MERGE_COPIES")) == 0);
     std::vector<int> wave_of_item(B);
     std::vector<cudaEvent_t> ev_copied, ev_done;
@@ -1054,7 +1070,10 @@ static int batch_impl(int device, const double *obs, int64_t n_obs, const double
     int rc = KDEJS_OK;
     int wave = 0;
     for (int i0 = 0; i0 < B && rc == KDEJS_OK; ++wave) {
-        const int items = std::min(wave == 0 ? std::min(cap, 4) : wave_size, B - i0);
+        int items = std::min(wave == 0 ? std::min(cap, first_wave) : wave_size, B - i0);
+        // the kernels of the last wave run after the last copy has landed: keep that wave short (tail_wave items)
+        if (tail_wave > 0 && B - i0 > tail_wave && B - i0 - items < tail_wave) items = B - i0 - tail_wave;
+        if (!wave_plan.empty()) items = std::min(wave_plan[std::min<size_t>(wave, wave_plan.size() - 1)], B - i0);
         cudaEvent_t ec, ed;
         if ((rc = new_event(ec)) != KDEJS_OK || (rc = new_event(ed)) != KDEJS_OK) break;
         ev_copied.push_back(ec);

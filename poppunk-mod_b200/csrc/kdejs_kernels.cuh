@@ -92,7 +92,8 @@ struct GridGeom {
     int32_t tile_row_begin, tile_row_end;   // tile rows (index of column 0) this launch covers
     int32_t tile_col_begin, tile_col_end;   // ... and tile columns (index of column 1): band mode shards along these,
                                             // because cell ROWS (the sort's major order) run along column 1
-    int32_t sets_per_group, pad3;           // work-list locality: sets [k*spg, (k+1)*spg) form group k (see kMaxGroups)
+    int32_t sets_per_group, split_cfg;      // work-list locality: sets [k*spg, (k+1)*spg) form group k (see kMaxGroups);
+                                            // split_cfg = split_log2 | part_log2 << 8 (very heavy tiles, see SplitBufs)
     int32_t heavy_log2, use_moments;        // tiles with >= 2^heavy_log2 candidates are processed per block;
                                             // use_moments: cells wholly inside a tile's support go in as moments
     // fp32 path (k_density_binned32): sorted points are also kept as 32-bit fixed point in units of h * 2^-q_shift
@@ -713,8 +714,9 @@ k_tile_classify(const __grid_constant__ WaveDesc wd, const GridGeom g,
             }
         } else if (sub == 0) {
             cls = tile_class(total, g.heavy_log2);
-            if (cls == 0 && total >= (1u << kSplitLog2)) {
-                K = min((uint32_t)kMaxParts, (total + (1u << kPartLog2) - 1u) >> kPartLog2);
+            const int split_log2 = g.split_cfg & 0xff, part_log2 = g.split_cfg >> 8;
+            if (cls == 0 && total >= (1u << split_log2)) {
+                K = min((uint32_t)kMaxParts, (total + (1u << part_log2) - 1u) >> part_log2);
                 pbase = atomicAdd(&counters[kSplitParts], K);
                 if (pbase + K > sb.parts_cap) K = 1u;                  // out of part slots: process it whole
             }

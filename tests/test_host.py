@@ -167,3 +167,35 @@ def test_default_algorithm_and_its_override():
     assert set(pk._native.ALGOS) == {"binned", "binned32", "dense", "dense64"}
     with pytest.raises(ValueError):
         pk.KDE_distance._common(100, 0.03, 1.0, 0.0, False, "epanechnikov", "fastest")
+
+
+def test_point_sets_list_and_3d_array_agree():
+    """PointSets: addresses and row counts of a batch without touching the device -- a (B,N,2) array and the list of
+    its rows give the same table; views that are not C-contiguous (N,2) float64 are copied, never mutated."""
+    import poppunk_mod_b200 as pk
+
+    nat = pk._native
+    arena = np.random.default_rng(0).random((9, 50, 2))
+    a, b = nat.PointSets([arena[i] for i in range(9)]), nat.PointSets(arena)
+    assert len(a) == len(b) == 9
+    np.testing.assert_array_equal(a.addr, b.addr)
+    np.testing.assert_array_equal(a.count, b.count)
+    np.testing.assert_array_equal(nat.PointSets(arena[::2]).addr, b.addr[::2])
+    ro = arena.copy()
+    ro.flags.writeable = False
+    c = nat.PointSets([ro[i] for i in range(9)])                       # read-only arrays: the slower address path
+    np.testing.assert_array_equal(c.addr - c.addr[0], a.addr - a.addr[0])
+    wide = np.arange(40.0).reshape(10, 4)
+    v = nat.PointSets([wide[:, :2], wide[:, 1:3], [[1, 2], [3, 4]], np.ones((3, 2), dtype=np.float32)])
+    assert all(k.flags.c_contiguous and k.dtype == np.float64 for k in v.keep)
+    assert v.count.tolist() == [10, 10, 2, 3] and v.sizes() == {2, 3, 10}
+    np.testing.assert_array_equal(v.keep[1], wide[:, 1:3])
+    f32 = nat.PointSets(arena.astype(np.float32))                      # wrong dtype: one contiguous float64 copy
+    assert f32.keep.dtype == np.float64 and f32.addr[1] - f32.addr[0] == 50 * 16
+    ptrs, counts, n, keep = b.pointers(slice(1, 9, 3))
+    assert n == 3 and keep[0].tolist() == b.addr[1:9:3].tolist()
+    for bad in (np.zeros((3, 0, 2)), np.zeros((3, 5, 3))):
+        with pytest.raises(ValueError):
+            nat.PointSets(bad)
+    with pytest.raises(ValueError):
+        nat.PointSets([np.zeros((0, 2))])

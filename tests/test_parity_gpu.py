@@ -96,6 +96,32 @@ def test_batch_equals_singles_bitwise(pk, ko):
     np.testing.assert_array_equal(again, got)                                  # run-to-run reproducible
 
 
+def test_batch_accepts_one_3d_array(pk):
+    """sims as ONE (B,N,2) array (an ELFI batch of equal-sized simulations): same values as the list of its rows, for
+    contiguous, strided and non-float64 inputs, on one device and dealt over the visible ones; summary_batch too."""
+    from oracle import workloads as wl
+
+    obs = wl.synthetic_target(8000)
+    arena = np.stack([wl.sim_batch_member(s, n=6000) for s in range(21)])
+    want = pk.KDE_JS_divergence_batch(obs, [arena[i] for i in range(21)], gamma=0.25, eps=0.0)
+    np.testing.assert_array_equal(pk.KDE_JS_divergence_batch(obs, arena, gamma=0.25, eps=0.0), want)
+    np.testing.assert_array_equal(pk.KDE_JS_divergence_batch(obs, arena[::2], gamma=0.25, eps=0.0), want[::2])
+    np.testing.assert_array_equal(pk.KDE_JS_divergence_batch(obs, arena[3:11], gamma=0.25, eps=0.0), want[3:11])
+    wide = np.zeros((21, 6000, 3)); wide[:, :, :2] = arena                      # rows not 16 bytes apart: copied
+    np.testing.assert_array_equal(pk.KDE_JS_divergence_batch(obs, wide[:, :, :2], gamma=0.25, eps=0.0), want)
+    assert pk.KDE_JS_divergence_batch(obs, arena[:0], gamma=0.25, eps=0.0).shape == (0,)
+    devs = list(range(pk._native.device_count()))
+    np.testing.assert_array_equal(pk.KDE_JS_divergence_batch(obs, arena, gamma=0.25, eps=0.0, devices=devs), want)
+    freqs = [np.linspace(0.0, 1.0, 50 + i) for i in range(21)]
+    observed = [0.0, 0.3, 0.3, 0.4]
+    s_list = pk.KDE_distance.summary_batch(obs, [arena[i] for i in range(21)], freqs, observed, 0.25, 0.95, 0.15)
+    s_3d = pk.KDE_distance.summary_batch(obs, arena, freqs, observed, 0.25, 0.95, 0.15)
+    for a, b in zip(s_list, s_3d):
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(ValueError):
+        pk.KDE_JS_divergence_batch(obs, np.zeros((4, 10, 3)), gamma=0.25, eps=0.0)
+
+
 def test_pairs_entry(pk, ko):
     from oracle import workloads as wl
 
