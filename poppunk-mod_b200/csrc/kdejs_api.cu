@@ -554,8 +554,9 @@ int run_wave(Ctx &c, Slot &sl, cudaStream_t st, const Params &p, const GridGeom 
     if (binned) {
         const size_t smem = (size_t)kSortWarps * ncells * sizeof(uint16_t);
         // one block per set scans <= 4096 cells over a few sort blocks fastest; otherwise one thread per cell
+        // (measured per wave, tools/wave_probe.py: 13 sort blocks per set 23 vs 25 us, 25 blocks 39 vs 21 us)
         static const int force_wide = getenv("KDEJS_SCAN_WIDE") ? atoi(getenv("KDEJS_SCAN_WIDE")) : -1;
-        const bool wide_scan = force_wide >= 0 ? force_wide != 0 : (ncells > 4096 || nb_max > 32);
+        const bool wide_scan = force_wide >= 0 ? force_wide != 0 : (ncells > 4096 || nb_max > 16);
         if (!io.presorted) {
             KTimer t(c, 1, st);
             k_scale_count<<<dim3(nb_max, n_sets), kSortThreads, smem, st>>>(

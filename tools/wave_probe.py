@@ -12,7 +12,7 @@ target, sims = bench.make_inputs(0, bench.POOL)
 db = bench.DeviceBench(torch, nat, dev, target, sims)
 algo = os.environ.get("ALGO", "binned32")
 splits = [tuple(a.split(",")) for a in sys.argv[1:]] or [("", "")]
-for split, batch in [(sp, b) for sp in splits for b in (1, 2, 4, 8, 16, 64)]:
+for split, batch in [(sp, b) for sp in splits for b in [int(x) for x in os.environ.get("WAVES", "1,2,4,8,16,64").split(",")]]:
     for k, v in zip(("KDEJS_SPLIT_LOG2", "KDEJS_PART_LOG2"), split):
         os.environ.pop(k, None)
         if v:
