@@ -38,6 +38,7 @@ extern "C" {
 #define KDEJS_ERR_CUDA 1     /* CUDA runtime failure or no device            -> RuntimeError */
 #define KDEJS_ERR_ARG 2      /* bad shape / size / parameter                 -> ValueError   */
 #define KDEJS_ERR_INF 3      /* input contains infinity (sklearn ValueError) -> ValueError   */
+#define KDEJS_ERR_CAPACITY 4 /* kdejs_tsv_load_into: the caller's buffer is too small (rows needed are reported) */
 
 /* kernel (sklearn KernelDensity(kernel=...), KDE_distance.py:50-51) */
 #define KDEJS_KERNEL_EPANECHNIKOV 0   /* the reference's kernel                            */
@@ -236,6 +237,12 @@ void kdejs_host_free(void *p);
  * Errors are reported through kdejs_io_last_error(). */
 int kdejs_tsv_load(const char *path, int skip_rows, int pinned, int threads, double **out_pts,
                    int64_t *out_rows);
+/* The same table parsed into the CALLER's buffer of capacity_rows x 2 doubles -- e.g. one slot of a page-locked
+ * (B,N,2) arena that a batch call then uploads as a whole (a sweep over thousands of files: no allocation per
+ * file).  *out_rows = data rows of the file, also when they do not fit: then nothing is written and the call
+ * returns KDEJS_ERR_CAPACITY. */
+int kdejs_tsv_load_into(const char *path, int skip_rows, int threads, double *dst, int64_t capacity_rows,
+                        int64_t *out_rows);
 void kdejs_tsv_free(double *pts, int pinned);
 const char *kdejs_io_last_error(void);
 

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkdejs.so")
 
-KDEJS_OK, KDEJS_ERR_CUDA, KDEJS_ERR_ARG, KDEJS_ERR_INF = 0, 1, 2, 3
+KDEJS_OK, KDEJS_ERR_CUDA, KDEJS_ERR_ARG, KDEJS_ERR_INF, KDEJS_ERR_CAPACITY = 0, 1, 2, 3, 4
 KERNELS = {"epanechnikov": 0, "gaussian": 1}
 ALGOS = {"binned": 0, "dense": 1, "dense64": 2, "binned32": 3}
 KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence", "classify", "moments",
@@ -90,6 +90,8 @@ _SIGNATURES = {
     "kdejs_host_free": (None, [ctypes.c_void_p]),
     "kdejs_tsv_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_void_p), _c_i64p]),
+    "kdejs_tsv_load_into": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_int64, _c_i64p]),
     "kdejs_tsv_free": (None, [ctypes.c_void_p, ctypes.c_int]),
     "kdejs_io_last_error": (ctypes.c_char_p, []),
     "kdejs_profile_enable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
@@ -311,3 +313,70 @@ class TsvTable:
 
     def close(self):
         self.array = None       # the memory is released when the last array referencing it goes away
+
+
+def tsv_load_into(path, dst, skip_rows=-1, threads=1):
+    """Parse a table into the (capacity,2) float64 array `dst` (kdejs_tsv_load_into).  Returns the number of rows;
+    when they do not fit, nothing is written and the NEGATED row count comes back."""
+    if dst.dtype != np.float64 or dst.ndim != 2 or dst.shape[1] != 2 or not dst.flags.c_contiguous:
+        raise ValueError("dst must be a C-contiguous (capacity,2) float64 array")
+    n = ctypes.c_int64()
+    rc = lib().kdejs_tsv_load_into(os.fsencode(path), int(skip_rows), int(threads), dst.ctypes.data, dst.shape[0],
+                                   ctypes.byref(n))
+    if rc == KDEJS_ERR_CAPACITY:
+        return -n.value
+    if rc != KDEJS_OK:
+        msg = (lib().kdejs_io_last_error() or b"").decode("utf-8", "replace")
+        raise (ValueError if rc == KDEJS_ERR_ARG else RuntimeError)(msg)
+    return n.value
+
+
+class TableArena:
+    """`slots` tables of up to `capacity_rows` rows each in ONE (slots, capacity_rows, 2) float64 array (page-locked
+    when a GPU is present): files are parsed straight into their slot by a pool of threads (ctypes releases the
+    GIL), nothing is allocated per file, and tables of equal length go to the batch entry points as one 3-D view."""
+
+    def __init__(self, slots, capacity_rows, pinned=None):
+        if pinned is None:
+            pinned = device_count() > 0
+        self._pool = PinnedPool() if pinned else None
+        shape = (int(slots), int(capacity_rows), 2)
+        self.array = self._pool.empty(shape) if pinned else np.empty(shape)
+        self.rows = np.zeros(int(slots), dtype=np.int64)
+        self.pinned = bool(pinned)
+
+    def load(self, paths, skip_rows=-1, workers=8, executor=None, overflow="raise"):
+        """Parse paths[k] into slot k.  Returns the tables as views: a (len(paths), rows, 2) array when all have the
+        same number of rows, else a list of (rows_k, 2) views.  A table that does not fit its slot raises, or with
+        overflow="alloc" is read into memory of its own (its entry of the returned list is then not a view)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        paths = list(paths)
+        if len(paths) > self.array.shape[0]:
+            raise ValueError(f"{len(paths)} tables for {self.array.shape[0]} slots")
+        spilled = {}
+
+        def one(k):
+            n = tsv_load_into(paths[k], self.array[k], skip_rows, 1)
+            if n < 0:
+                if overflow != "alloc":
+                    raise ValueError(f"{paths[k]}: {-n} rows do not fit a slot of {self.array.shape[1]} rows")
+                spilled[k] = TsvTable(paths[k], skip_rows=skip_rows, pinned=self.pinned, threads=1).array
+                n = -1
+            self.rows[k] = n
+
+        if executor is not None:
+            list(executor.map(one, range(len(paths))))
+        else:
+            with ThreadPoolExecutor(max_workers=max(1, int(workers))) as ex:
+                list(ex.map(one, range(len(paths))))
+        r = self.rows[:len(paths)]
+        if len(paths) and not spilled and (r == r[0]).all():
+            return self.array[:len(paths), :int(r[0])]
+        return [spilled[k] if k in spilled else self.array[k, :int(r[k])] for k in range(len(paths))]
+
+    def close(self):
+        self.array = None
+        if self._pool is not None:
+            self._pool.close()
+            self._pool = None

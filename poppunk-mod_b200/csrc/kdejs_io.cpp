@@ -4,6 +4,13 @@
 // KDE_distance.py:138-139; scripts/distance_to_gridsearch.py:49) and pd.read_csv(file, header=None,
 // sep='\t') + "last two columns" (scripts/pairwise_2D_distance.py:38-45; poppunk_mod.py:266-267).
 // Numbers are parsed with std::from_chars (correctly rounded, the same values float() gives numpy).
+//
+// Layout of the work: the file is read whole; it is cut into one byte range per thread, each range starting at a
+// line start; pass 1 counts the data rows of every range (blank lines and '#' comments do not count), which fixes
+// where each range's rows land in the output; pass 2 parses every range straight into its place.  A field goes to
+// from_chars first and is compared with pandas' missing-value spellings only when that fails -- the first version
+// checked the 18 spellings before every number and spent four fifths of its time there (100 000 rows of the
+// reference's example table: 21.7 -> 5.9 ms on one core).
 #include "../../include/kdejs.h"
 
 #include <cuda_runtime_api.h>
@@ -14,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -33,18 +41,21 @@ bool is_na_token(const char *b, const char *e) {
     return false;
 }
 
-bool parse_double(const char *b, const char *e, double &v) {
+inline bool parse_double(const char *b, const char *e, double &v) {
     while (b < e && (*b == ' ' || *b == '\r')) ++b;
     while (e > b && (e[-1] == ' ' || e[-1] == '\r')) --e;
-    if (b >= e || is_na_token(b, e)) { v = std::numeric_limits<double>::quiet_NaN(); return true; }
-    if (*b == '+') ++b;                                // from_chars rejects a leading '+'
-    if (b >= e) return false;
-    auto r = std::from_chars(b, e, v);
-    return r.ec == std::errc() && r.ptr == e;
+    if (b >= e) { v = std::numeric_limits<double>::quiet_NaN(); return true; }      // empty field: missing
+    const char *s = (*b == '+') ? b + 1 : b;           // from_chars rejects a leading '+'
+    if (s < e) {
+        auto r = std::from_chars(s, e, v);
+        if (r.ec == std::errc() && r.ptr == e) return true;
+    }
+    if (is_na_token(b, e)) { v = std::numeric_limits<double>::quiet_NaN(); return true; }
+    return false;
 }
 
 // last two tab-separated fields of [b, e)
-bool last_two(const char *b, const char *e, double &x, double &y) {
+inline bool last_two(const char *b, const char *e, double &x, double &y) {
     const char *p = e;
     const char *t2 = nullptr;          // tab before the last field
     const char *s1 = b;                // start of the field before it
@@ -58,75 +69,170 @@ bool last_two(const char *b, const char *e, double &x, double &y) {
     if (!t2) return false;             // fewer than two fields
     return parse_double(s1, t2, x) && parse_double(t2 + 1, e, y);
 }
+
+// a data line: not blank, not a '#' comment (np.loadtxt skips both)
+inline bool is_data_line(const char *p, const char *nl) {
+    while (p < nl && (*p == ' ' || *p == '\r' || *p == '\t')) ++p;
+    return p < nl && *p != '#';
+}
+
+struct Table {                 // the file in memory (one '\n' appended) and where its data rows begin
+    std::unique_ptr<char[]> buf;
+    const char *data = nullptr, *end = nullptr;
+};
+
+int read_table(const char *path, int skip_rows, Table &t) {
+    FILE *f = std::fopen(path, "rb");
+    if (!f) { g_io_err = std::string("cannot open ") + path; return KDEJS_ERR_ARG; }
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    t.buf.reset(new char[(size_t)std::max(0L, sz) + 1]);
+    const size_t got = sz > 0 ? std::fread(t.buf.get(), 1, (size_t)sz, f) : 0;
+    std::fclose(f);
+    t.buf[got] = '\n';
+    const char *p = t.buf.get();
+    t.end = p + got;
+    // rows dropped from the top: `skip_rows` data lines, or (auto, -1) one line if its last two fields are neither
+    // numbers nor missing-value tokens (a header)
+    int to_skip = std::max(skip_rows, 0);
+    bool probe_header = skip_rows < 0;
+    while (p < t.end && (to_skip > 0 || probe_header)) {
+        const char *nl = (const char *)std::memchr(p, '\n', (size_t)(t.end - p) + 1);
+        if (is_data_line(p, nl)) {
+            if (probe_header) {
+                double x, y;
+                if (last_two(p, nl, x, y)) break;          // numeric first row: nothing to drop
+                probe_header = false;
+            } else --to_skip;
+        }
+        p = nl + 1;
+    }
+    t.data = std::min(p, t.end);
+    return KDEJS_OK;
+}
+
+// Cuts [data, end) into nt ranges that start at line starts, counts each range's data rows (pass 1).
+void cut_and_count(const Table &t, int nt, std::vector<const char *> &cut, std::vector<int64_t> &rows) {
+    cut.assign((size_t)nt + 1, t.end);
+    cut[0] = t.data;
+    const size_t bytes = (size_t)(t.end - t.data);
+    for (int k = 1; k < nt; ++k) {
+        const char *p = t.data + bytes * (size_t)k / (size_t)nt;
+        p = std::max(p, cut[k - 1]);
+        if (p < t.end && p > t.data && p[-1] != '\n') {
+            const char *nl = (const char *)std::memchr(p, '\n', (size_t)(t.end - p) + 1);
+            p = std::min(nl + 1, t.end);
+        }
+        cut[k] = p;
+    }
+    rows.assign((size_t)nt, 0);
+    auto count = [&](int k) {
+        int64_t n = 0;
+        for (const char *p = cut[k]; p < cut[k + 1];) {
+            const char *nl = (const char *)std::memchr(p, '\n', (size_t)(t.end - p) + 1);
+            n += is_data_line(p, nl) ? 1 : 0;
+            p = nl + 1;
+        }
+        rows[k] = n;
+    };
+    if (nt == 1) count(0);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back(count, k);
+        for (auto &x : th) x.join();
+    }
+}
+
+// Pass 2: every range parses its rows into out + 2 * (rows of the ranges before it).  Returns the first bad data
+// row (0-based) or -1.
+int64_t parse_ranges(const Table &t, int nt, const std::vector<const char *> &cut, const std::vector<int64_t> &rows,
+                     double *out) {
+    std::vector<int64_t> first(nt + 1, 0), bad(nt, -1);
+    for (int k = 0; k < nt; ++k) first[k + 1] = first[k] + rows[k];
+    auto work = [&](int k) {
+        int64_t i = first[k];
+        for (const char *p = cut[k]; p < cut[k + 1];) {
+            const char *nl = (const char *)std::memchr(p, '\n', (size_t)(t.end - p) + 1);
+            if (is_data_line(p, nl)) {
+                double x, y;
+                if (!last_two(p, nl, x, y)) { if (bad[k] < 0) bad[k] = i; x = y = 0.0; }
+                out[2 * i] = x;
+                out[2 * i + 1] = y;
+                ++i;
+            }
+            p = nl + 1;
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int k = 0; k < nt; ++k) th.emplace_back(work, k);
+        for (auto &x : th) x.join();
+    }
+    for (int k = 0; k < nt; ++k)
+        if (bad[k] >= 0) return bad[k];
+    return -1;
+}
+
+int thread_count(int threads, size_t bytes) {
+    int nt = threads > 0 ? threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    return (int)std::max<size_t>(1, std::min<size_t>((size_t)nt, bytes / (128 * 1024)));     // a thread per >= 128 KB
+}
 }  // namespace
 
 extern "C" {
 
 const char *kdejs_io_last_error(void) { return g_io_err.c_str(); }
 
+int kdejs_tsv_load_into(const char *path, int skip_rows, int threads, double *dst, int64_t capacity_rows,
+                        int64_t *out_rows) {
+    if (!path || !out_rows || (capacity_rows > 0 && !dst)) { g_io_err = "null argument"; return KDEJS_ERR_ARG; }
+    *out_rows = 0;
+    Table t;
+    if (int rc = read_table(path, skip_rows, t)) return rc;
+    const int nt = thread_count(threads, (size_t)(t.end - t.data));
+    std::vector<const char *> cut;
+    std::vector<int64_t> rows;
+    cut_and_count(t, nt, cut, rows);
+    int64_t n = 0;
+    for (int64_t r : rows) n += r;
+    *out_rows = n;
+    if (n <= 0) { g_io_err = std::string("no data rows in ") + path; return KDEJS_ERR_ARG; }
+    if (n > capacity_rows) {
+        g_io_err = std::string(path) + ": " + std::to_string(n) + " data rows do not fit the buffer (" +
+                   std::to_string(capacity_rows) + " rows)";
+        return KDEJS_ERR_CAPACITY;
+    }
+    const int64_t bad = parse_ranges(t, nt, cut, rows, dst);
+    if (bad >= 0) {
+        g_io_err = std::string(path) + ": could not parse two numeric columns in data row " + std::to_string(bad + 1);
+        return KDEJS_ERR_ARG;
+    }
+    return KDEJS_OK;
+}
+
 int kdejs_tsv_load(const char *path, int skip_rows, int pinned, int threads, double **out_pts, int64_t *out_rows) {
     if (!path || !out_pts || !out_rows) { g_io_err = "null argument"; return KDEJS_ERR_ARG; }
-    FILE *f = std::fopen(path, "rb");
-    if (!f) { g_io_err = std::string("cannot open ") + path; return KDEJS_ERR_ARG; }
-    std::fseek(f, 0, SEEK_END);
-    long sz = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    std::vector<char> buf((size_t)std::max(0L, sz) + 1);
-    size_t got = sz > 0 ? std::fread(buf.data(), 1, (size_t)sz, f) : 0;
-    std::fclose(f);
-    buf[got] = '\n';
-    const char *base = buf.data(), *end = base + got;
-    // line starts (blank lines and '#' comments are skipped, as np.loadtxt does)
-    std::vector<const char *> lines;
-    lines.reserve(got / 24 + 16);
-    for (const char *p = base; p < end;) {
-        const char *nl = (const char *)std::memchr(p, '\n', (size_t)(end - p) + 1);
-        const char *q = p;
-        while (q < nl && (*q == ' ' || *q == '\r' || *q == '\t')) ++q;
-        if (q < nl && *q != '#') lines.push_back(p);
-        p = nl + 1;
-    }
-    size_t first = 0;
-    if (skip_rows < 0) {                 // auto: drop one header line if its last two fields are not numbers
-        if (!lines.empty()) {
-            const char *nl = (const char *)std::memchr(lines[0], '\n', (size_t)(end - lines[0]) + 1);
-            double x, y;
-            // a header is a first line whose last two fields are neither numbers nor missing-value tokens
-            if (!last_two(lines[0], nl, x, y)) first = 1;
-        }
-    } else first = std::min((size_t)skip_rows, lines.size());
-    const int64_t n = (int64_t)(lines.size() - first);
+    Table t;
+    if (int rc = read_table(path, skip_rows, t)) return rc;
+    const int nt = thread_count(threads, (size_t)(t.end - t.data));
+    std::vector<const char *> cut;
+    std::vector<int64_t> rows;
+    cut_and_count(t, nt, cut, rows);
+    int64_t n = 0;
+    for (int64_t r : rows) n += r;
     if (n <= 0) { g_io_err = std::string("no data rows in ") + path; return KDEJS_ERR_ARG; }
     double *out = nullptr;
     if (pinned) out = (double *)kdejs_host_alloc((size_t)n * 16);
     else out = (double *)std::malloc((size_t)n * 16);
     if (!out) { g_io_err = "allocation failed"; return KDEJS_ERR_CUDA; }
-    int nt = threads > 0 ? threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
-    nt = (int)std::min<int64_t>(nt, std::max<int64_t>(1, n / 4096));
-    std::vector<int64_t> bad(nt, -1);
-    auto work = [&](int t) {
-        const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
-        for (int64_t i = lo; i < hi; ++i) {
-            const char *b = lines[first + (size_t)i];
-            const char *nl = (const char *)std::memchr(b, '\n', (size_t)(end - b) + 1);
-            double x, y;
-            if (!last_two(b, nl, x, y)) { if (bad[t] < 0) bad[t] = i; x = y = 0.0; }
-            out[2 * i] = x;
-            out[2 * i + 1] = y;
-        }
-    };
-    if (nt == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
-        for (auto &x : th) x.join();
+    const int64_t bad = parse_ranges(t, nt, cut, rows, out);
+    if (bad >= 0) {
+        g_io_err = std::string(path) + ": could not parse two numeric columns in data row " + std::to_string(bad + 1);
+        kdejs_tsv_free(out, pinned);
+        return KDEJS_ERR_ARG;
     }
-    for (int t = 0; t < nt; ++t)
-        if (bad[t] >= 0) {
-            g_io_err = std::string(path) + ": could not parse two numeric columns in data row " + std::to_string(bad[t] + 1);
-            kdejs_tsv_free(out, pinned);
-            return KDEJS_ERR_ARG;
-        }
     *out_pts = out;
     *out_rows = n;
     return KDEJS_OK;

@@ -103,3 +103,66 @@ def test_log_discrepancy_of_host_summaries():
         d = sim.log_euclidean_discrepancy(s, o)
     assert d[0] == pytest.approx(np.log(np.sqrt(0.09 + 0.01 + 0.01)))
     assert d[1] == -np.inf
+
+
+def test_threaded_ranges_agree_with_one_thread_on_ragged_tables(nat, tmp_path):
+    """The file is cut into byte ranges, one per thread: blank lines, comments, CRLF endings, lines of very
+    different length and a missing final newline must land every row where one thread puts it."""
+    rng = np.random.default_rng(3)
+    lines, want = [], []
+    for i in range(60000):
+        r = rng.random()
+        if r < 0.02:
+            lines.append("")
+        elif r < 0.04:
+            lines.append("# comment " + "x" * int(rng.integers(0, 300)))
+        else:
+            x, y = float(rng.random() * 1e-3), float(rng.random())
+            ids = ["id" * int(rng.integers(1, 40)), "other"] if r < 0.5 else []
+            lines.append("\t".join(ids + [repr(x), f" {y!r} "]) + ("\r" if r > 0.9 else ""))
+            want.append((x, y))
+    p = tmp_path / "ragged.tsv"
+    p.write_text("\n".join(lines))                       # no newline at the end of the file
+    want = np.array(want)
+    for threads in (1, 2, 3, 8):
+        t = nat.TsvTable(str(p), skip_rows=0, pinned=False, threads=threads)
+        np.testing.assert_array_equal(t.array, want)
+    t = nat.TsvTable(str(p), skip_rows=5, pinned=False, threads=4)
+    np.testing.assert_array_equal(t.array, want[5:])
+
+
+def test_load_into_and_table_arena(nat, tmp_path):
+    """kdejs_tsv_load_into: the same rows as kdejs_tsv_load in the caller's buffer; a buffer that is too small is
+    left alone and the rows needed are reported.  TableArena: many files into one (slots, capacity, 2) array."""
+    rng = np.random.default_rng(5)
+    tabs, paths = [], []
+    for k, n in enumerate((3000, 3000, 3000, 4100, 17)):
+        a = np.column_stack([rng.random(n) * 2e-3, rng.random(n)])
+        q = tmp_path / f"s{k}.tsv"
+        _write(q, [[repr(float(x)), repr(float(y))] for x, y in a])
+        tabs.append(a)
+        paths.append(str(q))
+    dst = np.full((3500, 2), -1.0)
+    assert nat.tsv_load_into(paths[0], dst) == 3000
+    np.testing.assert_array_equal(dst[:3000], tabs[0])
+    assert (dst[3000:] == -1.0).all()
+    dst[:] = -1.0
+    assert nat.tsv_load_into(paths[3], dst) == -4100 and (dst == -1.0).all()
+    with pytest.raises(ValueError):
+        nat.tsv_load_into(paths[0], np.zeros((10, 3)))
+    with pytest.raises(ValueError, match="cannot open"):
+        nat.tsv_load_into(str(tmp_path / "none.tsv"), dst)
+    arena = nat.TableArena(5, 3500, pinned=False)
+    same = arena.load(paths[:3], workers=3)
+    assert isinstance(same, np.ndarray) and same.shape == (3, 3000, 2)      # equal lengths: one 3-D view
+    for k in range(3):
+        np.testing.assert_array_equal(same[k], tabs[k])
+    with pytest.raises(ValueError, match="do not fit"):
+        arena.load(paths, workers=2)
+    mixed = arena.load(paths, workers=2, overflow="alloc")                  # the long table gets memory of its own
+    assert isinstance(mixed, list) and [m.shape[0] for m in mixed] == [3000, 3000, 3000, 4100, 17]
+    for m, a in zip(mixed, tabs):
+        np.testing.assert_array_equal(m, a)
+    sets = nat.PointSets(same)
+    assert sets.addr[1] - sets.addr[0] == 3500 * 16 and sets.count.tolist() == [3000] * 3
+    arena.close()

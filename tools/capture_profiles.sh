@@ -21,4 +21,7 @@ C5_N=3000000 python tools/c5_probe.py > $OUT/plain_c5_${TAG}.log 2>&1 || exit 4
 C5_N=3000000 ncu --set full --clock-control none --import-source on -k 'regex:^k_density_binned$|k_cell_moments|k_scan_wide|k_scale_count' -s 4 -c 4 -o $OUT/prof_c5_${TAG} python tools/c5_probe.py > $OUT/ncu_c5.log 2>&1
 python tools/band_sort_probe.py 1250000 > $OUT/band_sort_probe_${TAG}.log 2>&1
 tools/ubench/match_probe > $OUT/match_probe_${TAG}.log 2>&1
+# what a wave costs whatever its size, and what that does to the host batch pipeline (first / middle / last wave sizes)
+WAVES=1,2,4,8,12,16,24,32,64 python tools/wave_probe.py > $OUT/wave_probe_${TAG}.log 2>&1
+python tools/tail_probe.py "3D=0" "3D=1" "3D=1;KDEJS_TAIL_WAVE=6" "3D=1;KDEJS_WAVE_PLAN=1,2,4,7,8,7" "3D=1;KDEJS_WAVE_PLAN=2,6,12,12,12,10,10" "3D=1;KDEJS_FIRST_WAVE=64;KDEJS_HOST_WAVE=64" > $OUT/tail_probe_${TAG}.log 2>&1
 for f in ncu_b32 ncu_s ncu_b64 ncu_c5; do tail -n 1 $OUT/$f.log; done

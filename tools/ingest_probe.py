@@ -1,0 +1,70 @@
+"""Tables on disk -> discrepancies: the sweep the reference runs with np.loadtxt + one CPU evaluation per file
+(scripts/distance_to_gridsearch.py:48-55, :109-125).  Parse-only rates and sweeps.gridsearch_best end to end.
+usage: python tools/ingest_probe.py [n_files]      (GPU box; writes its tables under a temporary directory)"""
+import os, shutil, sys, tempfile, time
+sys.path.insert(0, os.getcwd())
+import numpy as np
+import poppunk_mod_b200 as pk
+from poppunk_mod_b200 import sweeps
+from oracle import workloads as wl
+
+nat = pk._native
+n_files = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+d = tempfile.mkdtemp(prefix="kdejs_ingest_")
+try:
+    T = wl.example_target()
+    ref = os.path.join(d, "ref.tsv")
+    with open(ref, "w") as f:
+        f.writelines(f"{x!r}\t{y!r}\n" for x, y in T.tolist())          # the reference's own spelling: repr()
+    distinct = []
+    for s in range(32):
+        q = os.path.join(d, f"sim{s}.tsv")
+        with open(q, "w") as f:
+            f.writelines(f"{x!r}\t{y!r}\n" for x, y in wl.sim_batch_member(s).tolist())
+        distinct.append(q)
+    files = []
+    for k in range(n_files):
+        q = os.path.join(d, f"run{k}.tsv")
+        if k < 32:
+            os.rename(distinct[k], q)
+            distinct[k] = q
+        else:
+            shutil.copy(distinct[k % 32], q)
+        files.append(q)
+    mb = sum(os.path.getsize(q) for q in files) / 1e6
+    print(f"{n_files} tables of 100 000 rows, {mb / n_files:.2f} MB each; {os.cpu_count()} host cores", flush=True)
+    t0 = time.perf_counter(); a = np.loadtxt(files[0], delimiter="\t"); t_np = time.perf_counter() - t0
+    print(f"np.loadtxt (the reference's reader): {1e3 * t_np:.1f} ms per table = {1 / t_np:.0f} tables/s per core", flush=True)
+    for th in (1, 2, 4, 8):
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter(); t = nat.TsvTable(files[1], pinned=False, threads=th); ts.append(time.perf_counter() - t0)
+        print(f"kdejs_tsv_load, {th} thread(s): {1e3 * min(ts):.2f} ms per table ({mb / n_files / min(ts) / 1e3:.2f} GB/s)", flush=True)
+    assert np.array_equal(nat.TsvTable(files[0], pinned=False).array, a)
+    arena = nat.TableArena(64, 100000)
+    arena.load(files[:64], workers=8)                                     # first touch of the arena
+    for w in (4, 8, 16, 32):
+        t0 = time.perf_counter()
+        for c in range(0, n_files, 64):
+            arena.load(files[c:c + 64], skip_rows=0, workers=w)
+        dt = time.perf_counter() - t0
+        print(f"parse into a page-locked arena, {w} files at a time: {n_files / dt:.0f} tables/s ({mb / dt / 1e3:.2f} GB/s)", flush=True)
+    arena.close()
+    t0 = time.perf_counter()
+    for c in range(0, n_files, 64):
+        tabs = sweeps._load_many(files[c:c + 64], sweeps.read_file, 8)
+        for t in tabs:
+            t.close()
+    dt = time.perf_counter() - t0
+    print(f"one page-locked allocation per table (8 files x 2 threads at a time): {n_files / dt:.0f} tables/s", flush=True)
+    for io, chunk in ((8, 64), (16, 64), (16, 128), (16, 256), (32, 128)):
+        sweeps.gridsearch_best(ref, files[:64], gamma=0.25, eps=0.0, log=False, io_threads=io)      # warm-up
+        t0 = time.perf_counter()
+        best, dist = sweeps.gridsearch_best(ref, files, gamma=0.25, eps=0.0, log=False, io_threads=io, chunk=chunk)
+        dt = time.perf_counter() - t0
+        print(f"sweeps.gridsearch_best, files -> arg-min, io_threads={io}, {chunk} files per batch: {n_files / dt:.0f} "
+              f"tables/s ({dt:.2f} s; best {os.path.basename(best[0])} d={best[1]:.6f})", flush=True)
+    one = pk.KDE_JS_divergence(T, a, 0.25, 0.0)
+    assert dist[0] == one, (dist[0], one)
+finally:
+    shutil.rmtree(d, ignore_errors=True)
