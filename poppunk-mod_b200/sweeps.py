@@ -190,7 +190,7 @@ def main(argv=None):
     g.add_argument("--outpref", default="output")
     for name in ("core-min-bounds", "core-max-bounds", "acc-min-bounds", "acc-max-bounds"):
         g.add_argument("--" + name, type=str, default=None)
-    g.add_argument("--threads", type=int, default=8)
+    g.add_argument("--threads", type=int, default=None)
     o = ap.parse_args(argv)
     return _pairwise_main(o) if o.cmd == "pairwise" else _gridsearch_main(o)
 

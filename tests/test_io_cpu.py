@@ -166,3 +166,52 @@ def test_load_into_and_table_arena(nat, tmp_path):
     sets = nat.PointSets(same)
     assert sets.addr[1] - sets.addr[0] == 3500 * 16 and sets.count.tolist() == [3000] * 3
     arena.close()
+
+
+def test_decimal_conversion_is_correctly_rounded(nat, tmp_path):
+    """The reader's numbers against float() (what np.loadtxt and pandas produce): bit for bit, on the spellings tables
+    hold, on digit strings of every length, on decimals right next to the midpoint of two doubles, and out of range
+    (1e400 -> inf, 1e-400 -> 0: from_chars reports those as errors, the reader must not)."""
+    import math
+    import random
+    from decimal import ROUND_CEILING, ROUND_FLOOR, Decimal, localcontext
+
+    rng = np.random.default_rng(11)
+    random.seed(5)
+    strs = []
+    fmts = ["%r", "%.17g", "%.18e", "%.6f", "%.15g", "%.16g", "%.19g", "%.20g", "%.3f"]
+    vals = rng.random(40000) * 10.0 ** rng.uniform(-30, 30, 40000) * np.where(rng.random(40000) < 0.3, -1, 1)
+    for i, v in enumerate(vals.tolist()):
+        f = fmts[i % len(fmts)]
+        strs.append(repr(v) if f == "%r" else f % v)
+    strs += [repr(float(x)) for x in rng.random(20000).tolist()]
+    for _ in range(20000):
+        nd = random.randint(1, 20)
+        digs = "".join(random.choice("0123456789") for _ in range(nd))
+        pt = random.randint(0, nd)
+        s = digs[:pt] + "." + digs[pt:]
+        if s == ".":
+            s = "0."
+        if random.random() < 0.3:
+            s += random.choice("eE") + random.choice(["", "+", "-"]) + str(random.randint(0, 40))
+        strs.append(("-" if random.random() < 0.2 else "+" if random.random() < 0.05 else "") + s)
+    for v in (rng.random(10000) * 10.0 ** rng.uniform(-8, 8, 10000)).tolist():
+        with localcontext() as ctx:
+            ctx.prec = 60
+            mid = (Decimal(v) + Decimal(math.nextafter(v, math.inf))) / 2
+        for rounding in (ROUND_FLOOR, ROUND_CEILING):
+            with localcontext() as ctx:
+                ctx.prec, ctx.rounding = 19, rounding
+                strs.append(format(+mid, "e"))
+    strs += ["0", "-0.0", "0.000", "1.", ".5", "5e3", "1E+2", "00012.50", "inf", "-inf", "nan", "1e400", "1e-400",
+             "18446744073709551615", "18446744073709551616", "9007199254740993", "4.9e-324"]
+    if len(strs) % 2:
+        strs.append("1")
+    want = np.array([float(s) for s in strs]).reshape(-1, 2)
+    p = tmp_path / "numbers.tsv"
+    with open(p, "w") as f:
+        for i in range(0, len(strs), 2):
+            f.write(strs[i] + "\t" + strs[i + 1] + "\n")
+    got = nat.TsvTable(str(p), skip_rows=0, pinned=False, threads=3).array
+    bad = np.argwhere(got.view(np.uint64) != want.view(np.uint64))
+    assert len(bad) == 0, [(strs[2 * r + c], got[r, c], want[r, c]) for r, c in bad[:5]]
