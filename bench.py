@@ -518,6 +518,8 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    ingest = run_ingest(pk, target, sims, GAMMA, EPS) if extras and world == 1 else None
+
     # ---- roofline of the dominant kernel (density) ------------------------------------------------
     tf64, mhz = ctypes.c_double(), ctypes.c_double()
     nat.check(L.kdejs_peak_flops(dev, 1, ctypes.byref(tf64), ctypes.byref(mhz)))
@@ -657,6 +659,7 @@ def main():
         "c4_sweep": c4,
         "c5_row_sharded": c5,
         "r100": r100,
+        "ingest": ingest,
         "algos": algos,
         "single_call_latency_ms": single_ms,
         "dense_fp32": dense,
@@ -666,6 +669,51 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_ingest(pk, target, sims, gamma, eps, n_files=128, n_distinct=8):
+    """Tables on disk -> arg-min: the grid-search sweep of scripts/distance_to_gridsearch.py:48-55, :109-125 through
+    sweeps.gridsearch_best (tables parsed by the library's reader into page-locked arenas while the GPU works on the
+    previous chunk), with the reference's reader (np.loadtxt) timed beside it."""
+    import shutil
+    import tempfile
+
+    from poppunk_mod_b200 import sweeps
+
+    d = tempfile.mkdtemp(prefix="kdejs_bench_")
+    try:
+        def write(path, a):
+            with open(path, "w") as f:
+                f.writelines(f"{x!r}\t{y!r}\n" for x, y in a.tolist())       # the reference's spelling: repr()
+
+        ref = os.path.join(d, "target.tsv")
+        write(ref, target)
+        files = []
+        for k in range(n_files):
+            q = os.path.join(d, f"sim{k}.tsv")
+            if k < n_distinct:
+                write(q, sims[k])
+            else:
+                shutil.copy(files[k % n_distinct], q)
+            files.append(q)
+        t0 = time.perf_counter()
+        a = np.loadtxt(files[0], delimiter="\t")
+        t_np = time.perf_counter() - t0
+        assert np.array_equal(pk._native.TsvTable(files[0], pinned=False).array, a)
+        sweeps.gridsearch_best(ref, files[:64], gamma=gamma, eps=eps, log=False, resolution=100)        # warm-up
+        t0 = time.perf_counter()
+        best, dist_ = sweeps.gridsearch_best(ref, files, gamma=gamma, eps=eps, log=False, resolution=100)
+        dt = time.perf_counter() - t0
+        assert dist_[0] == pk.KDE_JS_divergence(target, a, gamma, eps) and best[0] is not None
+        return {"value": n_files / dt, "unit": "tables/s", "tables": n_files, "rows_per_table": int(a.shape[0]),
+                "mb_per_table": os.path.getsize(files[0]) / 1e6, "seconds": dt, "host_cores": os.cpu_count(),
+                "api": "sweeps.gridsearch_best(ref.tsv, [sim.tsv ...]) at the reference's 100x100 grid",
+                "np_loadtxt_tables_per_s_per_core": 1.0 / t_np,
+                "note": "files (page cache) -> kdejs_tsv_load_into -> page-locked arena -> batch -> arg-min; the "
+                        "reference reads each table with np.loadtxt and evaluates it on one core "
+                        "(scripts/distance_to_gridsearch.py:48-55)"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def run_c5(torch, dist, pk, D, nat, rank, world, dev, n_pairs, barrier, max_over_ranks):

@@ -38,8 +38,18 @@ def process_results_batch(simulations, simulations_freqs, obs, gamma, core_thres
     """(B,4) summary vectors for B simulations against one target.  With `observed` (the 4-vector of
     poppunk_mod.py:494) also returns the ELFI nodes d and log_d: (summary, d, log_d)."""
     obs_arr = _points(obs)
-    sims = [_points(s) for s in simulations]
-    freqs = [_freqs(f) for f in simulations_freqs]
+    simulations, simulations_freqs = list(simulations), list(simulations_freqs)
+    if len(simulations) > 1 and all(isinstance(s, (str, os.PathLike)) for s in simulations):
+        # tables on disk: parsed concurrently, one parser thread per file (ctypes releases the GIL); ordinary memory,
+        # which the library stages itself -- a page-locked allocation per file costs more than parsing it
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=max(1, min(16, os.cpu_count() or 1))) as ex:
+            sims = list(ex.map(lambda p: read_distfile(p, pinned=False, threads=1).array, simulations))
+            freqs = list(ex.map(_freqs, simulations_freqs))
+    else:
+        sims = [_points(s) for s in simulations]
+        freqs = [_freqs(f) for f in simulations_freqs]
     want_d = observed is not None
     summary, d, log_d = kd.summary_batch(obs_arr, sims, freqs, observed if want_d else [0.0, 0.0, 0.0, 0.0], gamma,
                                          core_threshold, rare_threshold, eps=0, log=False, resolution=resolution,

@@ -34,12 +34,12 @@ def read_file(path, pinned=None, threads=0):
     return nat.TsvTable(path, skip_rows=0, pinned=pinned, threads=threads)
 
 
-def read_distfile(path, pinned=None):
+def read_distfile(path, pinned=None, threads=0):
     """poppunk_mod.read_distfile (:255-269): a 2-column file is read whole; otherwise pandas' inferred
     header consumes the first line and the first two (id) columns are dropped."""
     with open(path, "r") as f:
         two_column = len(f.readline().rstrip().split("\t")) == 2
-    return nat.TsvTable(path, skip_rows=0 if two_column else 1, pinned=pinned)
+    return nat.TsvTable(path, skip_rows=0 if two_column else 1, pinned=pinned, threads=threads)
 
 
 def _bounds(a):
@@ -47,10 +47,12 @@ def _bounds(a):
 
 
 def _load_many(paths, reader, workers):
-    """Parse many tables concurrently: `workers` files at a time, two parser threads inside each (measured
-    best on 8 cores: 450 files/s for 100 000-row tables against 10 files/s for np.loadtxt)."""
+    """Parse many tables concurrently, `workers` files at a time with one parser thread each, into ordinary memory
+    (the library stages pageable uploads itself; a page-locked allocation per table costs more than parsing it:
+    measured on a 16-core host, 100 000-row tables: 150-340 tables/s with one allocation each, 1 350-1 740 into
+    slots of one page-locked arena -- gridsearch_best -- against 30 per core for np.loadtxt)."""
     with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:      # ctypes releases the GIL while parsing
-        return list(ex.map(lambda p: reader(p, threads=2), paths))
+        return list(ex.map(lambda p: reader(p, pinned=False, threads=1), paths))
 
 
 def pairwise_distances(files, gamma=0.25, eps=0.0, log=False, *, io_threads=8, device=None, resolution=100):

@@ -2,6 +2,7 @@
 (scripts/distance_to_gridsearch.py:48-55, :109-125).  Parse-only rates and sweeps.gridsearch_best end to end.
 usage: python tools/ingest_probe.py [n_files]      (GPU box; writes its tables under a temporary directory)"""
 import os, shutil, sys, tempfile, time
+from concurrent.futures import ThreadPoolExecutor
 sys.path.insert(0, os.getcwd())
 import numpy as np
 import poppunk_mod_b200 as pk
@@ -50,13 +51,15 @@ try:
         dt = time.perf_counter() - t0
         print(f"parse into a page-locked arena, {w} files at a time: {n_files / dt:.0f} tables/s ({mb / dt / 1e3:.2f} GB/s)", flush=True)
     arena.close()
-    t0 = time.perf_counter()
-    for c in range(0, n_files, 64):
-        tabs = sweeps._load_many(files[c:c + 64], sweeps.read_file, 8)
-        for t in tabs:
-            t.close()
-    dt = time.perf_counter() - t0
-    print(f"one page-locked allocation per table (8 files x 2 threads at a time): {n_files / dt:.0f} tables/s", flush=True)
+    for pinned in (True, False):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=16) as ex:
+            for c in range(0, n_files, 64):
+                tabs = list(ex.map(lambda p: nat.TsvTable(p, skip_rows=0, pinned=pinned, threads=1), files[c:c + 64]))
+                for t in tabs:
+                    t.close()
+        dt = time.perf_counter() - t0
+        print(f"one {'page-locked' if pinned else 'ordinary'} allocation per table, 16 files at a time: {n_files / dt:.0f} tables/s", flush=True)
     for io, chunk in ((8, 64), (16, 64), (16, 128), (16, 256), (32, 128)):
         sweeps.gridsearch_best(ref, files[:64], gamma=0.25, eps=0.0, log=False, io_threads=io)      # warm-up
         t0 = time.perf_counter()
