@@ -244,6 +244,36 @@ int kdejs_tsv_load(const char *path, int skip_rows, int pinned, int threads, dou
 int kdejs_tsv_load_into(const char *path, int skip_rows, int threads, double *dst, int64_t capacity_rows,
                         int64_t *out_rows);
 void kdejs_tsv_free(double *pts, int pinned);
+/* First byte of the data rows of a table that is already in memory (same header rule as kdejs_tsv_load). */
+int64_t kdejs_tsv_data_offset(const char *text, int64_t bytes, int skip_rows);
+/* n files read into slots of slot_bytes bytes (dst + i * slot_bytes), `threads` at a time; out_bytes[i] = bytes read,
+ * -(file size) when the file does not fit its slot, -1 when it cannot be opened.  No parsing. */
+int kdejs_files_read(const char *const *paths, int n, char *dst, int64_t slot_bytes, int64_t *out_bytes, int threads);
+
+/* ---- sweeps over tables on disk: the TEXT goes to the device ------------------------- */
+/* [KDE_JS_divergence(obs, table_i) for i in range(B)] where table_i is given as the bytes of its file
+ * (texts[i], text_bytes[i]; page-locked memory for asynchronous copies).  The text is uploaded as it is and parsed on
+ * the device (last two tab-separated columns, skip_rows as kdejs_tsv_load; csrc/kdejs_tsv.cuh) -- the loop of
+ * scripts/distance_to_gridsearch.py:48-55, :109-110 without a host parser in it.  Numbers get the bits float() gives
+ * them (csrc/kdejs_decimal.h).  out_rows[i] = data rows of table i; out_bounds[i] = (min, max) of column 0 and of
+ * column 1 as np.min / np.max give them (the bounds test of distance_to_gridsearch.py:112-125).  out_status[i]:
+ *   KDEJS_TABLE_OK    out_js[i] is the discrepancy
+ *   KDEJS_TABLE_HOST  the table holds something the device parser does not cover (a missing-value spelling, inf / nan,
+ *                     more than 19 digits, a malformed row) or no data rows: out_js[i] is NaN -- read that file with
+ *                     kdejs_tsv_load (which reports malformed rows) and evaluate it through the host entry points
+ *   KDEJS_TABLE_INF   the table parsed, but holds an infinity the path rejects (KDEJS_ERR_INF for a host call) */
+#define KDEJS_TABLE_OK 0
+#define KDEJS_TABLE_HOST 1
+#define KDEJS_TABLE_INF 2
+/* One table parsed by the device parser, rows copied back to out_pts (capacity_rows x 2 doubles): what
+ * kdejs_tsv_load_into gives, computed on the GPU (parity tests; callers that want the rows of a table they hold as
+ * text).  *out_status = KDEJS_TABLE_OK or KDEJS_TABLE_HOST (then the rows are not to be used). */
+int kdejs_tsv_parse_text(int device, const char *text, int64_t bytes, int skip_rows, double *out_pts,
+                         int64_t capacity_rows, int64_t *out_rows, int32_t *out_status);
+int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, const char *const *texts,
+                                 const int64_t *text_bytes, int B, int skip_rows, int resolution, double bandwidth,
+                                 double gamma, double eps, int log_flag, int kernel, int algo, double *out_js,
+                                 int64_t *out_rows, int32_t *out_status, double *out_bounds /* nullable, [B][4] */);
 const char *kdejs_io_last_error(void);
 
 /* ---- measurement support (bench.py, tests) ------------------------------------------- */

@@ -43,7 +43,7 @@ except ImportError:  # used as a top-level drop-in module: `sys.path.insert(0, "
     _spec.loader.exec_module(nat)
 
 __all__ = ["get_grid", "scale_KDE", "KDE_JS_divergence", "KDE_KL_divergence", "KDE_JS_divergence_batch",
-           "KDE_JS_divergence_pairs", "kde_density", "summary_batch", "rule_bandwidth", "default_device", "main"]
+           "KDE_JS_divergence_batch_text", "KDE_JS_divergence_pairs", "kde_density", "summary_batch", "rule_bandwidth", "default_device", "main"]
 
 _DEFAULT_RESOLUTION = 100      # KDE_distance.py:89
 _DEFAULT_BANDWIDTH = 0.03      # KDE_distance.py:50
@@ -214,6 +214,49 @@ def KDE_JS_divergence_batch(obs, sims, gamma=1.0, eps=1e-12, log=False, *,
             raise e
         raise RuntimeError(f"kdejs: {err}")
     return out
+
+
+def KDE_JS_divergence_batch_text(obs, texts, gamma=1.0, eps=1e-12, log=False, *, nbytes=None, skip_rows=-1,
+                                 resolution=_DEFAULT_RESOLUTION, bandwidth=_DEFAULT_BANDWIDTH, kernel="epanechnikov",
+                                 algo=None, device=None, bounds=False):
+    """[KDE_JS_divergence(obs, table_i)] for tables given as the BYTES of their files: the text is uploaded as it is
+    and parsed on the device (last two tab-separated columns, `skip_rows` as in TsvTable; kdejs_discrepancy_batch_text).
+
+    texts: a sequence of bytes-like objects / uint8 arrays, or ONE (B, slot_bytes) uint8 array with `nbytes[i]` valid
+    bytes in row i (a _native.TextArena).  Returns (js, rows, status[, bounds]): status[i] is _native.KDEJS_TABLE_OK,
+    KDEJS_TABLE_HOST (js[i] is NaN: the table holds something only the host reader covers -- a missing-value spelling,
+    inf / nan, more than 19 digits, a malformed row -- or no rows) or KDEJS_TABLE_INF; bounds[i] = (min, max) of
+    column 0, (min, max) of column 1."""
+    o = nat.as_points(obs, "obs")
+    if isinstance(texts, np.ndarray) and texts.ndim == 2:
+        if texts.dtype != np.uint8 or not texts.flags.c_contiguous or nbytes is None:
+            raise ValueError("a 2-D `texts` must be a C-contiguous uint8 array with `nbytes`")
+        keep = texts
+        B = len(nbytes)
+        if B > texts.shape[0]:
+            raise ValueError("more lengths than rows of `texts`")
+        lens = np.ascontiguousarray(nbytes, dtype=np.int64)
+        if B and (lens.min() < 0 or lens.max() > texts.shape[1]):
+            raise ValueError("nbytes out of range")
+        addr = np.uint64(texts.ctypes.data) + np.arange(B, dtype=np.uint64) * np.uint64(texts.strides[0])
+    else:
+        keep = [np.frombuffer(t, dtype=np.uint8) if not isinstance(t, np.ndarray) else np.ascontiguousarray(t).view(np.uint8).reshape(-1)
+                for t in texts]
+        B = len(keep)
+        lens = np.array([k.shape[0] for k in keep], dtype=np.int64)
+        addr = np.array([k.ctypes.data for k in keep], dtype=np.uint64)
+    if isinstance(bandwidth, str):
+        raise ValueError("a bandwidth rule needs the table sizes before the call; pass a number")
+    common = _common(resolution, float(bandwidth), gamma, eps, log, kernel, algo)
+    js, rows, status = np.empty(B), np.zeros(B, dtype=np.int64), np.zeros(B, dtype=np.int32)
+    bnd = np.empty((B, 4)) if bounds else None
+    if B:
+        dev = default_device() if device is None else int(device)
+        nat.check(nat.lib().kdejs_discrepancy_batch_text(
+            dev, nat.ptr(o), o.shape[0], addr.ctypes.data_as(nat._c_dpp), lens.ctypes.data_as(nat._c_i64p), B,
+            int(skip_rows), *common, nat.ptr(js), nat.ptr(rows), nat.ptr(status), nat.ptr(bnd)))
+    del keep
+    return (js, rows, status, bnd) if bounds else (js, rows, status)
 
 
 def KDE_JS_divergence_pairs(sets, pairs, gamma=1.0, eps=1e-12, log=False, *,

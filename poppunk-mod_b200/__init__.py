@@ -5,7 +5,8 @@ through the alias module `poppunk_mod_b200` at the repository root, or put this 
 sys.path and `import KDE_distance` exactly as the reference's callers do.
 """
 from . import KDE_distance  # noqa: F401
-from .KDE_distance import (KDE_JS_divergence, KDE_JS_divergence_batch, KDE_JS_divergence_pairs,  # noqa: F401
+from .KDE_distance import (KDE_JS_divergence, KDE_JS_divergence_batch, KDE_JS_divergence_batch_text,  # noqa: F401
+                           KDE_JS_divergence_pairs,
                            KDE_KL_divergence, default_device, get_grid, kde_density, scale_KDE)
 from . import _native  # noqa: F401
 from . import distributed, simulator, sweeps  # noqa: F401

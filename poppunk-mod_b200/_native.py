@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkdejs.so")
 
 KDEJS_OK, KDEJS_ERR_CUDA, KDEJS_ERR_ARG, KDEJS_ERR_INF, KDEJS_ERR_CAPACITY = 0, 1, 2, 3, 4
+KDEJS_TABLE_OK, KDEJS_TABLE_HOST, KDEJS_TABLE_INF = 0, 1, 2
 KERNELS = {"epanechnikov": 0, "gaussian": 1}
 ALGOS = {"binned": 0, "dense": 1, "dense64": 2, "binned32": 3}
 KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence", "classify", "moments",
@@ -93,6 +94,14 @@ _SIGNATURES = {
     "kdejs_tsv_load_into": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_int64, _c_i64p]),
     "kdejs_tsv_free": (None, [ctypes.c_void_p, ctypes.c_int]),
+    "kdejs_tsv_data_offset": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
+    "kdejs_files_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                        _c_i64p, ctypes.c_int]),
+    "kdejs_tsv_parse_text": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p,
+                                            ctypes.c_int64, _c_i64p, ctypes.POINTER(ctypes.c_int32)]),
+    "kdejs_discrepancy_batch_text": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p,
+                                                    ctypes.c_int, ctypes.c_int] + _COMMON +
+                                     [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "kdejs_io_last_error": (ctypes.c_char_p, []),
     "kdejs_profile_enable": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "kdejs_profile_read": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_dp, _c_i64p]),
@@ -380,3 +389,45 @@ class TableArena:
         if self._pool is not None:
             self._pool.close()
             self._pool = None
+
+
+class TextArena:
+    """The BYTES of up to `slots` files in one (slots, slot_bytes) uint8 array (page-locked when a GPU is present), read
+    by kdejs_files_read -- plain read(2), `threads` files at a time, no parsing: the device parses
+    (KDE_distance.KDE_JS_divergence_batch_text)."""
+
+    def __init__(self, slots, slot_bytes, pinned=None):
+        if pinned is None:
+            pinned = device_count() > 0
+        self._pool = PinnedPool() if pinned else None
+        shape = (int(slots), int(slot_bytes))
+        self.array = self._pool.empty(shape, np.uint8) if pinned else np.empty(shape, dtype=np.uint8)
+        self.nbytes = np.zeros(int(slots), dtype=np.int64)
+
+    def read(self, paths, threads=8):
+        """Reads paths[k] into slot k.  self.nbytes[k] = bytes read, -(file size) if the file does not fit its slot,
+        -1 if it cannot be opened."""
+        paths = [os.fsencode(p) for p in paths]
+        if len(paths) > self.array.shape[0]:
+            raise ValueError(f"{len(paths)} files for {self.array.shape[0]} slots")
+        arr = (ctypes.c_char_p * len(paths))(*paths)
+        check(lib().kdejs_files_read(arr, len(paths), self.array.ctypes.data, self.array.shape[1],
+                                     self.nbytes.ctypes.data_as(_c_i64p), int(threads)))
+        return self.nbytes[:len(paths)]
+
+    def close(self):
+        self.array = None
+        if self._pool is not None:
+            self._pool.close()
+            self._pool = None
+
+
+def tsv_parse_text(text, skip_rows=-1, device=0):
+    """The rows of a table held as bytes, parsed by the DEVICE parser (kdejs_tsv_parse_text): ((rows,2) float64,
+    status) with status KDEJS_TABLE_OK or KDEJS_TABLE_HOST (something only the host reader covers: ignore the rows)."""
+    buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
+    n, st = ctypes.c_int64(), ctypes.c_int32()
+    out = np.empty((max(1, buf.shape[0] // 4), 2))
+    check(lib().kdejs_tsv_parse_text(int(device), buf.ctypes.data, buf.shape[0], int(skip_rows), out.ctypes.data,
+                                     out.shape[0], ctypes.byref(n), ctypes.byref(st)))
+    return out[:n.value].copy(), st.value

@@ -10,6 +10,7 @@
 #include "../../include/kdejs.h"
 #include "kdejs_kernels.cuh"
 #include "kdejs_stager.h"
+#include "kdejs_tsv.cuh"
 
 #include <nvtx3/nvToolsExt.h>     // header-only NVTX 3: ranges cost nothing unless a profiler is attached
 
@@ -127,6 +128,10 @@ struct Ctx {
     bool busy_pending[kSlots] = {false, false};
     uint64_t last_use[kSlots] = {0, 0}, use_tick = 0;
     DevBuf pool_raw, js_out, status_out, sim_ring, summary;
+    // tables parsed on the device (kdejs_discrepancy_batch_text): two text buffers (the copy stream fills one while
+    // the other is parsed), chunk row counts and row totals per buffer, the parsed tables, per-file status
+    DevBuf tsv_text[2], tsv_chunkrows[2], tsv_rows[2], tsv_sims, tsv_status;
+    int64_t *h_tsv_rows = nullptr;        // pinned, 2 x kMaxTsvFiles
     std::vector<cudaEvent_t> free_plain_events;
     double *h_js = nullptr; int32_t *h_status = nullptr; size_t h_cap = 0;   // pinned results
     std::mutex mu;
@@ -205,7 +210,10 @@ void destroy_ctx(Ctx &c) {
     c.peer_world = 0; c.peer_rank = -1; c.peer_handle_valid = false;
     for (void *q : c.peer_retired) cudaFree(q);
     c.peer_retired.clear();
-    for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.sim_ring, &c.summary, &c.peer_buf}) {
+    if (c.h_tsv_rows) { cudaFreeHost(c.h_tsv_rows); c.h_tsv_rows = nullptr; }
+    for (DevBuf *b : {&c.pool_raw, &c.js_out, &c.status_out, &c.sim_ring, &c.summary, &c.peer_buf, &c.tsv_text[0],
+                      &c.tsv_text[1], &c.tsv_chunkrows[0], &c.tsv_chunkrows[1], &c.tsv_rows[0], &c.tsv_rows[1],
+                      &c.tsv_sims, &c.tsv_status}) {
         if (b->p) cudaFree(b->p);
         b->p = nullptr; b->cap = 0;
     }
@@ -1169,6 +1177,198 @@ static int batch_impl(int device, const double *obs, int64_t n_obs, const double
             if (sum->out_log_d) sum->out_log_d[i] = h_sum[6 * (size_t)i + 5];
         }
     return finish_status(c->h_status, B);
+}
+
+int kdejs_tsv_parse_text(int device, const char *text, int64_t bytes, int skip_rows, double *out_pts,
+                         int64_t capacity_rows, int64_t *out_rows, int32_t *out_status) {
+    if (!text || bytes < 0 || !out_rows || !out_status || (capacity_rows > 0 && !out_pts))
+        return fail(KDEJS_ERR_ARG, "null argument");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = c->s_compute;
+    OKR(acquire_scratch(*c, st));
+    const size_t text_stride = ((size_t)bytes + 64 + 255) / 256 * 256;
+    const int64_t begin = kdejs_tsv_data_offset(text, bytes, skip_rows);
+    const int chunks = std::max<int>(1, (int)((bytes - begin / kTsvChunk * kTsvChunk + kTsvChunk - 1) / kTsvChunk));
+    OKR(c->tsv_text[0].ensure(text_stride));
+    OKR(c->tsv_chunkrows[0].ensure((size_t)chunks * sizeof(uint32_t)));
+    OKR(c->tsv_rows[0].ensure(sizeof(int64_t)));
+    OKR(c->tsv_status.ensure(sizeof(unsigned)));
+    if (!c->h_tsv_rows) CU(cudaMallocHost(&c->h_tsv_rows, 2 * kMaxTsvFiles * sizeof(int64_t)));
+    TsvWave wv;
+    memset(&wv, 0, sizeof wv);
+    wv.f[0] = TsvFile{c->tsv_text[0].as<char>(), begin, bytes, nullptr, 0};
+    if (bytes > 0) CU(cudaMemcpyAsync(c->tsv_text[0].p, text, (size_t)bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->tsv_status.p, 0, sizeof(unsigned), st));
+    k_tsv_count<<<dim3(chunks, 1), kTsvThreads, 0, st>>>(wv, chunks, c->tsv_chunkrows[0].as<uint32_t>());
+    k_tsv_scan<<<1, 1024, 0, st>>>(chunks, c->tsv_chunkrows[0].as<uint32_t>(), c->tsv_rows[0].as<int64_t>());
+    CU(cudaMemcpyAsync(c->h_tsv_rows, c->tsv_rows[0].p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int64_t rows = c->h_tsv_rows[0];
+    *out_rows = rows;
+    *out_status = KDEJS_TABLE_OK;
+    c->launches += 2;
+    int rc = KDEJS_OK;
+    if (rows > capacity_rows) rc = fail(KDEJS_ERR_CAPACITY, std::to_string(rows) + " data rows do not fit the buffer");
+    else if (rows > 0) {
+        if ((rc = c->tsv_sims.ensure((size_t)rows * 16)) == KDEJS_OK) {
+            wv.f[0].out = c->tsv_sims.as<double2>();
+            wv.f[0].cap_rows = rows;
+            k_tsv_parse<<<dim3(chunks, 1), kTsvThreads, 0, st>>>(wv, chunks, c->tsv_chunkrows[0].as<uint32_t>(),
+                                                                 c->tsv_status.as<unsigned>());
+            c->launches += 1;
+            unsigned flags = 0u;
+            if (cudaMemcpyAsync(out_pts, c->tsv_sims.p, (size_t)rows * 16, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaMemcpyAsync(&flags, c->tsv_status.p, sizeof flags, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess)
+                rc = fail(KDEJS_ERR_CUDA, "device table parser failed");
+            else if (flags) *out_status = KDEJS_TABLE_HOST;
+        }
+    } else *out_status = KDEJS_TABLE_HOST;
+    release_scratch(*c, st, true);
+    return rc;
+}
+
+int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, const char *const *texts,
+                                 const int64_t *text_bytes, int B, int skip_rows, int resolution, double bandwidth,
+                                 double gamma, double eps, int log_flag, int kernel, int algo, double *out_js,
+                                 int64_t *out_rows, int32_t *out_status, double *out_bounds) {
+    NvtxRange nvtx_call("kdejs_discrepancy_batch_text");
+    Params p{resolution, bandwidth, gamma, eps, log_flag ? 1 : 0, kernel, algo};
+    OKR(check_params(p));
+    OKR(check_set(obs, n_obs, "obs"));
+    if (B < 0 || (B > 0 && (!texts || !text_bytes || !out_js || !out_rows || !out_status)))
+        return fail(KDEJS_ERR_ARG, "batch arrays missing");
+    int64_t max_bytes = 0;
+    for (int i = 0; i < B; ++i) {
+        if (!texts[i] || text_bytes[i] < 0) return fail(KDEJS_ERR_ARG, "table text missing");
+        max_bytes = std::max(max_bytes, text_bytes[i]);
+    }
+    if (B == 0) return KDEJS_OK;
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    OKR(acquire_scratch(*c, c->s_compute));
+    constexpr int W = 16;                                   // tables per wave
+    static_assert(W <= kMaxTsvFiles && W <= kMaxWaveItems, "wave size");
+    const size_t text_stride = ((size_t)max_bytes + 64 + 255) / 256 * 256;      // padded: the parser reads whole 32-byte segments
+    const int chunks_cap = (int)(text_stride / kTsvChunk) + 2;
+    for (int k = 0; k < 2; ++k) {
+        OKR(c->tsv_text[k].ensure(text_stride * W));
+        OKR(c->tsv_chunkrows[k].ensure((size_t)W * chunks_cap * sizeof(uint32_t)));
+        OKR(c->tsv_rows[k].ensure(W * sizeof(int64_t)));
+    }
+    OKR(c->tsv_status.ensure((size_t)B * sizeof(unsigned) + 256 + (size_t)B * 4 * sizeof(double)));
+    double *d_bounds = reinterpret_cast<double *>(c->tsv_status.as<char>() + ((size_t)B * sizeof(unsigned) + 255) / 256 * 256);
+    if (!c->h_tsv_rows) CU(cudaMallocHost(&c->h_tsv_rows, 2 * kMaxTsvFiles * sizeof(int64_t)));
+    OKR(c->pool_raw.ensure((size_t)n_obs * 16));
+    OKR(c->js_out.ensure(sizeof(double) * (size_t)B));
+    OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)B));
+    OKR(ensure_host_results(*c, (size_t)B));
+    OKR(h2d_ranges(device, {Stager::Range{c->pool_raw.p, obs, (size_t)n_obs * 16}}, c->s_compute));
+    CU(cudaMemsetAsync(c->tsv_status.p, 0, (size_t)B * sizeof(unsigned), c->s_compute));
+    std::vector<int64_t> begin(B);
+    for (int i = 0; i < B; ++i) begin[i] = kdejs_tsv_data_offset(texts[i], text_bytes[i], skip_rows);
+    const int n_waves = (B + W - 1) / W;
+    std::vector<cudaEvent_t> ev_counted(n_waves), ev_parsed(n_waves);
+    auto new_event = [&](cudaEvent_t &e) -> int {
+        if (!c->free_plain_events.empty()) { e = c->free_plain_events.back(); c->free_plain_events.pop_back(); return KDEJS_OK; }
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return KDEJS_OK;
+    };
+    for (int k = 0; k < n_waves; ++k) { OKR(new_event(ev_counted[k])); OKR(new_event(ev_parsed[k])); }
+    std::vector<TsvWave> waves(n_waves);
+    std::vector<int> wave_chunks(n_waves, 1);
+    // copy stream: the text of wave k, its line count per 8 KB chunk, the scan, the row totals back to the host
+    auto enqueue_copy_count = [&](int k) -> int {
+        const int i0 = k * W, nf = std::min(W, B - i0), buf = k & 1;
+        if (k >= 2) CU(cudaStreamWaitEvent(c->s_copy, ev_parsed[k - 2], 0));       // the parser is done with this buffer
+        TsvWave &wv = waves[k];
+        memset(&wv, 0, sizeof wv);
+        int chunks = 1;
+        for (int j = 0; j < nf; ++j) {
+            const int i = i0 + j;
+            char *dst = c->tsv_text[buf].as<char>() + text_stride * (size_t)j;
+            if (text_bytes[i] > 0) CU(cudaMemcpyAsync(dst, texts[i], (size_t)text_bytes[i], cudaMemcpyHostToDevice, c->s_copy));
+            wv.f[j] = TsvFile{dst, begin[i], text_bytes[i], nullptr, 0};
+            chunks = std::max<int>(chunks, (int)((text_bytes[i] - begin[i] / kTsvChunk * kTsvChunk + kTsvChunk - 1) / kTsvChunk));
+        }
+        wave_chunks[k] = chunks;
+        k_tsv_count<<<dim3(chunks, nf), kTsvThreads, 0, c->s_copy>>>(wv, chunks, c->tsv_chunkrows[buf].as<uint32_t>());
+        k_tsv_scan<<<nf, 1024, 0, c->s_copy>>>(chunks, c->tsv_chunkrows[buf].as<uint32_t>(), c->tsv_rows[buf].as<int64_t>());
+        c->launches += 2;
+        CU(cudaMemcpyAsync(c->h_tsv_rows + (size_t)buf * kMaxTsvFiles, c->tsv_rows[buf].p, (size_t)nf * sizeof(int64_t),
+                           cudaMemcpyDeviceToHost, c->s_copy));
+        CU(cudaEventRecord(ev_counted[k], c->s_copy));
+        CU(cudaGetLastError());
+        return KDEJS_OK;
+    };
+    int rc = enqueue_copy_count(0);
+    std::vector<int> item_of_slot;            // results are written densely: slot -> table
+    item_of_slot.reserve(B);
+    for (int k = 0; k < n_waves && rc == KDEJS_OK; ++k) {
+        const int i0 = k * W, nf = std::min(W, B - i0), buf = k & 1;
+        if (k + 1 < n_waves && (rc = enqueue_copy_count(k + 1)) != KDEJS_OK) break;
+        if (cudaEventSynchronize(ev_counted[k]) != cudaSuccess) { rc = fail(KDEJS_ERR_CUDA, "table upload / count failed"); break; }
+        const int64_t *rows = c->h_tsv_rows + (size_t)buf * kMaxTsvFiles;
+        size_t total = 0;
+        std::vector<size_t> off(nf);
+        for (int j = 0; j < nf; ++j) {
+            out_rows[i0 + j] = rows[j];
+            off[j] = total;
+            total += ((size_t)std::max<int64_t>(rows[j], 0) * 16 + 255) / 256 * 256;
+        }
+        if ((rc = c->tsv_sims.ensure(std::max<size_t>(total, 256))) != KDEJS_OK) break;
+        TsvWave &wv = waves[k];
+        std::vector<RawSet> pool(1, RawSet{(const double *)c->pool_raw.p, n_obs});
+        std::vector<int32_t> ia, ib;
+        const size_t slot0 = item_of_slot.size();
+        for (int j = 0; j < nf; ++j) {
+            wv.f[j].out = reinterpret_cast<double2 *>(c->tsv_sims.as<char>() + off[j]);
+            wv.f[j].cap_rows = rows[j];
+            if (rows[j] > 0 && rows[j] <= 0x7fffffffLL / 4) {
+                pool.push_back(RawSet{(const double *)wv.f[j].out, rows[j]});
+                ia.push_back(0);
+                ib.push_back((int32_t)pool.size() - 1);
+                item_of_slot.push_back(i0 + j);
+            }
+        }
+        k_tsv_parse<<<dim3(wave_chunks[k], nf), kTsvThreads, 0, c->s_compute>>>(
+            wv, wave_chunks[k], c->tsv_chunkrows[buf].as<uint32_t>(), c->tsv_status.as<unsigned>() + i0);
+        c->launches += 1;
+        if (out_bounds) { k_tsv_bounds<<<nf, 256, 0, c->s_compute>>>(wv, d_bounds + (size_t)i0 * 4); c->launches += 1; }
+        cudaEventRecord(ev_parsed[k], c->s_compute);
+        if (!ia.empty())
+            rc = run_pairs_dev(*c, c->s_compute, p, pool, ia.data(), ib.data(), (int64_t)ia.size(), c->js_out.as<double>(),
+                               c->status_out.as<int32_t>(), (int64_t)slot0, false);
+    }
+    std::vector<unsigned> tsv_status(B, 0u);
+    const size_t n_slots = item_of_slot.size();
+    if (rc == KDEJS_OK) {
+        if ((n_slots && (cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * n_slots, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
+                         cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess)) ||
+            cudaMemcpyAsync(tsv_status.data(), c->tsv_status.p, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
+            (out_bounds && cudaMemcpyAsync(out_bounds, d_bounds, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess))
+            rc = fail(KDEJS_ERR_CUDA, "D2H copy of the results failed");
+    }
+    cudaError_t se = cudaStreamSynchronize(c->s_compute);
+    cudaStreamSynchronize(c->s_copy);
+    release_scratch(*c, c->s_compute, true);
+    for (auto e : ev_counted) c->free_plain_events.push_back(e);
+    for (auto e : ev_parsed) c->free_plain_events.push_back(e);
+    if (rc != KDEJS_OK) return rc;
+    if (se != cudaSuccess) return fail(KDEJS_ERR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(se));
+    const double nan = std::nan("");
+    for (int i = 0; i < B; ++i) { out_js[i] = nan; out_status[i] = KDEJS_TABLE_HOST; }      // until shown otherwise
+    for (size_t s = 0; s < n_slots; ++s) {
+        const int i = item_of_slot[s];
+        if (tsv_status[i] != 0u) continue;                  // a field the device parser does not cover: host reader
+        if (c->h_status[s] == KDEJS_ERR_INF) { out_status[i] = KDEJS_TABLE_INF; continue; }
+        out_js[i] = c->h_js[s];
+        out_status[i] = KDEJS_TABLE_OK;
+    }
+    return KDEJS_OK;
 }
 
 int kdejs_discrepancy_batch(int device, const double *obs, int64_t n_obs, const double *const *sims,

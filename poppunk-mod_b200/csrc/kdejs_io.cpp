@@ -247,6 +247,58 @@ int kdejs_tsv_load(const char *path, int skip_rows, int pinned, int threads, dou
     return KDEJS_OK;
 }
 
+/* Where the data rows of a table begin, for text that is already in memory (the device parser gets this offset):
+ * the same rule as kdejs_tsv_load -- `skip_rows` data lines are dropped, or (-1) one line if its last two fields are
+ * not numeric.  The text need not end with a newline. */
+int64_t kdejs_tsv_data_offset(const char *text, int64_t bytes, int skip_rows) {
+    if (!text || bytes <= 0) return 0;
+    const char *p = text, *end = text + bytes;
+    int to_skip = std::max(skip_rows, 0);
+    bool probe_header = skip_rows < 0;
+    while (p < end && (to_skip > 0 || probe_header)) {
+        const char *nl = (const char *)std::memchr(p, '\n', (size_t)(end - p));
+        if (!nl) nl = end;
+        if (is_data_line(p, nl)) {
+            if (probe_header) {
+                double x, y;
+                if (last_two(p, nl, x, y)) break;
+                probe_header = false;
+            } else --to_skip;
+        }
+        p = nl < end ? nl + 1 : end;
+    }
+    return (int64_t)(p - text);
+}
+
+/* Reads n files into slots of `slot_bytes` bytes each (dst + i * slot_bytes), `threads` files at a time: plain
+ * read(2) into the caller's (page-locked) arena, no parsing.  out_bytes[i] = bytes read, or -(size of the file) when
+ * it does not fit its slot (nothing is read then), or -1 when the file cannot be opened. */
+int kdejs_files_read(const char *const *paths, int n, char *dst, int64_t slot_bytes, int64_t *out_bytes, int threads) {
+    if (n < 0 || (n > 0 && (!paths || !dst || !out_bytes)) || slot_bytes <= 0) { g_io_err = "bad argument"; return KDEJS_ERR_ARG; }
+    const int nt = std::max(1, std::min(threads > 0 ? threads : 8, n));
+    auto work = [&](int t) {
+        for (int i = t; i < n; i += nt) {
+            out_bytes[i] = -1;
+            FILE *f = std::fopen(paths[i], "rb");
+            if (!f) continue;
+            std::setvbuf(f, nullptr, _IONBF, 0);
+            std::fseek(f, 0, SEEK_END);
+            const long sz = std::ftell(f);
+            std::fseek(f, 0, SEEK_SET);
+            if (sz > slot_bytes) out_bytes[i] = -(int64_t)sz;
+            else out_bytes[i] = sz > 0 ? (int64_t)std::fread(dst + (size_t)i * (size_t)slot_bytes, 1, (size_t)sz, f) : 0;
+            std::fclose(f);
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    return KDEJS_OK;
+}
+
 void kdejs_tsv_free(double *pts, int pinned) {
     if (!pts) return;
     if (pinned) kdejs_host_free(pts);

@@ -189,4 +189,42 @@ k_tsv_parse(const __grid_constant__ TsvWave wv, int chunks_max, const uint32_t *
     if (flags) atomicOr(&status[blockIdx.y], flags);
 }
 
+// grid (files), 256 threads: (min, max) of both columns of a parsed table, as np.min / np.max give them (NaN when the
+// column holds one) -- the bounds scripts/distance_to_gridsearch.py:112-125 tests before it keeps a table as best.
+__global__ void __launch_bounds__(256)
+k_tsv_bounds(const __grid_constant__ TsvWave wv, double *__restrict__ bounds /*[file][4]*/) {
+    const TsvFile &f = wv.f[blockIdx.x];
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    double lo0 = inf, hi0 = -inf, lo1 = inf, hi1 = -inf;
+    bool nan0 = false, nan1 = false;
+    for (int64_t i = threadIdx.x; i < f.cap_rows; i += blockDim.x) {
+        const double2 v = f.out[i];
+        nan0 |= (v.x != v.x);
+        nan1 |= (v.y != v.y);
+        lo0 = fmin(lo0, v.x); hi0 = fmax(hi0, v.x);         // fmin / fmax ignore NaN
+        lo1 = fmin(lo1, v.y); hi1 = fmax(hi1, v.y);
+    }
+    __shared__ double s_v[4][256];
+    __shared__ int s_nan[2];
+    if (threadIdx.x < 2) s_nan[threadIdx.x] = 0;
+    __syncthreads();
+    if (nan0) s_nan[0] = 1;
+    if (nan1) s_nan[1] = 1;
+    s_v[0][threadIdx.x] = lo0; s_v[1][threadIdx.x] = hi0; s_v[2][threadIdx.x] = lo1; s_v[3][threadIdx.x] = hi1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s_v[0][threadIdx.x] = fmin(s_v[0][threadIdx.x], s_v[0][threadIdx.x + o]);
+            s_v[1][threadIdx.x] = fmax(s_v[1][threadIdx.x], s_v[1][threadIdx.x + o]);
+            s_v[2][threadIdx.x] = fmin(s_v[2][threadIdx.x], s_v[2][threadIdx.x + o]);
+            s_v[3][threadIdx.x] = fmax(s_v[3][threadIdx.x], s_v[3][threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) {
+        const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+        bounds[(size_t)blockIdx.x * 4 + threadIdx.x] = s_nan[threadIdx.x >> 1] ? nanv : s_v[threadIdx.x][0];
+    }
+}
+
 }  // namespace kdejs
