@@ -692,7 +692,9 @@ def run_ingest(pk, target, sims, gamma, eps, n_files=128, n_distinct=8):
         for k in range(n_files):
             q = os.path.join(d, f"sim{k}.tsv")
             if k < n_distinct:
-                write(q, sims[k])
+                a = sims[k].copy()
+                a[:, 0] = np.round(a[:, 0], 6)      # core distances as the simulator prints them (the example target: 0.000917)
+                write(q, a)
             else:
                 shutil.copy(files[k % n_distinct], q)
             files.append(q)
@@ -709,9 +711,9 @@ def run_ingest(pk, target, sims, gamma, eps, n_files=128, n_distinct=8):
                 "mb_per_table": os.path.getsize(files[0]) / 1e6, "seconds": dt, "host_cores": os.cpu_count(),
                 "api": "sweeps.gridsearch_best(ref.tsv, [sim.tsv ...]) at the reference's 100x100 grid",
                 "np_loadtxt_tables_per_s_per_core": 1.0 / t_np,
-                "note": "files (page cache) -> kdejs_tsv_load_into -> page-locked arena -> batch -> arg-min; the "
-                        "reference reads each table with np.loadtxt and evaluates it on one core "
-                        "(scripts/distance_to_gridsearch.py:48-55)"}
+                "note": "files (page cache) -> bytes into a page-locked arena (kdejs_files_read) -> H2D of the text -> "
+                        "parsed on the device (kdejs_tsv.cuh) -> batch -> arg-min; the reference reads each table with "
+                        "np.loadtxt and evaluates it on one core (scripts/distance_to_gridsearch.py:48-55)"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

@@ -279,9 +279,10 @@ const char *kdejs_io_last_error(void);
 /* ---- measurement support (bench.py, tests) ------------------------------------------- */
 /* Per-kernel CUDA-event timing on the launching stream.  which: 0 minmax, 1 scale+count,
  * 2 scan, 3 place, 4 density (the dominant kernel), 5 divergence, 6 tile classification,
- * 7 cell moments (fine grids only), 8 fp64 redo pass of KDEJS_ALGO_BINNED32, 9 summary vector.
+ * 7 cell moments (fine grids only), 8 fp64 redo pass of KDEJS_ALGO_BINNED32, 9 summary vector,
+ * 10 table text: count + scan, 11 table text: parse (+ bounds) (kdejs_discrepancy_batch_text).
  * Reading synchronises. */
-#define KDEJS_NUM_KERNELS 10
+#define KDEJS_NUM_KERNELS 12
 int kdejs_profile_enable(int device, int on);   /* 0 off, 1 every kernel, 2 the density kernel only */
 int kdejs_profile_read(int device, int which, double *ms_total, int64_t *launches);
 int kdejs_profile_reset(int device);

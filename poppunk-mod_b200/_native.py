@@ -16,7 +16,7 @@ KDEJS_TABLE_OK, KDEJS_TABLE_HOST, KDEJS_TABLE_INF = 0, 1, 2
 KERNELS = {"epanechnikov": 0, "gaussian": 1}
 ALGOS = {"binned": 0, "dense": 1, "dense64": 2, "binned32": 3}
 KERNEL_NAMES = ("minmax", "scale_count", "scan", "place", "density", "divergence", "classify", "moments",
-                "redo64", "summary")
+                "redo64", "summary", "tsv_count", "tsv_parse")
 
 _c_dp = ctypes.POINTER(ctypes.c_double)
 _c_dpp = ctypes.POINTER(ctypes.c_void_p)

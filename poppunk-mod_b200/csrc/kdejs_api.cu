@@ -1216,14 +1216,14 @@ int kdejs_tsv_parse_text(int device, const char *text, int64_t bytes, int skip_r
             wv.f[0].out = c->tsv_sims.as<double2>();
             wv.f[0].cap_rows = rows;
             k_tsv_parse<<<dim3(chunks, 1), kTsvThreads, 0, st>>>(wv, chunks, c->tsv_chunkrows[0].as<uint32_t>(),
-                                                                 c->tsv_status.as<unsigned>());
+                                                                 c->tsv_status.as<unsigned>(), nullptr);
             c->launches += 1;
             unsigned flags = 0u;
             if (cudaMemcpyAsync(out_pts, c->tsv_sims.p, (size_t)rows * 16, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaMemcpyAsync(&flags, c->tsv_status.p, sizeof flags, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
                 cudaStreamSynchronize(st) != cudaSuccess)
                 rc = fail(KDEJS_ERR_CUDA, "device table parser failed");
-            else if (flags) *out_status = KDEJS_TABLE_HOST;
+            else if (flags & kTsvBad) *out_status = KDEJS_TABLE_HOST;
         }
     } else *out_status = KDEJS_TABLE_HOST;
     release_scratch(*c, st, true);
@@ -1259,15 +1259,16 @@ int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, c
         OKR(c->tsv_chunkrows[k].ensure((size_t)W * chunks_cap * sizeof(uint32_t)));
         OKR(c->tsv_rows[k].ensure(W * sizeof(int64_t)));
     }
-    OKR(c->tsv_status.ensure((size_t)B * sizeof(unsigned) + 256 + (size_t)B * 4 * sizeof(double)));
-    double *d_bounds = reinterpret_cast<double *>(c->tsv_status.as<char>() + ((size_t)B * sizeof(unsigned) + 255) / 256 * 256);
+    const size_t keys_off = ((size_t)B * sizeof(unsigned) + 255) / 256 * 256;
+    OKR(c->tsv_status.ensure(keys_off + (size_t)B * 4 * sizeof(unsigned long long)));
+    unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(c->tsv_status.as<char>() + keys_off);
     if (!c->h_tsv_rows) CU(cudaMallocHost(&c->h_tsv_rows, 2 * kMaxTsvFiles * sizeof(int64_t)));
     OKR(c->pool_raw.ensure((size_t)n_obs * 16));
     OKR(c->js_out.ensure(sizeof(double) * (size_t)B));
     OKR(c->status_out.ensure(sizeof(int32_t) * (size_t)B));
     OKR(ensure_host_results(*c, (size_t)B));
     OKR(h2d_ranges(device, {Stager::Range{c->pool_raw.p, obs, (size_t)n_obs * 16}}, c->s_compute));
-    CU(cudaMemsetAsync(c->tsv_status.p, 0, (size_t)B * sizeof(unsigned), c->s_compute));
+    CU(cudaMemsetAsync(c->tsv_status.p, 0, keys_off + (size_t)B * 4 * sizeof(unsigned long long), c->s_compute));
     std::vector<int64_t> begin(B);
     for (int i = 0; i < B; ++i) begin[i] = kdejs_tsv_data_offset(texts[i], text_bytes[i], skip_rows);
     const int n_waves = (B + W - 1) / W;
@@ -1295,9 +1296,12 @@ int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, c
             chunks = std::max<int>(chunks, (int)((text_bytes[i] - begin[i] / kTsvChunk * kTsvChunk + kTsvChunk - 1) / kTsvChunk));
         }
         wave_chunks[k] = chunks;
-        k_tsv_count<<<dim3(chunks, nf), kTsvThreads, 0, c->s_copy>>>(wv, chunks, c->tsv_chunkrows[buf].as<uint32_t>());
-        k_tsv_scan<<<nf, 1024, 0, c->s_copy>>>(chunks, c->tsv_chunkrows[buf].as<uint32_t>(), c->tsv_rows[buf].as<int64_t>());
-        c->launches += 2;
+        {
+            KTimer t(*c, 10, c->s_copy);
+            k_tsv_count<<<dim3(chunks, nf), kTsvThreads, 0, c->s_copy>>>(wv, chunks, c->tsv_chunkrows[buf].as<uint32_t>());
+            k_tsv_scan<<<nf, 1024, 0, c->s_copy>>>(chunks, c->tsv_chunkrows[buf].as<uint32_t>(), c->tsv_rows[buf].as<int64_t>());
+        }
+        c->launches += 1;
         CU(cudaMemcpyAsync(c->h_tsv_rows + (size_t)buf * kMaxTsvFiles, c->tsv_rows[buf].p, (size_t)nf * sizeof(int64_t),
                            cudaMemcpyDeviceToHost, c->s_copy));
         CU(cudaEventRecord(ev_counted[k], c->s_copy));
@@ -1334,10 +1338,12 @@ int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, c
                 item_of_slot.push_back(i0 + j);
             }
         }
-        k_tsv_parse<<<dim3(wave_chunks[k], nf), kTsvThreads, 0, c->s_compute>>>(
-            wv, wave_chunks[k], c->tsv_chunkrows[buf].as<uint32_t>(), c->tsv_status.as<unsigned>() + i0);
-        c->launches += 1;
-        if (out_bounds) { k_tsv_bounds<<<nf, 256, 0, c->s_compute>>>(wv, d_bounds + (size_t)i0 * 4); c->launches += 1; }
+        {
+            KTimer t(*c, 11, c->s_compute);
+            k_tsv_parse<<<dim3(wave_chunks[k], nf), kTsvThreads, 0, c->s_compute>>>(
+                wv, wave_chunks[k], c->tsv_chunkrows[buf].as<uint32_t>(), c->tsv_status.as<unsigned>() + i0,
+                out_bounds ? d_keys + (size_t)i0 * 4 : nullptr);
+        }
         cudaEventRecord(ev_parsed[k], c->s_compute);
         if (!ia.empty())
             rc = run_pairs_dev(*c, c->s_compute, p, pool, ia.data(), ib.data(), (int64_t)ia.size(), c->js_out.as<double>(),
@@ -1349,7 +1355,7 @@ int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, c
         if ((n_slots && (cudaMemcpyAsync(c->h_js, c->js_out.p, sizeof(double) * n_slots, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
                          cudaMemcpyAsync(c->h_status, c->status_out.p, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess)) ||
             cudaMemcpyAsync(tsv_status.data(), c->tsv_status.p, sizeof(unsigned) * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess ||
-            (out_bounds && cudaMemcpyAsync(out_bounds, d_bounds, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess))
+            (out_bounds && cudaMemcpyAsync(out_bounds, d_keys, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, c->s_compute) != cudaSuccess))
             rc = fail(KDEJS_ERR_CUDA, "D2H copy of the results failed");
     }
     cudaError_t se = cudaStreamSynchronize(c->s_compute);
@@ -1361,9 +1367,19 @@ int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, c
     if (se != cudaSuccess) return fail(KDEJS_ERR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(se));
     const double nan = std::nan("");
     for (int i = 0; i < B; ++i) { out_js[i] = nan; out_status[i] = KDEJS_TABLE_HOST; }      // until shown otherwise
+    if (out_bounds)          // keys -> doubles: (min, max) per column as np.min / np.max give them (NaN if the column holds one)
+        for (int i = 0; i < B; ++i)
+            for (int q = 0; q < 4; ++q) {
+                unsigned long long k;
+                memcpy(&k, out_bounds + 4 * (size_t)i + q, sizeof k);
+                if (!(q & 1)) k = ~k;                        // minima were folded as the maximum of ~key
+                unsigned long long bits = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+                if (tsv_status[i] & ((q < 2) ? kTsvNan0 : kTsvNan1)) bits = 0x7ff8000000000000ull;
+                memcpy(out_bounds + 4 * (size_t)i + q, &bits, sizeof bits);
+            }
     for (size_t s = 0; s < n_slots; ++s) {
         const int i = item_of_slot[s];
-        if (tsv_status[i] != 0u) continue;                  // a field the device parser does not cover: host reader
+        if (tsv_status[i] & kTsvBad) continue;              // a field the device parser does not cover: host reader
         if (c->h_status[s] == KDEJS_ERR_INF) { out_status[i] = KDEJS_TABLE_INF; continue; }
         out_js[i] = c->h_js[s];
         out_status[i] = KDEJS_TABLE_OK;

@@ -8,7 +8,8 @@
 //   q <  0:  floor(w' * 2^S / D') is a 64-bit quotient with its top bit set (w', D' = w, 5^|q| shifted to the top),
 //            and its remainder says whether anything was cut off;
 // either way the 53 leading bits, the next bit and "anything below" give round-to-nearest-even exactly, and the power
-// of two that is left is applied by ldexp (no rounding: these values are far from the subnormal range).
+// of two that is left goes into the exponent field (no rounding: these values are far from the subnormal range).
+// Numbers of up to 15 digits take Clinger's shortcut: one IEEE operation on exact operands.
 // No table of rounded powers, no ambiguity, no fallback INSIDE the range; everything outside it (more digits, big
 // exponents, inf / nan / missing-value spellings, junk) is reported as "not handled" and goes to the host reader.
 #pragma once
@@ -87,6 +88,18 @@ KDEJS_HD double scale_exact(uint64_t w, int q) {
                              95367431640625ull, 476837158203125ull, 2384185791015625ull, 11920928955078125ull,
                              59604644775390625ull, 298023223876953125ull, 1490116119384765625ull,
                              7450580596923828125ull};
+    // Short numbers (the core-distance column: three or four digits): w < 2^53 and 10^|q| <= 10^22 are exact doubles,
+    // so ONE IEEE multiplication or division is the correctly rounded result (Clinger) -- a tenth of the integer path
+    if (w < (1ull << 53) && q >= -22 && q <= 22) {
+        const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+        const double d = (double)(long long)w;
+#if defined(__CUDA_ARCH__)
+        return q < 0 ? __ddiv_rn(d, p10[-q]) : __dmul_rn(d, p10[q]);
+#else
+        return q < 0 ? d / p10[-q] : d * p10[q];
+#endif
+    }
     if (q >= 0) {
         uint64_t hi, lo;
         mul64(w, p5[q], hi, lo);                              // exact product, value = (hi:lo) * 2^q

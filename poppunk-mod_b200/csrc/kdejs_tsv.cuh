@@ -13,7 +13,8 @@
 // Three launches per wave of files, grid (chunks, files), 256 threads x 32 bytes = 8 KB of text per block:
 //   k_tsv_count   data lines starting in each chunk
 //   k_tsv_scan    exclusive scan of a file's chunk counts -> first row of each chunk, rows of the file
-//   k_tsv_parse   every line start parses its line and writes row (x, y) to its place
+//   k_tsv_parse   the chunk is staged in shared memory (16-byte loads); every line start parses its line from there and
+//                 writes row (x, y) to its place; the table's column bounds are folded with integer atomics
 // HBM-bound byte work: the text is read twice (count, parse) with 16-byte loads, the rows are written once.
 #pragma once
 #include <cstdint>
@@ -27,7 +28,8 @@ constexpr int kTsvThreads = 256;
 constexpr int kTsvSeg = 32;                                   // bytes per thread
 constexpr int kTsvChunk = kTsvThreads * kTsvSeg;              // bytes per block
 constexpr int kMaxTsvFiles = 64;
-constexpr unsigned kTsvUnhandled = 1u, kTsvOverflow = 2u;     // status bits per file
+constexpr unsigned kTsvUnhandled = 1u, kTsvOverflow = 2u, kTsvNan0 = 4u, kTsvNan1 = 8u;     // status bits per file
+constexpr unsigned kTsvBad = kTsvUnhandled | kTsvOverflow;
 
 struct TsvFile {
     const char *text;          // 16-byte aligned base of the file's bytes on the device
@@ -37,17 +39,34 @@ struct TsvFile {
 };
 struct TsvWave { TsvFile f[kMaxTsvFiles]; };
 
+// The text as a kernel sees it: a window [lo, hi) of it staged in shared memory (k_tsv_parse) with global memory behind
+// it, or global memory only (k_tsv_count: every byte is read once, staging would not pay).
+struct TsvText {
+    const char *g;             // global: g[i] for any i in the file
+    const char *s;             // s[i] valid for lo <= i < hi (shared window, biased by -lo); null: no window
+    int64_t lo, hi;
+    __device__ __forceinline__ char at(int64_t i) const { return (s && i >= lo && i < hi) ? s[i] : g[i]; }
+    __device__ __forceinline__ const char *span(int64_t b, int64_t e) const {      // contiguous [b, e)
+        return (s && b >= lo && e <= hi) ? s + b : g + b;
+    }
+    __device__ __forceinline__ uint4 load16(int64_t i) const {                     // i multiple of 16
+        return (s && i >= lo && i + 16 <= hi) ? *reinterpret_cast<const uint4 *>(s + i)
+                                              : *reinterpret_cast<const uint4 *>(g + i);
+    }
+};
+
 // a data line: first non-blank byte is neither the end of the line nor '#'
-__device__ __forceinline__ bool tsv_is_data_line(const char *t, int64_t i, int64_t end) {
-    while (i < end && (t[i] == ' ' || t[i] == '\r' || t[i] == '\t')) ++i;
-    return i < end && t[i] != '\n' && t[i] != '#';
+__device__ __forceinline__ bool tsv_is_data_line(const TsvText &t, int64_t i, int64_t end) {
+    char c = 0;
+    while (i < end && ((c = t.at(i)) == ' ' || c == '\r' || c == '\t')) ++i;
+    return i < end && c != '\n' && c != '#';
 }
 
 // bit k of the result: byte (seg0 + k) starts a data line
-__device__ __forceinline__ uint32_t tsv_line_starts(const TsvFile &f, int64_t seg0) {
+__device__ __forceinline__ uint32_t tsv_line_starts(const TsvFile &f, const TsvText &t, int64_t seg0) {
     if (seg0 >= f.end || seg0 + kTsvSeg <= f.begin) return 0u;
-    const uint4 a = *reinterpret_cast<const uint4 *>(f.text + seg0);
-    const uint4 b = *reinterpret_cast<const uint4 *>(f.text + seg0 + 16);      // the text buffer is padded to 32 bytes
+    const uint4 a = t.load16(seg0);
+    const uint4 b = t.load16(seg0 + 16);                      // the text buffer is padded to 32 bytes
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     uint32_t nl = 0u;                                         // bit k: byte k is '\n'
 #pragma unroll
@@ -57,7 +76,7 @@ __device__ __forceinline__ uint32_t tsv_line_starts(const TsvFile &f, int64_t se
         nl |= (((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u)) << (4 * k);
     }
     uint32_t starts = nl << 1;                                // a line starts after every '\n' ...
-    const bool prev_nl = (seg0 == f.begin) || (seg0 > f.begin && f.text[seg0 - 1] == '\n');
+    const bool prev_nl = (seg0 == f.begin) || (seg0 > f.begin && t.at(seg0 - 1) == '\n');
     if (prev_nl) starts |= 1u;                                // ... and at the first byte of the data region
     // only positions inside [begin, end)
     if (seg0 < f.begin) starts &= ~0u << (int)(f.begin - seg0), starts |= 1u << (int)(f.begin - seg0);
@@ -65,7 +84,7 @@ __device__ __forceinline__ uint32_t tsv_line_starts(const TsvFile &f, int64_t se
     uint32_t data = 0u;
     for (uint32_t m = starts; m; m &= m - 1u) {
         const int k = __ffs(m) - 1;
-        if (tsv_is_data_line(f.text, seg0 + k, f.end)) data |= 1u << k;
+        if (tsv_is_data_line(t, seg0 + k, f.end)) data |= 1u << k;
     }
     return data;
 }
@@ -76,7 +95,8 @@ k_tsv_count(const __grid_constant__ TsvWave wv, int chunks_max, uint32_t *__rest
     const int64_t chunk0 = (f.begin / kTsvChunk + blockIdx.x) * (int64_t)kTsvChunk;     // chunks are aligned to 8 KB
     __shared__ uint32_t s_w[kTsvThreads / 32];
     uint32_t n = 0u;
-    if (chunk0 < f.end) n = __popc(tsv_line_starts(f, chunk0 + (int64_t)threadIdx.x * kTsvSeg));
+    const TsvText t{f.text, nullptr, 0, 0};
+    if (chunk0 < f.end) n = __popc(tsv_line_starts(f, t, chunk0 + (int64_t)threadIdx.x * kTsvSeg));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = n;
@@ -130,11 +150,12 @@ k_tsv_scan(int chunks_max, uint32_t *__restrict__ chunkrows, int64_t *__restrict
 }
 
 // one line [b, e): its last two tab-separated fields
-__device__ __forceinline__ bool tsv_parse_line(const char *t, int64_t b, int64_t e, double &x, double &y) {
+__device__ __forceinline__ bool tsv_parse_line(const TsvText &t, int64_t b, int64_t e, double &x, double &y) {
+    const char *q = t.span(b, e) - b;                         // q[i] for b <= i < e, one address space for the line
     int64_t p = e, t2 = -1, s1 = b;
     while (p > b) {
         --p;
-        if (t[p] == '\t') {
+        if (q[p] == '\t') {
             if (t2 < 0) t2 = p;
             else { s1 = p + 1; break; }
         }
@@ -144,87 +165,85 @@ __device__ __forceinline__ bool tsv_parse_line(const char *t, int64_t b, int64_t
     double v[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-        while (fb[k] < fe[k] && (t[fb[k]] == ' ' || t[fb[k]] == '\r')) ++fb[k];
-        while (fe[k] > fb[k] && (t[fe[k] - 1] == ' ' || t[fe[k] - 1] == '\r')) --fe[k];
+        while (fb[k] < fe[k] && (q[fb[k]] == ' ' || q[fb[k]] == '\r')) ++fb[k];
+        while (fe[k] > fb[k] && (q[fe[k] - 1] == ' ' || q[fe[k] - 1] == '\r')) --fe[k];
         if (fb[k] >= fe[k]) v[k] = __longlong_as_double(0x7ff8000000000000ll);          // empty field: missing
-        else if (!kdejs_decimal::parse_field(t + fb[k], t + fe[k], v[k])) return false;
+        else if (!kdejs_decimal::parse_field(q + fb[k], q + fe[k], v[k])) return false;
     }
     x = v[0];
     y = v[1];
     return true;
 }
 
+// order-preserving map double -> u64 (NaN excluded by the caller): bounds are folded with integer atomicMax
+__device__ __forceinline__ unsigned long long tsv_key(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+constexpr int kTsvTail = 1024;                                // bytes staged beyond a chunk: a line that starts in the
+                                                              // chunk and ends within them is parsed from shared memory
+// bkeys[file][4]: atomicMax of ~key(min col 0), key(max col 0), ~key(min col 1), key(max col 1); zero before the call
 __global__ void __launch_bounds__(kTsvThreads)
 k_tsv_parse(const __grid_constant__ TsvWave wv, int chunks_max, const uint32_t *__restrict__ chunkrows,
-            unsigned *__restrict__ status) {
+            unsigned *__restrict__ status, unsigned long long *__restrict__ bkeys) {
     const TsvFile &f = wv.f[blockIdx.y];
     const int64_t chunk0 = (f.begin / kTsvChunk + blockIdx.x) * (int64_t)kTsvChunk;
     if (chunk0 >= f.end) return;
+    // the chunk, 16 bytes before it (the byte that decides whether its first byte starts a line) and kTsvTail after
+    __shared__ __align__(16) char s_text[16 + kTsvChunk + kTsvTail];
+    const int64_t w0 = chunk0 >= 16 ? chunk0 - 16 : 0;
+    const int64_t w1 = min(w0 + (int64_t)sizeof s_text, (f.end + 15) / 16 * 16);         // the buffer is padded past `end`
+    for (int64_t i = w0 + (int64_t)threadIdx.x * 16; i < w1; i += kTsvThreads * 16)
+        *reinterpret_cast<uint4 *>(s_text + (i - w0)) = *reinterpret_cast<const uint4 *>(f.text + i);
+    __syncthreads();
+    const TsvText t{f.text, s_text - w0, w0, w1};
     const int64_t seg0 = chunk0 + (int64_t)threadIdx.x * kTsvSeg;
-    const uint32_t starts = tsv_line_starts(f, seg0);
+    const uint32_t starts = tsv_line_starts(f, t, seg0);
     const uint32_t n = __popc(starts);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t inc = n;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
     }
     __shared__ uint32_t s_w[kTsvThreads / 32];
+    __shared__ unsigned long long s_k[4][kTsvThreads / 32];
     if (lane == 31) s_w[w] = inc;
     __syncthreads();
     uint32_t before = 0u;
     for (int k = 0; k < w; ++k) before += s_w[k];
     int64_t row = (int64_t)chunkrows[(size_t)blockIdx.y * chunks_max + blockIdx.x] + before + inc - n;
     unsigned flags = 0u;
+    unsigned long long k4[4] = {0ull, 0ull, 0ull, 0ull};
     for (uint32_t m = starts; m; m &= m - 1u, ++row) {
         const int64_t b = seg0 + __ffs(m) - 1;
         int64_t e = b;
-        while (e < f.end && f.text[e] != '\n') ++e;
+        while (e < f.end && t.at(e) != '\n') ++e;
         double x, y;
-        if (!tsv_parse_line(f.text, b, e, x, y)) { flags |= kTsvUnhandled; x = y = 0.0; }
+        if (!tsv_parse_line(t, b, e, x, y)) { flags |= kTsvUnhandled; x = y = 0.0; }
         if (row < f.cap_rows) f.out[row] = make_double2(x, y);
         else flags |= kTsvOverflow;
+        if (x != x) flags |= kTsvNan0; else { const unsigned long long k = tsv_key(x); k4[0] = max(k4[0], ~k); k4[1] = max(k4[1], k); }
+        if (y != y) flags |= kTsvNan1; else { const unsigned long long k = tsv_key(y); k4[2] = max(k4[2], ~k); k4[3] = max(k4[3], k); }
     }
-    if (flags) atomicOr(&status[blockIdx.y], flags);
-}
-
-// grid (files), 256 threads: (min, max) of both columns of a parsed table, as np.min / np.max give them (NaN when the
-// column holds one) -- the bounds scripts/distance_to_gridsearch.py:112-125 tests before it keeps a table as best.
-__global__ void __launch_bounds__(256)
-k_tsv_bounds(const __grid_constant__ TsvWave wv, double *__restrict__ bounds /*[file][4]*/) {
-    const TsvFile &f = wv.f[blockIdx.x];
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    double lo0 = inf, hi0 = -inf, lo1 = inf, hi1 = -inf;
-    bool nan0 = false, nan1 = false;
-    for (int64_t i = threadIdx.x; i < f.cap_rows; i += blockDim.x) {
-        const double2 v = f.out[i];
-        nan0 |= (v.x != v.x);
-        nan1 |= (v.y != v.y);
-        lo0 = fmin(lo0, v.x); hi0 = fmax(hi0, v.x);         // fmin / fmax ignore NaN
-        lo1 = fmin(lo1, v.y); hi1 = fmax(hi1, v.y);
-    }
-    __shared__ double s_v[4][256];
-    __shared__ int s_nan[2];
-    if (threadIdx.x < 2) s_nan[threadIdx.x] = 0;
-    __syncthreads();
-    if (nan0) s_nan[0] = 1;
-    if (nan1) s_nan[1] = 1;
-    s_v[0][threadIdx.x] = lo0; s_v[1][threadIdx.x] = hi0; s_v[2][threadIdx.x] = lo1; s_v[3][threadIdx.x] = hi1;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-            s_v[0][threadIdx.x] = fmin(s_v[0][threadIdx.x], s_v[0][threadIdx.x + o]);
-            s_v[1][threadIdx.x] = fmax(s_v[1][threadIdx.x], s_v[1][threadIdx.x + o]);
-            s_v[2][threadIdx.x] = fmin(s_v[2][threadIdx.x], s_v[2][threadIdx.x + o]);
-            s_v[3][threadIdx.x] = fmax(s_v[3][threadIdx.x], s_v[3][threadIdx.x + o]);
+    if (bkeys) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) k4[c] = max(k4[c], __shfl_xor_sync(0xffffffffu, k4[c], o));
+            if (lane == 0) s_k[c][w] = k4[c];
         }
         __syncthreads();
+        if (threadIdx.x < 4) {
+            unsigned long long k = 0ull;
+#pragma unroll
+            for (int j = 0; j < kTsvThreads / 32; ++j) k = max(k, s_k[threadIdx.x][j]);
+            if (k) atomicMax(&bkeys[(size_t)blockIdx.y * 4 + threadIdx.x], k);
+        }
     }
-    if (threadIdx.x < 4) {
-        const double nanv = __longlong_as_double(0x7ff8000000000000ll);
-        bounds[(size_t)blockIdx.x * 4 + threadIdx.x] = s_nan[threadIdx.x >> 1] ? nanv : s_v[threadIdx.x][0];
-    }
+    if (flags) atomicOr(&status[blockIdx.y], flags);
 }
 
 }  // namespace kdejs

@@ -86,16 +86,83 @@ _SMALL_GAMMA_NOTE = (
     "(INTEGRATION.md section 5: arg-min differed, 5 % of pairs reordered on 200 simulations at gamma=1e-12)")
 
 
+_ARENAS = {}       # (kind, slots, capacity) -> arenas kept between calls: page-locked allocations of 100+ MB take ~0.1 s
+
+
+def _cached_arenas(kind, count, slots, capacity, make):
+    key = (kind, slots)
+    have = _ARENAS.get(key)
+    if have is None or have[0] < capacity or len(have[1]) < count:
+        if have is not None:
+            for a in have[1]:
+                a.close()
+        _ARENAS[key] = have = (capacity, [make(slots, capacity) for _ in range(count)])
+    return have[1][:count]
+
+
+def _accept(best, name, d, b, core_min_bounds, core_max_bounds, acc_min_bounds, acc_max_bounds):
+    """distance_to_gridsearch.py:112-125: a smaller distance replaces the best one if its table's bounds pass."""
+    if not d < best[1]:
+        return best
+    ok = True
+    if core_min_bounds is not None and core_max_bounds is not None:
+        ok &= _in(b[0], core_min_bounds) and _in(b[1], core_max_bounds)
+    if acc_min_bounds is not None and acc_max_bounds is not None:
+        ok &= _in(b[2], acc_min_bounds) and _in(b[3], acc_max_bounds)
+    return (name, d, tuple(b)) if ok else best
+
+
+def _gridsearch_device_parse(ref_arr, files, gamma, eps, log, bounds_kw, chunk, io_threads, device, resolution):
+    """The sweep with NO parser on the host: the bytes of the next chunk of files are read into a page-locked arena
+    (kdejs_files_read) while the GPU uploads, parses and evaluates the current one (kdejs_discrepancy_batch_text).
+    Tables the device parser does not cover (missing-value spellings, inf / nan, more than 19 digits, files larger
+    than a slot) go through the host reader."""
+    best = (None, 1.0)
+    distances = np.empty(len(files))
+    chunks = [files[i:i + chunk] for i in range(0, len(files), chunk)]
+    slot_bytes = int(os.path.getsize(files[0]) * 1.5) + 4096
+    arenas = _cached_arenas("text", min(2, len(chunks)), chunk, slot_bytes, lambda n, cap: nat.TextArena(n, cap))
+    slot_bytes = arenas[0].array.shape[1]
+    with ThreadPoolExecutor(max_workers=1) as prefetch:
+        read = lambda ci: arenas[ci % 2].read(chunks[ci], threads=io_threads).copy()
+        pending = prefetch.submit(read, 0)
+        pos = 0
+        for ci, names in enumerate(chunks):
+            nbytes = pending.result()
+            pending = prefetch.submit(read, ci + 1) if ci + 1 < len(chunks) else None
+            js, rows, status, bnd = kd.KDE_JS_divergence_batch_text(
+                ref_arr, arenas[ci % 2].array, gamma, eps, log, nbytes=np.maximum(nbytes, 0), skip_rows=0,
+                resolution=resolution, device=device, bounds=True)
+            redo = [k for k in range(len(names)) if nbytes[k] < 0 or status[k] == nat.KDEJS_TABLE_HOST]
+            if redo:        # the host reader decides (and reports malformed rows the way it always did)
+                tables = _load_many([names[k] for k in redo], read_file, io_threads)
+                js[redo] = kd.KDE_JS_divergence_batch(ref_arr, [t.array for t in tables], gamma, eps, log,
+                                                      devices=device, resolution=resolution)
+                for k, t in zip(redo, tables):
+                    bnd[k] = _bounds(t.array)
+            inf = [names[k] for k in range(len(names)) if status[k] == nat.KDEJS_TABLE_INF and k not in redo]
+            if inf:
+                raise ValueError(f"Input X contains infinity or a value too large for dtype('float64'). ({inf[0]})")
+            for name, d, b in zip(names, js, bnd):
+                distances[pos] = d
+                pos += 1
+                best = _accept(best, name, d, b, **bounds_kw)
+    return best, distances
+
+
 def gridsearch_best(ref, files, gamma=1e-12, eps=1e-12, log=True, *, core_min_bounds=None, core_max_bounds=None,
                     acc_min_bounds=None, acc_max_bounds=None, chunk=64, io_threads=None, devices=None,
-                    resolution=100):
+                    resolution=100, parse=None):
     """One reference against many simulations.  Defaults are the reference's call
     KDE_JS_divergence(df1, df2, 1e-12, log=True) (distance_to_gridsearch.py:50).  Bounds are absolute
     [lo, hi] pairs (the script multiplies its fractions by the reference's column maxima, :89-99).
-    Returns (best, distances) with best = (file, distance, bounds) or (None, 1.0), distances in file order."""
+    Returns (best, distances) with best = (file, distance, bounds) or (None, 1.0), distances in file order.
+
+    parse: "device" -- the files' bytes go to the GPU and are parsed there (default on one device); "host" -- the
+    library's host reader parses them into page-locked arenas (several devices, or KDEJS_PARSE=host)."""
     ref_arr = ref if isinstance(ref, np.ndarray) else read_file(ref).array
     files = [str(f) for f in files]
-    if io_threads is None:          # one parser thread per file; measured on a 16-core host: 560 tables/s with 8, 1170 with 16
+    if io_threads is None:          # one reader / parser thread per file; measured on a 16-core host: 560 tables/s with 8, 1170 with 16
         io_threads = max(1, min(16, os.cpu_count() or 1))
     if gamma < 0.05:
         warnings.warn(_SMALL_GAMMA_NOTE, stacklevel=2)
@@ -103,6 +170,18 @@ def gridsearch_best(ref, files, gamma=1e-12, eps=1e-12, log=True, *, core_min_bo
     distances = np.empty(len(files))
     if not files:
         return best, distances
+    one_device = devices is None or isinstance(devices, int) or len(list(devices)) == 1
+    if parse is None:
+        parse = os.environ.get("KDEJS_PARSE", "device" if one_device else "host")
+    if parse not in ("device", "host"):
+        raise ValueError("parse must be 'device' or 'host'")
+    bounds_kw = dict(core_min_bounds=core_min_bounds, core_max_bounds=core_max_bounds, acc_min_bounds=acc_min_bounds,
+                     acc_max_bounds=acc_max_bounds)
+    if parse == "device":
+        if not one_device:
+            raise ValueError("parse='device' runs on one device; use parse='host' with several")
+        dev = devices if isinstance(devices, int) else (list(devices)[0] if devices is not None else None)
+        return _gridsearch_device_parse(ref_arr, files, gamma, eps, log, bounds_kw, chunk, io_threads, dev, resolution)
     chunks = [files[i:i + chunk] for i in range(0, len(files), chunk)]
     # Two page-locked arenas of `chunk` slots: the files of chunk k+1 are parsed straight into their slots (one
     # parser thread per file, io_threads files at a time) while the GPU works on chunk k; nothing is allocated per
@@ -110,32 +189,21 @@ def gridsearch_best(ref, files, gamma=1e-12, eps=1e-12, log=True, *, core_min_bo
     first = read_file(files[0], pinned=False)
     cap = int(first.rows * 1.5) + 1024
     first.close()
-    arenas = [nat.TableArena(min(chunk, len(files)), cap) for _ in range(min(2, len(chunks)))]
-    try:
-        with ThreadPoolExecutor(max_workers=1) as prefetch, ThreadPoolExecutor(max_workers=max(1, io_threads)) as io:
-            load = lambda ci: arenas[ci % 2].load(chunks[ci], skip_rows=0, executor=io, overflow="alloc")   # np.loadtxt, :49
-            pending = prefetch.submit(load, 0)
-            pos = 0
-            for ci, names in enumerate(chunks):
-                tables = pending.result()
-                # chunk ci+1 is parsed into the OTHER arena (chunk ci-1's, whose batch has returned) during this batch
-                pending = prefetch.submit(load, ci + 1) if ci + 1 < len(chunks) else None
-                js = kd.KDE_JS_divergence_batch(ref_arr, tables, gamma, eps, log, devices=devices, resolution=resolution)
-                for name, t, d in zip(names, tables, js):
-                    distances[pos] = d
-                    pos += 1
-                    if d < best[1]:                                     # :112-125
-                        b = _bounds(t)
-                        ok = True
-                        if core_min_bounds is not None and core_max_bounds is not None:
-                            ok &= _in(b[0], core_min_bounds) and _in(b[1], core_max_bounds)
-                        if acc_min_bounds is not None and acc_max_bounds is not None:
-                            ok &= _in(b[2], acc_min_bounds) and _in(b[3], acc_max_bounds)
-                        if ok:
-                            best = (name, d, b)
-    finally:
-        for a in arenas:
-            a.close()
+    arenas = _cached_arenas("rows", min(2, len(chunks)), chunk, cap, lambda n, c: nat.TableArena(n, c))
+    with ThreadPoolExecutor(max_workers=1) as prefetch, ThreadPoolExecutor(max_workers=max(1, io_threads)) as io:
+        load = lambda ci: arenas[ci % 2].load(chunks[ci], skip_rows=0, executor=io, overflow="alloc")   # np.loadtxt, :49
+        pending = prefetch.submit(load, 0)
+        pos = 0
+        for ci, names in enumerate(chunks):
+            tables = pending.result()
+            # chunk ci+1 is parsed into the OTHER arena (chunk ci-1's, whose batch has returned) during this batch
+            pending = prefetch.submit(load, ci + 1) if ci + 1 < len(chunks) else None
+            js = kd.KDE_JS_divergence_batch(ref_arr, tables, gamma, eps, log, devices=devices, resolution=resolution)
+            for name, t, d in zip(names, tables, js):
+                distances[pos] = d
+                pos += 1
+                if d < best[1]:                                     # :112-125
+                    best = _accept(best, name, d, _bounds(t), **bounds_kw)
     return best, distances
 
 

@@ -192,3 +192,42 @@ def test_batch_text_equals_the_host_path(pk, tmp_path):
     assert small.read(paths[:1] + [str(tmp_path / "missing.tsv")]).tolist() == [-len(texts[0]), -1]
     arena.close()
     small.close()
+
+
+def test_gridsearch_device_and_host_parsing_agree(pk, tmp_path):
+    """sweeps.gridsearch_best with the files' bytes parsed on the device against the host-parser pipeline: the same
+    distances bit for bit, the same best file and bounds -- including a table only the host reader covers (NA), one
+    too long for its slot, varying lengths, and the bounds filter of distance_to_gridsearch.py:112-125."""
+    from oracle import workloads as wl
+    from poppunk_mod_b200 import sweeps
+
+    ref = wl.synthetic_target(15000)
+    sims = [wl.sim_batch_member(s, n=4000 + 503 * (s % 7)) for s in range(23)]
+    sims[13] = wl.sim_batch_member(13, n=30000)                                # far longer than 1.5 x the first table
+    texts = [_table_text(s) for s in sims]
+    texts[4] = texts[4].replace(b"\n", b"\nNA\t0.5\n", 1)
+    sims[4] = np.vstack([sims[4][:1], [[np.nan, 0.5]], sims[4][1:]])
+    paths = []
+    for k, t in enumerate(texts):
+        q = tmp_path / f"sim{k}.tsv"
+        q.write_bytes(t)
+        paths.append(str(q))
+    refp = tmp_path / "ref.tsv"
+    refp.write_bytes(_table_text(ref))
+    kw = dict(gamma=0.25, eps=0.0, log=False, chunk=8, io_threads=4)
+    best_d, dist_d = sweeps.gridsearch_best(str(refp), paths, parse="device", **kw)
+    best_h, dist_h = sweeps.gridsearch_best(str(refp), paths, parse="host", **kw)
+    np.testing.assert_array_equal(dist_d, dist_h)
+    assert best_d[0] == best_h[0] and best_d[1] == best_h[1]
+    np.testing.assert_array_equal(np.array(best_d[2]), np.array(best_h[2]))
+    want = pk.KDE_JS_divergence_batch(ref, sims, gamma=0.25, eps=0.0)
+    np.testing.assert_array_equal(dist_d, want)
+    # a bounds filter that excludes the overall best: both pipelines keep the same runner-up
+    order = np.argsort(want)
+    b0 = sims[order[0]]
+    lo = float(np.nanmax(b0[:, 1])) * 1.0000001
+    kwb = dict(acc_min_bounds=[0.0, 1.0], acc_max_bounds=[lo, 10.0]) if all(
+        np.nanmax(s[:, 1]) != np.nanmax(b0[:, 1]) for k, s in enumerate(sims) if k != order[0]) else {}
+    bd, _ = sweeps.gridsearch_best(str(refp), paths, parse="device", **kw, **kwb)
+    bh, _ = sweeps.gridsearch_best(str(refp), paths, parse="host", **kw, **kwb)
+    assert bd[0] == bh[0] and bd[1] == bh[1]

@@ -21,7 +21,9 @@ try:
     for s in range(32):
         q = os.path.join(d, f"sim{s}.tsv")
         with open(q, "w") as f:
-            f.writelines(f"{x!r}\t{y!r}\n" for x, y in wl.sim_batch_member(s).tolist())
+            a = wl.sim_batch_member(s)
+            a[:, 0] = np.round(a[:, 0], 6)          # core distances as the simulator prints them (the example target: 0.000917)
+            f.writelines(f"{x!r}\t{y!r}\n" for x, y in a.tolist())
         distinct.append(q)
     files = []
     for k in range(n_files):
@@ -60,13 +62,46 @@ try:
                     t.close()
         dt = time.perf_counter() - t0
         print(f"one {'page-locked' if pinned else 'ordinary'} allocation per table, 16 files at a time: {n_files / dt:.0f} tables/s", flush=True)
-    for io, chunk in ((8, 64), (16, 64), (16, 128), (16, 256), (32, 128)):
-        sweeps.gridsearch_best(ref, files[:64], gamma=0.25, eps=0.0, log=False, io_threads=io)      # warm-up
+    text = nat.TextArena(64, int(os.path.getsize(files[0]) * 1.5))
+    for w in (2, 4, 8, 16):
         t0 = time.perf_counter()
-        best, dist = sweeps.gridsearch_best(ref, files, gamma=0.25, eps=0.0, log=False, io_threads=io, chunk=chunk)
+        for c in range(0, n_files, 64):
+            text.read(files[c:c + 64], threads=w)
         dt = time.perf_counter() - t0
-        print(f"sweeps.gridsearch_best, files -> arg-min, io_threads={io}, {chunk} files per batch: {n_files / dt:.0f} "
-              f"tables/s ({dt:.2f} s; best {os.path.basename(best[0])} d={best[1]:.6f})", flush=True)
+        print(f"bytes into a page-locked arena (no parsing), {w} files at a time: {n_files / dt:.0f} tables/s ({mb / dt / 1e3:.2f} GB/s)", flush=True)
+    nb = text.read(files[:64], threads=8).copy()
+    for _ in range(2):
+        t0 = time.perf_counter()
+        js, rows, status = pk.KDE_JS_divergence_batch_text(T, text.array, 0.25, 0.0, nbytes=nb, skip_rows=0)
+        dt = time.perf_counter() - t0
+    print(f"kdejs_discrepancy_batch_text, 64 tables already in page-locked memory (upload + device parse + evaluate, "
+          f"100x100 grid): {64 / dt:.0f} tables/s ({dt * 1e3:.1f} ms)", flush=True)
+    assert (status == 0).all()
+    import ctypes
+    L = nat.lib()
+    nat.check(L.kdejs_profile_reset(0)); nat.check(L.kdejs_profile_enable(0, 1))
+    for _ in range(3):
+        pk.KDE_JS_divergence_batch_text(T, text.array, 0.25, 0.0, nbytes=nb, skip_rows=0, bounds=True)
+    pm, pn = ctypes.c_double(), ctypes.c_int64()
+    tb = 3 * float(nb.sum())
+    for which, name, traffic in ((10, "k_tsv_count + k_tsv_scan", tb), (11, "k_tsv_parse + k_tsv_bounds", tb + 3 * 2 * 16.0 * float(rows.sum()))):
+        nat.check(L.kdejs_profile_read(0, which, ctypes.byref(pm), ctypes.byref(pn)))
+        print(f"   {name}: {1e3 * pm.value / 3 / 64:.1f} us per table, {traffic / (pm.value * 1e-3) / 1e9:.0f} GB/s of algorithmic "
+              f"traffic (text once per kernel; rows written and read once)", flush=True)
+    nat.check(L.kdejs_profile_enable(0, 0))
+    text.close()
+    ref_dist = None
+    for parse, io, chunk in (("host", 16, 64), ("device", 4, 64), ("device", 8, 64), ("device", 16, 64), ("device", 8, 32)):
+        kw = dict(gamma=0.25, eps=0.0, log=False, io_threads=io, chunk=chunk, parse=parse)
+        sweeps.gridsearch_best(ref, files[:2 * chunk], **kw)      # warm-up (arenas are kept between calls)
+        t0 = time.perf_counter()
+        best, dist = sweeps.gridsearch_best(ref, files, **kw)
+        dt = time.perf_counter() - t0
+        print(f"sweeps.gridsearch_best, files -> arg-min, parse on the {parse}, io_threads={io}, {chunk} files per batch: "
+              f"{n_files / dt:.0f} tables/s ({dt:.2f} s; best {os.path.basename(best[0])} d={best[1]:.6f})", flush=True)
+        if ref_dist is None:
+            ref_dist = dist
+        assert np.array_equal(dist, ref_dist)
     one = pk.KDE_JS_divergence(T, a, 0.25, 0.0)
     assert dist[0] == one, (dist[0], one)
 finally:

@@ -65,7 +65,7 @@ if os.path.exists(f"{G}/prof_c5_{tag}.ncu-rep"):
          "-s 4 -c 4 over tools/c5_probe.py\n# fine-grid path: 3 M + 3 M points, R = 1024, 128 x 128 cells, moment cells\n")
 for name in (f"bench_{tag}_n1.json", f"bench_{tag}_n1_binned.json", f"bench_{tag}_reference.json", f"fp32_probe_{tag}.log",
              f"band_sort_probe_{tag}.log", f"match_probe_{tag}.log", f"h2d_probe_{tag}.jsonl", f"wave_probe_{tag}.log",
-             f"tail_probe_{tag}.log"):
+             f"tail_probe_{tag}.log", f"ingest_probe_{tag}.log"):
     if os.path.exists(f"{G}/{name}"):
         shutil.copy(f"{G}/{name}", f"profiles/{name}")
 d = json.load(open(f"{G}/bench_{tag}_n1.json"))
