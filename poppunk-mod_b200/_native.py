@@ -427,7 +427,7 @@ def tsv_parse_text(text, skip_rows=-1, device=0):
     status) with status KDEJS_TABLE_OK or KDEJS_TABLE_HOST (something only the host reader covers: ignore the rows)."""
     buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
     n, st = ctypes.c_int64(), ctypes.c_int32()
-    out = np.empty((max(1, buf.shape[0] // 4), 2))
+    out = np.empty((buf.shape[0] // 2 + 1, 2))          # a data line is at least one byte and a newline
     check(lib().kdejs_tsv_parse_text(int(device), buf.ctypes.data, buf.shape[0], int(skip_rows), out.ctypes.data,
                                      out.shape[0], ctypes.byref(n), ctypes.byref(st)))
     return out[:n.value].copy(), st.value

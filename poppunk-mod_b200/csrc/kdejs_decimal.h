@@ -23,6 +23,37 @@
 
 namespace kdejs_decimal {
 
+// 5^0 .. 5^27 and 10^0 .. 10^22 (exact).  On the device they live in constant memory: as local arrays they were
+// rebuilt on the stack by every call (ncu: 15 M local stores and 770 MB of DRAM writes per wave of 16 tables).
+#define KDEJS_P5_TABLE {1ull, 5ull, 25ull, 125ull, 625ull, 3125ull, 15625ull, 78125ull, 390625ull, 1953125ull, \
+                        9765625ull, 48828125ull, 244140625ull, 1220703125ull, 6103515625ull, 30517578125ull, \
+                        152587890625ull, 762939453125ull, 3814697265625ull, 19073486328125ull, \
+                        95367431640625ull, 476837158203125ull, 2384185791015625ull, 11920928955078125ull, \
+                        59604644775390625ull, 298023223876953125ull, 1490116119384765625ull, \
+                        7450580596923828125ull}
+#define KDEJS_P10_TABLE {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, \
+                         1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22}
+static const uint64_t kP5Host[28] = KDEJS_P5_TABLE;
+static const double kP10Host[23] = KDEJS_P10_TABLE;
+#if defined(__CUDACC__)
+static __constant__ uint64_t kP5Dev[28] = KDEJS_P5_TABLE;
+static __constant__ double kP10Dev[23] = KDEJS_P10_TABLE;
+#endif
+KDEJS_HD uint64_t pow5(int k) {
+#if defined(__CUDA_ARCH__)
+    return kP5Dev[k];
+#else
+    return kP5Host[k];
+#endif
+}
+KDEJS_HD double pow10d(int k) {
+#if defined(__CUDA_ARCH__)
+    return kP10Dev[k];
+#else
+    return kP10Host[k];
+#endif
+}
+
 KDEJS_HD int clz64(uint64_t x) {
 #if defined(__CUDA_ARCH__)
     return __clzll((long long)x);
@@ -81,28 +112,19 @@ KDEJS_HD double make_double(uint64_t mant53, int exp2) {       // mant53 * 2^exp
 
 // w * 10^q, correctly rounded (nearest, ties to even).  Requires w != 0 and -27 <= q <= 27.
 KDEJS_HD double scale_exact(uint64_t w, int q) {
-    // 5^0 .. 5^27
-    const uint64_t p5[28] = {1ull, 5ull, 25ull, 125ull, 625ull, 3125ull, 15625ull, 78125ull, 390625ull, 1953125ull,
-                             9765625ull, 48828125ull, 244140625ull, 1220703125ull, 6103515625ull, 30517578125ull,
-                             152587890625ull, 762939453125ull, 3814697265625ull, 19073486328125ull,
-                             95367431640625ull, 476837158203125ull, 2384185791015625ull, 11920928955078125ull,
-                             59604644775390625ull, 298023223876953125ull, 1490116119384765625ull,
-                             7450580596923828125ull};
     // Short numbers (the core-distance column: three or four digits): w < 2^53 and 10^|q| <= 10^22 are exact doubles,
     // so ONE IEEE multiplication or division is the correctly rounded result (Clinger) -- a tenth of the integer path
     if (w < (1ull << 53) && q >= -22 && q <= 22) {
-        const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
-                                1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
         const double d = (double)(long long)w;
 #if defined(__CUDA_ARCH__)
-        return q < 0 ? __ddiv_rn(d, p10[-q]) : __dmul_rn(d, p10[q]);
+        return q < 0 ? __ddiv_rn(d, pow10d(-q)) : __dmul_rn(d, pow10d(q));
 #else
-        return q < 0 ? d / p10[-q] : d * p10[q];
+        return q < 0 ? d / pow10d(-q) : d * pow10d(q);
 #endif
     }
     if (q >= 0) {
         uint64_t hi, lo;
-        mul64(w, p5[q], hi, lo);                              // exact product, value = (hi:lo) * 2^q
+        mul64(w, pow5(q), hi, lo);                              // exact product, value = (hi:lo) * 2^q
         // the 64 leading bits of the product and whether anything lies below them
         uint64_t top;
         bool below;
@@ -124,8 +146,9 @@ KDEJS_HD double scale_exact(uint64_t w, int q) {
         return make_double(m, shift + 11 + q);
     }
     const int k = -q;
-    const int cw = clz64(w), cd = clz64(p5[k]);
-    const uint64_t wn = w << cw, dn = p5[k] << cd;
+    const uint64_t d5 = pow5(k);
+    const int cw = clz64(w), cd = clz64(d5);
+    const uint64_t wn = w << cw, dn = d5 << cd;
     uint64_t nh, nl;
     int S;
     if (wn >= dn) { nh = wn >> 1; nl = (wn & 1) << 63; S = 63; }

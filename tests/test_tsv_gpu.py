@@ -231,3 +231,20 @@ def test_gridsearch_device_and_host_parsing_agree(pk, tmp_path):
     bd, _ = sweeps.gridsearch_best(str(refp), paths, parse="device", **kw, **kwb)
     bh, _ = sweeps.gridsearch_best(str(refp), paths, parse="host", **kw, **kwb)
     assert bd[0] == bh[0] and bd[1] == bh[1]
+
+
+def test_degenerate_tables_do_not_break_the_device_parser(pk):
+    """Thousands of two-byte lines in one 8 KB chunk (the most line starts a chunk can hold), lines much longer than the
+    window staged in shared memory, a table that is all tabs: flagged or parsed like the host reader, never out of bounds."""
+    nat = pk._native
+    _, st = nat.tsv_parse_text(b"x\n" * 20000, skip_rows=0)                    # rows without two fields
+    assert st == nat.KDEJS_TABLE_HOST
+    long_id = "L" * 5000                                                        # lines of 5 KB: across chunks and windows
+    text = "".join(f"{long_id}\tid\t{k * 0.5!r}\t{k * 0.25!r}\n" for k in range(300)).encode()
+    got, st = nat.tsv_parse_text(text, skip_rows=0)
+    assert st == nat.KDEJS_TABLE_OK
+    np.testing.assert_array_equal(got, [[k * 0.5, k * 0.25] for k in range(300)])
+    got, st = nat.tsv_parse_text(b"\t\t\t\n" * 5000 + b"1\t2\n", skip_rows=0)   # blank lines (tabs only) are skipped
+    assert st == nat.KDEJS_TABLE_OK and got.tolist() == [[1.0, 2.0]]
+    got, st = nat.tsv_parse_text(b"1\t2\n" * 70000, skip_rows=0)               # four-byte rows: 2 048 per chunk
+    assert st == nat.KDEJS_TABLE_OK and got.shape == (70000, 2) and (got == [1.0, 2.0]).all()
