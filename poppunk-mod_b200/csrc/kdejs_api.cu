@@ -1250,8 +1250,8 @@ int kdejs_discrepancy_batch_text(int device, const double *obs, int64_t n_obs, c
     OKR(get_ctx(device, &c));
     std::lock_guard<std::mutex> lk(c->mu);
     OKR(acquire_scratch(*c, c->s_compute));
-    constexpr int W = 16;                                   // tables per wave
-    static_assert(W <= kMaxTsvFiles && W <= kMaxWaveItems, "wave size");
+    int W = 16;                                             // tables per wave
+    if (const char *e = getenv("KDEJS_TEXT_WAVE")) W = std::max(1, std::min(std::min(kMaxTsvFiles, kMaxWaveItems), atoi(e)));
     const size_t text_stride = ((size_t)max_bytes + 64 + 255) / 256 * 256;      // padded: the parser reads whole 32-byte segments
     const int chunks_cap = (int)(text_stride / kTsvChunk) + 2;
     for (int k = 0; k < 2; ++k) {

@@ -26,4 +26,8 @@ WAVES=1,2,4,8,12,16,24,32,64 python tools/wave_probe.py > $OUT/wave_probe_${TAG}
 python tools/tail_probe.py "3D=0" "3D=1" "3D=1;KDEJS_TAIL_WAVE=6" "3D=1;KDEJS_WAVE_PLAN=1,2,4,7,8,7" "3D=1;KDEJS_WAVE_PLAN=2,6,12,12,12,10,10" "3D=1;KDEJS_FIRST_WAVE=64;KDEJS_HOST_WAVE=64" > $OUT/tail_probe_${TAG}.log 2>&1
 for f in ncu_b32 ncu_s ncu_b64 ncu_c5; do tail -n 1 $OUT/$f.log; done
 # tables on disk -> arg-min: host parser vs the parser on the device
-python tools/ingest_probe.py 1024 > $OUT/ingest_probe_${TAG}.log 2>&1
+python tools/ingest_probe.py 2048 > $OUT/ingest_probe_${TAG}.log 2>&1
+# the device table parser alone: a call over 64 tables held as text, then its three kernels under ncu
+TEXT_WAVES=16 python tools/tsv_probe.py 64 > $OUT/tsv_probe_${TAG}.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:k_tsv -s 6 -c 3 -o $OUT/prof_tsv_${TAG} python tools/tsv_probe.py 64 > $OUT/ncu_tsv.log 2>&1
+tail -n 1 $OUT/ncu_tsv.log

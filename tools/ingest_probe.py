@@ -91,7 +91,8 @@ try:
     nat.check(L.kdejs_profile_enable(0, 0))
     text.close()
     ref_dist = None
-    for parse, io, chunk in (("host", 16, 64), ("device", 4, 64), ("device", 8, 64), ("device", 16, 64), ("device", 8, 32)):
+    for parse, io, chunk in (("host", 16, 64), ("device", 4, 64), ("device", 8, 64), ("device", 16, 64), ("device", 8, 32),
+                            ("device", 16, 128), ("device", 16, 256)):
         kw = dict(gamma=0.25, eps=0.0, log=False, io_threads=io, chunk=chunk, parse=parse)
         sweeps.gridsearch_best(ref, files[:2 * chunk], **kw)      # warm-up (arenas are kept between calls)
         t0 = time.perf_counter()

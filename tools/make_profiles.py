@@ -63,9 +63,13 @@ if os.path.exists(f"{G}/prof_c5_{tag}.ncu-rep"):
     full(f"{G}/prof_c5_{tag}.ncu-rep", f"profiles/{tag}_c5_fine_grid_full.txt",
          "# C5_N=3000000 ncu --set full --clock-control none -k 'regex:^k_density_binned$|k_cell_moments|k_scan_wide|k_scale_count' "
          "-s 4 -c 4 over tools/c5_probe.py\n# fine-grid path: 3 M + 3 M points, R = 1024, 128 x 128 cells, moment cells\n")
+if os.path.exists(f"{G}/prof_tsv_{tag}.ncu-rep"):
+    full(f"{G}/prof_tsv_{tag}.ncu-rep", f"profiles/{tag}_tsv_kernels_full.txt",
+         "# ncu --set full --clock-control none --import-source on -k regex:k_tsv -s 6 -c 3 over tools/tsv_probe.py 64\n"
+         "# the device table parser: one wave of 16 tables of 100 000 rows (2.84 MB of text each) per launch\n")
 for name in (f"bench_{tag}_n1.json", f"bench_{tag}_n1_binned.json", f"bench_{tag}_reference.json", f"fp32_probe_{tag}.log",
              f"band_sort_probe_{tag}.log", f"match_probe_{tag}.log", f"h2d_probe_{tag}.jsonl", f"wave_probe_{tag}.log",
-             f"tail_probe_{tag}.log", f"ingest_probe_{tag}.log"):
+             f"tail_probe_{tag}.log", f"ingest_probe_{tag}.log", f"tsv_probe_{tag}.log"):
     if os.path.exists(f"{G}/{name}"):
         shutil.copy(f"{G}/{name}", f"profiles/{name}")
 d = json.load(open(f"{G}/bench_{tag}_n1.json"))
