@@ -671,7 +671,7 @@ def main():
     return 0
 
 
-def run_ingest(pk, target, sims, gamma, eps, n_files=128, n_distinct=8):
+def run_ingest(pk, target, sims, gamma, eps, n_files=512, n_distinct=8):
     """Tables on disk -> arg-min: the grid-search sweep of scripts/distance_to_gridsearch.py:48-55, :109-125 through
     sweeps.gridsearch_best (tables parsed by the library's reader into page-locked arenas while the GPU works on the
     previous chunk), with the reference's reader (np.loadtxt) timed beside it."""
@@ -702,7 +702,7 @@ def run_ingest(pk, target, sims, gamma, eps, n_files=128, n_distinct=8):
         a = np.loadtxt(files[0], delimiter="\t")
         t_np = time.perf_counter() - t0
         assert np.array_equal(pk._native.TsvTable(files[0], pinned=False).array, a)
-        sweeps.gridsearch_best(ref, files[:64], gamma=gamma, eps=eps, log=False, resolution=100)        # warm-up
+        sweeps.gridsearch_best(ref, files, gamma=gamma, eps=eps, log=False, resolution=100)             # warm-up (page-locked arenas)
         t0 = time.perf_counter()
         best, dist_ = sweeps.gridsearch_best(ref, files, gamma=gamma, eps=eps, log=False, resolution=100)
         dt = time.perf_counter() - t0

@@ -92,11 +92,13 @@ _ARENAS = {}       # (kind, slots, capacity) -> arenas kept between calls: page-
 def _cached_arenas(kind, count, slots, capacity, make):
     key = (kind, slots)
     have = _ARENAS.get(key)
-    if have is None or have[0] < capacity or len(have[1]) < count:
+    if have is None or have[0] < capacity:
         if have is not None:
             for a in have[1]:
                 a.close()
-        _ARENAS[key] = have = (capacity, [make(slots, capacity) for _ in range(count)])
+        _ARENAS[key] = have = (capacity, [])
+    while len(have[1]) < count:                     # a longer sweep than the last one: only the missing arena is added
+        have[1].append(make(slots, have[0]))
     return have[1][:count]
 
 
@@ -112,21 +114,19 @@ def _accept(best, name, d, b, core_min_bounds, core_max_bounds, acc_min_bounds, 
     return (name, d, tuple(b)) if ok else best
 
 
-def _gridsearch_device_parse(ref_arr, files, gamma, eps, log, bounds_kw, chunk, io_threads, device, resolution):
-    """The sweep with NO parser on the host: the bytes of the next chunk of files are read into a page-locked arena
-    (kdejs_files_read) while the GPU uploads, parses and evaluates the current one (kdejs_discrepancy_batch_text).
-    Tables the device parser does not cover (missing-value spellings, inf / nan, more than 19 digits, files larger
-    than a slot) go through the host reader."""
-    best = (None, 1.0)
-    distances = np.empty(len(files))
-    chunks = [files[i:i + chunk] for i in range(0, len(files), chunk)]
-    slot_bytes = int(os.path.getsize(files[0]) * 1.5) + 4096
-    arenas = _cached_arenas("text", min(2, len(chunks)), chunk, slot_bytes, lambda n, cap: nat.TextArena(n, cap))
-    slot_bytes = arenas[0].array.shape[1]
+def _device_parse_worker(ref_arr, chunks, gamma, eps, log, chunk, io_threads, device, resolution):
+    """One device's share of a sweep with NO parser on the host: the bytes of the next chunk of files are read into a
+    page-locked arena (kdejs_files_read) while the GPU uploads, parses and evaluates the current one
+    (kdejs_discrepancy_batch_text).  Tables the device parser does not cover (missing-value spellings, inf / nan, more
+    than 19 digits, files larger than a slot) go through the host reader.  Returns [(distances, bounds)] per chunk."""
+    out = []
+    if not chunks:
+        return out
+    slot_bytes = int(os.path.getsize(chunks[0][0]) * 1.5) + 4096
+    arenas = _cached_arenas(("text", device), min(2, len(chunks)), chunk, slot_bytes, lambda n, cap: nat.TextArena(n, cap))
     with ThreadPoolExecutor(max_workers=1) as prefetch:
         read = lambda ci: arenas[ci % 2].read(chunks[ci], threads=io_threads).copy()
         pending = prefetch.submit(read, 0)
-        pos = 0
         for ci, names in enumerate(chunks):
             nbytes = pending.result()
             pending = prefetch.submit(read, ci + 1) if ci + 1 < len(chunks) else None
@@ -143,10 +143,34 @@ def _gridsearch_device_parse(ref_arr, files, gamma, eps, log, bounds_kw, chunk, 
             inf = [names[k] for k in range(len(names)) if status[k] == nat.KDEJS_TABLE_INF and k not in redo]
             if inf:
                 raise ValueError(f"Input X contains infinity or a value too large for dtype('float64'). ({inf[0]})")
-            for name, d, b in zip(names, js, bnd):
-                distances[pos] = d
-                pos += 1
-                best = _accept(best, name, d, b, **bounds_kw)
+            out.append((js, bnd))
+    return out
+
+
+def _gridsearch_device_parse(ref_arr, files, gamma, eps, log, bounds_kw, chunk, io_threads, devices, resolution):
+    """Chunks of `chunk` files are dealt to the devices round-robin, one host thread per device (the ctypes calls
+    release the GIL); the running arg-min of distance_to_gridsearch.py:112-125 is then taken in file order, so the
+    result does not depend on the number of devices."""
+    chunks = [files[i:i + chunk] for i in range(0, len(files), chunk)]
+    n = max(1, min(len(devices), len(chunks)))
+    per_dev_threads = max(2, io_threads // n)
+    shares = [chunks[k::n] for k in range(n)]
+    if n == 1:
+        results = [_device_parse_worker(ref_arr, shares[0], gamma, eps, log, chunk, io_threads, devices[0], resolution)]
+    else:
+        with ThreadPoolExecutor(max_workers=n) as ex:
+            futs = [ex.submit(_device_parse_worker, ref_arr, shares[k], gamma, eps, log, chunk, per_dev_threads,
+                              devices[k], resolution) for k in range(n)]
+            results = [f.result() for f in futs]
+    best = (None, 1.0)
+    distances = np.empty(len(files))
+    pos = 0
+    for ci, names in enumerate(chunks):
+        js, bnd = results[ci % n][ci // n]
+        for name, d, b in zip(names, js, bnd):
+            distances[pos] = d
+            pos += 1
+            best = _accept(best, name, d, b, **bounds_kw)
     return best, distances
 
 
@@ -158,8 +182,8 @@ def gridsearch_best(ref, files, gamma=1e-12, eps=1e-12, log=True, *, core_min_bo
     [lo, hi] pairs (the script multiplies its fractions by the reference's column maxima, :89-99).
     Returns (best, distances) with best = (file, distance, bounds) or (None, 1.0), distances in file order.
 
-    parse: "device" -- the files' bytes go to the GPU and are parsed there (default on one device); "host" -- the
-    library's host reader parses them into page-locked arenas (several devices, or KDEJS_PARSE=host)."""
+    parse: "device" (default) -- the files' bytes go to the GPU(s) and are parsed there, chunks dealt to `devices`
+    round-robin; "host" (or KDEJS_PARSE=host) -- the library's host reader parses them into page-locked arenas."""
     ref_arr = ref if isinstance(ref, np.ndarray) else read_file(ref).array
     files = [str(f) for f in files]
     if io_threads is None:          # one reader / parser thread per file; measured on a 16-core host: 560 tables/s with 8, 1170 with 16
@@ -170,18 +194,15 @@ def gridsearch_best(ref, files, gamma=1e-12, eps=1e-12, log=True, *, core_min_bo
     distances = np.empty(len(files))
     if not files:
         return best, distances
-    one_device = devices is None or isinstance(devices, int) or len(list(devices)) == 1
     if parse is None:
-        parse = os.environ.get("KDEJS_PARSE", "device" if one_device else "host")
+        parse = os.environ.get("KDEJS_PARSE", "device")
     if parse not in ("device", "host"):
         raise ValueError("parse must be 'device' or 'host'")
     bounds_kw = dict(core_min_bounds=core_min_bounds, core_max_bounds=core_max_bounds, acc_min_bounds=acc_min_bounds,
                      acc_max_bounds=acc_max_bounds)
     if parse == "device":
-        if not one_device:
-            raise ValueError("parse='device' runs on one device; use parse='host' with several")
-        dev = devices if isinstance(devices, int) else (list(devices)[0] if devices is not None else None)
-        return _gridsearch_device_parse(ref_arr, files, gamma, eps, log, bounds_kw, chunk, io_threads, dev, resolution)
+        devs = [kd.default_device()] if devices is None else [devices] if isinstance(devices, int) else list(devices)
+        return _gridsearch_device_parse(ref_arr, files, gamma, eps, log, bounds_kw, chunk, io_threads, devs, resolution)
     chunks = [files[i:i + chunk] for i in range(0, len(files), chunk)]
     # Two page-locked arenas of `chunk` slots: the files of chunk k+1 are parsed straight into their slots (one
     # parser thread per file, io_threads files at a time) while the GPU works on chunk k; nothing is allocated per

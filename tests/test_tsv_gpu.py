@@ -248,3 +248,25 @@ def test_degenerate_tables_do_not_break_the_device_parser(pk):
     assert st == nat.KDEJS_TABLE_OK and got.tolist() == [[1.0, 2.0]]
     got, st = nat.tsv_parse_text(b"1\t2\n" * 70000, skip_rows=0)               # four-byte rows: 2 048 per chunk
     assert st == nat.KDEJS_TABLE_OK and got.shape == (70000, 2) and (got == [1.0, 2.0]).all()
+
+
+def test_gridsearch_over_several_devices_equals_one(pk, tmp_path):
+    """Chunks dealt to the visible devices round-robin (one host thread per device): the same distances and the same
+    best file as on one device."""
+    from oracle import workloads as wl
+    from poppunk_mod_b200 import sweeps
+
+    n_dev = pk._native.device_count()
+    if n_dev < 2:
+        pytest.skip("needs two GPUs")
+    ref = wl.synthetic_target(12000)
+    paths = []
+    for k in range(29):
+        q = tmp_path / f"sim{k}.tsv"
+        q.write_bytes(_table_text(wl.sim_batch_member(k, n=3000 + 97 * k)))
+        paths.append(str(q))
+    kw = dict(gamma=0.25, eps=0.0, log=False, chunk=4, io_threads=4)
+    best1, dist1 = sweeps.gridsearch_best(ref, paths, devices=0, **kw)
+    bestn, distn = sweeps.gridsearch_best(ref, paths, devices=list(range(n_dev)), **kw)
+    np.testing.assert_array_equal(distn, dist1)
+    assert bestn[0] == best1[0] and bestn[1] == best1[1]
