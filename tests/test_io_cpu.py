@@ -215,3 +215,52 @@ def test_decimal_conversion_is_correctly_rounded(nat, tmp_path):
     got = nat.TsvTable(str(p), skip_rows=0, pinned=False, threads=3).array
     bad = np.argwhere(got.view(np.uint64) != want.view(np.uint64))
     assert len(bad) == 0, [(strs[2 * r + c], got[r, c], want[r, c]) for r, c in bad[:5]]
+
+
+def test_device_parser_decimal_conversion_on_the_host(tmp_path):
+    """csrc/kdejs_decimal.h is the conversion the DEVICE table parser uses; it compiles for the host too: three million
+    spellings over its whole range against strtod, bit for bit, and the spellings it must leave to the host reader."""
+    import shutil
+    import subprocess
+
+    from conftest import ROOT
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "decimal_fuzz"
+    subprocess.run([gxx, "-O2", "-std=c++17", os.path.join(ROOT, "tests", "decimal", "decimal_fuzz.cpp"), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe), "1000000", "7"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "mismatches 0" in out.stdout and "ACCEPTED" not in out.stdout
+
+
+def test_file_bytes_reader_and_data_offset(nat, tmp_path):
+    """kdejs_files_read (bytes of many files into slots, no parsing) and kdejs_tsv_data_offset (where the data rows of a
+    table held as text begin: the header rule of kdejs_tsv_load)."""
+    blobs = [b"core\tacc\n0.1\t0.2\n", b"0.5\t0.25\n" * 1000, b"", b"x" * 5000]
+    paths = []
+    for k, b in enumerate(blobs):
+        q = tmp_path / f"f{k}.tsv"
+        q.write_bytes(b)
+        paths.append(str(q))
+    arena = nat.TextArena(5, 4096 * 3, pinned=False)
+    n = arena.read(paths + [str(tmp_path / "missing.tsv")], threads=3)
+    assert n.tolist() == [len(blobs[0]), len(blobs[1]), 0, 5000, -1]
+    for k in (0, 1, 3):
+        assert arena.array[k, :n[k]].tobytes() == blobs[k]
+    small = nat.TextArena(1, 100, pinned=False)
+    assert small.read(paths[1:2]).tolist() == [-len(blobs[1])]
+    L = nat.lib()
+
+    def offset(text, skip):
+        a = np.frombuffer(text, dtype=np.uint8)
+        return L.kdejs_tsv_data_offset(a.ctypes.data, len(text), skip)
+
+    assert offset(blobs[0], -1) == 9 and offset(blobs[0], 0) == 0 and offset(blobs[0], 1) == 9
+    assert offset(b"0.1\t0.2\n0.3\t0.4\n", -1) == 0                     # numeric first row: nothing dropped
+    assert offset(b"\n# note\nid\tcore\tacc\n1\t2\n", -1) == 20          # blank and comment lines are not the header
+    assert offset(b"a\tb\nc\td", 2) == 7 and offset(b"a\tb", 5) == 3     # no final newline; more to skip than there is
+    arena.close()
+    small.close()
