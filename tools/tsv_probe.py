@@ -21,12 +21,15 @@ for k in range(B):
     t = texts[k % 8]
     arena.array[k, :len(t)] = np.frombuffer(t, dtype=np.uint8)
     nb[k] = len(t)
-for wave in [int(x) for x in os.environ.get("TEXT_WAVES", "16").split(",")]:
+for wave, tail in [(int(x.split("/")[0]), x.split("/")[1] if "/" in x else "") for x in os.environ.get("TEXT_WAVES", "16").split(",")]:
     os.environ["KDEJS_TEXT_WAVE"] = str(wave)
+    os.environ.pop("KDEJS_TEXT_TAIL", None)
+    if tail:
+        os.environ["KDEJS_TEXT_TAIL"] = tail
     best = 1e9
     for rep in range(6):
         t0 = time.perf_counter()
         js, rows, status, bnd = pk.KDE_JS_divergence_batch_text(T, arena.array, 0.25, 0.0, nbytes=nb, skip_rows=0, bounds=True)
         best = min(best, time.perf_counter() - t0)
     assert (status == 0).all() and (rows == 100000).all()
-    print(f"{B} tables of {nb[0] / 1e6:.2f} MB, waves of {wave}: {1e3 * best:.2f} ms per call = {B / best:.0f} tables/s; js[0] = {js[0]!r}")
+    print(f"{B} tables of {nb[0] / 1e6:.2f} MB, waves of {wave} (last wave: {tail or "default"}): {1e3 * best:.2f} ms per call = {B / best:.0f} tables/s; js[0] = {js[0]!r}")
