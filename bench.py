@@ -518,7 +518,12 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    ingest = run_ingest(pk, target, sims, GAMMA, EPS) if extras and world == 1 else None
+    ingest = None
+    if extras and world == 1:
+        try:
+            ingest = run_ingest(pk, target, sims, GAMMA, EPS)
+        except (OSError, MemoryError) as e:          # no room for 1.5 GB of tables under the temporary directory
+            ingest = {"unavailable": f"{type(e).__name__}: {e}"}
 
     # ---- roofline of the dominant kernel (density) ------------------------------------------------
     tf64, mhz = ctypes.c_double(), ctypes.c_double()
