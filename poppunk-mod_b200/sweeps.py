@@ -19,6 +19,7 @@ import itertools
 import math
 import os
 import sys
+import threading
 import warnings
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
@@ -86,20 +87,53 @@ _SMALL_GAMMA_NOTE = (
     "(INTEGRATION.md section 5: arg-min differed, 5 % of pairs reordered on 200 simulations at gamma=1e-12)")
 
 
-_ARENAS = {}       # (kind, slots, capacity) -> arenas kept between calls: page-locked allocations of 100+ MB take ~0.1 s
+# Page-locked arenas are kept between sweeps (allocating 100+ MB of page-locked memory takes ~0.1 s, as long as a
+# short sweep itself): key -> [capacity, arenas, in use].  A sweep that finds its key in use (another thread sweeping
+# on the same device) works with arenas of its own and frees them afterwards.  release_arenas() gives the memory back.
+_ARENAS = {}
+_ARENAS_LOCK = threading.Lock()
 
 
-def _cached_arenas(kind, count, slots, capacity, make):
-    key = (kind, slots)
-    have = _ARENAS.get(key)
-    if have is None or have[0] < capacity:
-        if have is not None:
-            for a in have[1]:
+class _ArenaLease:
+    def __init__(self, kind, count, slots, capacity, make):
+        self.key, self.count, self.slots, self.capacity, self.make = (kind, slots), count, slots, capacity, make
+        self.private = None
+
+    def __enter__(self):
+        with _ARENAS_LOCK:
+            have = _ARENAS.get(self.key)
+            if have is not None and have[2]:
+                self.private = []                    # the cached arenas are busy: this sweep gets its own
+            else:
+                if have is None or have[0] < self.capacity:
+                    if have is not None:
+                        for a in have[1]:
+                            a.close()
+                    _ARENAS[self.key] = have = [self.capacity, [], False]
+                have[2] = True
+        if self.private is not None:
+            self.private = [self.make(self.slots, self.capacity) for _ in range(self.count)]
+            return self.private
+        while len(have[1]) < self.count:             # a longer sweep than the last one: only the missing arena is added
+            have[1].append(self.make(self.slots, have[0]))
+        return have[1][:self.count]
+
+    def __exit__(self, *exc):
+        if self.private is not None:
+            for a in self.private:
                 a.close()
-        _ARENAS[key] = have = (capacity, [])
-    while len(have[1]) < count:                     # a longer sweep than the last one: only the missing arena is added
-        have[1].append(make(slots, have[0]))
-    return have[1][:count]
+        else:
+            with _ARENAS_LOCK:
+                _ARENAS[self.key][2] = False
+        return False
+
+
+def release_arenas():
+    """Frees the page-locked arenas the sweep drivers keep between calls (up to ~0.5 GB per device)."""
+    with _ARENAS_LOCK:
+        for key in [k for k, v in _ARENAS.items() if not v[2]]:
+            for a in _ARENAS.pop(key)[1]:
+                a.close()
 
 
 def _accept(best, name, d, b, core_min_bounds, core_max_bounds, acc_min_bounds, acc_max_bounds):
@@ -123,8 +157,8 @@ def _device_parse_worker(ref_arr, chunks, gamma, eps, log, chunk, io_threads, de
     if not chunks:
         return out
     slot_bytes = int(os.path.getsize(chunks[0][0]) * 1.5) + 4096
-    arenas = _cached_arenas(("text", device), min(2, len(chunks)), chunk, slot_bytes, lambda n, cap: nat.TextArena(n, cap))
-    with ThreadPoolExecutor(max_workers=1) as prefetch:
+    with _ArenaLease(("text", device), min(2, len(chunks)), chunk, slot_bytes, lambda n, cap: nat.TextArena(n, cap)) as arenas, \
+            ThreadPoolExecutor(max_workers=1) as prefetch:
         read = lambda ci: arenas[ci % 2].read(chunks[ci], threads=io_threads).copy()
         pending = prefetch.submit(read, 0)
         for ci, names in enumerate(chunks):
@@ -210,8 +244,8 @@ def gridsearch_best(ref, files, gamma=1e-12, eps=1e-12, log=True, *, core_min_bo
     first = read_file(files[0], pinned=False)
     cap = int(first.rows * 1.5) + 1024
     first.close()
-    arenas = _cached_arenas("rows", min(2, len(chunks)), chunk, cap, lambda n, c: nat.TableArena(n, c))
-    with ThreadPoolExecutor(max_workers=1) as prefetch, ThreadPoolExecutor(max_workers=max(1, io_threads)) as io:
+    with _ArenaLease("rows", min(2, len(chunks)), chunk, cap, lambda n, c: nat.TableArena(n, c)) as arenas, \
+            ThreadPoolExecutor(max_workers=1) as prefetch, ThreadPoolExecutor(max_workers=max(1, io_threads)) as io:
         load = lambda ci: arenas[ci % 2].load(chunks[ci], skip_rows=0, executor=io, overflow="alloc")   # np.loadtxt, :49
         pending = prefetch.submit(load, 0)
         pos = 0

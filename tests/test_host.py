@@ -199,3 +199,31 @@ def test_point_sets_list_and_3d_array_agree():
             nat.PointSets(bad)
     with pytest.raises(ValueError):
         nat.PointSets([np.zeros((0, 2))])
+
+
+def test_sweep_arenas_are_leased_not_shared():
+    """The page-locked arenas the sweep drivers keep between calls: reused by the next sweep, grown when a longer or
+    larger one comes, never handed to two sweeps at once, given back by release_arenas()."""
+    from poppunk_mod_b200 import sweeps
+
+    class Arena:
+        made = 0
+
+        def __init__(self, slots, cap):
+            Arena.made += 1
+            self.cap, self.closed = cap, False
+
+        def close(self):
+            self.closed = True
+
+    make = lambda n, c: Arena(n, c)
+    with sweeps._ArenaLease("test", 1, 4, 100, make) as first:
+        with sweeps._ArenaLease("test", 2, 4, 100, make) as second:            # the key is busy: arenas of its own
+            assert len(second) == 2 and second[0] is not first[0]
+        assert all(a.closed for a in second) and not first[0].closed
+    with sweeps._ArenaLease("test", 2, 4, 50, make) as again:                   # reused, one arena added
+        assert again[0] is first[0] and len(again) == 2
+    with sweeps._ArenaLease("test", 1, 4, 500, make) as larger:                 # too small: replaced
+        assert larger[0] is not first[0] and first[0].closed and larger[0].cap == 500
+    sweeps.release_arenas()
+    assert larger[0].closed and ("test", 4) not in sweeps._ARENAS and Arena.made == 5
