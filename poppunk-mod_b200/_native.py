@@ -340,6 +340,18 @@ def tsv_load_into(path, dst, skip_rows=-1, threads=1):
     return n.value
 
 
+def _arena_memory(shape, dtype, pinned):
+    """(pool or None, array): page-locked memory when asked for and available, ordinary memory otherwise (the library
+    stages pageable uploads itself -- slower, never wrong)."""
+    if pinned:
+        pool = PinnedPool()
+        try:
+            return pool, pool.empty(shape, dtype)
+        except MemoryError:
+            pool.close()
+    return None, np.empty(shape, dtype=dtype)
+
+
 class TableArena:
     """`slots` tables of up to `capacity_rows` rows each in ONE (slots, capacity_rows, 2) float64 array (page-locked
     when a GPU is present): files are parsed straight into their slot by a pool of threads (ctypes releases the
@@ -348,11 +360,10 @@ class TableArena:
     def __init__(self, slots, capacity_rows, pinned=None):
         if pinned is None:
             pinned = device_count() > 0
-        self._pool = PinnedPool() if pinned else None
         shape = (int(slots), int(capacity_rows), 2)
-        self.array = self._pool.empty(shape) if pinned else np.empty(shape)
+        self._pool, self.array = _arena_memory(shape, np.float64, pinned)
         self.rows = np.zeros(int(slots), dtype=np.int64)
-        self.pinned = bool(pinned)
+        self.pinned = self._pool is not None
 
     def load(self, paths, skip_rows=-1, workers=8, executor=None, overflow="raise"):
         """Parse paths[k] into slot k.  Returns the tables as views: a (len(paths), rows, 2) array when all have the
@@ -399,9 +410,7 @@ class TextArena:
     def __init__(self, slots, slot_bytes, pinned=None):
         if pinned is None:
             pinned = device_count() > 0
-        self._pool = PinnedPool() if pinned else None
-        shape = (int(slots), int(slot_bytes))
-        self.array = self._pool.empty(shape, np.uint8) if pinned else np.empty(shape, dtype=np.uint8)
+        self._pool, self.array = _arena_memory((int(slots), int(slot_bytes)), np.uint8, pinned)
         self.nbytes = np.zeros(int(slots), dtype=np.int64)
 
     def read(self, paths, threads=8):
