@@ -244,6 +244,9 @@ int kdejs_tsv_load(const char *path, int skip_rows, int pinned, int threads, dou
 int kdejs_tsv_load_into(const char *path, int skip_rows, int threads, double *dst, int64_t capacity_rows,
                         int64_t *out_rows);
 void kdejs_tsv_free(double *pts, int pinned);
+/* Every number of a small text file as one vector (the simulator's gene frequencies, poppunk_mod.py:361): separated by
+ * blanks, tabs or newlines; '#' comments; pandas' missing-value spellings are NaN.  Free with kdejs_tsv_free(p, 0). */
+int kdejs_numbers_load(const char *path, double **out, int64_t *out_n);
 /* First byte of the data rows of a table that is already in memory (same header rule as kdejs_tsv_load). */
 int64_t kdejs_tsv_data_offset(const char *text, int64_t bytes, int skip_rows);
 /* n files read into slots of slot_bytes bytes (dst + i * slot_bytes), `threads` at a time; out_bytes[i] = bytes read,

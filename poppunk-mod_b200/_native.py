@@ -94,6 +94,7 @@ _SIGNATURES = {
     "kdejs_tsv_load_into": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_int64, _c_i64p]),
     "kdejs_tsv_free": (None, [ctypes.c_void_p, ctypes.c_int]),
+    "kdejs_numbers_load": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), _c_i64p]),
     "kdejs_tsv_data_offset": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
     "kdejs_files_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                         _c_i64p, ctypes.c_int]),
@@ -440,3 +441,17 @@ def tsv_parse_text(text, skip_rows=-1, device=0):
     check(lib().kdejs_tsv_parse_text(int(device), buf.ctypes.data, buf.shape[0], int(skip_rows), out.ctypes.data,
                                      out.shape[0], ctypes.byref(n), ctypes.byref(st)))
     return out[:n.value].copy(), st.value
+
+
+def load_numbers(path) -> np.ndarray:
+    """Every number of a small text file as a float64 vector (kdejs_numbers_load; np.loadtxt(path).reshape(-1) for
+    the simulator's gene-frequency files, without the GIL)."""
+    p, n = ctypes.c_void_p(), ctypes.c_int64()
+    rc = lib().kdejs_numbers_load(os.fsencode(path), ctypes.byref(p), ctypes.byref(n))
+    if rc != KDEJS_OK:
+        msg = (lib().kdejs_io_last_error() or b"").decode("utf-8", "replace")
+        raise (ValueError if rc == KDEJS_ERR_ARG else RuntimeError)(msg)
+    try:
+        return np.ctypeslib.as_array(ctypes.cast(p, _c_dp), shape=(n.value,)).copy()
+    finally:
+        lib().kdejs_tsv_free(p, 0)

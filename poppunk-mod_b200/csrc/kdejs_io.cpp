@@ -299,6 +299,41 @@ int kdejs_files_read(const char *const *paths, int n, char *dst, int64_t slot_by
     return KDEJS_OK;
 }
 
+/* Every number of a small text file -- the simulator's gene-frequency vector (poppunk_mod.py:361: np.loadtxt of
+ * "<outpref>_freqs.txt", one value per line or per tab) -- as one malloc'ed vector: fields separated by blanks, tabs
+ * or newlines, '#' starts a comment that runs to the end of its line.  Free with kdejs_tsv_free(ptr, 0). */
+int kdejs_numbers_load(const char *path, double **out, int64_t *out_n) {
+    if (!path || !out || !out_n) { g_io_err = "null argument"; return KDEJS_ERR_ARG; }
+    *out = nullptr;
+    *out_n = 0;
+    Table t;
+    if (int rc = read_table(path, 0, t)) return rc;
+    const char *p = t.buf.get(), *end = t.end;
+    std::vector<double> v;
+    v.reserve((size_t)(end - p) / 8 + 16);
+    while (p < end) {
+        while (p < end && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+        if (p >= end) break;
+        if (*p == '#') { while (p < end && *p != '\n') ++p; continue; }
+        const char *q = p;
+        while (q < end && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r' && *q != '#') ++q;
+        double x;
+        if (!parse_double(p, q, x)) {
+            g_io_err = std::string(path) + ": could not parse number " + std::to_string(v.size() + 1) + " ('" + std::string(p, q) + "')";
+            return KDEJS_ERR_ARG;
+        }
+        v.push_back(x);
+        p = q;
+    }
+    if (v.empty()) { g_io_err = std::string("no numbers in ") + path; return KDEJS_ERR_ARG; }
+    double *mem = (double *)std::malloc(v.size() * sizeof(double));
+    if (!mem) { g_io_err = "allocation failed"; return KDEJS_ERR_CUDA; }
+    std::memcpy(mem, v.data(), v.size() * sizeof(double));
+    *out = mem;
+    *out_n = (int64_t)v.size();
+    return KDEJS_OK;
+}
+
 void kdejs_tsv_free(double *pts, int pinned) {
     if (!pts) return;
     if (pinned) kdejs_host_free(pts);

@@ -18,6 +18,7 @@ import os
 import numpy as np
 
 from . import KDE_distance as kd
+from . import _native as nat
 from .sweeps import read_distfile
 
 
@@ -29,7 +30,10 @@ def _points(x):
 
 def _freqs(x):
     if isinstance(x, (str, os.PathLike)):
-        return np.loadtxt(x, delimiter="\t", dtype="float64")
+        try:                    # the library's reader: the same values, several times faster, and it releases the GIL
+            return nat.load_numbers(x)
+        except ValueError:      # anything it does not read (e.g. another delimiter): what the reference does, :361
+            return np.loadtxt(x, delimiter="\t", dtype="float64")
     return np.asarray(x, dtype=np.float64)
 
 

@@ -264,3 +264,31 @@ def test_file_bytes_reader_and_data_offset(nat, tmp_path):
     assert offset(b"a\tb\nc\td", 2) == 7 and offset(b"a\tb", 5) == 3     # no final newline; more to skip than there is
     arena.close()
     small.close()
+
+
+def test_number_vector_reader_matches_loadtxt(nat, tmp_path):
+    """kdejs_numbers_load (the simulator's gene-frequency files, poppunk_mod.py:361) against np.loadtxt: a column, a
+    tab-separated row, comments, a missing value; anything else is an error the caller can fall back from."""
+    rng = np.random.default_rng(2)
+    v = rng.random(3000)
+    col = tmp_path / "col.txt"
+    np.savetxt(col, v)
+    row = tmp_path / "row.txt"
+    row.write_text("# gene frequencies\n" + "\t".join(repr(float(x)) for x in v) + "\n")
+    for p in (col, row):
+        np.testing.assert_array_equal(nat.load_numbers(str(p)), np.loadtxt(p, delimiter="\t", dtype="float64").reshape(-1))
+    mixed = tmp_path / "mixed.txt"
+    mixed.write_text("0.5 1\tNA\r\n2e-3  # tail\n")
+    got = nat.load_numbers(str(mixed))
+    assert got[:2].tolist() == [0.5, 1.0] and np.isnan(got[2]) and got[3] == 2e-3 and got.shape == (4,)
+    for bad, text in (("commas.txt", "1,2,3\n"), ("empty.txt", "\n# nothing\n")):
+        q = tmp_path / bad
+        q.write_text(text)
+        with pytest.raises(ValueError):
+            nat.load_numbers(str(q))
+    from poppunk_mod_b200 import simulator
+
+    np.testing.assert_array_equal(simulator._freqs(str(col)), v)
+    commas = tmp_path / "c.txt"
+    commas.write_text("0.25\n0.5\n")
+    np.testing.assert_array_equal(simulator._freqs(str(commas)), [0.25, 0.5])
