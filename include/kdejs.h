@@ -109,6 +109,15 @@ int kdejs_summary_batch(int device, const double *obs, int64_t n_obs, const doub
                         double bandwidth, double gamma, double eps, int log_flag, int kernel, int algo,
                         double *out_summary, double *out_d, double *out_log_d);
 
+/* The same summary step for discrepancies that were computed by another entry point -- kdejs_discrepancy_batch_text,
+ * when the simulator's tables are parsed on the device (process_result reads them with np.loadtxt,
+ * poppunk_mod.py:360-361): js = B discrepancies (HOST); the same kernel as kdejs_summary_batch runs on them, so the
+ * vectors equal that call's bit for bit (calculate_gene_freqs :285-291, the result vector :379, the ELFI nodes
+ * :571-572). */
+int kdejs_summary_from_js(int device, const double *js, const double *const *freqs, const int64_t *n_freqs, int B,
+                          double core_threshold, double rare_threshold, const double observed[4],
+                          double *out_summary, double *out_d, double *out_log_d);
+
 /* General pairs: out_js[i] = KDE_JS_divergence(sets[ia[i]], sets[ib[i]]) over a pool of
  * n_sets HOST point sets, each uploaded once (the itertools.combinations loop at
  * scripts/pairwise_2D_distance.py:112-118). */

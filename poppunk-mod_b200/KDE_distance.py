@@ -44,7 +44,7 @@ except ImportError:  # used as a top-level drop-in module: `sys.path.insert(0, "
     _spec.loader.exec_module(nat)
 
 __all__ = ["get_grid", "scale_KDE", "KDE_JS_divergence", "KDE_KL_divergence", "KDE_JS_divergence_batch",
-           "KDE_JS_divergence_batch_text", "KDE_JS_divergence_pairs", "kde_density", "summary_batch", "rule_bandwidth", "default_device", "main"]
+           "KDE_JS_divergence_batch_text", "KDE_JS_divergence_pairs", "kde_density", "summary_batch", "summary_from_js", "rule_bandwidth", "default_device", "main"]
 
 _DEFAULT_RESOLUTION = 100      # KDE_distance.py:89
 _DEFAULT_BANDWIDTH = 0.03      # KDE_distance.py:50
@@ -304,6 +304,30 @@ def summary_batch(obs, sims, sims_freqs, observed, gamma, core_threshold, rare_t
     nat.check(nat.lib().kdejs_summary_batch(dev, nat.ptr(o), o.shape[0], ptrs, counts, fptrs, fcnt, B,
                                             float(core_threshold), float(rare_threshold), nat.ptr(obs4), *common,
                                             nat.ptr(summary), nat.ptr(d), nat.ptr(logd)))
+    return summary, d, logd
+
+
+def summary_from_js(js, sims_freqs, observed, core_threshold, rare_threshold, *, device=None):
+    """summary_batch's last step for discrepancies that already exist (KDE_JS_divergence_batch_text: tables parsed on
+    the device): the same kernel turns js (B,) and the B gene-frequency vectors into (summary (B,4), d, log_d)
+    (kdejs_summary_from_js; poppunk_mod.py:285-291, :379, :571-572)."""
+    js = np.ascontiguousarray(np.asarray(js, dtype=np.float64).reshape(-1))
+    freqs = [np.ascontiguousarray(np.asarray(f, dtype=np.float64).reshape(-1)) for f in sims_freqs]
+    B = js.shape[0]
+    if len(freqs) != B:
+        raise ValueError("one gene-frequency vector per simulation is required")
+    obs4 = np.ascontiguousarray(np.asarray(observed, dtype=np.float64).reshape(-1))
+    if obs4.shape != (4,):
+        raise ValueError("observed must be the 4-vector [0, freq_core, freq_intermediate, freq_rare]")
+    summary, d, logd = np.empty((B, 4)), np.empty(B), np.empty(B)
+    if B == 0:
+        return summary, d, logd
+    fptrs = (ctypes.c_void_p * B)(*[f.ctypes.data for f in freqs])
+    fcnt = (ctypes.c_int64 * B)(*[f.shape[0] for f in freqs])
+    dev = default_device() if device is None else int(device)
+    nat.check(nat.lib().kdejs_summary_from_js(dev, nat.ptr(js), fptrs, fcnt, B, float(core_threshold),
+                                              float(rare_threshold), nat.ptr(obs4), nat.ptr(summary), nat.ptr(d),
+                                              nat.ptr(logd)))
     return summary, d, logd
 
 

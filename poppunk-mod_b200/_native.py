@@ -43,6 +43,9 @@ _SIGNATURES = {
     "kdejs_summary_batch": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p, _c_dpp, _c_i64p,
                                            ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p] + _COMMON +
                             [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "kdejs_summary_from_js": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, _c_dpp, _c_i64p, ctypes.c_int, ctypes.c_double,
+                                             ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     "kdejs_discrepancy_pairs": (ctypes.c_int, [ctypes.c_int, _c_dpp, _c_i64p, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p, ctypes.c_int64] + _COMMON + [ctypes.c_void_p]),
     "kdejs_discrepancy_batch_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_int64, _c_dpp, _c_i64p,

@@ -1421,6 +1421,59 @@ int kdejs_summary_batch(int device, const double *obs, int64_t n_obs, const doub
                       nullptr, &sa);
 }
 
+int kdejs_summary_from_js(int device, const double *js, const double *const *freqs, const int64_t *n_freqs, int B,
+                          double core_threshold, double rare_threshold, const double observed[4],
+                          double *out_summary, double *out_d, double *out_log_d) {
+    NvtxRange nvtx_call("kdejs_summary_from_js");
+    if (B < 0) return fail(KDEJS_ERR_ARG, "negative batch size");
+    if (B == 0) return KDEJS_OK;
+    if (!js || !freqs || !n_freqs || !observed || !out_summary) return fail(KDEJS_ERR_ARG, "summary arrays missing");
+    for (int i = 0; i < B; ++i)
+        if (n_freqs[i] < 0 || (n_freqs[i] > 0 && !freqs[i])) return fail(KDEJS_ERR_ARG, "bad gene-frequency vector");
+    Ctx *c;
+    OKR(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaStream_t st = c->s_compute;
+    OKR(acquire_scratch(*c, st));
+    // the layout of batch_impl's summary step: offsets | frequencies | results, and the discrepancies in js_out
+    std::vector<int64_t> h_offs((size_t)B + 1, 0);
+    for (int i = 0; i < B; ++i) h_offs[i + 1] = h_offs[i] + n_freqs[i];
+    std::vector<double> h_freqs((size_t)std::max<int64_t>(h_offs[B], 1));
+    for (int i = 0; i < B; ++i)
+        if (n_freqs[i] > 0) memcpy(h_freqs.data() + h_offs[i], freqs[i], sizeof(double) * (size_t)n_freqs[i]);
+    const size_t off_bytes = ((size_t)(B + 1) * 8 + 255) / 256 * 256, fr_bytes = (h_freqs.size() * 8 + 255) / 256 * 256;
+    OKR(c->summary.ensure(off_bytes + fr_bytes + (size_t)B * 48));
+    OKR(c->js_out.ensure(sizeof(double) * (size_t)B));
+    char *base = c->summary.as<char>();
+    std::vector<double> h_sum((size_t)B * 6);
+    int rc = KDEJS_OK;
+    if (cudaMemcpyAsync(c->js_out.p, js, sizeof(double) * (size_t)B, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(base, h_offs.data(), (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(base + off_bytes, h_freqs.data(), h_freqs.size() * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = fail(KDEJS_ERR_CUDA, "H2D copy of the discrepancies / gene frequencies failed");
+    if (rc == KDEJS_OK) {
+        {
+            KTimer t(*c, 9, st);
+            k_summary<<<B, 256, 0, st>>>(reinterpret_cast<const double *>(base + off_bytes), reinterpret_cast<const int64_t *>(base),
+                                        core_threshold, rare_threshold, c->js_out.as<double>(), observed[0], observed[1],
+                                        observed[2], observed[3], reinterpret_cast<double *>(base + off_bytes + fr_bytes));
+        }
+        if (cudaGetLastError() != cudaSuccess ||
+            cudaMemcpyAsync(h_sum.data(), base + off_bytes + fr_bytes, (size_t)B * 48, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = fail(KDEJS_ERR_CUDA, "summary kernel / D2H copy of the summary vectors failed");
+    }
+    const cudaError_t se = cudaStreamSynchronize(st);         // the host vectors above are read until here
+    release_scratch(*c, st, true);
+    if (rc != KDEJS_OK) return rc;
+    if (se != cudaSuccess) return fail(KDEJS_ERR_CUDA, std::string("kernel execution failed: ") + cudaGetErrorString(se));
+    for (int i = 0; i < B; ++i) {
+        memcpy(out_summary + 4 * (size_t)i, h_sum.data() + 6 * (size_t)i, 32);
+        if (out_d) out_d[i] = h_sum[6 * (size_t)i + 4];
+        if (out_log_d) out_log_d[i] = h_sum[6 * (size_t)i + 5];
+    }
+    return KDEJS_OK;
+}
+
 int kdejs_discrepancy_batch_dev(int device, const double *obs_dev, int64_t n_obs, const double *const *sims_dev,
                                 const int64_t *n_sims, int B, int resolution, double bandwidth, double gamma,
                                 double eps, int log_flag, int kernel, int algo, double *out_js_dev,

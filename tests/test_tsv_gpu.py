@@ -270,3 +270,58 @@ def test_gridsearch_over_several_devices_equals_one(pk, tmp_path):
     bestn, distn = sweeps.gridsearch_best(ref, paths, devices=list(range(n_dev)), **kw)
     np.testing.assert_array_equal(distn, dist1)
     assert bestn[0] == best1[0] and bestn[1] == best1[1]
+
+
+def test_simulator_batch_from_files_device_parser_equals_host_reader(pk, tmp_path):
+    """simulator.process_results_batch over files (process_result's loads, poppunk_mod.py:360-361): with the tables
+    parsed on the device and the summary kernel run on the resulting discrepancies (kdejs_summary_from_js) the vectors
+    and both ELFI nodes equal the host-parsed kdejs_summary_batch path bit for bit -- including a table the device
+    parser hands back to the host reader and more than one chunk of files."""
+    from oracle import workloads as wl
+    from poppunk_mod_b200 import simulator
+
+    rng = np.random.default_rng(5)
+    obs = wl.synthetic_target(6000)
+    B = 9
+    sim_paths, freq_paths, freqs = [], [], []
+    for i in range(B):
+        a = wl.sim_batch_member(i, n=3000 + 211 * i)
+        p = tmp_path / f"sim_{i}.tsv"
+        np.savetxt(p, a, delimiter="\t", fmt="%.17g" if i % 2 else "%.6f")
+        if i == 4:                                  # a missing value: only the host reader covers the spelling
+            lines = p.read_text().split("\n")
+            lines[7] = lines[7].split("\t")[0] + "\tNA"
+            p.write_text("\n".join(lines))
+        f = np.round(rng.beta(0.3, 0.3, 2000 + 37 * i), 3) * (rng.random(2000 + 37 * i) > 0.2)
+        fp = tmp_path / f"sim_{i}_freqs.txt"
+        np.savetxt(fp, f, fmt="%.3f")
+        sim_paths.append(str(p))
+        freq_paths.append(str(fp))
+        freqs.append(np.loadtxt(fp))
+    observed = np.array([0.0, 0.3, 0.2, 0.5])
+    args = (obs, 0.25, 0.95, 0.05)
+    host = simulator.process_results_batch(sim_paths, freq_paths, *args, observed=observed, parse="host")
+    dev = simulator.process_results_batch(sim_paths, freq_paths, *args, observed=observed, parse="device")
+    for got, want in zip(dev, host):
+        assert np.isfinite(want).all()
+        np.testing.assert_array_equal(_bits(got), _bits(want))
+    # several chunks of files, the last one short
+    chunked = simulator._from_files_on_device(obs, sim_paths, freq_paths, 0.25, 0.95, 0.05, observed, None, 100, chunk=4)
+    for got, want in zip(chunked, host):
+        np.testing.assert_array_equal(_bits(got), _bits(want))
+    # the summary step on its own: the discrepancies of the array path in, kdejs_summary_batch's vectors out
+    arrays = [np.loadtxt(p, delimiter="\t") for k, p in enumerate(sim_paths) if k != 4]
+    fr = [f for k, f in enumerate(freqs) if k != 4]
+    s_ref, d_ref, l_ref = pk.KDE_distance.summary_batch(obs, arrays, fr, observed, 0.25, 0.95, 0.05)
+    s_js, d_js, l_js = pk.KDE_distance.summary_from_js(s_ref[:, 0], fr, observed, 0.95, 0.05)
+    for got, want in ((s_js, s_ref), (d_js, d_ref), (l_js, l_ref)):
+        np.testing.assert_array_equal(_bits(got), _bits(want))
+    keep = [k for k in range(B) if k != 4]
+    np.testing.assert_array_equal(_bits(s_ref), _bits(host[0][keep]))
+    # without `observed` only the vectors come back; one file alone takes the host reader
+    only = simulator.process_results_batch(sim_paths[:3], freq_paths[:3], *args)
+    np.testing.assert_array_equal(_bits(only), _bits(host[0][:3]))
+    one = simulator.process_result(sim_paths[1], freq_paths[1], *args)
+    np.testing.assert_array_equal(_bits(one), _bits(host[0][1]))
+    with pytest.raises(ValueError, match="parse"):
+        simulator.process_results_batch(sim_paths, freq_paths, *args, parse="gpu")
