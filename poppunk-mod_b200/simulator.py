@@ -43,6 +43,15 @@ def _two_column(path):
         return f.readline().rstrip().count(b"\t") == 1
 
 
+def _all_two_column(paths):
+    if len(paths) < 64:
+        return all(_two_column(p) for p in paths)
+    from concurrent.futures import ThreadPoolExecutor
+
+    with ThreadPoolExecutor(max_workers=8) as ex:       # an open + a read per file: the system calls release the GIL
+        return all(ex.map(_two_column, paths))
+
+
 def _from_files_on_device(obs_arr, files, freq_files, gamma, core_threshold, rare_threshold, observed, device,
                           resolution, chunk=64):
     """Simulations on disk without a parser on the host: the tables' BYTES go to the GPU in chunks and are parsed and
@@ -81,7 +90,7 @@ def process_results_batch(simulations, simulations_freqs, obs, gamma, core_thres
     if parse not in ("device", "host"):
         raise ValueError("parse must be 'device' or 'host'")
     on_disk = len(simulations) > 1 and all(isinstance(s, (str, os.PathLike)) for s in simulations)
-    if on_disk and parse == "device" and algo is None and all(_two_column(s) for s in simulations):
+    if on_disk and parse == "device" and algo is None and _all_two_column(simulations):
         summary, d, log_d = _from_files_on_device(obs_arr, [os.fspath(s) for s in simulations], simulations_freqs, gamma,
                                                   core_threshold, rare_threshold, obs4, device, resolution)
         return (summary, d, log_d) if want_d else summary
