@@ -524,6 +524,12 @@ def main():
             ingest = run_ingest(pk, target, sims, GAMMA, EPS)
         except (OSError, MemoryError) as e:          # no room for 1.5 GB of tables under the temporary directory
             ingest = {"unavailable": f"{type(e).__name__}: {e}"}
+    pairwise = None
+    if extras and world == 1:
+        try:
+            pairwise = run_pairwise(pk, GAMMA, EPS)
+        except Exception as e:                       # a side leg never takes the headline line down with it
+            pairwise = {"unavailable": f"{type(e).__name__}: {e}"}
 
     # ---- roofline of the dominant kernel (density) ------------------------------------------------
     tf64, mhz = ctypes.c_double(), ctypes.c_double()
@@ -665,6 +671,7 @@ def main():
         "c5_row_sharded": c5,
         "r100": r100,
         "ingest": ingest,
+        "pairwise": pairwise,
         "algos": algos,
         "single_call_latency_ms": single_ms,
         "dense_fp32": dense,
@@ -712,8 +719,13 @@ def run_ingest(pk, target, sims, gamma, eps, n_files=512, n_distinct=8):
         best, dist_ = sweeps.gridsearch_best(ref, files, gamma=gamma, eps=eps, log=False, resolution=100)
         dt = time.perf_counter() - t0
         assert dist_[0] == pk.KDE_JS_divergence(target, a, gamma, eps) and best[0] is not None
+        try:
+            simulator_leg = run_simulator_files(pk, d, target, files[:256], gamma)
+        except Exception as e:                       # a side leg never takes the ingest figure down with it
+            simulator_leg = {"unavailable": f"{type(e).__name__}: {e}"}
         return {"value": n_files / dt, "unit": "tables/s", "tables": n_files, "rows_per_table": int(a.shape[0]),
                 "mb_per_table": os.path.getsize(files[0]) / 1e6, "seconds": dt, "host_cores": os.cpu_count(),
+                "simulator_files": simulator_leg,
                 "api": "sweeps.gridsearch_best(ref.tsv, [sim.tsv ...]) at the reference's 100x100 grid",
                 "np_loadtxt_tables_per_s_per_core": 1.0 / t_np,
                 "note": "files (page cache) -> bytes into a page-locked arena (kdejs_files_read) -> H2D of the text -> "
@@ -721,6 +733,65 @@ def run_ingest(pk, target, sims, gamma, eps, n_files=512, n_distinct=8):
                         "np.loadtxt and evaluates it on one core (scripts/distance_to_gridsearch.py:48-55)"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def run_simulator_files(pk, d, target, files, gamma, n_genes=5000):
+    """Simulator output files -> process_result's summary vectors and the two ELFI nodes (poppunk_mod.py:351-382,
+    :571-572) for a batch: simulator.process_results_batch with the tables parsed on the device, the host-parsed
+    pipeline timed beside it and compared bit for bit."""
+    from poppunk_mod_b200 import simulator
+
+    rng = np.random.default_rng(1)
+    freq_files = []
+    for k in range(len(files)):
+        fq = os.path.join(d, f"sim{k}_freqs.txt")
+        if k < 8:
+            np.savetxt(fq, np.round(rng.beta(0.3, 0.3, n_genes), 4), fmt="%.4f")
+        else:
+            import shutil
+
+            shutil.copy(freq_files[k % 8], fq)
+        freq_files.append(fq)
+    observed = [0.0, 0.3, 0.2, 0.5]
+    out, secs = {}, {}
+    for parse in ("host", "device"):
+        simulator.process_results_batch(files[:64], freq_files[:64], target, gamma, 0.95, 0.05, observed=observed, parse=parse)
+        t0 = time.perf_counter()
+        out[parse] = simulator.process_results_batch(files, freq_files, target, gamma, 0.95, 0.05, observed=observed, parse=parse)
+        secs[parse] = time.perf_counter() - t0
+    same = all(np.array_equal(x, y) for x, y in zip(out["host"], out["device"]))
+    return {"value": len(files) / secs["device"], "unit": "simulations/s", "simulations": len(files),
+            "host_parsed": len(files) / secs["host"], "bit_identical_to_host_parsed": bool(same),
+            "api": "simulator.process_results_batch(sim files, freq files, target, ..., observed=[0, fc, fi, fr]) at the "
+                   "reference's 100x100 grid: (summary, d, log d)",
+            "note": f"100 000-row tables + {n_genes} gene frequencies per simulation; tables parsed on the device "
+                    "(kdejs_discrepancy_batch_text + kdejs_summary_from_js) vs by the host reader (kdejs_summary_batch)"}
+
+
+def run_pairwise(pk, gamma, eps, n_species=64):
+    """All pairs of species tables (scripts/pairwise_2D_distance.py:100-118) on parsed arrays: every set uploaded
+    once, one evaluation per pair under that pair's joint scaler, the reference's 100x100 grid."""
+    import itertools
+
+    from oracle import workloads as wl
+
+    rng = np.random.default_rng(7)
+    sizes = rng.integers(20706, 100001, n_species)       # the row counts of the reference's distances/2_column tables
+    sets = [wl.sim_batch_member(s, n=int(sizes[s])) for s in range(n_species)]
+    pairs = list(itertools.combinations(range(n_species), 2))
+    pk.KDE_JS_divergence_pairs(sets[:8], pairs[:7], gamma, eps)                  # warm-up
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        js = pk.KDE_JS_divergence_pairs(sets, pairs, gamma, eps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    k = len(pairs) // 2
+    single = pk.KDE_JS_divergence(sets[pairs[k][0]], sets[pairs[k][1]], gamma, eps)
+    return {"value": len(pairs) / best, "unit": "pairs/s", "species": n_species, "pairs": len(pairs),
+            "rows_per_table": [int(sizes.min()), int(sizes.max())], "seconds": best,
+            "equals_single_call": bool(js[k] == single),
+            "api": "KDE_JS_divergence_pairs(sets, combinations) from ordinary numpy arrays (H2D of every set inside)"}
 
 
 def run_c5(torch, dist, pk, D, nat, rank, world, dev, n_pairs, barrier, max_over_ranks):
