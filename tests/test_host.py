@@ -227,3 +227,23 @@ def test_sweep_arenas_are_leased_not_shared():
         assert larger[0] is not first[0] and first[0].closed and larger[0].cap == 500
     sweeps.release_arenas()
     assert larger[0].closed and ("test", 4) not in sweeps._ARENAS and Arena.made == 5
+
+
+def test_simulator_batch_checks_and_table_shape_detection(tmp_path):
+    """simulator.process_results_batch: argument errors surface before any CUDA work; the device parser is only
+    chosen for tables read_distfile (poppunk_mod.py:255-269) would read whole -- two tab-separated columns."""
+    from poppunk_mod_b200 import simulator
+
+    obs = np.random.default_rng(0).random((10, 2))
+    with pytest.raises(ValueError, match="parse"):
+        simulator.process_results_batch([obs], [[0.1]], obs, 0.25, 0.95, 0.05, parse="gpu")
+    with pytest.raises(ValueError, match="one gene-frequency vector per simulation"):
+        simulator.process_results_batch([obs, obs], [[0.1]], obs, 0.25, 0.95, 0.05)
+    two, four, trailing = tmp_path / "two.tsv", tmp_path / "four.tsv", tmp_path / "trailing.tsv"
+    two.write_text("0.001\t0.2\n0.002\t0.3\n")
+    four.write_text("A\tB\t0.001\t0.2\n")
+    trailing.write_text("0.001\t0.2\t\r\n")                # str.rstrip() drops the trailing tab, as in read_distfile
+    assert simulator._two_column(two) and simulator._two_column(trailing) and not simulator._two_column(four)
+    many = [str(two)] * 70
+    assert simulator._all_two_column(many) and not simulator._all_two_column(many + [str(four)])
+    assert not simulator._all_two_column([str(four), str(two)])
