@@ -90,6 +90,18 @@ def test_argument_validation_happens_before_cuda():
         pk.KDE_JS_divergence(good, good, bandwidth=-1.0)
     with pytest.raises(ValueError):
         pk.KDE_JS_divergence(good, good, kernel="gaussian", algo="binned")
+    # the summary step on existing discrepancies: shape errors are raised by the wrapper, an empty batch needs no GPU
+    kd = pk.KDE_distance
+    with pytest.raises(ValueError, match="one gene-frequency vector"):
+        kd.summary_from_js([0.5, 0.6], [[0.1]], [0, 0.3, 0.2, 0.5], 0.95, 0.05)
+    with pytest.raises(ValueError, match="4-vector"):
+        kd.summary_from_js([0.5], [[0.1]], [0, 0.3, 0.2], 0.95, 0.05)
+    summary, d, log_d = kd.summary_from_js([], [], [0, 0.3, 0.2, 0.5], 0.95, 0.05)
+    assert summary.shape == (0, 4) and d.shape == (0,) and log_d.shape == (0,)
+    lib = pk._native.lib()
+    assert lib.kdejs_summary_from_js(0, None, None, None, -1, 0.95, 0.05, None, None, None, None) == pk._native.KDEJS_ERR_ARG
+    assert lib.kdejs_summary_from_js(0, None, None, None, 0, 0.95, 0.05, None, None, None, None) == pk._native.KDEJS_OK
+    assert lib.kdejs_summary_from_js(0, None, None, None, 3, 0.95, 0.05, None, None, None, None) == pk._native.KDEJS_ERR_ARG
 
 
 def test_inputs_are_not_mutated_and_views_are_accepted():
